@@ -1,0 +1,819 @@
+// pipeline.cu — host side of libbzb200: context, device memory, stage orchestration and the C ABI of
+// include/bzb200.h.  No CPU implementation of any stage lives here: if CUDA is unavailable every compute entry
+// point returns BZB200_E_CUDA.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/bzb200.h"
+#include "common.cuh"
+#include "kernels.h"
+
+using namespace bzb;
+
+// ============================================================== Launcher
+cudaEvent_t Launcher::get_event() {
+  if (!pool.empty()) {
+    cudaEvent_t e = pool.back();
+    pool.pop_back();
+    return e;
+  }
+  cudaEvent_t e;
+  cudaEventCreate(&e);
+  return e;
+}
+
+void Launcher::raw_launch(const char* name, const void* fn, dim3 grid, dim3 block, size_t smem, void** args) {
+  if (err != cudaSuccess) return;
+  Pending p{name, nullptr, nullptr};
+  if (profiling) {
+    p.a = get_event();
+    p.b = get_event();
+    cudaEventRecord(p.a, stream);
+  }
+  cudaError_t e = cudaLaunchKernel(fn, grid, block, args, smem, stream);
+  if (e != cudaSuccess) {
+    err = e;
+    err_kernel = name;
+    return;
+  }
+  ++launches;
+  if (profiling) {
+    cudaEventRecord(p.b, stream);
+    pending.push_back(p);
+  }
+}
+
+void Launcher::resolve() {
+  if (pending.empty()) return;
+  cudaStreamSynchronize(stream);
+  for (auto& p : pending) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, p.a, p.b);
+    bool found = false;
+    for (auto& r : recs)
+      if (strcmp(r.name, p.name) == 0) {
+        r.launches += 1;
+        r.ms += ms;
+        found = true;
+        break;
+      }
+    if (!found) recs.push_back(Rec{p.name, 1, (double)ms});
+    pool.push_back(p.a);
+    pool.push_back(p.b);
+  }
+  pending.clear();
+}
+
+void Launcher::clear_profile() {
+  resolve();
+  recs.clear();
+}
+
+Launcher::~Launcher() {
+  for (auto& p : pending) {
+    cudaEventDestroy(p.a);
+    cudaEventDestroy(p.b);
+  }
+  for (auto e : pool) cudaEventDestroy(e);
+}
+
+// ============================================================== context
+namespace {
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+};
+
+constexpr uint32_t MAX_BATCH_BLOCKS = 32768;
+
+}  // namespace
+
+struct bzb200_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  Launcher L;
+  std::string err;
+
+  // ---- plan ----
+  int level = 0;
+  uint32_t T = 0;
+  const uint8_t* d_in = nullptr;
+  uint64_t n_in = 0;
+  uint32_t nblocks = 0;
+  uint32_t max_block_len = 0;
+  bool planned = false;
+  DevBuf tile_head, tile_carry, tile_cnt, tile_E, in_off, rle_off, txt, crc, inuse, scal;
+  std::vector<uint64_t> h_in_off, h_rle_off;
+  std::vector<uint32_t> h_crc;
+
+  // ---- batch scratch ----
+  DevBuf desc, A, B, rank, cnt, hist, tsum, state, shift, stats, rounds, global, last, origptr;
+  DevBuf chunk_state, chunk_zle, chunk_base, sym, freq, mtf_count;
+  DevBuf lens, rfreq, sel, selmtf, codes, gbits, meta, lm_scratch, lm_list, lm_count, blockbit, bitcursor, combined;
+  uint64_t batch_elems_cap = (uint64_t)1400 * 1000 * 1000;
+
+  // ---- last batch (debug) ----
+  uint32_t batch_b0 = 0, batch_nb = 0;
+  std::vector<BlockDesc> h_desc;
+  std::vector<uint64_t> h_blockbit;
+  uint8_t* last_out = nullptr;
+  uint32_t sort_rounds = 0, sort_passes = 0;
+  uint64_t sort_elems = 0;
+
+  std::vector<DevBuf*> all;
+};
+
+namespace {
+
+#define CK(ctx, call)                                                                                  \
+  do {                                                                                                 \
+    cudaError_t e__ = (call);                                                                          \
+    if (e__ != cudaSuccess) {                                                                          \
+      (ctx)->err = std::string(#call) + ": " + cudaGetErrorString(e__);                                \
+      return BZB200_E_CUDA;                                                                            \
+    }                                                                                                  \
+  } while (0)
+
+int ensure(bzb200_ctx* c, DevBuf& b, size_t bytes) {
+  if (bytes == 0) bytes = 16;
+  if (b.cap >= bytes) return BZB200_OK;
+  if (b.p) {
+    CK(c, cudaStreamSynchronize(c->stream));
+    CK(c, cudaFree(b.p));
+    b.p = nullptr;
+    b.cap = 0;
+  }
+  size_t want = bytes + bytes / 16 + 256;
+  cudaError_t e = cudaMalloc(&b.p, want);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    want = bytes;
+    e = cudaMalloc(&b.p, want);
+  }
+  if (e != cudaSuccess) {
+    c->err = std::string("cudaMalloc(") + std::to_string(want) + "): " + cudaGetErrorString(e);
+    b.p = nullptr;
+    return BZB200_E_CUDA;
+  }
+  b.cap = want;
+  return BZB200_OK;
+}
+
+int check_launch(bzb200_ctx* c) {
+  if (c->L.err != cudaSuccess) {
+    c->err = std::string("kernel launch ") + (c->L.err_kernel ? c->L.err_kernel : "?") + ": " +
+             cudaGetErrorString(c->L.err);
+    c->L.err = cudaSuccess;
+    return BZB200_E_CUDA;
+  }
+  return BZB200_OK;
+}
+
+template <class T>
+T* ptr(DevBuf& b) {
+  return reinterpret_cast<T*>(b.p);
+}
+
+#define TRY(x)                \
+  do {                        \
+    int r__ = (x);            \
+    if (r__ != BZB200_OK) return r__; \
+  } while (0)
+
+int set_device(bzb200_ctx* c) {
+  CK(c, cudaSetDevice(c->device));
+  return BZB200_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* bzb200_version(void) { return "bzb200 0.1 (sm_100a)"; }
+
+int bzb200_ctx_create(int device, void* stream, bzb200_ctx** out) {
+  if (!out) return BZB200_E_ARG;
+  *out = nullptr;
+  bzb200_ctx* c = new bzb200_ctx();
+  if (device < 0) {
+    cudaError_t e = cudaGetDevice(&device);
+    if (e != cudaSuccess) {
+      c->err = std::string("cudaGetDevice: ") + cudaGetErrorString(e);
+      *out = c;  // returned so that the caller can read the message
+      return BZB200_E_CUDA;
+    }
+  }
+  c->device = device;
+  cudaError_t e = cudaSetDevice(device);
+  if (e != cudaSuccess) {
+    c->err = std::string("cudaSetDevice: ") + cudaGetErrorString(e);
+    *out = c;
+    return BZB200_E_CUDA;
+  }
+  if (stream) {
+    c->stream = reinterpret_cast<cudaStream_t>(stream);
+  } else {
+    e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+      c->err = std::string("cudaStreamCreate: ") + cudaGetErrorString(e);
+      *out = c;
+      return BZB200_E_CUDA;
+    }
+    c->own_stream = true;
+  }
+  c->L.stream = c->stream;
+  const char* be = getenv("BZB200_BATCH_ELEMS");
+  if (be) {
+    unsigned long long v = strtoull(be, nullptr, 10);
+    if (v >= 1000) c->batch_elems_cap = v;
+  }
+  c->all = {&c->tile_head, &c->tile_carry, &c->tile_cnt, &c->tile_E, &c->in_off, &c->rle_off, &c->txt, &c->crc,
+            &c->inuse, &c->scal, &c->desc, &c->A, &c->B, &c->rank, &c->cnt, &c->hist, &c->tsum, &c->state, &c->shift,
+            &c->stats, &c->rounds, &c->global, &c->last, &c->origptr, &c->chunk_state, &c->chunk_zle, &c->chunk_base,
+            &c->sym, &c->freq, &c->mtf_count, &c->lens, &c->rfreq, &c->sel, &c->selmtf, &c->codes, &c->gbits, &c->meta,
+            &c->lm_scratch, &c->lm_list, &c->lm_count, &c->blockbit, &c->bitcursor, &c->combined};
+  *out = c;
+  return BZB200_OK;
+}
+
+void bzb200_ctx_destroy(bzb200_ctx* c) {
+  if (!c) return;
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  for (DevBuf* b : c->all)
+    if (b->p) cudaFree(b->p);
+  if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+const char* bzb200_last_error(const bzb200_ctx* c) { return c ? c->err.c_str() : "null context"; }
+
+int bzb200_sync(bzb200_ctx* c) {
+  if (!c) return BZB200_E_ARG;
+  CK(c, cudaStreamSynchronize(c->stream));
+  return BZB200_OK;
+}
+
+size_t bzb200_max_output_bytes(int level, size_t n) {
+  if (level < 1 || level > 9) level = 1;
+  size_t T = (size_t)level * 100000 - 19;
+  size_t nblocks = (n + n / 4) / T + 2;
+  size_t bytes = n + n / 2 + nblocks * 4096 + 1024;
+  return (bytes + 7) & ~(size_t)7;
+}
+
+// ------------------------------------------------------------------ plan (K1 + K5)
+int bzb200_plan(bzb200_ctx* c, int level, const uint8_t* d_in, size_t n, uint32_t* nblocks) {
+  if (!c) return BZB200_E_ARG;
+  if (level < 1 || level > 9) {
+    c->err = "invalid level";
+    return BZB200_E_LEVEL;
+  }
+  if (!d_in && n) return BZB200_E_ARG;
+  TRY(set_device(c));
+  c->planned = false;
+  c->level = level;
+  c->T = (uint32_t)level * 100000u - 19u;  // encoder.rs:186
+  c->d_in = d_in;
+  c->n_in = n;
+  c->nblocks = 0;
+  c->max_block_len = 0;
+  c->h_in_off.assign(1, 0);
+  c->h_rle_off.assign(1, 0);
+  c->h_crc.clear();
+  c->batch_nb = 0;
+  if (n == 0) {
+    c->planned = true;
+    if (nblocks) *nblocks = 0;
+    return BZB200_OK;
+  }
+  const uint64_t nt = k1_num_tiles(n);
+  const uint64_t emax = (uint64_t)n + n / 4 + 64;
+  const uint64_t max_blocks64 = emax / c->T + 2;
+  if (max_blocks64 > 0x7FFFFFF0ull) return BZB200_E_ARG;
+  const uint32_t max_blocks = (uint32_t)max_blocks64;
+  TRY(ensure(c, c->tile_head, nt * 8));
+  TRY(ensure(c, c->tile_carry, nt * 8));
+  TRY(ensure(c, c->tile_cnt, nt * 4));
+  TRY(ensure(c, c->tile_E, (nt + 1) * 8));
+  TRY(ensure(c, c->in_off, ((size_t)max_blocks + 1) * 8));
+  TRY(ensure(c, c->rle_off, ((size_t)max_blocks + 1) * 8));
+  TRY(ensure(c, c->scal, 64));
+  TRY(ensure(c, c->txt, emax));
+  launch_k1_plan(c->L, d_in, n, c->T, ptr<long long>(c->tile_head), ptr<long long>(c->tile_carry),
+                 ptr<uint32_t>(c->tile_cnt), ptr<uint64_t>(c->tile_E), ptr<uint64_t>(c->in_off),
+                 ptr<uint64_t>(c->rle_off), max_blocks, ptr<uint32_t>(c->scal), ptr<uint32_t>(c->scal) + 1);
+  launch_k1_scatter(c->L, d_in, n, ptr<long long>(c->tile_carry), ptr<uint64_t>(c->tile_E), ptr<uint8_t>(c->txt));
+  TRY(check_launch(c));
+  uint32_t sc[2] = {0, 0};
+  CK(c, cudaMemcpyAsync(sc, c->scal.p, sizeof(sc), cudaMemcpyDeviceToHost, c->stream));
+  CK(c, cudaStreamSynchronize(c->stream));
+  const uint32_t nb = sc[0];
+  if (nb == 0 || nb > max_blocks) {
+    c->err = "cut chain produced an invalid block count";
+    return BZB200_E_INTERNAL;
+  }
+  c->nblocks = nb;
+  c->max_block_len = sc[1];
+  c->h_in_off.resize((size_t)nb + 1);
+  c->h_rle_off.resize((size_t)nb + 1);
+  c->h_crc.resize(nb);
+  TRY(ensure(c, c->crc, (size_t)nb * 4));
+  TRY(ensure(c, c->inuse, (size_t)nb * 32));
+  launch_k5_crc(c->L, d_in, ptr<uint64_t>(c->in_off), nb, ptr<uint32_t>(c->crc));
+  launch_k1_inuse(c->L, ptr<uint8_t>(c->txt), ptr<uint64_t>(c->rle_off), nb, ptr<uint32_t>(c->inuse));
+  TRY(check_launch(c));
+  CK(c, cudaMemcpyAsync(c->h_in_off.data(), c->in_off.p, ((size_t)nb + 1) * 8, cudaMemcpyDeviceToHost, c->stream));
+  CK(c, cudaMemcpyAsync(c->h_rle_off.data(), c->rle_off.p, ((size_t)nb + 1) * 8, cudaMemcpyDeviceToHost, c->stream));
+  CK(c, cudaMemcpyAsync(c->h_crc.data(), c->crc.p, (size_t)nb * 4, cudaMemcpyDeviceToHost, c->stream));
+  CK(c, cudaStreamSynchronize(c->stream));
+  if (c->max_block_len > (uint32_t)level * 100000u || c->max_block_len > MAX_BLOCK) {
+    c->err = "block longer than level*100000";
+    return BZB200_E_INTERNAL;
+  }
+  c->planned = true;
+  if (nblocks) *nblocks = nb;
+  return BZB200_OK;
+}
+
+uint32_t bzb200_num_blocks(const bzb200_ctx* c) { return (c && c->planned) ? c->nblocks : 0; }
+
+int bzb200_block_table(bzb200_ctx* c, uint64_t* in_off, uint64_t* rle_off, uint32_t* crc) {
+  if (!c || !c->planned) return BZB200_E_STATE;
+  if (in_off) memcpy(in_off, c->h_in_off.data(), c->h_in_off.size() * 8);
+  if (rle_off) memcpy(rle_off, c->h_rle_off.data(), c->h_rle_off.size() * 8);
+  if (crc && c->nblocks) memcpy(crc, c->h_crc.data(), (size_t)c->nblocks * 4);
+  return BZB200_OK;
+}
+
+// ------------------------------------------------------------------ encode (K2..K6)
+static int encode_batch(bzb200_ctx* c, uint32_t b0, uint32_t nb, uint8_t* d_out, size_t cap_bytes) {
+  const uint64_t base = c->h_rle_off[b0];
+  const uint64_t M = c->h_rle_off[b0 + nb] - base;
+  // descriptors
+  c->h_desc.resize(nb);
+  uint32_t nmax = 0;
+  uint64_t symoff = 0;
+  for (uint32_t i = 0; i < nb; ++i) {
+    BlockDesc& d = c->h_desc[i];
+    d.off = (uint32_t)(c->h_rle_off[b0 + i] - base);
+    d.n = (uint32_t)(c->h_rle_off[b0 + i + 1] - c->h_rle_off[b0 + i]);
+    d.symoff = (uint32_t)symoff;
+    d.pad = 0;
+    symoff += ((uint64_t)d.n + 1 + 7) & ~7ull;
+    nmax = std::max(nmax, d.n);
+  }
+  if (symoff >= 0xFFFFFFF0ull || M >= 0xFFFFFFF0ull) return BZB200_E_INTERNAL;
+  const uint32_t tile = bwt_tile_elems();
+  const uint32_t tiles = (nmax + tile - 1) / tile;
+  const uint32_t chunk = mtf_chunk_elems();
+  const uint32_t chunks = (nmax + chunk - 1) / chunk;
+  const uint32_t max_groups = (nmax + 1 + G_SIZE - 1) / G_SIZE;
+
+  TRY(ensure(c, c->desc, (size_t)nb * sizeof(BlockDesc)));
+  TRY(ensure(c, c->A, M * 8));
+  TRY(ensure(c, c->B, M * 8));
+  TRY(ensure(c, c->rank, M * 4));
+  TRY(ensure(c, c->cnt, (size_t)nb * 4));
+  TRY(ensure(c, c->hist, (size_t)nb * tiles * 256 * 4));
+  TRY(ensure(c, c->tsum, (size_t)nb * tiles * sizeof(int2)));
+  TRY(ensure(c, c->state, (size_t)nb * 4));
+  TRY(ensure(c, c->shift, (size_t)nb * 4));
+  TRY(ensure(c, c->stats, (size_t)nb * 16));
+  TRY(ensure(c, c->rounds, (size_t)nb * 4));
+  TRY(ensure(c, c->global, 64));
+  TRY(ensure(c, c->last, M));
+  TRY(ensure(c, c->origptr, (size_t)nb * 4));
+  TRY(ensure(c, c->chunk_state, (size_t)nb * chunks * 256 * 4));
+  TRY(ensure(c, c->chunk_zle, (size_t)nb * chunks * sizeof(uint4)));
+  TRY(ensure(c, c->chunk_base, (size_t)nb * chunks * sizeof(uint2)));
+  TRY(ensure(c, c->sym, symoff * 2));
+  TRY(ensure(c, c->freq, (size_t)nb * MAX_ALPHA * 4));
+  TRY(ensure(c, c->mtf_count, (size_t)nb * 4));
+  TRY(ensure(c, c->lens, (size_t)nb * 5 * MAX_GROUPS * MAX_ALPHA));
+  TRY(ensure(c, c->rfreq, (size_t)nb * MAX_GROUPS * MAX_ALPHA * 4));
+  TRY(ensure(c, c->sel, (size_t)nb * MAX_SELECTORS));
+  TRY(ensure(c, c->selmtf, (size_t)nb * MAX_SELECTORS));
+  TRY(ensure(c, c->codes, (size_t)nb * MAX_GROUPS * MAX_ALPHA * 4));
+  TRY(ensure(c, c->gbits, (size_t)nb * MAX_SELECTORS * 4));
+  TRY(ensure(c, c->meta, (size_t)nb * 8 * 4));
+  const uint32_t lm_slots = 512;
+  TRY(ensure(c, c->lm_scratch, (size_t)lm_slots * huff_lm_scratch_bytes()));
+  TRY(ensure(c, c->lm_list, (size_t)nb * MAX_GROUPS * 4));
+  TRY(ensure(c, c->lm_count, 16));
+  TRY(ensure(c, c->blockbit, ((size_t)nb + 1) * 8));
+
+  CK(c, cudaMemcpyAsync(c->desc.p, c->h_desc.data(), (size_t)nb * sizeof(BlockDesc), cudaMemcpyHostToDevice, c->stream));
+  const uint8_t* d_txt = ptr<uint8_t>(c->txt) + base;
+  const BlockDesc* d_desc = ptr<BlockDesc>(c->desc);
+  const uint32_t* d_inuse = ptr<uint32_t>(c->inuse) + (size_t)b0 * 8;
+  const uint32_t* d_crc = ptr<uint32_t>(c->crc) + b0;
+
+  BwtScratch S;
+  S.A = ptr<uint64_t>(c->A);
+  S.B = ptr<uint64_t>(c->B);
+  S.rank = ptr<uint32_t>(c->rank);
+  S.cnt = ptr<uint32_t>(c->cnt);
+  S.hist = ptr<uint32_t>(c->hist);
+  S.tsum = ptr<int2>(c->tsum);
+  S.state = ptr<uint32_t>(c->state);
+  S.shift = ptr<uint32_t>(c->shift);
+  S.stats = ptr<uint32_t>(c->stats);
+  S.rounds = ptr<uint32_t>(c->rounds);
+  S.global = ptr<uint32_t>(c->global);
+  S.tiles_cap = tiles;
+  uint32_t rounds = 0, passes = 0;
+  uint64_t elems = 0;
+  int r = run_bwt(c->L, d_txt, d_desc, nb, nmax, M, S, ptr<uint8_t>(c->last), ptr<uint32_t>(c->origptr), &rounds,
+                  &passes, &elems);
+  c->sort_rounds = std::max(c->sort_rounds, rounds);
+  c->sort_passes += passes;
+  c->sort_elems += elems;
+  if (r != 0) {
+    TRY(check_launch(c));
+    cudaError_t e = cudaGetLastError();
+    c->err = r == -5 ? "rotation sort did not converge (internal)"
+                     : std::string("rotation sort: ") + cudaGetErrorString(e);
+    return r == -5 ? BZB200_E_INTERNAL : BZB200_E_CUDA;
+  }
+
+  launch_mtf(c->L, ptr<uint8_t>(c->last), d_desc, d_inuse, nb, nmax, ptr<int>(c->chunk_state),
+             ptr<uint4>(c->chunk_zle), ptr<uint2>(c->chunk_base), chunks, ptr<uint16_t>(c->sym),
+             ptr<uint32_t>(c->freq), ptr<uint32_t>(c->mtf_count));
+
+  HuffBuffers H;
+  H.lens = ptr<uint8_t>(c->lens);
+  H.rfreq = ptr<uint32_t>(c->rfreq);
+  H.sel = ptr<uint8_t>(c->sel);
+  H.selmtf = ptr<uint8_t>(c->selmtf);
+  H.codes = ptr<uint32_t>(c->codes);
+  H.gbits = ptr<uint32_t>(c->gbits);
+  H.meta = ptr<uint32_t>(c->meta);
+  H.lm_scratch = ptr<uint8_t>(c->lm_scratch);
+  H.lm_list = ptr<uint32_t>(c->lm_list);
+  H.lm_count = ptr<uint32_t>(c->lm_count);
+  H.lm_slots = lm_slots;
+  launch_huffman(c->L, ptr<uint16_t>(c->sym), d_desc, ptr<uint32_t>(c->mtf_count), ptr<uint32_t>(c->freq), d_inuse, nb,
+                 max_groups, H);
+  TRY(check_launch(c));
+
+  // bit offsets first, so that the capacity can be checked before a single bit is written
+  uint64_t cursor_before = 0, cursor_after = 0;
+  CK(c, cudaMemcpyAsync(&cursor_before, c->bitcursor.p, 8, cudaMemcpyDeviceToHost, c->stream));
+  launch_pack(c->L, ptr<uint16_t>(c->sym), d_desc, ptr<uint32_t>(c->mtf_count), d_inuse, d_crc,
+              ptr<uint32_t>(c->origptr), nb, max_groups, H, ptr<uint64_t>(c->blockbit), ptr<uint64_t>(c->bitcursor),
+              nullptr);  // offsets only (d_out == nullptr)
+  TRY(check_launch(c));
+  CK(c, cudaMemcpyAsync(&cursor_after, c->bitcursor.p, 8, cudaMemcpyDeviceToHost, c->stream));
+  CK(c, cudaStreamSynchronize(c->stream));
+  (void)cursor_before;
+  if ((cursor_after + 7) / 8 + 16 > cap_bytes) {
+    c->err = "output buffer too small: need " + std::to_string((cursor_after + 7) / 8 + 16) + " bytes";
+    return BZB200_E_ARG;
+  }
+  launch_pack(c->L, ptr<uint16_t>(c->sym), d_desc, ptr<uint32_t>(c->mtf_count), d_inuse, d_crc,
+              ptr<uint32_t>(c->origptr), nb, max_groups, H, ptr<uint64_t>(c->blockbit), nullptr, d_out);
+  TRY(check_launch(c));
+  // device-side invariants
+  c->batch_b0 = b0;
+  c->batch_nb = nb;
+  c->last_out = d_out;
+  return BZB200_OK;
+}
+
+int bzb200_encode_blocks(bzb200_ctx* c, uint32_t b0, uint32_t b1, uint8_t* d_out, size_t cap_bytes,
+                         uint64_t start_bit, uint64_t* end_bit) {
+  if (!c) return BZB200_E_ARG;
+  if (!c->planned) {
+    c->err = "bzb200_encode_blocks before bzb200_plan";
+    return BZB200_E_STATE;
+  }
+  if (b0 > b1 || b1 > c->nblocks || !d_out || (reinterpret_cast<uintptr_t>(d_out) & 3)) {
+    c->err = "bad block range or unaligned output";
+    return BZB200_E_ARG;
+  }
+  TRY(set_device(c));
+  TRY(ensure(c, c->bitcursor, 16));
+  CK(c, cudaMemcpyAsync(c->bitcursor.p, &start_bit, 8, cudaMemcpyHostToDevice, c->stream));
+  CK(c, cudaStreamSynchronize(c->stream));
+  c->sort_rounds = 0;
+  c->sort_passes = 0;
+  c->sort_elems = 0;
+  uint32_t b = b0;
+  while (b < b1) {
+    uint32_t e = b;
+    uint64_t elems = 0;
+    while (e < b1 && e - b < MAX_BATCH_BLOCKS) {
+      uint64_t n = c->h_rle_off[e + 1] - c->h_rle_off[e];
+      if (e > b && elems + n > c->batch_elems_cap) break;
+      elems += n;
+      ++e;
+    }
+    TRY(encode_batch(c, b, e - b, d_out, cap_bytes));
+    b = e;
+  }
+  uint64_t cur = start_bit;
+  CK(c, cudaMemcpyAsync(&cur, c->bitcursor.p, 8, cudaMemcpyDeviceToHost, c->stream));
+  CK(c, cudaStreamSynchronize(c->stream));
+  TRY(check_launch(c));
+  if (end_bit) *end_bit = cur;
+  return BZB200_OK;
+}
+
+int bzb200_bit_append(bzb200_ctx* c, uint8_t* d_dst, size_t dst_cap_bytes, uint64_t dst_bit, const uint8_t* d_src,
+                      uint64_t nbits) {
+  if (!c || !d_dst || (!d_src && nbits)) return BZB200_E_ARG;
+  if ((reinterpret_cast<uintptr_t>(d_dst) & 3) || (reinterpret_cast<uintptr_t>(d_src) & 3)) return BZB200_E_ARG;
+  if (((dst_bit + nbits + 31) / 32) * 4 > dst_cap_bytes) {
+    c->err = "bit_append: destination too small";
+    return BZB200_E_ARG;
+  }
+  TRY(set_device(c));
+  launch_bit_append(c->L, d_dst, dst_bit, d_src, nbits);
+  return check_launch(c);
+}
+
+uint32_t bzb200_combine_crc(uint32_t seed, const uint32_t* crc, size_t n) {
+  uint32_t c = seed;
+  for (size_t i = 0; i < n; ++i) c = ((c << 1) | (c >> 31)) ^ crc[i];
+  return c;
+}
+
+int bzb200_write_stream_header(bzb200_ctx* c, int level, uint8_t* d_out, size_t cap_bytes) {
+  if (!c || !d_out || cap_bytes < 4 || (reinterpret_cast<uintptr_t>(d_out) & 3)) return BZB200_E_ARG;
+  if (level < 1 || level > 9) return BZB200_E_LEVEL;
+  TRY(set_device(c));
+  launch_write_header(c->L, level, d_out);
+  return check_launch(c);
+}
+
+int bzb200_write_stream_trailer(bzb200_ctx* c, uint8_t* d_out, size_t cap_bytes, uint64_t at_bit, uint32_t combined_crc,
+                                size_t* total_bytes) {
+  if (!c || !d_out || (reinterpret_cast<uintptr_t>(d_out) & 3)) return BZB200_E_ARG;
+  const size_t total = (size_t)((at_bit + 80 + 7) / 8);
+  if (((at_bit + 80 + 31) / 32) * 4 > cap_bytes) {
+    c->err = "trailer: output buffer too small";
+    return BZB200_E_ARG;
+  }
+  TRY(set_device(c));
+  launch_write_trailer(c->L, d_out, at_bit, combined_crc);
+  if (total_bytes) *total_bytes = total;
+  return check_launch(c);
+}
+
+int bzb200_compress_device(bzb200_ctx* c, int level, const uint8_t* d_in, size_t n, uint8_t* d_out, size_t cap_bytes,
+                           size_t* out_n) {
+  if (!c || !d_out || !out_n) return BZB200_E_ARG;
+  uint32_t nb = 0;
+  TRY(bzb200_plan(c, level, d_in, n, &nb));
+  TRY(bzb200_write_stream_header(c, level, d_out, cap_bytes));
+  uint64_t end_bit = 32;
+  if (nb) TRY(bzb200_encode_blocks(c, 0, nb, d_out, cap_bytes, 32, &end_bit));
+  const uint32_t combined = bzb200_combine_crc(0, c->h_crc.data(), nb);
+  TRY(bzb200_write_stream_trailer(c, d_out, cap_bytes, end_bit, combined, out_n));
+  CK(c, cudaStreamSynchronize(c->stream));
+  return BZB200_OK;
+}
+
+// ------------------------------------------------------------------ instrumentation
+int bzb200_debug_stage(bzb200_ctx* c, uint32_t block, int field, void* host_dst, size_t cap_elems, size_t* count) {
+  if (!c || !c->planned) return BZB200_E_STATE;
+  if (block < c->batch_b0 || block >= c->batch_b0 + c->batch_nb) {
+    c->err = "debug_stage: block is not in the most recent batch";
+    return BZB200_E_ARG;
+  }
+  TRY(set_device(c));
+  CK(c, cudaStreamSynchronize(c->stream));
+  const uint32_t i = block - c->batch_b0;
+  const BlockDesc& d = c->h_desc[i];
+  uint32_t meta[8];
+  CK(c, cudaMemcpy(meta, ptr<uint32_t>(c->meta) + (size_t)i * 8, sizeof(meta), cudaMemcpyDeviceToHost));
+  uint32_t mc = 0;
+  CK(c, cudaMemcpy(&mc, ptr<uint32_t>(c->mtf_count) + i, 4, cudaMemcpyDeviceToHost));
+  const void* src = nullptr;
+  size_t n = 0, esz = 1;
+  switch (field) {
+    case BZB200_F_RLE: src = ptr<uint8_t>(c->txt) + c->h_rle_off[block]; n = d.n; esz = 1; break;
+    case BZB200_F_RANK: src = ptr<uint32_t>(c->rank) + d.off; n = d.n; esz = 4; break;
+    case BZB200_F_LAST: src = ptr<uint8_t>(c->last) + d.off; n = d.n; esz = 1; break;
+    case BZB200_F_MTF: src = ptr<uint16_t>(c->sym) + d.symoff; n = mc; esz = 2; break;
+    case BZB200_F_FREQ: src = ptr<uint32_t>(c->freq) + (size_t)i * MAX_ALPHA; n = meta[0]; esz = 4; break;
+    case BZB200_F_SEL: src = ptr<uint8_t>(c->sel) + (size_t)i * MAX_SELECTORS; n = meta[2]; esz = 1; break;
+    case BZB200_F_LEN0: case BZB200_F_LEN1: case BZB200_F_LEN2: case BZB200_F_LEN3: case BZB200_F_LEN4: {
+      // gather [ngroups][alpha] out of the padded [6][258] layout
+      const int slot = field - BZB200_F_LEN0;
+      const size_t alpha = meta[0], ng = meta[1];
+      std::vector<uint8_t> tmp((size_t)MAX_GROUPS * MAX_ALPHA);
+      CK(c, cudaMemcpy(tmp.data(), ptr<uint8_t>(c->lens) + (((size_t)i * 5 + slot) * MAX_GROUPS) * MAX_ALPHA, tmp.size(),
+                       cudaMemcpyDeviceToHost));
+      n = ng * alpha;
+      if (count) *count = n;
+      uint8_t* o = (uint8_t*)host_dst;
+      size_t k = 0;
+      for (size_t t = 0; t < ng; ++t)
+        for (size_t s = 0; s < alpha; ++s, ++k)
+          if (o && k < cap_elems) o[k] = tmp[t * MAX_ALPHA + s];
+      return BZB200_OK;
+    }
+    case BZB200_F_INFO: {
+      uint64_t info[16] = {0};
+      uint32_t op = 0, rounds = 0, st[4] = {0, 0, 0, 0}, iu[8];
+      CK(c, cudaMemcpy(&op, ptr<uint32_t>(c->origptr) + i, 4, cudaMemcpyDeviceToHost));
+      CK(c, cudaMemcpy(&rounds, ptr<uint32_t>(c->rounds) + i, 4, cudaMemcpyDeviceToHost));
+      CK(c, cudaMemcpy(st, ptr<uint32_t>(c->stats) + (size_t)i * 4, 16, cudaMemcpyDeviceToHost));
+      CK(c, cudaMemcpy(iu, ptr<uint32_t>(c->inuse) + (size_t)block * 8, 32, cudaMemcpyDeviceToHost));
+      uint64_t bb[2] = {0, 0};
+      CK(c, cudaMemcpy(bb, ptr<uint64_t>(c->blockbit) + i, 16, cudaMemcpyDeviceToHost));
+      info[0] = c->h_in_off[block]; info[1] = c->h_in_off[block + 1]; info[2] = d.n; info[3] = c->h_crc[block];
+      info[4] = op; info[5] = mc; info[6] = meta[0]; info[7] = meta[1]; info[8] = meta[2];
+      info[9] = bb[0]; info[10] = bb[1]; info[11] = rounds; info[12] = st[3];
+      info[13] = meta[5];  // package-merge fallbacks taken
+      info[14] = meta[6];  // device-side error flags
+      n = 16;
+      if (count) *count = 16 + 8;
+      uint64_t* o = (uint64_t*)host_dst;
+      for (size_t k = 0; k < 16 && o && k < cap_elems; ++k) o[k] = info[k];
+      for (size_t k = 0; k < 8 && o && 16 + k < cap_elems; ++k) o[16 + k] = iu[k];
+      return BZB200_OK;
+    }
+    default: return BZB200_E_ARG;
+  }
+  if (count) *count = n;
+  size_t ncopy = std::min(n, cap_elems);
+  if (host_dst && ncopy) CK(c, cudaMemcpy(host_dst, src, ncopy * esz, cudaMemcpyDeviceToHost));
+  return BZB200_OK;
+}
+
+int bzb200_profile(bzb200_ctx* c, int on) {
+  if (!c) return BZB200_E_ARG;
+  if (on) {
+    c->L.clear_profile();
+    c->L.profiling = true;
+  } else {
+    c->L.resolve();
+    c->L.profiling = false;
+  }
+  return BZB200_OK;
+}
+int bzb200_profile_count(bzb200_ctx* c) {
+  if (!c) return 0;
+  c->L.resolve();
+  return (int)c->L.recs.size();
+}
+int bzb200_profile_get(bzb200_ctx* c, int i, const char** name, uint64_t* launches, double* total_ms) {
+  if (!c || i < 0 || i >= (int)c->L.recs.size()) return BZB200_E_ARG;
+  if (name) *name = c->L.recs[i].name;
+  if (launches) *launches = c->L.recs[i].launches;
+  if (total_ms) *total_ms = c->L.recs[i].ms;
+  return BZB200_OK;
+}
+uint64_t bzb200_launch_count(const bzb200_ctx* c) { return c ? c->L.launches : 0; }
+int bzb200_sort_stats(const bzb200_ctx* c, uint32_t* rounds, uint32_t* radix_passes, uint64_t* elems_sorted) {
+  if (!c) return BZB200_E_ARG;
+  if (rounds) *rounds = c->sort_rounds;
+  if (radix_passes) *radix_passes = c->sort_passes;
+  if (elems_sorted) *elems_sorted = c->sort_elems;
+  return BZB200_OK;
+}
+
+// ------------------------------------------------------------------ streaming encoder (BZip2Encoder)
+struct bzb200_enc {
+  int level = 9;
+  int device = -1;
+  bzb200_ctx* ctx = nullptr;
+  std::vector<uint8_t> in;
+  std::vector<uint8_t> out;
+  size_t rd = 0;
+  bool finished = false;
+  std::string err;
+};
+
+int bzb200_enc_create(int level, int device, bzb200_enc** out) {
+  if (!out) return BZB200_E_ARG;
+  *out = nullptr;
+  if (level < 1 || level > 9) return BZB200_E_LEVEL;  // BZip2Encoder::new panics "invalid level"
+  bzb200_enc* e = new bzb200_enc();
+  e->level = level;
+  e->device = device;
+  *out = e;
+  return BZB200_OK;
+}
+
+int bzb200_enc_write(bzb200_enc* e, const uint8_t* p, size_t n) {
+  if (!e || (!p && n)) return BZB200_E_ARG;
+  if (e->finished) {
+    e->err = "write after finish";
+    return BZB200_E_STATE;
+  }
+  e->in.insert(e->in.end(), p, p + n);
+  return BZB200_OK;
+}
+
+static int compress_host_with_ctx(bzb200_ctx* c, int level, const uint8_t* in, size_t n, std::vector<uint8_t>& out) {
+  DevBuf din, dout;
+  const size_t cap = bzb200_max_output_bytes(level, n);
+  int r = BZB200_OK;
+  do {
+    if ((r = ensure(c, din, n + 16)) != BZB200_OK) break;
+    if ((r = ensure(c, dout, cap)) != BZB200_OK) break;
+    if (n && cudaMemcpyAsync(din.p, in, n, cudaMemcpyHostToDevice, c->stream) != cudaSuccess) { r = BZB200_E_CUDA; break; }
+    if (cudaMemsetAsync(dout.p, 0, cap, c->stream) != cudaSuccess) { r = BZB200_E_CUDA; break; }
+    size_t out_n = 0;
+    if ((r = bzb200_compress_device(c, level, (const uint8_t*)din.p, n, (uint8_t*)dout.p, cap, &out_n)) != BZB200_OK) break;
+    out.resize(out_n);
+    if (cudaMemcpyAsync(out.data(), dout.p, out_n, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) { r = BZB200_E_CUDA; break; }
+    if (cudaStreamSynchronize(c->stream) != cudaSuccess) { r = BZB200_E_CUDA; break; }
+  } while (0);
+  if (r == BZB200_E_CUDA && c->err.empty()) c->err = std::string("cuda: ") + cudaGetErrorString(cudaGetLastError());
+  if (din.p) cudaFree(din.p);
+  if (dout.p) cudaFree(dout.p);
+  return r;
+}
+
+int bzb200_enc_finish(bzb200_enc* e) {
+  if (!e) return BZB200_E_ARG;
+  if (e->finished) return BZB200_OK;
+  if (!e->ctx) {
+    int r = bzb200_ctx_create(e->device, nullptr, &e->ctx);
+    if (r != BZB200_OK) {
+      e->err = e->ctx ? e->ctx->err : "context creation failed";
+      if (e->ctx) { bzb200_ctx_destroy(e->ctx); e->ctx = nullptr; }
+      return r;
+    }
+  }
+  int r = compress_host_with_ctx(e->ctx, e->level, e->in.data(), e->in.size(), e->out);
+  if (r != BZB200_OK) {
+    e->err = e->ctx->err;
+    return r;
+  }
+  e->in.clear();
+  e->in.shrink_to_fit();
+  e->rd = 0;
+  e->finished = true;
+  return BZB200_OK;
+}
+
+size_t bzb200_enc_read(bzb200_enc* e, uint8_t* dst, size_t cap) {
+  if (!e || !e->finished || !dst) return 0;
+  size_t n = std::min(cap, e->out.size() - e->rd);
+  if (n) memcpy(dst, e->out.data() + e->rd, n);
+  e->rd += n;
+  return n;
+}
+
+size_t bzb200_enc_output_size(const bzb200_enc* e) { return (e && e->finished) ? e->out.size() : 0; }
+
+int bzb200_enc_reset(bzb200_enc* e) {
+  if (!e) return BZB200_E_ARG;
+  e->in.clear();
+  e->out.clear();
+  e->rd = 0;
+  e->finished = false;
+  e->err.clear();
+  return BZB200_OK;
+}
+
+void bzb200_enc_destroy(bzb200_enc* e) {
+  if (!e) return;
+  if (e->ctx) bzb200_ctx_destroy(e->ctx);
+  delete e;
+}
+
+const char* bzb200_enc_last_error(const bzb200_enc* e) { return e ? e->err.c_str() : "null encoder"; }
+
+int bzb200_compress(int level, int device, const uint8_t* in, size_t n, uint8_t** out, size_t* out_n) {
+  if (!out || !out_n || (!in && n)) return BZB200_E_ARG;
+  *out = nullptr;
+  *out_n = 0;
+  if (level < 1 || level > 9) return BZB200_E_LEVEL;
+  bzb200_ctx* c = nullptr;
+  int r = bzb200_ctx_create(device, nullptr, &c);
+  if (r != BZB200_OK) {
+    if (c) bzb200_ctx_destroy(c);
+    return r;
+  }
+  std::vector<uint8_t> o;
+  r = compress_host_with_ctx(c, level, in, n, o);
+  if (r == BZB200_OK) {
+    *out = (uint8_t*)malloc(o.size() ? o.size() : 1);
+    if (!*out) r = BZB200_E_ARG;
+    else {
+      memcpy(*out, o.data(), o.size());
+      *out_n = o.size();
+    }
+  }
+  bzb200_ctx_destroy(c);
+  return r;
+}
+
+void bzb200_free(void* p) { free(p); }
+
+}  // extern "C"

@@ -1,0 +1,176 @@
+"""Device-resident job API (section 2/3 of include/bzb200.h) over torch tensors.
+
+torch is plumbing here: it owns device memory, the CUDA stream and (in sharded.py) torch.distributed. Every
+stage runs in libbzb200.so.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from .encoder import CompressionError
+
+FIELDS = {
+    "rle": (0, np.uint8), "rank": (1, np.uint32), "last": (2, np.uint8), "mtf": (3, np.uint16), "freq": (4, np.uint32),
+    "sel": (5, np.uint8), "len0": (6, np.uint8), "len1": (7, np.uint8), "len2": (8, np.uint8), "len3": (9, np.uint8),
+    "len4": (10, np.uint8), "info": (11, np.uint64),
+}
+INFO_KEYS = ["in_start", "in_end", "nblock", "crc", "orig_ptr", "mtf_count", "alpha", "ngroups", "nselectors",
+             "bit_start", "bit_end", "sort_rounds", "periodic", "lm_used", "dev_error"]
+
+
+def max_output_bytes(level, n):
+    return int(_lib.lib().bzb200_max_output_bytes(level, n))
+
+
+class Context:
+    """One context = one GPU + one stream (defaults to torch's current stream on the current device)."""
+
+    def __init__(self, device=None, stream=None):
+        L = _lib.lib()
+        if device is None:
+            device = torch.cuda.current_device()
+        self.device = torch.device("cuda", device if isinstance(device, int) else torch.device(device).index)
+        if stream is None:
+            stream = torch.cuda.current_stream(self.device)
+        self.stream = stream
+        self._h = C.c_void_p()
+        rc = L.bzb200_ctx_create(self.device.index, C.c_void_p(stream.cuda_stream), C.byref(self._h))
+        if rc != _lib.OK:
+            msg = L.bzb200_last_error(self._h).decode() if self._h else ""
+            if self._h:
+                L.bzb200_ctx_destroy(self._h)
+                self._h = None
+            raise CompressionError("Unexpected", f"bzb200_ctx_create rc={rc}: {msg}")
+        self.level = None
+        self.nblocks = 0
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _lib.lib().bzb200_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, what):
+        if rc != _lib.OK:
+            msg = _lib.lib().bzb200_last_error(self._h)
+            if rc == _lib.E_LEVEL:
+                raise ValueError("invalid level")
+            raise CompressionError("Unexpected", f"{what} rc={rc}: {msg.decode() if msg else ''}")
+
+    @staticmethod
+    def _u8(t):
+        assert t.is_cuda and t.dtype == torch.uint8 and t.is_contiguous()
+        return t
+
+    def sync(self):
+        self._check(_lib.lib().bzb200_sync(self._h), "bzb200_sync")
+
+    def plan(self, level, d_in):
+        self._u8(d_in)
+        nb = C.c_uint32(0)
+        self._check(_lib.lib().bzb200_plan(self._h, level, C.c_void_p(d_in.data_ptr()), d_in.numel(), C.byref(nb)),
+                    "bzb200_plan")
+        self._keep_in = d_in
+        self.level = level
+        self.nblocks = nb.value
+        return nb.value
+
+    def block_table(self):
+        nb = self.nblocks = int(_lib.lib().bzb200_num_blocks(self._h))
+        in_off = np.zeros(nb + 1, dtype=np.uint64)
+        rle_off = np.zeros(nb + 1, dtype=np.uint64)
+        crc = np.zeros(max(nb, 1), dtype=np.uint32)
+        self._check(_lib.lib().bzb200_block_table(self._h, in_off.ctypes.data, rle_off.ctypes.data, crc.ctypes.data),
+                    "bzb200_block_table")
+        return in_off, rle_off, crc[:nb]
+
+    def encode_blocks(self, b0, b1, d_out, start_bit):
+        self._u8(d_out)
+        end = C.c_uint64(0)
+        self._check(_lib.lib().bzb200_encode_blocks(self._h, b0, b1, C.c_void_p(d_out.data_ptr()), d_out.numel(),
+                                                    start_bit, C.byref(end)), "bzb200_encode_blocks")
+        return end.value
+
+    def bit_append(self, d_dst, dst_bit, d_src, nbits):
+        self._u8(d_dst)
+        self._u8(d_src)
+        self._check(_lib.lib().bzb200_bit_append(self._h, C.c_void_p(d_dst.data_ptr()), d_dst.numel(), dst_bit,
+                                                 C.c_void_p(d_src.data_ptr()), nbits), "bzb200_bit_append")
+
+    def write_stream_header(self, level, d_out):
+        self._check(_lib.lib().bzb200_write_stream_header(self._h, level, C.c_void_p(d_out.data_ptr()), d_out.numel()),
+                    "bzb200_write_stream_header")
+
+    def write_stream_trailer(self, d_out, at_bit, combined_crc):
+        total = C.c_size_t(0)
+        self._check(_lib.lib().bzb200_write_stream_trailer(self._h, C.c_void_p(d_out.data_ptr()), d_out.numel(), at_bit,
+                                                           combined_crc, C.byref(total)), "bzb200_write_stream_trailer")
+        return total.value
+
+    @staticmethod
+    def combine_crc(crcs, seed=0):
+        a = np.ascontiguousarray(crcs, dtype=np.uint32)
+        return int(_lib.lib().bzb200_combine_crc(seed, a.ctypes.data, a.size))
+
+    def compress_device(self, level, d_in, d_out):
+        """Whole stream, device in -> device out; d_out must be zero-filled. Returns the stream length in bytes."""
+        self._u8(d_in)
+        self._u8(d_out)
+        n = C.c_size_t(0)
+        self._check(_lib.lib().bzb200_compress_device(self._h, level, C.c_void_p(d_in.data_ptr()), d_in.numel(),
+                                                      C.c_void_p(d_out.data_ptr()), d_out.numel(), C.byref(n)),
+                    "bzb200_compress_device")
+        self.level = level
+        return n.value
+
+    # ---- instrumentation ----
+    def debug_stage(self, block, name):
+        fid, dt = FIELDS[name]
+        cnt = C.c_size_t(0)
+        self._check(_lib.lib().bzb200_debug_stage(self._h, block, fid, None, 0, C.byref(cnt)), "bzb200_debug_stage")
+        out = np.zeros(max(cnt.value, 1), dtype=dt)
+        self._check(_lib.lib().bzb200_debug_stage(self._h, block, fid, out.ctypes.data, out.size, C.byref(cnt)),
+                    "bzb200_debug_stage")
+        out = out[:cnt.value]
+        if name == "info":
+            d = {k: int(out[i]) for i, k in enumerate(INFO_KEYS)}
+            d["in_use"] = out[16:24].astype(np.uint32)
+            return d
+        return out
+
+    def profile(self, on):
+        self._check(_lib.lib().bzb200_profile(self._h, 1 if on else 0), "bzb200_profile")
+
+    def profile_records(self):
+        L = _lib.lib()
+        recs = {}
+        for i in range(L.bzb200_profile_count(self._h)):
+            name = C.c_char_p()
+            n = C.c_uint64(0)
+            ms = C.c_double(0)
+            L.bzb200_profile_get(self._h, i, C.byref(name), C.byref(n), C.byref(ms))
+            recs[name.value.decode()] = (int(n.value), float(ms.value))
+        return recs
+
+    def launch_count(self):
+        return int(_lib.lib().bzb200_launch_count(self._h))
+
+    def sort_stats(self):
+        r, p, e = C.c_uint32(0), C.c_uint32(0), C.c_uint64(0)
+        _lib.lib().bzb200_sort_stats(self._h, C.byref(r), C.byref(p), C.byref(e))
+        return {"rounds": r.value, "radix_passes": p.value, "elems_sorted": e.value}
+
+
+def compress_tensor(ctx, level, d_in):
+    """Convenience: device tensor in -> device tensor holding exactly the .bz2 stream."""
+    cap = max_output_bytes(level, d_in.numel())
+    d_out = torch.zeros(cap, dtype=torch.uint8, device=d_in.device)
+    n = ctx.compress_device(level, d_in, d_out)
+    return d_out[:n]
