@@ -1,0 +1,320 @@
+#!/usr/bin/env python3
+"""bench.py — bzip2 block-compression throughput on B200 (BASELINE.json metric: uncompressed MB/s, bit-exact).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+N>1 is launched by torchrun (one rank per GPU). A "step" is one pass of the whole hot path (K1..K7) over the
+synthetic corpus: every GPU holds the corpus in HBM and compresses its contiguous range of blocks; the compressed
+bit strings are gathered to rank 0 over NCCL and joined at bit granularity into ONE .bz2 stream.
+Weak scaling: 1 GiB of text per GPU (N GiB corpus at N GPUs).  One JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+LEVEL = 9
+METRIC = "bzip2 compress MB/s (uncompressed)"
+BYTES_PER_GPU = int(os.environ.get("BZB200_BENCH_BYTES", str(1 << 30)))
+CPU_SAMPLE_BYTES = int(os.environ.get("BZB200_CPU_SAMPLE_BYTES", str(128 << 20)))
+ALG_BYTES_PER_ELEM = {  # algorithmic HBM bytes per sort element and launch (DESIGN.md "Kernels")
+    "k2_rs_scatter": 16.0,  # 8 B element read + 8 B element written
+    "k2_rs_hist": 8.0,      # 8 B element read
+}
+
+
+def workload_name(n_gpus):
+    gib = BYTES_PER_GPU / float(1 << 30)
+    return (f"{gib:g} GiB synthetic English-like text per GPU, level {LEVEL} (~{int(BYTES_PER_GPU / 899981)} blocks of "
+            f"900 kB per GPU), one .bz2 stream sharded block-wise over {n_gpus} GPU(s)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.rows = []
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms",
+                                       "200", "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL,
+                                      text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.p = None
+
+    def _read(self):
+        for line in self.p.stdout:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) >= 9:
+                self.rows.append(f)
+
+    def stop(self):
+        if not self.p:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=2)
+        except Exception:
+            self.p.kill()
+        sm = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if r[2].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            for k, nm in enumerate(names):
+                if r[5 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(self.rows)}
+
+
+def gen_slice(rank, nbytes):
+    import gen
+    return gen.text(1 + rank, nbytes)
+
+
+def run_reference(args, rank):
+    """Reference arm: the reference's CPU implementation of the path. The Rust crate cannot be built here (no
+    rustc/cargo), so this times the C++ oracle port (oracle/), block-parallel over all host cores: each worker
+    compresses its own contiguous slice as an independent stream (the reference itself is single-threaded)."""
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    cores = os.cpu_count() or 1
+    per = int(os.environ.get("BZB200_REF_BYTES_PER_CORE", str(16 << 20)))
+    with mp.Pool(cores) as pool:
+        def step(seed):
+            t = time.perf_counter()
+            outs = pool.map(_ref_worker, [(seed * 1000 + i, per) for i in range(cores)])
+            return time.perf_counter() - t, sum(outs)
+        for w in range(args.warmup):
+            step(w)
+        tot = 0.0
+        for k in range(args.steps):
+            dt, _ = step(100 + k)
+            tot += dt
+    nbytes = per * cores
+    ms = tot / args.steps * 1e3
+    val = nbytes / (ms / 1e3) / 1e6
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "MB/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u8", "data": "synthetic",
+        "config": {"workload": workload_name(args.gpus), "level": LEVEL},
+        "cpu_baseline": {"value": val, "unit": "MB/s", "cores": cores, "kind": "port",
+                         "sample": f"{cores} workers x {per >> 20} MiB of the same synthetic text per step, each worker "
+                                   "one independent level-9 stream (C++ oracle port of the reference; rustc unavailable)"},
+        "e2e": {"value": val, "unit": "MB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def _ref_worker(a):
+    seed, n = a
+    import gen
+    from oracle import orc
+    data = gen.text(seed, n)
+    return len(orc.compress(data, LEVEL))
+
+
+def cpu_baseline(sample):
+    from oracle import orc
+    t = time.perf_counter()
+    out = orc.compress(sample, LEVEL)
+    dt = time.perf_counter() - t
+    return {"value": len(sample) / dt / 1e6, "unit": "MB/s", "cores": 1, "kind": "port",
+            "sample": f"first {len(sample) >> 20} MiB of rank 0's corpus, level {LEVEL}, single thread (the reference is "
+                      f"single-threaded); C++ oracle port, ratio {len(sample) / max(1, len(out)):.3f}"}
+
+
+def check_prefix(stream, corpus_prefix):
+    """Bit-exact parity of the stream's leading blocks against the oracle run on a prefix of the corpus (block cuts
+    depend only on preceding input, so all but the oracle's last block must match bit for bit)."""
+    from oracle import orc
+    r = orc.Run(corpus_prefix, LEVEL)
+    if r.nblocks < 2:
+        return "skipped"
+    bits = r.info(r.nblocks - 2)["bit_end"]
+    nb = bits // 8
+    ok = stream[:nb] == r.out[:nb]
+    if ok and bits % 8:
+        m = (0xFF << (8 - bits % 8)) & 0xFF
+        ok = (stream[nb] & m) == (r.out[nb] & m)
+    return f"{r.nblocks - 1} leading blocks ({bits} bits) bit-exact vs oracle" if ok else "MISMATCH"
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    import rust_compression_b200  # noqa: F401  (fails loudly if libbzb200.so is missing)
+    from rust_compression_b200 import device as dv
+    from rust_compression_b200 import sharded
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    # ---- synthetic corpus: each rank generates its slice; slices are all-gathered so every GPU holds the corpus
+    t0 = time.time()
+    raw = gen_slice(rank, BYTES_PER_GPU)
+    h_slice = torch.frombuffer(bytearray(raw), dtype=torch.uint8).pin_memory()
+    d_slice = h_slice.to(dev)
+    if world > 1:
+        d_full = torch.empty(world * BYTES_PER_GPU, dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(d_full, d_slice)
+    else:
+        d_full = d_slice
+    gen_s = time.time() - t0
+    h_out = torch.empty(dv.max_output_bytes(LEVEL, world * BYTES_PER_GPU), dtype=torch.uint8).pin_memory() \
+        if rank == 0 else None
+
+    ctx = dv.Context()
+    total_bytes = world * BYTES_PER_GPU
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        res = None
+        for _ in range(steps):
+            res = fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()), res
+
+    def step_device():
+        return sharded.compress_sharded(ctx, LEVEL, d_full)
+
+    def step_e2e():
+        if world == 1:
+            n = ctx.compress_host(LEVEL, h_slice, h_out)
+            return h_out[:n], {"h2d_bytes": h_slice.numel(), "d2h_bytes": n}
+        return sharded.compress_host_sharded(ctx, LEVEL, h_slice, h_out)
+
+    # ---- device-resident throughput
+    for _ in range(args.warmup):
+        step_device()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = ctx.launch_count()
+    ctx.profile(True)
+    ms_total, (d_stream, info) = timed(step_device, args.steps)
+    ctx.profile(False)
+    launches = ctx.launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    recs = ctx.profile_records()
+    sstats = ctx.sort_stats()
+    ms_step = ms_total / args.steps
+    value = total_bytes / (ms_step / 1e3) / 1e6
+
+    # ---- end to end with host buffers
+    for _ in range(max(1, args.warmup // 2)):
+        step_e2e()
+    e2e_steps = max(2, args.steps // 2)
+    ms_e2e, (h_stream, einfo) = timed(step_e2e, e2e_steps)
+    e2e_value = total_bytes / (ms_e2e / e2e_steps / 1e3) / 1e6
+
+    lsum = torch.tensor([launches], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(lsum)
+
+    if rank == 0:
+        stream = h_stream.numpy().tobytes()
+        out_bytes = len(stream)
+        dev_stream = d_stream.cpu().numpy().tobytes()
+        verified = "device and e2e streams identical; " if dev_stream == stream else "DEVICE/E2E STREAMS DIFFER; "
+        verified += check_prefix(stream, raw[: min(len(raw), 6 << 20)])
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+        # dominant kernel by device time inside the timed region
+        top = sorted(recs.items(), key=lambda kv: -kv[1][1])
+        name, (nl, kms) = top[0] if top else ("none", (0, 0.0))
+        step_ms_kernels = sum(v[1] for v in recs.values()) / args.steps
+        if name in ALG_BYTES_PER_ELEM:
+            # elements sorted per step on this rank x radix passes -> launches of the pass kernel
+            alg_bytes_total = ALG_BYTES_PER_ELEM[name] * sstats["elems_sorted"] * 5 * args.steps
+        else:
+            alg_bytes_total = (total_bytes / world + out_bytes / world) * args.steps
+        achieved = alg_bytes_total / (kms / 1e3) / 1e9 if kms > 0 else 0.0
+        roofline = {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                    "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                    "launches_per_step": nl / args.steps, "avg_launch_ms": kms / max(1, nl),
+                    "kernel_share_of_step": (kms / args.steps) / ms_step,
+                    "algorithmic_bytes_per_launch": alg_bytes_total / max(1, nl),
+                    "path": {"achieved": (total_bytes + out_bytes) / (ms_step / 1e3) / 1e9 / world, "unit": "GB/s per GPU",
+                             "frac": (total_bytes + out_bytes) / (ms_step / 1e3) / 1e9 / world / peak,
+                             "note": "whole path: (input + output bytes) / device time (SURVEY.md 8(d))"}}
+        line = {
+            "metric": METRIC, "value": value, "unit": "MB/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": workload_name(world), "level": LEVEL, "bytes_per_gpu": BYTES_PER_GPU,
+                       "blocks": info["nblocks"], "compressed_bytes": out_bytes,
+                       "ratio": total_bytes / max(1, out_bytes),
+                       "l2": "inputs (1 GiB per GPU) are larger than the 126 MB L2; no explicit flush",
+                       "sort": sstats, "verified": verified, "corpus_gen_s": round(gen_s, 1)},
+            "e2e": {"value": e2e_value, "unit": "MB/s", "h2d_bytes_per_step": int(total_bytes),
+                    "d2h_bytes_per_step": int(out_bytes), "steps": e2e_steps,
+                    "api": "bzb200_compress_host (C ABI, pinned host in/out)" if world == 1 else
+                           "sharded.compress_host_sharded (pinned slices H2D + NCCL all-gather + C ABI + D2H)"},
+            "gpu_launches": int(lsum.item()),
+            "roofline": roofline,
+            "kernels_ms_per_step": {k: round(v[1] / args.steps, 3) for k, v in top[:12]},
+            "kernel_time_ms_per_step": round(step_ms_kernels, 3),
+            "cpu_baseline": cpu_baseline(raw[:CPU_SAMPLE_BYTES]),
+            "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

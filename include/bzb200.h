@@ -124,6 +124,12 @@ BZB200_API size_t bzb200_max_output_bytes(int level, size_t n);
 BZB200_API int bzb200_compress_device(bzb200_ctx* c, int level, const uint8_t* d_in, size_t n, uint8_t* d_out, size_t cap_bytes,
                            size_t* out_n);
 
+/* Whole stream, HOST in -> HOST out on the context's device and stream: H2D copy, bzb200_compress_device, D2H
+ * copy of exactly *out_n bytes, synchronised on return.  Device staging buffers live in the context and are reused
+ * across calls.  Pinned (page-locked) host buffers make both copies asynchronous DMA; pageable buffers work too. */
+BZB200_API int bzb200_compress_host(bzb200_ctx* c, int level, const uint8_t* h_in, size_t n, uint8_t* h_out, size_t cap_bytes,
+                         size_t* out_n);
+
 /* ------------------------------------------------------------------------
  * 3. Instrumentation (parity tests, bench roofline).  Not needed by a shim.
  * ------------------------------------------------------------------------ */

@@ -34,6 +34,7 @@ SIGNATURES = {
     "bzb200_write_stream_trailer": (C.c_int, [_P, _P, C.c_size_t, C.c_uint64, C.c_uint32, C.POINTER(C.c_size_t)]),
     "bzb200_max_output_bytes": (C.c_size_t, [C.c_int, C.c_size_t]),
     "bzb200_compress_device": (C.c_int, [_P, C.c_int, _P, C.c_size_t, _P, C.c_size_t, C.POINTER(C.c_size_t)]),
+    "bzb200_compress_host": (C.c_int, [_P, C.c_int, _P, C.c_size_t, _P, C.c_size_t, C.POINTER(C.c_size_t)]),
     "bzb200_debug_stage": (C.c_int, [_P, C.c_uint32, C.c_int, _P, C.c_size_t, C.POINTER(C.c_size_t)]),
     "bzb200_profile": (C.c_int, [_P, C.c_int]),
     "bzb200_profile_count": (C.c_int, [_P]),

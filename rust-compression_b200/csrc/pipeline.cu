@@ -119,6 +119,7 @@ struct bzb200_ctx {
   DevBuf desc, A, B, rank, cnt, hist, tsum, state, shift, stats, rounds, global, last, origptr;
   DevBuf chunk_state, chunk_zle, chunk_base, sym, freq, mtf_count;
   DevBuf lens, rfreq, sel, selmtf, codes, gbits, meta, lm_scratch, lm_list, lm_count, blockbit, bitcursor, combined;
+  DevBuf stage_in, stage_out;  // bzb200_compress_host staging
   uint64_t batch_elems_cap = (uint64_t)1400 * 1000 * 1000;
 
   // ---- last batch (debug) ----
@@ -240,7 +241,8 @@ int bzb200_ctx_create(int device, void* stream, bzb200_ctx** out) {
             &c->inuse, &c->scal, &c->desc, &c->A, &c->B, &c->rank, &c->cnt, &c->hist, &c->tsum, &c->state, &c->shift,
             &c->stats, &c->rounds, &c->global, &c->last, &c->origptr, &c->chunk_state, &c->chunk_zle, &c->chunk_base,
             &c->sym, &c->freq, &c->mtf_count, &c->lens, &c->rfreq, &c->sel, &c->selmtf, &c->codes, &c->gbits, &c->meta,
-            &c->lm_scratch, &c->lm_list, &c->lm_count, &c->blockbit, &c->bitcursor, &c->combined};
+            &c->lm_scratch, &c->lm_list, &c->lm_count, &c->blockbit, &c->bitcursor, &c->combined, &c->stage_in,
+            &c->stage_out};
   *out = c;
   return BZB200_OK;
 }
@@ -580,6 +582,31 @@ int bzb200_compress_device(bzb200_ctx* c, int level, const uint8_t* d_in, size_t
   const uint32_t combined = bzb200_combine_crc(0, c->h_crc.data(), nb);
   TRY(bzb200_write_stream_trailer(c, d_out, cap_bytes, end_bit, combined, out_n));
   CK(c, cudaStreamSynchronize(c->stream));
+  return BZB200_OK;
+}
+
+int bzb200_compress_host(bzb200_ctx* c, int level, const uint8_t* h_in, size_t n, uint8_t* h_out, size_t cap_bytes,
+                         size_t* out_n) {
+  if (!c || !h_out || !out_n || (!h_in && n)) return BZB200_E_ARG;
+  if (level < 1 || level > 9) {
+    c->err = "invalid level";
+    return BZB200_E_LEVEL;
+  }
+  TRY(set_device(c));
+  const size_t cap = bzb200_max_output_bytes(level, n);
+  TRY(ensure(c, c->stage_in, n + 16));
+  TRY(ensure(c, c->stage_out, cap));
+  if (n) CK(c, cudaMemcpyAsync(c->stage_in.p, h_in, n, cudaMemcpyHostToDevice, c->stream));
+  CK(c, cudaMemsetAsync(c->stage_out.p, 0, cap, c->stream));
+  size_t got = 0;
+  TRY(bzb200_compress_device(c, level, ptr<uint8_t>(c->stage_in), n, ptr<uint8_t>(c->stage_out), cap, &got));
+  if (got > cap_bytes) {
+    c->err = "compress_host: output buffer too small: need " + std::to_string(got) + " bytes";
+    return BZB200_E_ARG;
+  }
+  CK(c, cudaMemcpyAsync(h_out, c->stage_out.p, got, cudaMemcpyDeviceToHost, c->stream));
+  CK(c, cudaStreamSynchronize(c->stream));
+  *out_n = got;
   return BZB200_OK;
 }
 

@@ -130,6 +130,15 @@ class Context:
         self.level = level
         return n.value
 
+    def compress_host(self, level, h_in, h_out):
+        """Whole stream, host tensor in -> host tensor out (pinned tensors give async DMA). Returns bytes written."""
+        assert (not h_in.is_cuda) and (not h_out.is_cuda) and h_in.dtype == torch.uint8 and h_out.dtype == torch.uint8
+        n = C.c_size_t(0)
+        self._check(_lib.lib().bzb200_compress_host(self._h, level, C.c_void_p(h_in.data_ptr()), h_in.numel(),
+                                                    C.c_void_p(h_out.data_ptr()), h_out.numel(), C.byref(n)),
+                    "bzb200_compress_host")
+        return n.value
+
     # ---- instrumentation ----
     def debug_stage(self, block, name):
         fid, dt = FIELDS[name]

@@ -79,3 +79,29 @@ def compress_sharded(ctx: Context, level, d_in, group=None, gather=True):
         if nbytes:
             dist.send(d_out[:nbytes], dst=dist.get_global_rank(group, 0) if group else 0, group=group)
         return None, info
+
+
+def compress_host_sharded(ctx: Context, level, h_slice, h_out=None, group=None):
+    """End-to-end call with HOST buffers: every rank passes its own slice of the input (pinned host uint8 tensor);
+    slices are copied H2D, all-gathered over NCCL/NVLink into the whole input on every GPU, compressed block-wise
+    (compress_sharded) and the finished stream is copied D2H on rank 0 (into h_out if given).
+    Returns (host tensor view holding the stream or None, info)."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    dev = ctx.device
+    d_slice = h_slice.to(dev, non_blocking=True)
+    if world > 1:
+        d_full = torch.empty(world * d_slice.numel(), dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(d_full, d_slice, group=group)
+    else:
+        d_full = d_slice
+    d_stream, info = compress_sharded(ctx, level, d_full, group=group)
+    if d_stream is None:
+        return None, info
+    n = d_stream.numel()
+    if h_out is None:
+        h_out = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+    h_out[:n].copy_(d_stream, non_blocking=True)
+    torch.cuda.current_stream(dev).synchronize()
+    info["h2d_bytes"] = int(h_slice.numel())
+    info["d2h_bytes"] = int(n)
+    return h_out[:n], info
