@@ -14,12 +14,12 @@ from .device import Context, max_output_bytes
 
 def block_range(nblocks, rank, world):
     """Contiguous ranges: block b belongs to rank floor(b*world/nblocks)."""
-    lo = (nblocks * rank + world - 1) // world if False else (nblocks * rank) // world
+    lo = (nblocks * rank) // world
     hi = (nblocks * (rank + 1)) // world
     return lo, hi
 
 
-def compress_sharded(ctx: Context, level, d_in, group=None, gather=True):
+def compress_sharded(ctx, level, d_in, group=None, gather=True):
     """Returns (d_stream or None, info). On rank 0 d_stream holds the complete .bz2 stream (device uint8 tensor).
 
     d_in: the WHOLE input, resident on this rank's GPU (every rank holds the same bytes).
@@ -31,7 +31,7 @@ def compress_sharded(ctx: Context, level, d_in, group=None, gather=True):
     in_off, rle_off, crc = ctx.block_table()
     b0, b1 = block_range(nb, rank, world)
     my_in = int(in_off[b1] - in_off[b0]) if nb else 0
-    cap = max_output_bytes(level, my_in) + 64
+    cap = (max_output_bytes(level, my_in) + 64 + 3) & ~3
     d_out = torch.zeros(cap, dtype=torch.uint8, device=dev)
     start = 32 if rank == 0 else 0
     if rank == 0:

@@ -152,3 +152,13 @@ def mixed(seed, n):
             r = splitmix64(seed * 31337 + s, seg // 8).view(np.uint8)
             o[:] = (r & 15) + 65
     return out[:n].tobytes()
+
+
+def geometric(seed, n, ratio=1.7, nsym=60):
+    """i.i.d. bytes with P(40+k) ~ ratio^-(k+1): skewed enough that plain Huffman depths exceed 17, which drives
+    the reference's reverse package-merge fallback (cano_huff_table.rs:58-151)."""
+    p = np.array([ratio ** -(i + 1) for i in range(nsym)], dtype=np.float64)
+    cdf = np.floor(np.cumsum(p / p.sum()) * float(1 << 32)).astype(np.uint64)
+    u = splitmix64(seed, n) >> np.uint64(32)
+    k = np.minimum(np.searchsorted(cdf, u, side="right"), nsym - 1)
+    return (k.astype(np.uint8) + np.uint8(40)).tobytes()
