@@ -214,7 +214,11 @@ def main():
         e0.record()
         res = None
         for _ in range(steps):
+            tw = time.perf_counter()
             res = fn()
+            if os.environ.get("BZB200_BENCH_DEBUG"):
+                torch.cuda.synchronize()
+                sys.stderr.write(f"[rank {rank}] {fn.__name__} wall {1e3 * (time.perf_counter() - tw):.1f} ms\n")
         e1.record()
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)

@@ -77,7 +77,8 @@ BZB200_API void bzb200_free(void* p);
  * ------------------------------------------------------------------------ */
 typedef struct bzb200_ctx bzb200_ctx;
 
-/* stream: a cudaStream_t passed as void* (NULL = the context creates its own). */
+/* stream: a cudaStream_t passed as void*; NULL = the device's default stream (what torch calls the default current
+ * stream).  All work of the context is enqueued on that stream, so the caller's earlier work on it is ordered before. */
 BZB200_API int bzb200_ctx_create(int device, void* stream, bzb200_ctx** out);
 BZB200_API void bzb200_ctx_destroy(bzb200_ctx* c);
 BZB200_API const char* bzb200_last_error(const bzb200_ctx* c);

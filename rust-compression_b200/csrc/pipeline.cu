@@ -201,7 +201,7 @@ extern "C" {
 
 const char* bzb200_version(void) { return "bzb200 0.1 (sm_100a)"; }
 
-int bzb200_ctx_create(int device, void* stream, bzb200_ctx** out) {
+static int ctx_create_impl(int device, void* stream, bool own_stream, bzb200_ctx** out) {
   if (!out) return BZB200_E_ARG;
   *out = nullptr;
   bzb200_ctx* c = new bzb200_ctx();
@@ -220,9 +220,7 @@ int bzb200_ctx_create(int device, void* stream, bzb200_ctx** out) {
     *out = c;
     return BZB200_E_CUDA;
   }
-  if (stream) {
-    c->stream = reinterpret_cast<cudaStream_t>(stream);
-  } else {
+  if (own_stream) {
     e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) {
       c->err = std::string("cudaStreamCreate: ") + cudaGetErrorString(e);
@@ -230,6 +228,8 @@ int bzb200_ctx_create(int device, void* stream, bzb200_ctx** out) {
       return BZB200_E_CUDA;
     }
     c->own_stream = true;
+  } else {
+    c->stream = reinterpret_cast<cudaStream_t>(stream);  // NULL = the device's default stream
   }
   c->L.stream = c->stream;
   const char* be = getenv("BZB200_BATCH_ELEMS");
@@ -246,6 +246,8 @@ int bzb200_ctx_create(int device, void* stream, bzb200_ctx** out) {
   *out = c;
   return BZB200_OK;
 }
+
+int bzb200_ctx_create(int device, void* stream, bzb200_ctx** out) { return ctx_create_impl(device, stream, false, out); }
 
 void bzb200_ctx_destroy(bzb200_ctx* c) {
   if (!c) return;
@@ -769,7 +771,7 @@ int bzb200_enc_finish(bzb200_enc* e) {
   if (!e) return BZB200_E_ARG;
   if (e->finished) return BZB200_OK;
   if (!e->ctx) {
-    int r = bzb200_ctx_create(e->device, nullptr, &e->ctx);
+    int r = ctx_create_impl(e->device, nullptr, true, &e->ctx);
     if (r != BZB200_OK) {
       e->err = e->ctx ? e->ctx->err : "context creation failed";
       if (e->ctx) { bzb200_ctx_destroy(e->ctx); e->ctx = nullptr; }
@@ -822,7 +824,7 @@ int bzb200_compress(int level, int device, const uint8_t* in, size_t n, uint8_t*
   *out_n = 0;
   if (level < 1 || level > 9) return BZB200_E_LEVEL;
   bzb200_ctx* c = nullptr;
-  int r = bzb200_ctx_create(device, nullptr, &c);
+  int r = ctx_create_impl(device, nullptr, true, &c);
   if (r != BZB200_OK) {
     if (c) bzb200_ctx_destroy(c);
     return r;
