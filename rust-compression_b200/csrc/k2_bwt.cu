@@ -6,14 +6,20 @@
 // (periodic block) by DESCENDING (pos - shift) mod n, shift = smallest start of a minimal rotation;
 // origPtr = rank of rotation 0 (src/bzip2/encoder.rs:332-334).
 //
-// Method: one 64-bit sort element per unresolved rotation,  [59:40] g | [39:20] k2 | [19:0] pos
-//   round 0 : g|k2 = the rotation's first 5 bytes (40 bits)           -> classes by 5-byte prefix
-//   round r : g = rank_h[pos] (slot of the class head), k2 = rank_h[(pos+h) mod n]   -> classes by 2h prefix
-//   fix-up  : k2 = n-1-((pos-shift) mod n) once a block's partition stops refining (periodic block)
-// Each round: compact unresolved rotations in position order (coalesced), LSD radix sort on bits 20..59
-// (5 passes of 8 bits, per-block segments, stable), then regroup: new rank = g + (start of (g,k2) run - start of
-// g run); singletons are marked resolved and leave the active set.  rank[] is the only persistent state; the
-// last column is scattered from it at the end.  All blocks of the batch advance together.
+// State per block:  SA[slot] = pos | HEAD | BIG | SINGLE   (rotations in the order established so far; a *group* is
+//                                a maximal run of slots whose rotations are still tied; HEAD marks its first slot)
+//                   rank[pos] = slot of the head of pos's group (| RESOLVED once the group is a singleton)
+// Round 0  : 64-bit elements [59:20] first 5 bytes | [19:0] pos, LSD radix sort (5 passes of 8 bits, per-block
+//            segments), regroup -> SA, rank.
+// Round r  : step h = 5, 10, 20, ...  key of a tied rotation = rank[(pos + h) mod n]:
+//   k2_gather      every unresolved slot fetches its key (slot order, coalesced SA read, L2-resident rank gather);
+//                  members of BIG groups (> LOCAL_MAX slots) are emitted as [59:40] g | [39:20] key | [19:0] pos
+//   k2_local_sort  one CTA per 2048-slot tile sorts every small group it owns inside shared memory (enumeration
+//                  sort on (group, key)), splits it, writes SA and rank in place
+//   BIG groups     LSD radix sort of the emitted elements + regroup (the round-0 machinery on a shorter list)
+//   k2_round_finalize  per-block state machine: done / periodic fix-up pending / active
+// Fix-up   : a round that splits nothing means the block is periodic and the groups are the sets of equal
+//            rotations; one more round with key = n-1-((pos-shift) mod n) applies the reference's tie-break.
 #include "common.cuh"
 #include "kernels.h"
 
@@ -179,24 +185,39 @@ __global__ void __launch_bounds__(RS_NT) k2_rs_scatter(const uint64_t* __restric
   }
 }
 
-// ------------------------------------------------------------------ regroup
-// Tile summaries: index of the last (g,k2)-run head and of the last g-run head inside the tile (or -1).
+
+// ------------------------------------------------------------------ SA entry layout / local-sort geometry
+constexpr uint32_t SA_HEAD = 0x80000000u;    // first slot of a group
+constexpr uint32_t SA_BIG = 0x40000000u;     // member of a group with more than LOCAL_MAX slots (radix path)
+constexpr uint32_t SA_SINGLE = 0x20000000u;  // group of one: final position
+constexpr uint32_t NONE = 0xFFFFFFFFu;
+constexpr int LS_NT = 256;
+constexpr int LS_T = 2048;       // slots per tile (k2_gather, k2_local_sort)
+constexpr int LOCAL_MAX = 256;   // largest group sorted inside a CTA
+constexpr int LS_CAP = LS_T + LOCAL_MAX;
+constexpr int LS_IPT = (LS_CAP + LS_NT - 1) / LS_NT;  // 9 (odd: blocked shared-memory access is conflict-free)
+static_assert(LS_CAP < 4096, "group start must fit the 12 bits above the 20-bit key");
+
+uint32_t bwt_ls_tile_elems() { return LS_T; }
+
+// ------------------------------------------------------------------ regroup (after a radix sort)
+// Tile summaries: last (g,k2)-run head, last g-run head, first (g,k2)-run head inside the tile.
 __global__ void __launch_bounds__(RS_NT) k2_rg_flags(const uint64_t* __restrict__ srt, const BlockDesc* __restrict__ desc,
-                                                     const uint32_t* __restrict__ cnt, int2* __restrict__ tsum,
+                                                     const uint32_t* __restrict__ cnt, int4* __restrict__ tsum,
                                                      uint32_t tiles_cap, int initial) {
-  __shared__ int sh[RS_WARPS], sg[RS_WARPS];
+  __shared__ int sh[RS_WARPS], sg[RS_WARPS], sf[RS_WARPS];
   const uint32_t c = cnt[blockIdx.y];
   const uint32_t base = blockIdx.x * RS_TILE;
   if (base >= c) return;
   const uint64_t* s = srt + desc[blockIdx.y].off;
-  int lh = -1, lg = -1;
+  int lh = -1, lg = -1, fh = 0x7FFFFFFF;
 #pragma unroll 4
   for (int k = 0; k < RS_IPT; ++k) {
     uint32_t a = base + threadIdx.x + k * RS_NT;
     if (a < c) {
       uint64_t cur = s[a] >> KEY_LO;
       uint64_t prv = a > 0 ? (s[a - 1] >> KEY_LO) : ~0ull;
-      if (cur != prv) lh = (int)a;
+      if (cur != prv) { lh = max(lh, (int)a); fh = min(fh, (int)a); }
       bool hg = initial ? (a == 0) : ((cur >> 20) != (prv >> 20));
       if (hg) lg = (int)a;
     }
@@ -205,61 +226,86 @@ __global__ void __launch_bounds__(RS_NT) k2_rg_flags(const uint64_t* __restrict_
   for (int d = 16; d > 0; d >>= 1) {
     lh = max(lh, __shfl_xor_sync(0xffffffffu, lh, d));
     lg = max(lg, __shfl_xor_sync(0xffffffffu, lg, d));
+    fh = min(fh, __shfl_xor_sync(0xffffffffu, fh, d));
   }
-  if (lane_id() == 0) { sh[threadIdx.x >> 5] = lh; sg[threadIdx.x >> 5] = lg; }
+  if (lane_id() == 0) { sh[threadIdx.x >> 5] = lh; sg[threadIdx.x >> 5] = lg; sf[threadIdx.x >> 5] = fh; }
   __syncthreads();
   if (threadIdx.x == 0) {
-    for (int w = 1; w < RS_WARPS; ++w) { lh = max(lh, sh[w]); lg = max(lg, sg[w]); }
-    tsum[(uint64_t)blockIdx.y * tiles_cap + blockIdx.x] = make_int2(lh, lg);
+    for (int w = 1; w < RS_WARPS; ++w) { lh = max(lh, sh[w]); lg = max(lg, sg[w]); fh = min(fh, sf[w]); }
+    tsum[(uint64_t)blockIdx.y * tiles_cap + blockIdx.x] = make_int4(lh, lg, fh, 0);
   }
 }
 
-// One warp per block: exclusive max-scan of the tile summaries (in place).
-__global__ void __launch_bounds__(32) k2_rg_scan(const uint32_t* __restrict__ cnt, int2* __restrict__ tsum,
+__device__ __forceinline__ int warp_incl_scan_min(int v) {
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    int t = __shfl_up_sync(0xffffffffu, v, d);
+    if ((int)lane_id() >= d) v = min(v, t);
+  }
+  return v;
+}
+
+// One warp per block: exclusive max-scan of (x, y) over the tiles, exclusive reverse min-scan of z (in place).
+__global__ void __launch_bounds__(32) k2_rg_scan(const uint32_t* __restrict__ cnt, int4* __restrict__ tsum,
                                                  uint32_t tiles_cap) {
   const uint32_t c = cnt[blockIdx.x];
   if (c == 0) return;
   const uint32_t nt = (c + RS_TILE - 1) / RS_TILE;
-  int2* ts = tsum + (uint64_t)blockIdx.x * tiles_cap;
+  int4* ts = tsum + (uint64_t)blockIdx.x * tiles_cap;
   int ch = -1, cg = -1;
   for (uint32_t t0 = 0; t0 < nt; t0 += 32) {
     uint32_t t = t0 + lane_id();
-    int2 v = t < nt ? ts[t] : make_int2(-1, -1);
+    int4 v = t < nt ? ts[t] : make_int4(-1, -1, 0, 0);
     int ih = warp_incl_scan_max(v.x), ig = warp_incl_scan_max(v.y);
     int eh = __shfl_up_sync(0xffffffffu, ih, 1), eg = __shfl_up_sync(0xffffffffu, ig, 1);
     if (lane_id() == 0) { eh = -1; eg = -1; }
     eh = max(eh, ch); eg = max(eg, cg);
-    if (t < nt) ts[t] = make_int2(eh, eg);
+    if (t < nt) { ts[t].x = eh; ts[t].y = eg; }
     ch = max(ch, __shfl_sync(0xffffffffu, ih, 31));
     cg = max(cg, __shfl_sync(0xffffffffu, ig, 31));
   }
+  int cn = (int)c;  // first head after the tiles handled so far (walking backwards); c = end of the list
+  for (uint32_t k0 = 0; k0 < nt; k0 += 32) {
+    uint32_t k = k0 + lane_id();
+    uint32_t t = nt - 1 - k;
+    int v = k < nt ? ts[t].z : 0x7FFFFFFF;
+    int im = warp_incl_scan_min(v);
+    int em = __shfl_up_sync(0xffffffffu, im, 1);
+    if (lane_id() == 0) em = 0x7FFFFFFF;
+    em = min(em, cn);
+    if (k < nt) ts[t].z = em;
+    cn = min(cn, __shfl_sync(0xffffffffu, im, 31));
+  }
 }
 
-// New ranks, resolved flags, per-block statistics.
+// New ranks, SA slots with flags, per-block statistics.  For the element at index a of the sorted list:
+//   fa = start of its g-run, ha = start of its (g,k2)-run, he = end of that run
+//   slot = g + (a - fa)        new rank = g + (ha - fa)        run size = he - ha
 __global__ void __launch_bounds__(RS_NT) k2_rg_apply(const uint64_t* __restrict__ srt, const BlockDesc* __restrict__ desc,
-                                                     const uint32_t* __restrict__ cnt, const int2* __restrict__ tsum,
+                                                     const uint32_t* __restrict__ cnt, const int4* __restrict__ tsum,
                                                      uint32_t tiles_cap, int initial, uint32_t* __restrict__ rank,
-                                                     uint32_t* __restrict__ stats, uint32_t* __restrict__ shift) {
-  __shared__ int wsh[RS_WARPS], wsg[RS_WARPS];
-  __shared__ uint32_t red[4][RS_WARPS];
+                                                     uint32_t* __restrict__ sa, uint32_t* __restrict__ stats) {
+  __shared__ int wsh[RS_WARPS], wsg[RS_WARPS], wsf[RS_WARPS];
+  __shared__ uint32_t red[3][RS_WARPS];
   const uint32_t c = cnt[blockIdx.y];
   const uint32_t base = blockIdx.x * RS_TILE;
   if (base >= c) return;
   const uint32_t off = desc[blockIdx.y].off;
   const uint64_t* s = srt + off;
   uint32_t* rk = rank + off;
-  const int2 carry = tsum[(uint64_t)blockIdx.y * tiles_cap + blockIdx.x];
+  uint32_t* so = sa + off;
+  const int4 carry = tsum[(uint64_t)blockIdx.y * tiles_cap + blockIdx.x];
 
   // blocked arrangement: thread t owns elements base + t*16 .. +15
   const uint32_t a0 = base + threadIdx.x * RS_IPT;
-  uint64_t e[RS_IPT + 1];
+  uint64_t e[RS_IPT];
   uint64_t prv = ~0ull;
   if (a0 < c) {
     if (a0 > 0) prv = s[a0 - 1] >> KEY_LO;
 #pragma unroll
-    for (int j = 0; j <= RS_IPT; ++j) e[j] = (a0 + j < c) ? s[a0 + j] : ~0ull;
+    for (int j = 0; j < RS_IPT; ++j) e[j] = (a0 + j < c) ? s[a0 + j] : ~0ull;
   }
-  int lh = -1, lg = -1;
+  int lh = -1, lg = -1, fh = 0x7FFFFFFF;
   uint32_t hmask = 0, gmask = 0;
   if (a0 < c) {
     uint64_t p = prv;
@@ -273,70 +319,87 @@ __global__ void __launch_bounds__(RS_NT) k2_rg_apply(const uint64_t* __restrict_
         p = cur;
       }
     }
+    if (hmask) fh = (int)a0 + __ffs(hmask) - 1;
   }
-  // CTA exclusive max-scan of (lh, lg)
+  // CTA exclusive max-scan of (lh, lg); exclusive reverse min-scan of fh
   int ih = warp_incl_scan_max(lh), ig = warp_incl_scan_max(lg);
+  int rf = fh;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    int t = __shfl_down_sync(0xffffffffu, rf, d);
+    if ((int)lane_id() + d < 32) rf = min(rf, t);
+  }
   const int w = threadIdx.x >> 5;
   if (lane_id() == 31) { wsh[w] = ih; wsg[w] = ig; }
+  if (lane_id() == 0) wsf[w] = rf;
   __syncthreads();
   int eh = __shfl_up_sync(0xffffffffu, ih, 1), eg = __shfl_up_sync(0xffffffffu, ig, 1);
   if (lane_id() == 0) { eh = -1; eg = -1; }
   for (int ww = 0; ww < w; ++ww) { eh = max(eh, wsh[ww]); eg = max(eg, wsg[ww]); }
   eh = max(eh, carry.x);
   eg = max(eg, carry.y);
+  int nh = __shfl_down_sync(0xffffffffu, rf, 1);
+  if (lane_id() == 31) nh = 0x7FFFFFFF;
+  for (int ww = w + 1; ww < RS_WARPS; ++ww) nh = min(nh, wsf[ww]);
+  nh = min(nh, carry.z);  // first head after this thread's elements (c when none)
 
-  uint32_t n_h = 0, n_g = 0, n_unres = 0, min_pos0 = 0xFFFFFFFFu;
+  uint32_t n_new = 0, n_big = 0, n_unres = 0;
   if (a0 < c) {
     int ha = eh, fa = eg;
 #pragma unroll
     for (int j = 0; j < RS_IPT; ++j) {
       if (a0 + j < c) {
         const int a = (int)(a0 + j);
-        if (hmask & (1u << j)) { ha = a; ++n_h; }
-        if (gmask & (1u << j)) { fa = a; ++n_g; }
-        const uint64_t cur = e[j] >> KEY_LO;
+        const bool is_h = hmask & (1u << j);
+        const bool is_g = gmask & (1u << j);
+        if (is_h) ha = a;
+        if (is_g) fa = a;
+        if (is_h && !is_g) ++n_new;
+        const uint32_t later = j < RS_IPT - 1 ? (hmask >> (j + 1)) : 0u;
+        const int he = later ? a + __ffs(later) : nh;
+        const uint32_t size = (uint32_t)(he - ha);
         const uint32_t pos = (uint32_t)(e[j] & POS_MASK);
-        const uint32_t g = initial ? 0u : (uint32_t)(cur >> 20);
+        const uint32_t g = initial ? 0u : (uint32_t)(e[j] >> 40) & RANK_MASK;
         const uint32_t nr = g + (uint32_t)(ha - fa);
-        // singleton <=> this element heads its run and the next element (if any) heads another
-        const bool next_head = (a0 + j + 1 >= c) || ((e[j + 1] >> KEY_LO) != cur);
-        const bool single = (ha == a) && next_head;
-        rk[pos] = nr | (single ? RANK_RESOLVED : 0u);
-        if (!single) ++n_unres;
-        if (nr == 0) min_pos0 = min(min_pos0, pos);
+        const uint32_t slot = g + (uint32_t)(a - fa);
+        uint32_t fl = is_h ? SA_HEAD : 0u;
+        if (size == 1) fl |= SA_SINGLE;
+        else {
+          ++n_unres;
+          if (size > (uint32_t)LOCAL_MAX) { fl |= SA_BIG; ++n_big; }
+        }
+        rk[pos] = nr | (size == 1 ? RANK_RESOLVED : 0u);
+        so[slot] = pos | fl;
       }
     }
   }
-  // CTA reductions -> one atomic per statistic
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) {
-    n_h += __shfl_xor_sync(0xffffffffu, n_h, d);
-    n_g += __shfl_xor_sync(0xffffffffu, n_g, d);
+    n_new += __shfl_xor_sync(0xffffffffu, n_new, d);
+    n_big += __shfl_xor_sync(0xffffffffu, n_big, d);
     n_unres += __shfl_xor_sync(0xffffffffu, n_unres, d);
-    min_pos0 = min(min_pos0, __shfl_xor_sync(0xffffffffu, min_pos0, d));
   }
-  if (lane_id() == 0) { red[0][w] = n_h; red[1][w] = n_g; red[2][w] = n_unres; red[3][w] = min_pos0; }
+  if (lane_id() == 0) { red[0][w] = n_new; red[1][w] = n_big; red[2][w] = n_unres; }
   __syncthreads();
   if (threadIdx.x == 0) {
-    uint32_t a = 0, b = 0, u = 0, m = 0xFFFFFFFFu;
-    for (int ww = 0; ww < RS_WARPS; ++ww) { a += red[0][ww]; b += red[1][ww]; u += red[2][ww]; m = min(m, red[3][ww]); }
+    uint32_t a = 0, b = 0, u = 0;
+    for (int ww = 0; ww < RS_WARPS; ++ww) { a += red[0][ww]; b += red[1][ww]; u += red[2][ww]; }
     uint32_t* st = stats + blockIdx.y * 4;
     if (a) atomicAdd(&st[0], a);
     if (b) atomicAdd(&st[1], b);
     if (u) atomicAdd(&st[2], u);
-    if (m != 0xFFFFFFFFu) atomicMin(&shift[blockIdx.y], m);
   }
 }
 
 // Per-block state machine after a round. state: 0 active, 1 fix-up pending, 2 done.
+// stats[b] = {groups created by splitting, members of BIG groups, unresolved rotations, periodic flag}
 __global__ void k2_round_finalize(uint32_t nb, uint32_t round_no, uint32_t* __restrict__ cnt,
                                   uint32_t* __restrict__ stats, uint32_t* __restrict__ state,
-                                  uint32_t* __restrict__ shift, uint32_t* __restrict__ rounds,
-                                  uint32_t* __restrict__ global) {
+                                  uint32_t* __restrict__ rounds, uint32_t* __restrict__ global) {
   uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= nb) return;
   uint32_t* st = stats + b * 4;
-  const uint32_t heads_h = st[0], heads_g = st[1], unres = st[2];
+  const uint32_t created = st[0], big = st[1], unres = st[2];
   uint32_t s = state[b];
   if (s != 2) {
     if (unres == 0) {
@@ -345,89 +408,281 @@ __global__ void k2_round_finalize(uint32_t nb, uint32_t round_no, uint32_t* __re
     } else if (s == 1) {
       atomicOr(&global[2], 1u);  // the fix-up key makes every rotation distinct; anything else is a bug
       s = 2;
-    } else if (heads_h == heads_g) {
-      s = 1;  // the partition did not refine: the block is periodic, classes are sets of equal rotations
+    } else if (created == 0) {
+      s = 1;  // nothing split: the block is periodic, the groups are the sets of equal rotations
       st[3] = 1;
-    } else {
-      shift[b] = 0xFFFFFFFFu;
     }
     state[b] = s;
     if (s != 2) {
       atomicAdd(&global[0], unres);
-      atomicMax(&global[1], unres);
+      atomicMax(&global[1], big);
     }
   }
   st[0] = 0; st[1] = 0; st[2] = 0;
   cnt[b] = 0;
 }
 
-// ------------------------------------------------------------------ next round's elements
-__global__ void __launch_bounds__(RS_NT) k2_build_active(const BlockDesc* __restrict__ desc,
-                                                         const uint32_t* __restrict__ rank,
+// ------------------------------------------------------------------ periodic blocks: shift = min pos of group 0
+// One CTA per block; does work only for a block that has just entered the fix-up state.
+__global__ void __launch_bounds__(256) k2_periodic_shift(const BlockDesc* __restrict__ desc,
                                                          const uint32_t* __restrict__ state,
-                                                         const uint32_t* __restrict__ shiftv, uint32_t h,
-                                                         uint64_t* __restrict__ A, uint32_t* __restrict__ cnt) {
-  __shared__ uint32_t ws[RS_NT / 32 + 1];
-  __shared__ uint32_t s_base;
+                                                         const uint32_t* __restrict__ sa, uint32_t* __restrict__ shift) {
+  __shared__ uint32_t s_min, s_end;
+  const uint32_t b = blockIdx.x;
+  if (state[b] != 1 || shift[b] != NONE) return;
+  const BlockDesc d = desc[b];
+  const uint32_t* s = sa + d.off;
+  if (threadIdx.x == 0) { s_min = NONE; s_end = 0; }
+  __syncthreads();
+  uint32_t mine = NONE;
+  for (uint32_t base = 0; base < d.n; base += 256) {
+    const uint32_t i = base + threadIdx.x;
+    uint32_t e = i < d.n ? s[i] : SA_HEAD;
+    const bool stop = (i > 0) && (e & SA_HEAD);  // head of the second group (or past the end)
+    if (stop) atomicMin(&s_min, i), atomicOr(&s_end, 1u);
+    __syncthreads();
+    const uint32_t lim = s_min;  // first slot not in group 0 (NONE while not seen)
+    if (i < lim && i < d.n) mine = min(mine, e & RANK_MASK);
+    const bool done = s_end != 0;
+    __syncthreads();
+    if (done) break;
+  }
+#pragma unroll
+  for (int dlt = 16; dlt > 0; dlt >>= 1) mine = min(mine, __shfl_xor_sync(0xffffffffu, mine, dlt));
+  if (threadIdx.x == 0) s_min = NONE;
+  __syncthreads();
+  if (lane_id() == 0) atomicMin(&s_min, mine);
+  __syncthreads();
+  if (threadIdx.x == 0) shift[b] = s_min;
+}
+
+// ------------------------------------------------------------------ k2_gather: keys of the next round
+// Slot order.  Small groups: key[slot].  BIG groups: 64-bit element appended to A (any order) and counted in cnt[b].
+// Also publishes, per tile, the first HEAD slot and whether the tile holds any active small-group slot.
+__global__ void __launch_bounds__(LS_NT) k2_gather(const BlockDesc* __restrict__ desc, const uint32_t* __restrict__ rank,
+                                                   const uint32_t* __restrict__ sa, const uint32_t* __restrict__ state,
+                                                   const uint32_t* __restrict__ shiftv, uint32_t h,
+                                                   uint32_t* __restrict__ key, uint64_t* __restrict__ A,
+                                                   uint32_t* __restrict__ cnt, uint32_t* __restrict__ first_head,
+                                                   uint32_t* __restrict__ tile_active, uint32_t ls_tiles_cap) {
+  __shared__ uint32_t ws[LS_NT / 32 + 1];
+  __shared__ uint32_t s_base, s_fh, s_act;
+  constexpr int IPT = LS_T / LS_NT;  // 8
   const BlockDesc d = desc[blockIdx.y];
   const uint32_t n = d.n;
-  const uint32_t base = blockIdx.x * RS_TILE;
+  const uint32_t base = blockIdx.x * LS_T;
   if (base >= n) return;
   const uint32_t st = state[blockIdx.y];
   if (st == 2) return;
+  if (threadIdx.x == 0) { s_fh = NONE; s_act = 0; }
   const uint32_t* rk = rank + d.off;
+  const uint32_t* s = sa + d.off;
+  uint32_t* ko = key + d.off;
   const uint32_t hm = h % n;
   const uint32_t sh = st == 1 ? shiftv[blockIdx.y] : 0u;
-  // blocked: thread t owns positions base + t*16 .. +15 (keeps the compaction order-preserving inside the CTA)
-  const uint32_t p0 = base + threadIdx.x * RS_IPT;
-  uint64_t e[RS_IPT];
-  uint32_t m = 0;
+  uint32_t ev[IPT];
 #pragma unroll
-  for (int j = 0; j < RS_IPT; ++j) {
-    uint32_t pos = p0 + j;
-    if (pos < n) {
-      uint32_t r = rk[pos];
-      if (!(r & RANK_RESOLVED)) {
-        uint32_t k2;
-        if (st == 0) {
-          uint32_t p2 = pos + hm;
-          if (p2 >= n) p2 -= n;
-          k2 = rk[p2] & RANK_MASK;
-        } else {
-          uint32_t rel = pos >= sh ? pos - sh : pos + n - sh;  // (pos - shift) mod n
-          k2 = n - 1 - rel;
-        }
-        e[j] = ((uint64_t)(r & RANK_MASK) << 40) | ((uint64_t)k2 << 20) | pos;
-        m |= 1u << j;
+  for (int k = 0; k < IPT; ++k) {
+    const uint32_t i = base + threadIdx.x + k * LS_NT;
+    ev[k] = i < n ? s[i] : SA_SINGLE;
+  }
+  uint32_t fh = NONE, act = 0, nbig = 0;
+  uint64_t be[IPT];
+#pragma unroll
+  for (int k = 0; k < IPT; ++k) {
+    const uint32_t i = base + threadIdx.x + k * LS_NT;
+    const uint32_t e = ev[k];
+    if (i < n && (e & SA_HEAD)) fh = min(fh, i);
+    be[k] = 0;
+    if (!(e & SA_SINGLE)) {
+      const uint32_t pos = e & RANK_MASK;
+      uint32_t k2;
+      if (st == 0) {
+        uint32_t p2 = pos + hm;
+        if (p2 >= n) p2 -= n;
+        k2 = rk[p2] & RANK_MASK;
+      } else {
+        const uint32_t rel = pos >= sh ? pos - sh : pos + n - sh;  // (pos - shift) mod n
+        k2 = n - 1 - rel;
+      }
+      if (e & SA_BIG) {
+        const uint32_t g = rk[pos] & RANK_MASK;
+        be[k] = ((uint64_t)g << 40) | ((uint64_t)k2 << 20) | pos | (1ull << 63);
+        ++nbig;
+      } else {
+        ko[i] = k2;
+        act = 1;
       }
     }
   }
+#pragma unroll
+  for (int dlt = 16; dlt > 0; dlt >>= 1) fh = min(fh, __shfl_xor_sync(0xffffffffu, fh, dlt));
+  act = __any_sync(0xffffffffu, act);
+  __syncthreads();
+  if (lane_id() == 0) {
+    if (fh != NONE) atomicMin(&s_fh, fh);
+    if (act) s_act = 1;
+  }
+  const int anybig = __syncthreads_or((int)nbig);
+  if (threadIdx.x == 0) {
+    first_head[(uint64_t)blockIdx.y * ls_tiles_cap + blockIdx.x] = s_fh;
+    tile_active[(uint64_t)blockIdx.y * ls_tiles_cap + blockIdx.x] = s_act;
+  }
+  if (!anybig) return;
   uint32_t total;
-  uint32_t ex = cta_excl_scan_add<RS_NT>(__popc(m), ws, &total);
-  if (threadIdx.x == 0) s_base = total ? atomicAdd(&cnt[blockIdx.y], total) : 0u;
+  const uint32_t ex = cta_excl_scan_add<LS_NT>(nbig, ws, &total);
+  if (threadIdx.x == 0) s_base = atomicAdd(&cnt[blockIdx.y], total);
   __syncthreads();
   uint64_t* o = A + d.off + s_base + ex;
 #pragma unroll
-  for (int j = 0; j < RS_IPT; ++j)
-    if (m & (1u << j)) *o++ = e[j];
+  for (int k = 0; k < IPT; ++k)
+    if (be[k]) *o++ = be[k] & ~(1ull << 63);
 }
 
-// ------------------------------------------------------------------ last column + origPtr
-__global__ void __launch_bounds__(RS_NT) k2_finish(const uint8_t* __restrict__ txt, const BlockDesc* __restrict__ desc,
-                                                   const uint32_t* __restrict__ rank, uint8_t* __restrict__ last,
+// ------------------------------------------------------------------ k2_local_sort: small groups, in shared memory
+// CTA (b, t) owns the groups whose HEAD lies in tile t; it loads slots [first head of the tile, first head at or
+// after the tile end) — at most LS_T + LOCAL_MAX of them, no other CTA touches these — sorts every active group by
+// key with an enumeration sort on the composite (group start << 20 | key), splits it at key changes and writes SA
+// and rank back in place.
+__global__ void __launch_bounds__(LS_NT) k2_local_sort(const BlockDesc* __restrict__ desc,
+                                                       const uint32_t* __restrict__ state, uint32_t* __restrict__ sa,
+                                                       const uint32_t* __restrict__ key, uint32_t* __restrict__ rank,
+                                                       const uint32_t* __restrict__ first_head,
+                                                       const uint32_t* __restrict__ tile_active, uint32_t ls_tiles_cap,
+                                                       uint32_t* __restrict__ stats) {
+  __shared__ uint32_t s_sa[LS_CAP];
+  __shared__ uint32_t s_ck[LS_CAP + 1];
+  __shared__ int wsm[LS_NT / 32];
+  __shared__ uint32_t red[2][LS_NT / 32];
+  const uint32_t b = blockIdx.y, t = blockIdx.x;
+  const BlockDesc d = desc[b];
+  const uint32_t n = d.n;
+  if (t * LS_T >= n) return;
+  if (state[b] == 2) return;
+  const uint64_t ti = (uint64_t)b * ls_tiles_cap + t;
+  if (!tile_active[ti]) return;
+  const uint32_t start = first_head[ti];
+  if (start == NONE) return;
+  const uint32_t tile_end = min(n, (t + 1) * LS_T);
+  uint32_t end = n;
+  if (tile_end < n) {
+    const uint32_t fh = first_head[ti + 1];
+    end = fh != NONE ? fh : n;
+    end = min(end, tile_end + LOCAL_MAX);  // anything longer is a BIG group and is skipped anyway
+  }
+  const uint32_t count = end - start;  // <= LS_CAP
+  uint32_t* s = sa + d.off + start;
+  const uint32_t* kin = key + d.off + start;
+
+  for (uint32_t r = threadIdx.x; r < count; r += LS_NT) {
+    const uint32_t e = s[r];
+    s_sa[r] = e;
+    s_ck[r] = (e & (SA_SINGLE | SA_BIG)) ? 0u : kin[r];
+  }
+  if (threadIdx.x == 0) s_ck[count] = NONE;
+  __syncthreads();
+
+  // group start of every slot: blocked max-scan of head indices
+  {
+    const uint32_t r0 = threadIdx.x * LS_IPT;
+    int lh = -1;
+#pragma unroll
+    for (int j = 0; j < LS_IPT; ++j)
+      if (r0 + j < count && (s_sa[r0 + j] & SA_HEAD)) lh = (int)(r0 + j);
+    int ih = warp_incl_scan_max(lh);
+    const int w = threadIdx.x >> 5;
+    if (lane_id() == 31) wsm[w] = ih;
+    __syncthreads();
+    int gs = __shfl_up_sync(0xffffffffu, ih, 1);
+    if (lane_id() == 0) gs = -1;
+    for (int ww = 0; ww < w; ++ww) gs = max(gs, wsm[ww]);
+#pragma unroll
+    for (int j = 0; j < LS_IPT; ++j) {
+      if (r0 + j < count) {
+        if (s_sa[r0 + j] & SA_HEAD) gs = (int)(r0 + j);
+        s_ck[r0 + j] = ((uint32_t)gs << 20) | (s_ck[r0 + j] & RANK_MASK);  // slot 0 is a HEAD, so gs >= 0
+      }
+    }
+  }
+  __syncthreads();
+
+  uint32_t n_new = 0, n_unres = 0;
+  uint32_t o_slot[LS_IPT], o_val[LS_IPT], o_rank[LS_IPT];
+#pragma unroll
+  for (int k = 0; k < LS_IPT; ++k) {
+    const uint32_t r = threadIdx.x + k * LS_NT;
+    o_slot[k] = NONE;
+    o_rank[k] = NONE;
+    if (r < count) {
+      const uint32_t e = s_sa[r];
+      if (!(e & (SA_SINGLE | SA_BIG))) {
+        const uint32_t mine = s_ck[r];
+        const uint32_t gs = mine >> 20;
+        uint32_t lt = 0, eq = 0, eqb = 0;
+        uint32_t j = gs;
+        uint32_t c = s_ck[j];
+        while ((c >> 20) == gs) {
+          lt += c < mine;
+          const bool same = c == mine;
+          eq += same;
+          eqb += same && (j < r);
+          c = s_ck[++j];
+        }
+        // j = end of the group; a group cut by the load window can only be BIG, never active
+        const uint32_t np = gs + lt + eqb;
+        uint32_t fl = eqb == 0 ? SA_HEAD : 0u;
+        if (eq == 1) fl |= SA_SINGLE; else ++n_unres;
+        if (eqb == 0 && lt != 0) ++n_new;
+        o_slot[k] = np;
+        o_val[k] = (e & RANK_MASK) | fl;
+        if (lt != 0 || eq == 1) o_rank[k] = (start + gs + lt) | (eq == 1 ? RANK_RESOLVED : 0u);
+      }
+    }
+  }
+  uint32_t* rk = rank + d.off;
+#pragma unroll
+  for (int k = 0; k < LS_IPT; ++k) {
+    if (o_slot[k] != NONE) {
+      s[o_slot[k]] = o_val[k];
+      if (o_rank[k] != NONE) rk[o_val[k] & RANK_MASK] = o_rank[k];
+    }
+  }
+#pragma unroll
+  for (int dlt = 16; dlt > 0; dlt >>= 1) {
+    n_new += __shfl_xor_sync(0xffffffffu, n_new, dlt);
+    n_unres += __shfl_xor_sync(0xffffffffu, n_unres, dlt);
+  }
+  const int w = threadIdx.x >> 5;
+  if (lane_id() == 0) { red[0][w] = n_new; red[1][w] = n_unres; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t a = 0, u = 0;
+    for (int ww = 0; ww < LS_NT / 32; ++ww) { a += red[0][ww]; u += red[1][ww]; }
+    uint32_t* stp = stats + b * 4;
+    if (a) atomicAdd(&stp[0], a);
+    if (u) atomicAdd(&stp[2], u);
+  }
+}
+
+// ------------------------------------------------------------------ last column + origPtr (slot order)
+__global__ void __launch_bounds__(LS_NT) k2_finish(const uint8_t* __restrict__ txt, const BlockDesc* __restrict__ desc,
+                                                   const uint32_t* __restrict__ sa, uint8_t* __restrict__ last,
                                                    uint32_t* __restrict__ origptr) {
   const BlockDesc d = desc[blockIdx.y];
   const uint32_t n = d.n;
-  const uint32_t base = blockIdx.x * RS_TILE;
+  const uint32_t base = blockIdx.x * (LS_NT * 16);
   if (base >= n) return;
   const uint8_t* t = txt + d.off;
+  const uint32_t* s = sa + d.off;
+  // 4 consecutive slots per thread and step: one 128-bit SA load, one 32-bit store of the last column
+  // (d.off is not 4-aligned in general, so the vector path is taken only where both addresses are aligned)
 #pragma unroll 4
-  for (int k = 0; k < RS_IPT; ++k) {
-    uint32_t pos = base + threadIdx.x + k * RS_NT;
-    if (pos < n) {
-      uint32_t r = rank[d.off + pos] & RANK_MASK;
-      last[d.off + r] = t[pos == 0 ? n - 1 : pos - 1];
-      if (pos == 0) origptr[blockIdx.y] = r;
+  for (int k = 0; k < 16; ++k) {
+    const uint32_t i = base + threadIdx.x + k * LS_NT;
+    if (i < n) {
+      const uint32_t pos = s[i] & RANK_MASK;
+      last[d.off + i] = t[pos == 0 ? n - 1 : pos - 1];
+      if (pos == 0) origptr[blockIdx.y] = i;
     }
   }
 }
@@ -447,14 +702,12 @@ static void radix_sort40(Launcher& L, uint64_t*& src, uint64_t*& dst, const Bloc
 }
 
 static void regroup(Launcher& L, const uint64_t* srt, const BlockDesc* d_desc, uint32_t nb, uint32_t maxcnt,
-                    BwtScratch& S, int initial, uint32_t round_no) {
+                    BwtScratch& S, int initial) {
   const uint32_t tiles = (maxcnt + RS_TILE - 1) / RS_TILE;
   L.launch("k2_rg_flags", k2_rg_flags, dim3(tiles, nb), dim3(RS_NT), srt, d_desc, S.cnt, S.tsum, S.tiles_cap, initial);
   L.launch("k2_rg_scan", k2_rg_scan, dim3(nb), dim3(32), S.cnt, S.tsum, S.tiles_cap);
   L.launch("k2_rg_apply", k2_rg_apply, dim3(tiles, nb), dim3(RS_NT), srt, d_desc, S.cnt, S.tsum, S.tiles_cap, initial,
-           S.rank, S.stats, S.shift);
-  L.launch("k2_round_finalize", k2_round_finalize, dim3((nb + 255) / 256), dim3(256), nb, round_no, S.cnt, S.stats,
-           S.state, S.shift, S.rounds, S.global);
+           S.rank, S.sa, S.stats);
 }
 
 int run_bwt(Launcher& L, const uint8_t* d_txt, const BlockDesc* d_desc, uint32_t nb, uint32_t nmax, uint64_t M,
@@ -462,6 +715,7 @@ int run_bwt(Launcher& L, const uint8_t* d_txt, const BlockDesc* d_desc, uint32_t
             uint64_t* h_elems) {
   cudaStream_t st = L.stream;
   const uint32_t tiles_n = (nmax + RS_TILE - 1) / RS_TILE;
+  const uint32_t ls_tiles = (nmax + LS_T - 1) / LS_T;
   cudaMemsetAsync(S.state, 0, nb * sizeof(uint32_t), st);
   cudaMemsetAsync(S.shift, 0xFF, nb * sizeof(uint32_t), st);
   cudaMemsetAsync(S.stats, 0, nb * 4 * sizeof(uint32_t), st);
@@ -475,7 +729,9 @@ int run_bwt(Launcher& L, const uint8_t* d_txt, const BlockDesc* d_desc, uint32_t
   radix_sort40(L, src, dst, d_desc, nb, nmax, S);
   passes += 5;
   elems += M;
-  regroup(L, src, d_desc, nb, nmax, S, 1, 0);
+  regroup(L, src, d_desc, nb, nmax, S, 1);
+  L.launch("k2_round_finalize", k2_round_finalize, dim3((nb + 255) / 256), dim3(256), nb, 0u, S.cnt, S.stats, S.state,
+           S.rounds, S.global);
 
   uint32_t g[4];
   if (L.err != cudaSuccess) return -2;
@@ -487,26 +743,31 @@ int run_bwt(Launcher& L, const uint8_t* d_txt, const BlockDesc* d_desc, uint32_t
     if (g[2]) return -5;
     ++rounds;
     if (rounds > 64) return -5;
-    const uint32_t maxact = g[1];
-    elems += g[0];
     cudaMemsetAsync(S.global, 0, 2 * sizeof(uint32_t), st);
-    // the sorted result of the previous round lives in `src`; build the new list into the other buffer
-    uint64_t* build = dst;
-    L.launch("k2_build_active", k2_build_active, dim3(tiles_n, nb), dim3(RS_NT), d_desc, S.rank, S.state, S.shift, h,
-             build, S.cnt);
-    uint64_t *s2 = build, *d2 = src;
-    radix_sort40(L, s2, d2, d_desc, nb, maxact, S);
-    passes += 5;
-    src = s2;
-    dst = d2;
-    regroup(L, src, d_desc, nb, maxact, S, 0, rounds);
+    L.launch("k2_periodic_shift", k2_periodic_shift, dim3(nb), dim3(256), d_desc, S.state, S.sa, S.shift);
+    // BIG-group elements go to S.A (both radix buffers are free between rounds)
+    L.launch("k2_gather", k2_gather, dim3(ls_tiles, nb), dim3(LS_NT), d_desc, S.rank, S.sa, S.state, S.shift, h, S.key,
+             S.A, S.cnt, S.first_head, S.tile_active, S.ls_tiles_cap);
+    L.launch("k2_local_sort", k2_local_sort, dim3(ls_tiles, nb), dim3(LS_NT), d_desc, S.state, S.sa, S.key, S.rank,
+             S.first_head, S.tile_active, S.ls_tiles_cap, S.stats);
+    const uint32_t maxbig = g[1];
+    if (maxbig > 0) {
+      uint64_t *s2 = S.A, *d2 = S.B;
+      radix_sort40(L, s2, d2, d_desc, nb, maxbig, S);
+      passes += 5;
+      regroup(L, s2, d_desc, nb, maxbig, S, 0);
+    }
+    elems += g[0];
+    L.launch("k2_round_finalize", k2_round_finalize, dim3((nb + 255) / 256), dim3(256), nb, rounds, S.cnt, S.stats,
+             S.state, S.rounds, S.global);
     if (L.err != cudaSuccess) return -2;
     if (cudaMemcpyAsync(g, S.global, sizeof(g), cudaMemcpyDeviceToHost, st) != cudaSuccess) return -2;
     if (cudaStreamSynchronize(st) != cudaSuccess) return -2;
     if (h < (1u << 21)) h *= 2;
   }
   if (g[2]) return -5;
-  L.launch("k2_finish", k2_finish, dim3(tiles_n, nb), dim3(RS_NT), d_txt, d_desc, S.rank, d_last, d_origptr);
+  const uint32_t ftiles = (nmax + LS_NT * 16 - 1) / (LS_NT * 16);
+  L.launch("k2_finish", k2_finish, dim3(ftiles, nb), dim3(LS_NT), d_txt, d_desc, S.sa, d_last, d_origptr);
   if (h_rounds) *h_rounds = rounds;
   if (h_passes) *h_passes = passes;
   if (h_elems) *h_elems = elems;

@@ -77,18 +77,24 @@ void launch_k1_inuse(Launcher& L, const uint8_t* d_txt, const uint64_t* d_rle_of
 struct BwtScratch {
   uint64_t* A;          // [M] sort elements (ping)
   uint64_t* B;          // [M] sort elements (pong)
-  uint32_t* rank;       // [M]
+  uint32_t* rank;       // [M] rank[pos] = slot of the head of pos's group
+  uint32_t* sa;         // [M] sa[slot] = pos | flags (rotations in the order established so far)
+  uint32_t* key;        // [M] per-slot sort key of the current round (small groups)
+  uint32_t* first_head; // [nb][ls_tiles] first group head inside each local-sort tile
+  uint32_t* tile_active;// [nb][ls_tiles]
+  uint32_t ls_tiles_cap;
   uint32_t* cnt;        // [nb] active elements per block
   uint32_t* hist;       // [nb][tiles][256]
-  int2* tsum;           // [nb][tiles] regroup tile summaries
+  int4* tsum;           // [nb][tiles] regroup tile summaries
   uint32_t* state;      // [nb] 0 active, 1 fix-up pending, 2 done
   uint32_t* shift;      // [nb]
-  uint32_t* stats;      // [nb][4]: heads_h, heads_g, unresolved, spare
+  uint32_t* stats;      // [nb][4]: groups created, BIG members, unresolved, periodic flag
   uint32_t* rounds;     // [nb] rounds until done (instrumentation)
   uint32_t* global;     // [4]: total unresolved, max active per block, error flag, spare
   uint32_t tiles_cap;   // tiles per block the hist/tsum arrays were sized for
 };
 uint32_t bwt_tile_elems();
+uint32_t bwt_ls_tile_elems();
 // Runs the whole rotation sort for a batch. txt = batch slice of the RLE1 stream, desc[nb] on device.
 // Outputs: last column L[M] (same layout as txt), origptr[nb]. Returns 0 or a negative internal error.
 int run_bwt(Launcher& L, const uint8_t* d_txt, const BlockDesc* d_desc, uint32_t nb, uint32_t nmax, uint64_t M,
