@@ -191,12 +191,16 @@ constexpr uint32_t SA_HEAD = 0x80000000u;    // first slot of a group
 constexpr uint32_t SA_BIG = 0x40000000u;     // member of a group with more than LOCAL_MAX slots (radix path)
 constexpr uint32_t SA_SINGLE = 0x20000000u;  // group of one: final position
 constexpr uint32_t NONE = 0xFFFFFFFFu;
-constexpr int LS_NT = 256;
+constexpr int G_NT = 256;        // k2_gather / k2_finish threads
+constexpr int LS_NT = 512;       // k2_local_sort threads
 constexpr int LS_T = 2048;       // slots per tile (k2_gather, k2_local_sort)
-constexpr int LOCAL_MAX = 256;   // largest group sorted inside a CTA
+constexpr int LOCAL_MAX = 1535;  // largest group sorted inside a CTA
+constexpr int ENUM_MAX = 16;     // largest group sorted by plain enumeration (larger ones are bucketed first)
 constexpr int LS_CAP = LS_T + LOCAL_MAX;
-constexpr int LS_IPT = (LS_CAP + LS_NT - 1) / LS_NT;  // 9 (odd: blocked shared-memory access is conflict-free)
-static_assert(LS_CAP < 4096, "group start must fit the 12 bits above the 20-bit key");
+constexpr int LS_IPT = (LS_CAP + LS_NT - 1) / LS_NT;  // 7 (odd: blocked shared-memory access is conflict-free)
+static_assert(LS_CAP < 4095, "group start must fit the 12 bits above the 20-bit key (4095 = sentinel)");
+static_assert(LS_CAP + 1 <= LS_NT * LS_IPT, "the prefix sum covers slot `count` too");
+static_assert(LOCAL_MAX <= LS_T, "a group owned by tile t must end inside tile t+1");
 
 uint32_t bwt_ls_tile_elems() { return LS_T; }
 
@@ -393,8 +397,9 @@ __global__ void __launch_bounds__(RS_NT) k2_rg_apply(const uint64_t* __restrict_
 
 // Per-block state machine after a round. state: 0 active, 1 fix-up pending, 2 done.
 // stats[b] = {groups created by splitting, members of BIG groups, unresolved rotations, periodic flag}
-__global__ void k2_round_finalize(uint32_t nb, uint32_t round_no, uint32_t* __restrict__ cnt,
-                                  uint32_t* __restrict__ stats, uint32_t* __restrict__ state,
+__global__ void k2_round_finalize(uint32_t nb, uint32_t round_no, const BlockDesc* __restrict__ desc,
+                                  uint32_t* __restrict__ cnt, uint32_t* __restrict__ stats,
+                                  uint32_t* __restrict__ state, uint32_t* __restrict__ sparse,
                                   uint32_t* __restrict__ rounds, uint32_t* __restrict__ global) {
   uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= nb) return;
@@ -414,8 +419,12 @@ __global__ void k2_round_finalize(uint32_t nb, uint32_t round_no, uint32_t* __re
     }
     state[b] = s;
     if (s != 2) {
+      // few unresolved rotations left: the whole block takes the radix path next round (the per-tile cost of the
+      // local sort would dominate)
+      const bool sp = unres < (desc[b].n >> 5);
+      sparse[b] = sp ? 1u : 0u;
       atomicAdd(&global[0], unres);
-      atomicMax(&global[1], big);
+      atomicMax(&global[1], sp ? unres : big);
     }
   }
   st[0] = 0; st[1] = 0; st[2] = 0;
@@ -459,15 +468,16 @@ __global__ void __launch_bounds__(256) k2_periodic_shift(const BlockDesc* __rest
 // ------------------------------------------------------------------ k2_gather: keys of the next round
 // Slot order.  Small groups: key[slot].  BIG groups: 64-bit element appended to A (any order) and counted in cnt[b].
 // Also publishes, per tile, the first HEAD slot and whether the tile holds any active small-group slot.
-__global__ void __launch_bounds__(LS_NT) k2_gather(const BlockDesc* __restrict__ desc, const uint32_t* __restrict__ rank,
+__global__ void __launch_bounds__(G_NT) k2_gather(const BlockDesc* __restrict__ desc, const uint32_t* __restrict__ rank,
                                                    const uint32_t* __restrict__ sa, const uint32_t* __restrict__ state,
-                                                   const uint32_t* __restrict__ shiftv, uint32_t h,
+                                                   const uint32_t* __restrict__ shiftv,
+                                                   const uint32_t* __restrict__ sparse, uint32_t h,
                                                    uint32_t* __restrict__ key, uint64_t* __restrict__ A,
                                                    uint32_t* __restrict__ cnt, uint32_t* __restrict__ first_head,
                                                    uint32_t* __restrict__ tile_active, uint32_t ls_tiles_cap) {
-  __shared__ uint32_t ws[LS_NT / 32 + 1];
+  __shared__ uint32_t ws[G_NT / 32 + 1];
   __shared__ uint32_t s_base, s_fh, s_act;
-  constexpr int IPT = LS_T / LS_NT;  // 8
+  constexpr int IPT = LS_T / G_NT;  // 8
   const BlockDesc d = desc[blockIdx.y];
   const uint32_t n = d.n;
   const uint32_t base = blockIdx.x * LS_T;
@@ -480,17 +490,18 @@ __global__ void __launch_bounds__(LS_NT) k2_gather(const BlockDesc* __restrict__
   uint32_t* ko = key + d.off;
   const uint32_t hm = h % n;
   const uint32_t sh = st == 1 ? shiftv[blockIdx.y] : 0u;
+  const bool sp = sparse[blockIdx.y] != 0;  // sparse block: every unresolved slot is emitted to the radix path
   uint32_t ev[IPT];
 #pragma unroll
   for (int k = 0; k < IPT; ++k) {
-    const uint32_t i = base + threadIdx.x + k * LS_NT;
+    const uint32_t i = base + threadIdx.x + k * G_NT;
     ev[k] = i < n ? s[i] : SA_SINGLE;
   }
   uint32_t fh = NONE, act = 0, nbig = 0;
   uint64_t be[IPT];
 #pragma unroll
   for (int k = 0; k < IPT; ++k) {
-    const uint32_t i = base + threadIdx.x + k * LS_NT;
+    const uint32_t i = base + threadIdx.x + k * G_NT;
     const uint32_t e = ev[k];
     if (i < n && (e & SA_HEAD)) fh = min(fh, i);
     be[k] = 0;
@@ -505,7 +516,7 @@ __global__ void __launch_bounds__(LS_NT) k2_gather(const BlockDesc* __restrict__
         const uint32_t rel = pos >= sh ? pos - sh : pos + n - sh;  // (pos - shift) mod n
         k2 = n - 1 - rel;
       }
-      if (e & SA_BIG) {
+      if (sp || (e & SA_BIG)) {
         const uint32_t g = rk[pos] & RANK_MASK;
         be[k] = ((uint64_t)g << 40) | ((uint64_t)k2 << 20) | pos | (1ull << 63);
         ++nbig;
@@ -530,7 +541,7 @@ __global__ void __launch_bounds__(LS_NT) k2_gather(const BlockDesc* __restrict__
   }
   if (!anybig) return;
   uint32_t total;
-  const uint32_t ex = cta_excl_scan_add<LS_NT>(nbig, ws, &total);
+  const uint32_t ex = cta_excl_scan_add<G_NT>(nbig, ws, &total);
   if (threadIdx.x == 0) s_base = atomicAdd(&cnt[blockIdx.y], total);
   __syncthreads();
   uint64_t* o = A + d.off + s_base + ex;
@@ -539,21 +550,40 @@ __global__ void __launch_bounds__(LS_NT) k2_gather(const BlockDesc* __restrict__
     if (be[k]) *o++ = be[k] & ~(1ull << 63);
 }
 
-// ------------------------------------------------------------------ k2_local_sort: small groups, in shared memory
+// ------------------------------------------------------------------ k2_local_sort: groups up to LOCAL_MAX slots
 // CTA (b, t) owns the groups whose HEAD lies in tile t; it loads slots [first head of the tile, first head at or
-// after the tile end) — at most LS_T + LOCAL_MAX of them, no other CTA touches these — sorts every active group by
-// key with an enumeration sort on the composite (group start << 20 | key), splits it at key changes and writes SA
-// and rank back in place.
-__global__ void __launch_bounds__(LS_NT) k2_local_sort(const BlockDesc* __restrict__ desc,
-                                                       const uint32_t* __restrict__ state, uint32_t* __restrict__ sa,
-                                                       const uint32_t* __restrict__ key, uint32_t* __restrict__ rank,
-                                                       const uint32_t* __restrict__ first_head,
-                                                       const uint32_t* __restrict__ tile_active, uint32_t ls_tiles_cap,
-                                                       uint32_t* __restrict__ stats) {
-  __shared__ uint32_t s_sa[LS_CAP];
-  __shared__ uint32_t s_ck[LS_CAP + 1];
-  __shared__ int wsm[LS_NT / 32];
-  __shared__ uint32_t red[2][LS_NT / 32];
+// after the tile end) — at most LS_T + LOCAL_MAX of them, no other CTA touches these — and sorts every active
+// group by key.  Elements live in registers; shared memory holds, per window slot, the composite
+// (group start << 20 | key) of the element currently placed there.
+//   * split levels: a group larger than ENUM_MAX whose keys are not all equal is partitioned into key-range
+//     buckets (range [min,max] of its keys, ~2-4 slots per bucket, counting pass with shared-memory atomics); the
+//     buckets are groups of their own from then on; repeated until every group is small or flat (all keys equal —
+//     nothing to sort, which is what heavy duplicates end as);
+//   * enumeration: the final slot of an element = group start + #{smaller keys} + #{equal keys placed earlier};
+//     equal keys stay one (smaller) group.
+// SA and rank are written back in place.
+constexpr uint32_t GS_FLAT = 0x8000u;
+struct LsSmem {
+  uint32_t ck[LS_CAP + 8];
+  uint32_t cnt[LS_CAP + 8];
+  uint32_t gmin[LS_CAP + 8];
+  uint32_t gmax[LS_CAP + 8];
+  uint16_t gsize[LS_CAP + 8];
+  int wsa[LS_NT / 32], wsb[LS_NT / 32];
+  uint32_t wsc[LS_NT / 32 + 1];
+  uint32_t red[3][LS_NT / 32];
+};
+size_t bwt_ls_smem_bytes() { return sizeof(LsSmem); }
+
+__global__ void __launch_bounds__(LS_NT, 2) k2_local_sort(const BlockDesc* __restrict__ desc,
+                                                          const uint32_t* __restrict__ state,
+                                                          uint32_t* __restrict__ sa, const uint32_t* __restrict__ key,
+                                                          uint32_t* __restrict__ rank,
+                                                          const uint32_t* __restrict__ first_head,
+                                                          const uint32_t* __restrict__ tile_active,
+                                                          uint32_t ls_tiles_cap, uint32_t* __restrict__ stats) {
+  extern __shared__ __align__(16) uint8_t ls_raw[];
+  LsSmem& sm = *reinterpret_cast<LsSmem*>(ls_raw);
   const uint32_t b = blockIdx.y, t = blockIdx.x;
   const BlockDesc d = desc[b];
   const uint32_t n = d.n;
@@ -573,104 +603,239 @@ __global__ void __launch_bounds__(LS_NT) k2_local_sort(const BlockDesc* __restri
   const uint32_t count = end - start;  // <= LS_CAP
   uint32_t* s = sa + d.off + start;
   const uint32_t* kin = key + d.off + start;
+  const int w = threadIdx.x >> 5;
 
-  for (uint32_t r = threadIdx.x; r < count; r += LS_NT) {
-    const uint32_t e = s[r];
-    s_sa[r] = e;
-    s_ck[r] = (e & (SA_SINGLE | SA_BIG)) ? 0u : kin[r];
-  }
-  if (threadIdx.x == 0) s_ck[count] = NONE;
-  __syncthreads();
-
-  // group start of every slot: blocked max-scan of head indices
-  {
-    const uint32_t r0 = threadIdx.x * LS_IPT;
-    int lh = -1;
-#pragma unroll
-    for (int j = 0; j < LS_IPT; ++j)
-      if (r0 + j < count && (s_sa[r0 + j] & SA_HEAD)) lh = (int)(r0 + j);
-    int ih = warp_incl_scan_max(lh);
-    const int w = threadIdx.x >> 5;
-    if (lane_id() == 31) wsm[w] = ih;
-    __syncthreads();
-    int gs = __shfl_up_sync(0xffffffffu, ih, 1);
-    if (lane_id() == 0) gs = -1;
-    for (int ww = 0; ww < w; ++ww) gs = max(gs, wsm[ww]);
-#pragma unroll
-    for (int j = 0; j < LS_IPT; ++j) {
-      if (r0 + j < count) {
-        if (s_sa[r0 + j] & SA_HEAD) gs = (int)(r0 + j);
-        s_ck[r0 + j] = ((uint32_t)gs << 20) | (s_ck[r0 + j] & RANK_MASK);  // slot 0 is a HEAD, so gs >= 0
-      }
-    }
-  }
-  __syncthreads();
-
-  uint32_t n_new = 0, n_unres = 0;
-  uint32_t o_slot[LS_IPT], o_val[LS_IPT], o_rank[LS_IPT];
+  // ---- A: striped load. Per element: ev = SA entry, kv = key, gp = group start | current slot << 12 | pending << 31
+  uint32_t ev[LS_IPT], kv[LS_IPT], gp[LS_IPT];
+  uint32_t heads_before = 0;
 #pragma unroll
   for (int k = 0; k < LS_IPT; ++k) {
     const uint32_t r = threadIdx.x + k * LS_NT;
-    o_slot[k] = NONE;
-    o_rank[k] = NONE;
+    ev[k] = SA_SINGLE;
+    kv[k] = 0;
     if (r < count) {
-      const uint32_t e = s_sa[r];
+      const uint32_t e = s[r];
+      ev[k] = e;
       if (!(e & (SA_SINGLE | SA_BIG))) {
-        const uint32_t mine = s_ck[r];
-        const uint32_t gs = mine >> 20;
-        uint32_t lt = 0, eq = 0, eqb = 0;
-        uint32_t j = gs;
-        uint32_t c = s_ck[j];
-        while ((c >> 20) == gs) {
-          lt += c < mine;
-          const bool same = c == mine;
-          eq += same;
-          eqb += same && (j < r);
-          c = s_ck[++j];
+        kv[k] = kin[r];
+        heads_before += e >> 31;
+      }
+      sm.ck[r] = kv[k] | (e & SA_HEAD);
+    }
+  }
+  if (threadIdx.x < 8) sm.ck[count + threadIdx.x] = NONE;
+  __syncthreads();
+
+  // ---- B: blocked scans over the head flags: group start (forward max) and group end (reverse min) of every slot
+  {
+    const uint32_t r0 = threadIdx.x * LS_IPT;
+    int lh = -1, fh = 0x7FFFFFFF;
+    uint32_t hm = 0;
+#pragma unroll
+    for (int j = 0; j < LS_IPT; ++j)
+      if (r0 + j < count && (sm.ck[r0 + j] & SA_HEAD)) {
+        hm |= 1u << j;
+        lh = (int)(r0 + j);
+        if (fh == 0x7FFFFFFF) fh = (int)(r0 + j);
+      }
+    int ih = warp_incl_scan_max(lh);
+    int rf = fh;
+#pragma unroll
+    for (int dl = 1; dl < 32; dl <<= 1) {
+      int tt = __shfl_down_sync(0xffffffffu, rf, dl);
+      if ((int)lane_id() + dl < 32) rf = min(rf, tt);
+    }
+    if (lane_id() == 31) sm.wsa[w] = ih;
+    if (lane_id() == 0) sm.wsb[w] = rf;
+    __syncthreads();
+    int gs = __shfl_up_sync(0xffffffffu, ih, 1);
+    if (lane_id() == 0) gs = -1;
+    for (int ww = 0; ww < w; ++ww) gs = max(gs, sm.wsa[ww]);
+    int nh = __shfl_down_sync(0xffffffffu, rf, 1);
+    if (lane_id() == 31) nh = 0x7FFFFFFF;
+    for (int ww = w + 1; ww < LS_NT / 32; ++ww) nh = min(nh, sm.wsb[ww]);
+    nh = min(nh, (int)count);
+#pragma unroll
+    for (int j = 0; j < LS_IPT; ++j) {
+      if (r0 + j < count) {
+        if (hm & (1u << j)) {
+          gs = (int)(r0 + j);  // slot 0 of the window is a HEAD, so gs >= 0 everywhere
+          const uint32_t later = j < LS_IPT - 1 ? (hm >> (j + 1)) : 0u;
+          const int ge = later ? (int)(r0 + j) + __ffs(later) : nh;
+          sm.gsize[r0 + j] = (uint16_t)(ge - gs);
+          sm.gmin[r0 + j] = NONE;
+          sm.gmax[r0 + j] = 0;
         }
-        // j = end of the group; a group cut by the load window can only be BIG, never active
-        const uint32_t np = gs + lt + eqb;
-        uint32_t fl = eqb == 0 ? SA_HEAD : 0u;
-        if (eq == 1) fl |= SA_SINGLE; else ++n_unres;
-        if (eqb == 0 && lt != 0) ++n_new;
-        o_slot[k] = np;
-        o_val[k] = (e & RANK_MASK) | fl;
-        if (lt != 0 || eq == 1) o_rank[k] = (start + gs + lt) | (eq == 1 ? RANK_RESOLVED : 0u);
+        sm.ck[r0 + j] = ((uint32_t)gs << 20) | (sm.ck[r0 + j] & RANK_MASK);
       }
     }
   }
+  __syncthreads();
+  bool any_pend = false;
+#pragma unroll
+  for (int k = 0; k < LS_IPT; ++k) {
+    const uint32_t r = threadIdx.x + k * LS_NT;
+    gp[k] = 0;
+    if (r < count && !(ev[k] & (SA_SINGLE | SA_BIG))) {
+      const uint32_t gs = sm.ck[r] >> 20;
+      const bool pend = sm.gsize[gs] > (uint32_t)ENUM_MAX;
+      gp[k] = gs | (r << 12) | (pend ? 0x80000000u : 0u);
+      any_pend |= pend;
+    }
+  }
+
+  // ---- split levels
+  for (int level = 0; level < 24; ++level) {
+    if (!__syncthreads_or((int)any_pend)) break;
+    for (uint32_t r = threadIdx.x; r <= count; r += LS_NT) sm.cnt[r] = 0;
+#pragma unroll
+    for (int k = 0; k < LS_IPT; ++k)
+      if (gp[k] >> 31) {
+        const uint32_t gs = gp[k] & 0xFFFu;
+        atomicMin(&sm.gmin[gs], kv[k]);
+        atomicMax(&sm.gmax[gs], kv[k]);
+      }
+    __syncthreads();
+    uint32_t bi[LS_IPT];  // bucket slot | arrival index << 12
+#pragma unroll
+    for (int k = 0; k < LS_IPT; ++k) {
+      bi[k] = NONE;
+      if (gp[k] >> 31) {
+        const uint32_t gs = gp[k] & 0xFFFu;
+        const uint32_t mn = sm.gmin[gs], mx = sm.gmax[gs];
+        const uint32_t size = sm.gsize[gs] & 0xFFFu;
+        if (mn == mx) {  // all keys equal: nothing to sort
+          gp[k] &= 0x7FFFFFFFu;
+          if (((gp[k] >> 12) & 0xFFFu) == gs) sm.gsize[gs] = (uint16_t)(size | GS_FLAT);
+        } else {
+          const int lnb = 31 - __clz(size >> 1);       // buckets = largest power of two <= size/2
+          const int rb = 32 - __clz(mx - mn);           // bits of the key range
+          const int sh = max(rb - lnb, 0);
+          const uint32_t bs = gs + ((kv[k] - mn) >> sh);
+          bi[k] = bs | (atomicAdd(&sm.cnt[bs], 1u) << 12);
+        }
+      }
+    }
+    __syncthreads();
+    {  // exclusive prefix sum of the bucket counters over slots 0..count (blocked), in place
+      const uint32_t r0 = threadIdx.x * LS_IPT;
+      uint32_t loc[LS_IPT];
+      uint32_t sum = 0;
+#pragma unroll
+      for (int j = 0; j < LS_IPT; ++j) {
+        loc[j] = (r0 + j <= count) ? sm.cnt[r0 + j] : 0u;
+        sum += loc[j];
+      }
+      uint32_t ex = cta_excl_scan_add<LS_NT>(sum, sm.wsc, nullptr);
+#pragma unroll
+      for (int j = 0; j < LS_IPT; ++j) {
+        if (r0 + j <= count) sm.cnt[r0 + j] = ex;
+        ex += loc[j];
+      }
+    }
+    __syncthreads();
+    any_pend = false;
+#pragma unroll
+    for (int k = 0; k < LS_IPT; ++k) {
+      if (bi[k] != NONE) {
+        const uint32_t gs = gp[k] & 0xFFFu;
+        const uint32_t bs = bi[k] & 0xFFFu, idx = bi[k] >> 12;
+        const uint32_t pb = sm.cnt[bs];
+        const uint32_t bstart = gs + (pb - sm.cnt[gs]);
+        const uint32_t bcount = sm.cnt[bs + 1] - pb;
+        const uint32_t np = bstart + idx;
+        sm.ck[np] = (bstart << 20) | kv[k];
+        if (idx == 0) {
+          sm.gsize[bstart] = (uint16_t)bcount;
+          sm.gmin[bstart] = NONE;
+          sm.gmax[bstart] = 0;
+        }
+        const bool pend = bcount > (uint32_t)ENUM_MAX;
+        gp[k] = bstart | (np << 12) | (pend ? 0x80000000u : 0u);
+        any_pend |= pend;
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- enumeration inside every group / bucket: lt = #{keys below mine}, eq = #{keys equal}, eqb = #{equal keys
+  // at an earlier slot};  new slot = start + lt + eqb, the head of the (sub)group sits at start + lt.  The scan runs
+  // over 128-bit vectors from the aligned start of the group: slots of earlier groups in the first vector compare
+  // below (subtracted again), slots of later groups in the last vector compare above.
+  uint32_t n_heads = 0, n_unres = 0;
   uint32_t* rk = rank + d.off;
 #pragma unroll
   for (int k = 0; k < LS_IPT; ++k) {
-    if (o_slot[k] != NONE) {
-      s[o_slot[k]] = o_val[k];
-      if (o_rank[k] != NONE) rk[o_val[k] & RANK_MASK] = o_rank[k];
+    const uint32_t e = ev[k];
+    if (!(e & (SA_SINGLE | SA_BIG))) {
+      const uint32_t gs = gp[k] & 0xFFFu, r = (gp[k] >> 12) & 0xFFFu;
+      const uint32_t gz = sm.gsize[gs];
+      uint32_t lt = 0, eq, eqb;
+      if (gz & GS_FLAT) {
+        eq = gz & 0xFFFu;
+        eqb = r - gs;
+      } else {
+        const uint32_t mine = (gs << 20) | kv[k];
+        const uint32_t m1 = mine + 1;
+        const uint32_t je = gs + (gz & 0xFFFu);
+        uint32_t jb = gs & ~3u;
+        const uint32_t rb = r & ~3u;
+        uint32_t le = 0;
+        lt = 0;
+        for (; jb < rb; jb += 4) {
+          const uint4 c = *reinterpret_cast<const uint4*>(&sm.ck[jb]);
+          lt += (c.x < mine) + (c.y < mine) + (c.z < mine) + (c.w < mine);
+          le += (c.x < m1) + (c.y < m1) + (c.z < m1) + (c.w < m1);
+        }
+        eqb = le - lt;
+        {
+          const uint4 c = *reinterpret_cast<const uint4*>(&sm.ck[jb]);
+          const uint32_t dd = r & 3u;
+          lt += (c.x < mine) + (c.y < mine) + (c.z < mine) + (c.w < mine);
+          le += (c.x < m1) + (c.y < m1) + (c.z < m1) + (c.w < m1);
+          eqb += (dd > 0 && c.x == mine) + (dd > 1 && c.y == mine) + (dd > 2 && c.z == mine);
+          jb += 4;
+        }
+        for (; jb < je; jb += 4) {
+          const uint4 c = *reinterpret_cast<const uint4*>(&sm.ck[jb]);
+          lt += (c.x < mine) + (c.y < mine) + (c.z < mine) + (c.w < mine);
+          le += (c.x < m1) + (c.y < m1) + (c.z < m1) + (c.w < m1);
+        }
+        eq = le - lt;
+        lt -= gs & 3u;  // the slots of earlier groups in the first vector
+      }
+      uint32_t fl = 0;
+      if (eqb == 0) { fl = SA_HEAD; ++n_heads; }
+      if (eq == 1) fl |= SA_SINGLE; else ++n_unres;
+      const uint32_t pos = e & RANK_MASK;
+      s[gs + lt + eqb] = pos | fl;
+      rk[pos] = (start + gs + lt) | (eq == 1 ? RANK_RESOLVED : 0u);
     }
   }
 #pragma unroll
   for (int dlt = 16; dlt > 0; dlt >>= 1) {
-    n_new += __shfl_xor_sync(0xffffffffu, n_new, dlt);
+    n_heads += __shfl_xor_sync(0xffffffffu, n_heads, dlt);
     n_unres += __shfl_xor_sync(0xffffffffu, n_unres, dlt);
+    heads_before += __shfl_xor_sync(0xffffffffu, heads_before, dlt);
   }
-  const int w = threadIdx.x >> 5;
-  if (lane_id() == 0) { red[0][w] = n_new; red[1][w] = n_unres; }
+  if (lane_id() == 0) { sm.red[0][w] = n_heads; sm.red[1][w] = n_unres; sm.red[2][w] = heads_before; }
   __syncthreads();
   if (threadIdx.x == 0) {
-    uint32_t a = 0, u = 0;
-    for (int ww = 0; ww < LS_NT / 32; ++ww) { a += red[0][ww]; u += red[1][ww]; }
+    uint32_t a = 0, u = 0, hb = 0;
+    for (int ww = 0; ww < LS_NT / 32; ++ww) { a += sm.red[0][ww]; u += sm.red[1][ww]; hb += sm.red[2][ww]; }
     uint32_t* stp = stats + b * 4;
-    if (a) atomicAdd(&stp[0], a);
+    if (a > hb) atomicAdd(&stp[0], a - hb);
     if (u) atomicAdd(&stp[2], u);
   }
 }
 
 // ------------------------------------------------------------------ last column + origPtr (slot order)
-__global__ void __launch_bounds__(LS_NT) k2_finish(const uint8_t* __restrict__ txt, const BlockDesc* __restrict__ desc,
+__global__ void __launch_bounds__(G_NT) k2_finish(const uint8_t* __restrict__ txt, const BlockDesc* __restrict__ desc,
                                                    const uint32_t* __restrict__ sa, uint8_t* __restrict__ last,
                                                    uint32_t* __restrict__ origptr) {
   const BlockDesc d = desc[blockIdx.y];
   const uint32_t n = d.n;
-  const uint32_t base = blockIdx.x * (LS_NT * 16);
+  const uint32_t base = blockIdx.x * (G_NT * 16);
   if (base >= n) return;
   const uint8_t* t = txt + d.off;
   const uint32_t* s = sa + d.off;
@@ -678,7 +843,7 @@ __global__ void __launch_bounds__(LS_NT) k2_finish(const uint8_t* __restrict__ t
   // (d.off is not 4-aligned in general, so the vector path is taken only where both addresses are aligned)
 #pragma unroll 4
   for (int k = 0; k < 16; ++k) {
-    const uint32_t i = base + threadIdx.x + k * LS_NT;
+    const uint32_t i = base + threadIdx.x + k * G_NT;
     if (i < n) {
       const uint32_t pos = s[i] & RANK_MASK;
       last[d.off + i] = t[pos == 0 ? n - 1 : pos - 1];
@@ -720,8 +885,14 @@ int run_bwt(Launcher& L, const uint8_t* d_txt, const BlockDesc* d_desc, uint32_t
   cudaMemsetAsync(S.shift, 0xFF, nb * sizeof(uint32_t), st);
   cudaMemsetAsync(S.stats, 0, nb * 4 * sizeof(uint32_t), st);
   cudaMemsetAsync(S.rounds, 0, nb * sizeof(uint32_t), st);
+  cudaMemsetAsync(S.sparse, 0, nb * sizeof(uint32_t), st);
   cudaMemsetAsync(S.global, 0, 4 * sizeof(uint32_t), st);
 
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute((const void*)k2_local_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LsSmem));
+    attr_set = true;
+  }
   uint32_t rounds = 0, passes = 0;
   uint64_t elems = 0;
   uint64_t *src = S.A, *dst = S.B;
@@ -730,8 +901,8 @@ int run_bwt(Launcher& L, const uint8_t* d_txt, const BlockDesc* d_desc, uint32_t
   passes += 5;
   elems += M;
   regroup(L, src, d_desc, nb, nmax, S, 1);
-  L.launch("k2_round_finalize", k2_round_finalize, dim3((nb + 255) / 256), dim3(256), nb, 0u, S.cnt, S.stats, S.state,
-           S.rounds, S.global);
+  L.launch("k2_round_finalize", k2_round_finalize, dim3((nb + 255) / 256), dim3(256), nb, 0u, d_desc, S.cnt, S.stats,
+           S.state, S.sparse, S.rounds, S.global);
 
   uint32_t g[4];
   if (L.err != cudaSuccess) return -2;
@@ -746,10 +917,11 @@ int run_bwt(Launcher& L, const uint8_t* d_txt, const BlockDesc* d_desc, uint32_t
     cudaMemsetAsync(S.global, 0, 2 * sizeof(uint32_t), st);
     L.launch("k2_periodic_shift", k2_periodic_shift, dim3(nb), dim3(256), d_desc, S.state, S.sa, S.shift);
     // BIG-group elements go to S.A (both radix buffers are free between rounds)
-    L.launch("k2_gather", k2_gather, dim3(ls_tiles, nb), dim3(LS_NT), d_desc, S.rank, S.sa, S.state, S.shift, h, S.key,
+    L.launch("k2_gather", k2_gather, dim3(ls_tiles, nb), dim3(G_NT), d_desc, S.rank, S.sa, S.state, S.shift, S.sparse, h,
+             S.key,
              S.A, S.cnt, S.first_head, S.tile_active, S.ls_tiles_cap);
-    L.launch("k2_local_sort", k2_local_sort, dim3(ls_tiles, nb), dim3(LS_NT), d_desc, S.state, S.sa, S.key, S.rank,
-             S.first_head, S.tile_active, S.ls_tiles_cap, S.stats);
+    L.launch_smem("k2_local_sort", k2_local_sort, dim3(ls_tiles, nb), dim3(LS_NT), sizeof(LsSmem), d_desc, S.state,
+                  S.sa, S.key, S.rank, S.first_head, S.tile_active, S.ls_tiles_cap, S.stats);
     const uint32_t maxbig = g[1];
     if (maxbig > 0) {
       uint64_t *s2 = S.A, *d2 = S.B;
@@ -758,16 +930,16 @@ int run_bwt(Launcher& L, const uint8_t* d_txt, const BlockDesc* d_desc, uint32_t
       regroup(L, s2, d_desc, nb, maxbig, S, 0);
     }
     elems += g[0];
-    L.launch("k2_round_finalize", k2_round_finalize, dim3((nb + 255) / 256), dim3(256), nb, rounds, S.cnt, S.stats,
-             S.state, S.rounds, S.global);
+    L.launch("k2_round_finalize", k2_round_finalize, dim3((nb + 255) / 256), dim3(256), nb, rounds, d_desc, S.cnt,
+             S.stats, S.state, S.sparse, S.rounds, S.global);
     if (L.err != cudaSuccess) return -2;
     if (cudaMemcpyAsync(g, S.global, sizeof(g), cudaMemcpyDeviceToHost, st) != cudaSuccess) return -2;
     if (cudaStreamSynchronize(st) != cudaSuccess) return -2;
     if (h < (1u << 21)) h *= 2;
   }
   if (g[2]) return -5;
-  const uint32_t ftiles = (nmax + LS_NT * 16 - 1) / (LS_NT * 16);
-  L.launch("k2_finish", k2_finish, dim3(ftiles, nb), dim3(LS_NT), d_txt, d_desc, S.sa, d_last, d_origptr);
+  const uint32_t ftiles = (nmax + G_NT * 16 - 1) / (G_NT * 16);
+  L.launch("k2_finish", k2_finish, dim3(ftiles, nb), dim3(G_NT), d_txt, d_desc, S.sa, d_last, d_origptr);
   if (h_rounds) *h_rounds = rounds;
   if (h_passes) *h_passes = passes;
   if (h_elems) *h_elems = elems;

@@ -88,6 +88,7 @@ struct BwtScratch {
   int4* tsum;           // [nb][tiles] regroup tile summaries
   uint32_t* state;      // [nb] 0 active, 1 fix-up pending, 2 done
   uint32_t* shift;      // [nb]
+  uint32_t* sparse;     // [nb] 1: few unresolved rotations left, the block takes the radix path
   uint32_t* stats;      // [nb][4]: groups created, BIG members, unresolved, periodic flag
   uint32_t* rounds;     // [nb] rounds until done (instrumentation)
   uint32_t* global;     // [4]: total unresolved, max active per block, error flag, spare

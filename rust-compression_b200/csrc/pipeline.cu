@@ -116,7 +116,7 @@ struct bzb200_ctx {
   std::vector<uint32_t> h_crc;
 
   // ---- batch scratch ----
-  DevBuf desc, A, B, rank, sa, key, first_head, tile_active, cnt, hist, tsum, state, shift, stats, rounds, global, last, origptr;
+  DevBuf desc, A, B, rank, sa, key, first_head, tile_active, cnt, hist, tsum, state, shift, sparse, stats, rounds, global, last, origptr;
   DevBuf chunk_state, chunk_zle, chunk_base, sym, freq, mtf_count;
   DevBuf lens, rfreq, sel, selmtf, codes, gbits, meta, lm_scratch, lm_list, lm_count, blockbit, bitcursor, combined;
   DevBuf stage_in, stage_out;  // bzb200_compress_host staging
@@ -239,7 +239,7 @@ static int ctx_create_impl(int device, void* stream, bool own_stream, bzb200_ctx
   }
   c->all = {&c->tile_head, &c->tile_carry, &c->tile_cnt, &c->tile_E, &c->in_off, &c->rle_off, &c->txt, &c->crc,
             &c->inuse, &c->scal, &c->desc, &c->A, &c->B, &c->rank, &c->sa, &c->key,
-            &c->first_head, &c->tile_active, &c->cnt, &c->hist, &c->tsum, &c->state, &c->shift,
+            &c->first_head, &c->tile_active, &c->cnt, &c->hist, &c->tsum, &c->state, &c->shift, &c->sparse,
             &c->stats, &c->rounds, &c->global, &c->last, &c->origptr, &c->chunk_state, &c->chunk_zle, &c->chunk_base,
             &c->sym, &c->freq, &c->mtf_count, &c->lens, &c->rfreq, &c->sel, &c->selmtf, &c->codes, &c->gbits, &c->meta,
             &c->lm_scratch, &c->lm_list, &c->lm_count, &c->blockbit, &c->bitcursor, &c->combined, &c->stage_in,
@@ -398,6 +398,7 @@ static int encode_batch(bzb200_ctx* c, uint32_t b0, uint32_t nb, uint8_t* d_out,
   TRY(ensure(c, c->tsum, (size_t)nb * tiles * sizeof(int4)));
   TRY(ensure(c, c->state, (size_t)nb * 4));
   TRY(ensure(c, c->shift, (size_t)nb * 4));
+  TRY(ensure(c, c->sparse, (size_t)nb * 4));
   TRY(ensure(c, c->stats, (size_t)nb * 16));
   TRY(ensure(c, c->rounds, (size_t)nb * 4));
   TRY(ensure(c, c->global, 64));
@@ -442,6 +443,7 @@ static int encode_batch(bzb200_ctx* c, uint32_t b0, uint32_t nb, uint8_t* d_out,
   S.tsum = ptr<int4>(c->tsum);
   S.state = ptr<uint32_t>(c->state);
   S.shift = ptr<uint32_t>(c->shift);
+  S.sparse = ptr<uint32_t>(c->sparse);
   S.stats = ptr<uint32_t>(c->stats);
   S.rounds = ptr<uint32_t>(c->rounds);
   S.global = ptr<uint32_t>(c->global);
