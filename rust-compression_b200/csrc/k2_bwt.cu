@@ -186,6 +186,203 @@ __global__ void __launch_bounds__(RS_NT) k2_rs_scatter(const uint64_t* __restric
 }
 
 
+// ------------------------------------------------------------------ one-sweep LSD radix pass (per-block segments)
+// Digit histograms of all five passes are taken once (k2_os_hist*), turned into bucket offsets (k2_os_offsets), and
+// each pass is then ONE kernel: a CTA ranks its tile (warp match + per-warp counters), publishes the tile's digit
+// counts, obtains the counts of the preceding tiles of its block by decoupled look-back over the status words of
+// those tiles, and scatters through shared memory.  Tiles of a block are numbered by a ticket, so a tile only ever
+// waits for tiles that are already running.  The grid is (block, tile): CTAs in flight belong to different blocks,
+// which keeps the look-back chains short.
+constexpr int OS_NT = 512;
+constexpr int OS_IPT = 8;
+constexpr int OS_TILE = OS_NT * OS_IPT;   // 4096
+constexpr int OS_WARPS = OS_NT / 32;      // 16
+constexpr int OS_WCH = OS_TILE / OS_WARPS;  // 256 elements per warp
+static_assert(OS_TILE == RS_TILE, "hist/status arrays are sized by RS_TILE tiles");
+constexpr uint32_t ST_AGG = 1u << 20, ST_PREFIX = 2u << 20, ST_VAL = 0xFFFFFu;
+
+struct OsSmem {
+  uint64_t stage[OS_TILE];
+  uint32_t wcnt[OS_WARPS][256];
+  uint32_t dstart[256];
+  int goff[256];
+  uint32_t ws[OS_NT / 32 + 1];
+  uint32_t tile;
+};
+
+// Byte histogram of a block's text = digit histogram of every pass of the initial sort (every byte of the block is
+// digit p of exactly one rotation).  grid (chunks, nb); hist[b][p][d] accumulated with global atomics.
+__global__ void __launch_bounds__(256) k2_os_hist_txt(const uint8_t* __restrict__ txt, const BlockDesc* __restrict__ desc,
+                                                      uint32_t* __restrict__ hist, uint32_t chunk) {
+  __shared__ uint32_t h[8][256];
+  const BlockDesc d = desc[blockIdx.y];
+  const uint32_t lo = blockIdx.x * chunk;
+  if (lo >= d.n) return;
+  const uint32_t hi = min(d.n, lo + chunk);
+  for (int i = threadIdx.x; i < 8 * 256; i += 256) (&h[0][0])[i] = 0;
+  __syncthreads();
+  const uint8_t* t = txt + d.off;
+  uint32_t* hw = h[(threadIdx.x >> 5) & 7];
+  for (uint32_t i = lo + threadIdx.x; i < hi; i += 256) atomicAdd(&hw[t[i]], 1u);
+  __syncthreads();
+  uint32_t v = 0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) v += h[k][threadIdx.x];
+  if (v) {
+    uint32_t* o = hist + (uint64_t)blockIdx.y * 5 * 256 + threadIdx.x;
+#pragma unroll
+    for (int p = 0; p < 5; ++p) atomicAdd(o + p * 256, v);
+  }
+}
+
+// Digit histograms of the five passes from the 64-bit elements themselves (rounds).  grid (chunks, nb).
+__global__ void __launch_bounds__(256) k2_os_hist(const uint64_t* __restrict__ src, const BlockDesc* __restrict__ desc,
+                                                  const uint32_t* __restrict__ cnt, uint32_t* __restrict__ hist,
+                                                  uint32_t chunk) {
+  __shared__ uint32_t h[4][5][256];
+  const uint32_t c = cnt[blockIdx.y];
+  const uint32_t lo = blockIdx.x * chunk;
+  if (lo >= c) return;
+  const uint32_t hi = min(c, lo + chunk);
+  for (int i = threadIdx.x; i < 4 * 5 * 256; i += 256) (&h[0][0][0])[i] = 0;
+  __syncthreads();
+  const uint64_t* s = src + desc[blockIdx.y].off;
+  uint32_t(*hw)[256] = h[(threadIdx.x >> 5) & 3];
+  for (uint32_t i = lo + threadIdx.x; i < hi; i += 256) {
+    const uint64_t k = s[i] >> KEY_LO;
+#pragma unroll
+    for (int p = 0; p < 5; ++p) atomicAdd(&hw[p][(uint32_t)(k >> (8 * p)) & 255u], 1u);
+  }
+  __syncthreads();
+  uint32_t* o = hist + (uint64_t)blockIdx.y * 5 * 256 + threadIdx.x;
+#pragma unroll
+  for (int p = 0; p < 5; ++p) {
+    const uint32_t v = h[0][p][threadIdx.x] + h[1][p][threadIdx.x] + h[2][p][threadIdx.x] + h[3][p][threadIdx.x];
+    if (v) atomicAdd(o + p * 256, v);
+  }
+}
+
+// counts -> exclusive bucket offsets, per block and pass.  grid (nb), 256 threads.
+__global__ void __launch_bounds__(256) k2_os_offsets(uint32_t* __restrict__ hist) {
+  __shared__ uint32_t ws[256 / 32 + 1];
+  uint32_t* h = hist + (uint64_t)blockIdx.x * 5 * 256;
+  for (int p = 0; p < 5; ++p) {
+    const uint32_t v = h[p * 256 + threadIdx.x];
+    h[p * 256 + threadIdx.x] = cta_excl_scan_add<256>(v, ws, nullptr);
+  }
+}
+
+__device__ __forceinline__ uint32_t ld_status(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_status(uint32_t* p, uint32_t v) {
+  asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+__global__ void __launch_bounds__(OS_NT, 2) k2_os_scatter(const uint64_t* __restrict__ src, uint64_t* __restrict__ dst,
+                                                          const BlockDesc* __restrict__ desc,
+                                                          const uint32_t* __restrict__ cnt,
+                                                          const uint32_t* __restrict__ bucket_off,
+                                                          uint32_t* __restrict__ status, uint32_t* __restrict__ ticket,
+                                                          uint32_t ticket_base, uint32_t tiles_cap, uint32_t epoch,
+                                                          int pass) {
+  extern __shared__ __align__(16) uint8_t os_raw[];
+  OsSmem& sm = *reinterpret_cast<OsSmem*>(os_raw);
+  const uint32_t b = blockIdx.x;
+  const uint32_t c = cnt[b];
+  if (threadIdx.x == 0) sm.tile = atomicAdd(&ticket[b], 1u) - ticket_base;
+  const int w = threadIdx.x >> 5;
+  const uint32_t lane = lane_id();
+#pragma unroll
+  for (int i = lane; i < 256; i += 32) sm.wcnt[w][i] = 0;
+  __syncthreads();
+  const uint32_t tile = sm.tile;
+  const uint32_t base = tile * OS_TILE;
+  if (base >= c) return;
+  const uint32_t tcount = min((uint32_t)OS_TILE, c - base);
+  const uint32_t off = desc[b].off;
+  const uint64_t* s = src + off + base;
+  const int shift = KEY_LO + 8 * pass;
+
+  // ---- rank inside the warp's 256-element chunk; memory order == (warp, row, lane), so the pass is stable
+  uint64_t e[OS_IPT];
+  uint32_t rk[OS_IPT];
+#pragma unroll
+  for (int it = 0; it < OS_IPT; ++it) {
+    const uint32_t li = w * OS_WCH + it * 32 + lane;
+    e[it] = li < tcount ? s[li] : ~0ull;
+  }
+#pragma unroll
+  for (int it = 0; it < OS_IPT; ++it) {
+    const uint32_t li = w * OS_WCH + it * 32 + lane;
+    const bool valid = li < tcount;
+    const uint32_t dgt = valid ? (uint32_t)(e[it] >> shift) & 255u : 0xFFFFu;
+    const uint32_t peers = __match_any_sync(0xffffffffu, dgt);
+    const int leader = __ffs(peers) - 1;
+    uint32_t old = 0;
+    if (valid && (int)lane == leader) old = atomicAdd(&sm.wcnt[w][dgt], (uint32_t)__popc(peers));
+    old = __shfl_sync(0xffffffffu, old, leader);
+    rk[it] = old + __popc(peers & lanemask_lt());
+  }
+  __syncthreads();
+
+  // ---- per digit: exclusive prefix over the warps, tile count, start inside the tile; publish + look back
+  uint32_t run = 0;
+  if (threadIdx.x < 256) {
+#pragma unroll
+    for (int ww = 0; ww < OS_WARPS; ++ww) {
+      const uint32_t t = sm.wcnt[ww][threadIdx.x];
+      sm.wcnt[ww][threadIdx.x] = run;
+      run += t;
+    }
+  }
+  const uint32_t ds = cta_excl_scan_add<OS_NT>(run, sm.ws, nullptr);
+  if (threadIdx.x < 256) {
+    const uint32_t dgt = threadIdx.x;
+    uint32_t* st = status + ((uint64_t)b * tiles_cap) * 256 + dgt;
+    const uint32_t tag = epoch << 22;
+    uint32_t excl = 0;
+    if (tile == 0) {
+      st_status(st, tag | ST_PREFIX | run);
+    } else {
+      st_status(st + (uint64_t)tile * 256, tag | ST_AGG | run);
+      for (int t = (int)tile - 1; t >= 0; --t) {
+        uint32_t v;
+        do {
+          v = ld_status(st + (uint64_t)t * 256);
+        } while ((v >> 22) != epoch);
+        excl += v & ST_VAL;
+        if (v & ST_PREFIX) break;
+      }
+      st_status(st + (uint64_t)tile * 256, tag | ST_PREFIX | (excl + run));
+    }
+    sm.dstart[dgt] = ds;
+    sm.goff[dgt] = (int)(bucket_off[((uint64_t)b * 5 + pass) * 256 + dgt] + excl) - (int)ds;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int it = 0; it < OS_IPT; ++it) {
+    const uint32_t li = w * OS_WCH + it * 32 + lane;
+    if (li < tcount) {
+      const uint32_t dgt = (uint32_t)(e[it] >> shift) & 255u;
+      sm.stage[sm.dstart[dgt] + sm.wcnt[w][dgt] + rk[it]] = e[it];
+    }
+  }
+  __syncthreads();
+  uint64_t* o = dst + off;
+#pragma unroll
+  for (int k = 0; k < OS_IPT; ++k) {
+    const uint32_t i = threadIdx.x + k * OS_NT;
+    if (i < tcount) {
+      const uint64_t v = sm.stage[i];
+      const uint32_t dgt = (uint32_t)(v >> shift) & 255u;
+      o[sm.goff[dgt] + (int)i] = v;
+    }
+  }
+}
+
 // ------------------------------------------------------------------ SA entry layout / local-sort geometry
 constexpr uint32_t SA_HEAD = 0x80000000u;    // first slot of a group
 constexpr uint32_t SA_BIG = 0x40000000u;     // member of a group with more than LOCAL_MAX slots (radix path)
@@ -853,15 +1050,34 @@ __global__ void __launch_bounds__(G_NT) k2_finish(const uint8_t* __restrict__ tx
 }
 
 // ------------------------------------------------------------------ host driver
-static void radix_sort40(Launcher& L, uint64_t*& src, uint64_t*& dst, const BlockDesc* d_desc, uint32_t nb,
-                         uint32_t maxcnt, BwtScratch& S) {
-  const uint32_t tiles = (maxcnt + RS_TILE - 1) / RS_TILE;
+// One 40-bit LSD sort of every block's list (cnt[b] elements at src + desc[b].off).  `txt` non-null: the list is
+// the initial key list and the digit histograms are the block's byte histogram.
+struct OsState {
+  uint32_t epoch = 0;        // status-word tag of the most recent pass (10 bits; status is cleared at 0)
+  uint32_t ticket_base = 0;  // tickets handed out per block so far
+};
+
+static void radix_sort40(Launcher& L, uint64_t*& src, uint64_t*& dst, const uint8_t* d_txt, const BlockDesc* d_desc,
+                         uint32_t nb, uint32_t maxcnt, BwtScratch& S, OsState& os) {
+  const uint32_t tiles = (maxcnt + OS_TILE - 1) / OS_TILE;
+  if (tiles == 0) return;
+  cudaMemsetAsync(S.oshist, 0, (size_t)nb * 5 * 256 * sizeof(uint32_t), L.stream);
+  const uint32_t chunk = 16 * OS_TILE;
+  const uint32_t chunks = (maxcnt + chunk - 1) / chunk;
+  if (d_txt)
+    L.launch("k2_os_hist_txt", k2_os_hist_txt, dim3(chunks, nb), dim3(256), d_txt, d_desc, S.oshist, chunk);
+  else
+    L.launch("k2_os_hist", k2_os_hist, dim3(chunks, nb), dim3(256), src, d_desc, S.cnt, S.oshist, chunk);
+  L.launch("k2_os_offsets", k2_os_offsets, dim3(nb), dim3(256), S.oshist);
   for (int p = 0; p < 5; ++p) {
-    const int shift = KEY_LO + 8 * p;
-    L.launch("k2_rs_hist", k2_rs_hist, dim3(tiles, nb), dim3(RS_NT), src, d_desc, S.cnt, S.hist, S.tiles_cap, shift);
-    L.launch("k2_rs_scan", k2_rs_scan, dim3(nb), dim3(256), S.cnt, S.hist, S.tiles_cap);
-    L.launch("k2_rs_scatter", k2_rs_scatter, dim3(tiles, nb), dim3(RS_NT), src, dst, d_desc, S.cnt, S.hist,
-             S.tiles_cap, shift);
+    if (os.epoch == 1023) {  // tag space exhausted: start over with a clean status array
+      cudaMemsetAsync(S.hist, 0, (size_t)nb * S.tiles_cap * 256 * sizeof(uint32_t), L.stream);
+      os.epoch = 0;
+    }
+    ++os.epoch;
+    L.launch_smem("k2_rs_scatter", k2_os_scatter, dim3(nb, tiles), dim3(OS_NT), sizeof(OsSmem), src, dst, d_desc, S.cnt,
+                  S.oshist, S.hist, S.ticket, os.ticket_base, S.tiles_cap, os.epoch, p);
+    os.ticket_base += tiles;
     uint64_t* t = src; src = dst; dst = t;
   }
 }
@@ -891,13 +1107,17 @@ int run_bwt(Launcher& L, const uint8_t* d_txt, const BlockDesc* d_desc, uint32_t
   static bool attr_set = false;
   if (!attr_set) {
     cudaFuncSetAttribute((const void*)k2_local_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LsSmem));
+    cudaFuncSetAttribute((const void*)k2_os_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(OsSmem));
     attr_set = true;
   }
   uint32_t rounds = 0, passes = 0;
   uint64_t elems = 0;
   uint64_t *src = S.A, *dst = S.B;
   L.launch("k2_init_keys", k2_init_keys, dim3(tiles_n, nb), dim3(RS_NT), d_txt, d_desc, S.A, S.cnt);
-  radix_sort40(L, src, dst, d_desc, nb, nmax, S);
+  OsState os;
+  cudaMemsetAsync(S.hist, 0, (size_t)nb * S.tiles_cap * 256 * sizeof(uint32_t), st);
+  cudaMemsetAsync(S.ticket, 0, nb * sizeof(uint32_t), st);
+  radix_sort40(L, src, dst, d_txt, d_desc, nb, nmax, S, os);
   passes += 5;
   elems += M;
   regroup(L, src, d_desc, nb, nmax, S, 1);
@@ -925,7 +1145,7 @@ int run_bwt(Launcher& L, const uint8_t* d_txt, const BlockDesc* d_desc, uint32_t
     const uint32_t maxbig = g[1];
     if (maxbig > 0) {
       uint64_t *s2 = S.A, *d2 = S.B;
-      radix_sort40(L, s2, d2, d_desc, nb, maxbig, S);
+      radix_sort40(L, s2, d2, nullptr, d_desc, nb, maxbig, S, os);
       passes += 5;
       regroup(L, s2, d_desc, nb, maxbig, S, 0);
     }

@@ -84,7 +84,9 @@ struct BwtScratch {
   uint32_t* tile_active;// [nb][ls_tiles]
   uint32_t ls_tiles_cap;
   uint32_t* cnt;        // [nb] active elements per block
-  uint32_t* hist;       // [nb][tiles][256]
+  uint32_t* hist;       // [nb][tiles][256] radix pass: per-tile status words (decoupled look-back)
+  uint32_t* oshist;     // [nb][5][256] digit histograms -> bucket offsets of the five passes
+  uint32_t* ticket;     // [nb] tile tickets
   int4* tsum;           // [nb][tiles] regroup tile summaries
   uint32_t* state;      // [nb] 0 active, 1 fix-up pending, 2 done
   uint32_t* shift;      // [nb]
