@@ -662,46 +662,55 @@ __global__ void __launch_bounds__(256) k2_periodic_shift(const BlockDesc* __rest
   if (threadIdx.x == 0) shift[b] = s_min;
 }
 
-// ------------------------------------------------------------------ k2_gather: keys of the next round
-// Slot order.  Small groups: key[slot].  BIG groups: 64-bit element appended to A (any order) and counted in cnt[b].
-// Also publishes, per tile, the first HEAD slot and whether the tile holds any active small-group slot.
+// ------------------------------------------------------------------ k2_gather: work lists of the next round
+// Slot order, one CTA per 2048-slot tile.  Every unresolved slot fetches its key rank[(pos+h) mod n] and the head
+// slot g = rank[pos] of its group.
+//   small groups : a 64-bit entry  [19:0] pos | [39:20] key | [50:40] slot - g | [61:51] slot - tile base  is appended
+//                  to the tile's dense list (slot order kept: warp w owns slots w*256.., rows of 32) in `lst`;
+//                  tile_meta[b][t] = (entries, entries before the tile's first HEAD slot) lets the CTA that owns a
+//                  group spanning two tiles pick up its tail.
+//   BIG groups / sparse blocks : [59:40] g | [39:20] key | [19:0] pos appended to A (any order), counted in cnt[b].
 __global__ void __launch_bounds__(G_NT) k2_gather(const BlockDesc* __restrict__ desc, const uint32_t* __restrict__ rank,
-                                                   const uint32_t* __restrict__ sa, const uint32_t* __restrict__ state,
-                                                   const uint32_t* __restrict__ shiftv,
-                                                   const uint32_t* __restrict__ sparse, uint32_t h,
-                                                   uint32_t* __restrict__ key, uint64_t* __restrict__ A,
-                                                   uint32_t* __restrict__ cnt, uint32_t* __restrict__ first_head,
-                                                   uint32_t* __restrict__ tile_active, uint32_t ls_tiles_cap) {
+                                                  const uint32_t* __restrict__ sa, const uint32_t* __restrict__ state,
+                                                  const uint32_t* __restrict__ shiftv,
+                                                  const uint32_t* __restrict__ sparse, uint32_t h,
+                                                  uint64_t* __restrict__ lst, uint64_t* __restrict__ A,
+                                                  uint32_t* __restrict__ cnt, uint2* __restrict__ tile_meta,
+                                                  uint32_t ls_tiles_cap) {
   __shared__ uint32_t ws[G_NT / 32 + 1];
-  __shared__ uint32_t s_base, s_fh, s_act;
-  constexpr int IPT = LS_T / G_NT;  // 8
+  __shared__ uint32_t s_wtot[G_NT / 32];
+  __shared__ uint32_t s_base, s_fh, s_lead;
+  constexpr int ROWS = LS_T / G_NT;  // 8 rows of 32 slots per warp
   const BlockDesc d = desc[blockIdx.y];
   const uint32_t n = d.n;
   const uint32_t base = blockIdx.x * LS_T;
   if (base >= n) return;
   const uint32_t st = state[blockIdx.y];
   if (st == 2) return;
-  if (threadIdx.x == 0) { s_fh = NONE; s_act = 0; }
+  if (threadIdx.x == 0) { s_fh = NONE; s_lead = 0; }
   const uint32_t* rk = rank + d.off;
   const uint32_t* s = sa + d.off;
-  uint32_t* ko = key + d.off;
   const uint32_t hm = h % n;
   const uint32_t sh = st == 1 ? shiftv[blockIdx.y] : 0u;
   const bool sp = sparse[blockIdx.y] != 0;  // sparse block: every unresolved slot is emitted to the radix path
-  uint32_t ev[IPT];
+  const int w = threadIdx.x >> 5;
+  const uint32_t lane = lane_id();
+  uint32_t ev[ROWS];
 #pragma unroll
-  for (int k = 0; k < IPT; ++k) {
-    const uint32_t i = base + threadIdx.x + k * G_NT;
+  for (int k = 0; k < ROWS; ++k) {
+    const uint32_t i = base + w * (ROWS * 32) + k * 32 + lane;
     ev[k] = i < n ? s[i] : SA_SINGLE;
   }
-  uint32_t fh = NONE, act = 0, nbig = 0;
-  uint64_t be[IPT];
+  uint32_t fh = NONE, nbig = 0, wrun = 0;
+  uint64_t ent[ROWS];      // 0: nothing; bit 63: BIG-path element; else small-group entry (bit 62 set as marker)
+  uint32_t lidx[ROWS];     // index of the small-group entry inside the warp's part of the list
 #pragma unroll
-  for (int k = 0; k < IPT; ++k) {
-    const uint32_t i = base + threadIdx.x + k * G_NT;
+  for (int k = 0; k < ROWS; ++k) {
+    const uint32_t i = base + w * (ROWS * 32) + k * 32 + lane;
     const uint32_t e = ev[k];
     if (i < n && (e & SA_HEAD)) fh = min(fh, i);
-    be[k] = 0;
+    ent[k] = 0;
+    bool small = false;
     if (!(e & SA_SINGLE)) {
       const uint32_t pos = e & RANK_MASK;
       uint32_t k2;
@@ -713,29 +722,50 @@ __global__ void __launch_bounds__(G_NT) k2_gather(const BlockDesc* __restrict__ 
         const uint32_t rel = pos >= sh ? pos - sh : pos + n - sh;  // (pos - shift) mod n
         k2 = n - 1 - rel;
       }
+      const uint32_t g = rk[pos] & RANK_MASK;
       if (sp || (e & SA_BIG)) {
-        const uint32_t g = rk[pos] & RANK_MASK;
-        be[k] = ((uint64_t)g << 40) | ((uint64_t)k2 << 20) | pos | (1ull << 63);
+        ent[k] = ((uint64_t)g << 40) | ((uint64_t)k2 << 20) | pos | (1ull << 63);
         ++nbig;
       } else {
-        ko[i] = k2;
-        act = 1;
+        ent[k] = (uint64_t)pos | ((uint64_t)k2 << 20) | ((uint64_t)(i - g) << 40) | ((uint64_t)(i - base) << 51) |
+                 (1ull << 62);
+        small = true;
       }
     }
+    const uint32_t bal = __ballot_sync(0xffffffffu, small);
+    lidx[k] = wrun + __popc(bal & lanemask_lt());
+    wrun += __popc(bal);
   }
 #pragma unroll
   for (int dlt = 16; dlt > 0; dlt >>= 1) fh = min(fh, __shfl_xor_sync(0xffffffffu, fh, dlt));
-  act = __any_sync(0xffffffffu, act);
   __syncthreads();
-  if (lane_id() == 0) {
+  if (lane == 0) {
     if (fh != NONE) atomicMin(&s_fh, fh);
-    if (act) s_act = 1;
+    s_wtot[w] = wrun;
   }
   const int anybig = __syncthreads_or((int)nbig);
-  if (threadIdx.x == 0) {
-    first_head[(uint64_t)blockIdx.y * ls_tiles_cap + blockIdx.x] = s_fh;
-    tile_active[(uint64_t)blockIdx.y * ls_tiles_cap + blockIdx.x] = s_act;
+  const uint32_t cfh = s_fh;
+  uint32_t wbase = 0, acnt = 0;
+#pragma unroll
+  for (int ww = 0; ww < G_NT / 32; ++ww) {
+    if (ww < w) wbase += s_wtot[ww];
+    acnt += s_wtot[ww];
   }
+  // entries before the tile's first HEAD slot belong to a group owned by the previous tile
+  uint32_t lead = 0;
+  uint64_t* lo = lst + d.off + base;
+#pragma unroll
+  for (int k = 0; k < ROWS; ++k) {
+    const uint32_t i = base + w * (ROWS * 32) + k * 32 + lane;
+    const bool small = (ent[k] >> 62) == 1;
+    if (small) lo[wbase + lidx[k]] = ent[k] & ~(1ull << 62);
+    lead += small && (i < cfh);
+  }
+#pragma unroll
+  for (int dlt = 16; dlt > 0; dlt >>= 1) lead += __shfl_xor_sync(0xffffffffu, lead, dlt);
+  if (lane == 0 && lead) atomicAdd(&s_lead, lead);
+  __syncthreads();
+  if (threadIdx.x == 0) tile_meta[(uint64_t)blockIdx.y * ls_tiles_cap + blockIdx.x] = make_uint2(acnt, s_lead);
   if (!anybig) return;
   uint32_t total;
   const uint32_t ex = cta_excl_scan_add<G_NT>(nbig, ws, &total);
@@ -743,30 +773,31 @@ __global__ void __launch_bounds__(G_NT) k2_gather(const BlockDesc* __restrict__ 
   __syncthreads();
   uint64_t* o = A + d.off + s_base + ex;
 #pragma unroll
-  for (int k = 0; k < IPT; ++k)
-    if (be[k]) *o++ = be[k] & ~(1ull << 63);
+  for (int k = 0; k < ROWS; ++k)
+    if (ent[k] >> 63) *o++ = ent[k] & ~(1ull << 63);
 }
 
 // ------------------------------------------------------------------ k2_local_sort: groups up to LOCAL_MAX slots
-// CTA (b, t) owns the groups whose HEAD lies in tile t; it loads slots [first head of the tile, first head at or
-// after the tile end) — at most LS_T + LOCAL_MAX of them, no other CTA touches these — and sorts every active
-// group by key.  Elements live in registers; shared memory holds, per window slot, the composite
-// (group start << 20 | key) of the element currently placed there.
+// CTA (b, t) owns the groups whose HEAD lies in tile t: its window is the tile's list minus the leading entries
+// that continue a group of tile t-1, plus the leading entries of tile t+1's list — at most LS_T + LOCAL_MAX
+// entries, dense (resolved slots are not in the lists).  Elements live in registers; shared memory holds, per
+// window index, the composite (group start << 20 | key) of the element currently placed there.
 //   * split levels: a group larger than ENUM_MAX whose keys are not all equal is partitioned into key-range
-//     buckets (range [min,max] of its keys, ~2-4 slots per bucket, counting pass with shared-memory atomics); the
-//     buckets are groups of their own from then on; repeated until every group is small or flat (all keys equal —
-//     nothing to sort, which is what heavy duplicates end as);
-//   * enumeration: the final slot of an element = group start + #{smaller keys} + #{equal keys placed earlier};
+//     buckets (range [min,max] of its keys, ~2-4 entries per bucket, counting pass with shared-memory atomics);
+//     the buckets are groups of their own from then on; repeated until every group is small or flat (all keys
+//     equal — nothing to sort, which is what heavy duplicates end as);
+//   * enumeration: final index of an element = group start + #{smaller keys} + #{equal keys placed earlier};
 //     equal keys stay one (smaller) group.
-// SA and rank are written back in place.
+// A group occupies consecutive slots, so window index i of a group maps to slot (head slot + i - group start);
+// SA and rank are written in place.
 constexpr uint32_t GS_FLAT = 0x8000u;
+constexpr int LS_PAD = ENUM_MAX + 8;
 struct LsSmem {
-  uint32_t ck[LS_CAP + 8];
+  uint32_t ck[LS_CAP + LS_PAD];
   uint32_t cnt[LS_CAP + 8];
   uint32_t gmin[LS_CAP + 8];
   uint32_t gmax[LS_CAP + 8];
-  uint16_t gsize[LS_CAP + 8];
-  int wsa[LS_NT / 32], wsb[LS_NT / 32];
+  uint32_t gsz[LS_CAP + 8];
   uint32_t wsc[LS_NT / 32 + 1];
   uint32_t red[3][LS_NT / 32];
 };
@@ -774,109 +805,64 @@ size_t bwt_ls_smem_bytes() { return sizeof(LsSmem); }
 
 __global__ void __launch_bounds__(LS_NT, 2) k2_local_sort(const BlockDesc* __restrict__ desc,
                                                           const uint32_t* __restrict__ state,
-                                                          uint32_t* __restrict__ sa, const uint32_t* __restrict__ key,
+                                                          const uint32_t* __restrict__ sparse,
+                                                          uint32_t* __restrict__ sa, const uint64_t* __restrict__ lst,
                                                           uint32_t* __restrict__ rank,
-                                                          const uint32_t* __restrict__ first_head,
-                                                          const uint32_t* __restrict__ tile_active,
+                                                          const uint2* __restrict__ tile_meta,
                                                           uint32_t ls_tiles_cap, uint32_t* __restrict__ stats) {
   extern __shared__ __align__(16) uint8_t ls_raw[];
   LsSmem& sm = *reinterpret_cast<LsSmem*>(ls_raw);
   const uint32_t b = blockIdx.y, t = blockIdx.x;
   const BlockDesc d = desc[b];
   const uint32_t n = d.n;
-  if (t * LS_T >= n) return;
-  if (state[b] == 2) return;
+  const uint32_t tbase = t * LS_T;
+  if (tbase >= n) return;
+  if (state[b] == 2 || sparse[b]) return;
   const uint64_t ti = (uint64_t)b * ls_tiles_cap + t;
-  if (!tile_active[ti]) return;
-  const uint32_t start = first_head[ti];
-  if (start == NONE) return;
-  const uint32_t tile_end = min(n, (t + 1) * LS_T);
-  uint32_t end = n;
-  if (tile_end < n) {
-    const uint32_t fh = first_head[ti + 1];
-    end = fh != NONE ? fh : n;
-    end = min(end, tile_end + LOCAL_MAX);  // anything longer is a BIG group and is skipped anyway
-  }
-  const uint32_t count = end - start;  // <= LS_CAP
-  uint32_t* s = sa + d.off + start;
-  const uint32_t* kin = key + d.off + start;
+  const uint2 m0 = tile_meta[ti];
+  const uint2 m1 = (tbase + LS_T < n) ? tile_meta[ti + 1] : make_uint2(0u, 0u);
+  const uint32_t own = m0.x - m0.y, over = m1.y;
+  const uint32_t count = own + over;  // <= LS_T + LOCAL_MAX
+  if (count == 0) return;
+  const uint64_t* l0 = lst + d.off + tbase + m0.y;
+  const uint64_t* l1 = lst + d.off + tbase + LS_T;
+  uint32_t* s = sa + d.off;
   const int w = threadIdx.x >> 5;
 
-  // ---- A: striped load. Per element: ev = SA entry, kv = key, gp = group start | current slot << 12 | pending << 31
-  uint32_t ev[LS_IPT], kv[LS_IPT], gp[LS_IPT];
+  // ---- load. Per element: pv = pos, kv = key, hv = head slot of its group, gp = group start | index << 12 | pending << 31
+  uint32_t pv[LS_IPT], kv[LS_IPT], hv[LS_IPT], gp[LS_IPT];
   uint32_t heads_before = 0;
 #pragma unroll
   for (int k = 0; k < LS_IPT; ++k) {
     const uint32_t r = threadIdx.x + k * LS_NT;
-    ev[k] = SA_SINGLE;
-    kv[k] = 0;
+    gp[k] = NONE;
     if (r < count) {
-      const uint32_t e = s[r];
-      ev[k] = e;
-      if (!(e & (SA_SINGLE | SA_BIG))) {
-        kv[k] = kin[r];
-        heads_before += e >> 31;
-      }
-      sm.ck[r] = kv[k] | (e & SA_HEAD);
-    }
-  }
-  if (threadIdx.x < 8) sm.ck[count + threadIdx.x] = NONE;
-  __syncthreads();
-
-  // ---- B: blocked scans over the head flags: group start (forward max) and group end (reverse min) of every slot
-  {
-    const uint32_t r0 = threadIdx.x * LS_IPT;
-    int lh = -1, fh = 0x7FFFFFFF;
-    uint32_t hm = 0;
-#pragma unroll
-    for (int j = 0; j < LS_IPT; ++j)
-      if (r0 + j < count && (sm.ck[r0 + j] & SA_HEAD)) {
-        hm |= 1u << j;
-        lh = (int)(r0 + j);
-        if (fh == 0x7FFFFFFF) fh = (int)(r0 + j);
-      }
-    int ih = warp_incl_scan_max(lh);
-    int rf = fh;
-#pragma unroll
-    for (int dl = 1; dl < 32; dl <<= 1) {
-      int tt = __shfl_down_sync(0xffffffffu, rf, dl);
-      if ((int)lane_id() + dl < 32) rf = min(rf, tt);
-    }
-    if (lane_id() == 31) sm.wsa[w] = ih;
-    if (lane_id() == 0) sm.wsb[w] = rf;
-    __syncthreads();
-    int gs = __shfl_up_sync(0xffffffffu, ih, 1);
-    if (lane_id() == 0) gs = -1;
-    for (int ww = 0; ww < w; ++ww) gs = max(gs, sm.wsa[ww]);
-    int nh = __shfl_down_sync(0xffffffffu, rf, 1);
-    if (lane_id() == 31) nh = 0x7FFFFFFF;
-    for (int ww = w + 1; ww < LS_NT / 32; ++ww) nh = min(nh, sm.wsb[ww]);
-    nh = min(nh, (int)count);
-#pragma unroll
-    for (int j = 0; j < LS_IPT; ++j) {
-      if (r0 + j < count) {
-        if (hm & (1u << j)) {
-          gs = (int)(r0 + j);  // slot 0 of the window is a HEAD, so gs >= 0 everywhere
-          const uint32_t later = j < LS_IPT - 1 ? (hm >> (j + 1)) : 0u;
-          const int ge = later ? (int)(r0 + j) + __ffs(later) : nh;
-          sm.gsize[r0 + j] = (uint16_t)(ge - gs);
-          sm.gmin[r0 + j] = NONE;
-          sm.gmax[r0 + j] = 0;
-        }
-        sm.ck[r0 + j] = ((uint32_t)gs << 20) | (sm.ck[r0 + j] & RANK_MASK);
+      const uint64_t en = r < own ? l0[r] : l1[r - own];
+      const uint32_t dist = (uint32_t)(en >> 40) & 0x7FFu;
+      const uint32_t slot = (r < own ? tbase : tbase + LS_T) + ((uint32_t)(en >> 51) & 0x7FFu);
+      pv[k] = (uint32_t)en & RANK_MASK;
+      kv[k] = (uint32_t)(en >> 20) & RANK_MASK;
+      hv[k] = slot - dist;
+      const uint32_t gs = r - dist;
+      gp[k] = gs | (r << 12);
+      sm.ck[r] = (gs << 20) | kv[k];
+      if (dist == 0) {
+        ++heads_before;
+        sm.gsz[r] = 0;
+        sm.gmin[r] = NONE;
+        sm.gmax[r] = 0;
       }
     }
   }
+  for (uint32_t r = count + threadIdx.x; r < count + LS_PAD; r += LS_NT) sm.ck[r] = NONE;
   __syncthreads();
   bool any_pend = false;
 #pragma unroll
   for (int k = 0; k < LS_IPT; ++k) {
-    const uint32_t r = threadIdx.x + k * LS_NT;
-    gp[k] = 0;
-    if (r < count && !(ev[k] & (SA_SINGLE | SA_BIG))) {
-      const uint32_t gs = sm.ck[r] >> 20;
-      const bool pend = sm.gsize[gs] > (uint32_t)ENUM_MAX;
-      gp[k] = gs | (r << 12) | (pend ? 0x80000000u : 0u);
+    if (gp[k] != NONE) {
+      const uint32_t gs = gp[k] & 0xFFFu;
+      const bool pend = (sm.ck[gs + ENUM_MAX] >> 20) == gs;  // more than ENUM_MAX entries
+      if (pend) gp[k] |= 0x80000000u;
       any_pend |= pend;
     }
   }
@@ -887,23 +873,24 @@ __global__ void __launch_bounds__(LS_NT, 2) k2_local_sort(const BlockDesc* __res
     for (uint32_t r = threadIdx.x; r <= count; r += LS_NT) sm.cnt[r] = 0;
 #pragma unroll
     for (int k = 0; k < LS_IPT; ++k)
-      if (gp[k] >> 31) {
+      if (gp[k] != NONE && (gp[k] >> 31)) {
         const uint32_t gs = gp[k] & 0xFFFu;
         atomicMin(&sm.gmin[gs], kv[k]);
         atomicMax(&sm.gmax[gs], kv[k]);
+        if (level == 0) atomicAdd(&sm.gsz[gs], 1u);
       }
     __syncthreads();
-    uint32_t bi[LS_IPT];  // bucket slot | arrival index << 12
+    uint32_t bi[LS_IPT];  // bucket index | arrival index << 12
 #pragma unroll
     for (int k = 0; k < LS_IPT; ++k) {
       bi[k] = NONE;
-      if (gp[k] >> 31) {
+      if (gp[k] != NONE && (gp[k] >> 31)) {
         const uint32_t gs = gp[k] & 0xFFFu;
         const uint32_t mn = sm.gmin[gs], mx = sm.gmax[gs];
-        const uint32_t size = sm.gsize[gs] & 0xFFFu;
+        const uint32_t size = sm.gsz[gs] & 0xFFFu;
         if (mn == mx) {  // all keys equal: nothing to sort
           gp[k] &= 0x7FFFFFFFu;
-          if (((gp[k] >> 12) & 0xFFFu) == gs) sm.gsize[gs] = (uint16_t)(size | GS_FLAT);
+          if (((gp[k] >> 12) & 0xFFFu) == gs) sm.gsz[gs] = size | GS_FLAT;
         } else {
           const int lnb = 31 - __clz(size >> 1);       // buckets = largest power of two <= size/2
           const int rb = 32 - __clz(mx - mn);           // bits of the key range
@@ -914,7 +901,7 @@ __global__ void __launch_bounds__(LS_NT, 2) k2_local_sort(const BlockDesc* __res
       }
     }
     __syncthreads();
-    {  // exclusive prefix sum of the bucket counters over slots 0..count (blocked), in place
+    {  // exclusive prefix sum of the bucket counters over indices 0..count (blocked), in place
       const uint32_t r0 = threadIdx.x * LS_IPT;
       uint32_t loc[LS_IPT];
       uint32_t sum = 0;
@@ -943,10 +930,11 @@ __global__ void __launch_bounds__(LS_NT, 2) k2_local_sort(const BlockDesc* __res
         const uint32_t np = bstart + idx;
         sm.ck[np] = (bstart << 20) | kv[k];
         if (idx == 0) {
-          sm.gsize[bstart] = (uint16_t)bcount;
+          sm.gsz[bstart] = bcount;
           sm.gmin[bstart] = NONE;
           sm.gmax[bstart] = 0;
         }
+        hv[k] += bstart - gs;  // slot of the (new) group's first entry
         const bool pend = bcount > (uint32_t)ENUM_MAX;
         gp[k] = bstart | (np << 12) | (pend ? 0x80000000u : 0u);
         any_pend |= pend;
@@ -956,57 +944,57 @@ __global__ void __launch_bounds__(LS_NT, 2) k2_local_sort(const BlockDesc* __res
   __syncthreads();
 
   // ---- enumeration inside every group / bucket: lt = #{keys below mine}, eq = #{keys equal}, eqb = #{equal keys
-  // at an earlier slot};  new slot = start + lt + eqb, the head of the (sub)group sits at start + lt.  The scan runs
-  // over 128-bit vectors from the aligned start of the group: slots of earlier groups in the first vector compare
-  // below (subtracted again), slots of later groups in the last vector compare above.
+  // at an earlier index};  new index = start + lt + eqb, the head of the (sub)group sits at start + lt.  The scan
+  // runs over 128-bit vectors from the aligned start of the group until a vector ends outside the group: entries
+  // of earlier groups in the first vector compare below (subtracted again), entries of later groups compare above.
   uint32_t n_heads = 0, n_unres = 0;
   uint32_t* rk = rank + d.off;
 #pragma unroll
   for (int k = 0; k < LS_IPT; ++k) {
-    const uint32_t e = ev[k];
-    if (!(e & (SA_SINGLE | SA_BIG))) {
+    if (gp[k] != NONE) {
       const uint32_t gs = gp[k] & 0xFFFu, r = (gp[k] >> 12) & 0xFFFu;
-      const uint32_t gz = sm.gsize[gs];
       uint32_t lt = 0, eq, eqb;
+      const uint32_t gz = sm.gsz[gs];
       if (gz & GS_FLAT) {
         eq = gz & 0xFFFu;
         eqb = r - gs;
       } else {
         const uint32_t mine = (gs << 20) | kv[k];
         const uint32_t m1 = mine + 1;
-        const uint32_t je = gs + (gz & 0xFFFu);
         uint32_t jb = gs & ~3u;
         const uint32_t rb = r & ~3u;
         uint32_t le = 0;
-        lt = 0;
         for (; jb < rb; jb += 4) {
           const uint4 c = *reinterpret_cast<const uint4*>(&sm.ck[jb]);
           lt += (c.x < mine) + (c.y < mine) + (c.z < mine) + (c.w < mine);
           le += (c.x < m1) + (c.y < m1) + (c.z < m1) + (c.w < m1);
         }
         eqb = le - lt;
+        uint32_t lastw;
         {
           const uint4 c = *reinterpret_cast<const uint4*>(&sm.ck[jb]);
           const uint32_t dd = r & 3u;
           lt += (c.x < mine) + (c.y < mine) + (c.z < mine) + (c.w < mine);
           le += (c.x < m1) + (c.y < m1) + (c.z < m1) + (c.w < m1);
           eqb += (dd > 0 && c.x == mine) + (dd > 1 && c.y == mine) + (dd > 2 && c.z == mine);
+          lastw = c.w;
           jb += 4;
         }
-        for (; jb < je; jb += 4) {
+        while ((lastw >> 20) == gs) {
           const uint4 c = *reinterpret_cast<const uint4*>(&sm.ck[jb]);
           lt += (c.x < mine) + (c.y < mine) + (c.z < mine) + (c.w < mine);
           le += (c.x < m1) + (c.y < m1) + (c.z < m1) + (c.w < m1);
+          lastw = c.w;
+          jb += 4;
         }
         eq = le - lt;
-        lt -= gs & 3u;  // the slots of earlier groups in the first vector
+        lt -= gs & 3u;  // the entries of earlier groups in the first vector
       }
       uint32_t fl = 0;
       if (eqb == 0) { fl = SA_HEAD; ++n_heads; }
       if (eq == 1) fl |= SA_SINGLE; else ++n_unres;
-      const uint32_t pos = e & RANK_MASK;
-      s[gs + lt + eqb] = pos | fl;
-      rk[pos] = (start + gs + lt) | (eq == 1 ? RANK_RESOLVED : 0u);
+      s[hv[k] + lt + eqb] = pv[k] | fl;
+      rk[pv[k]] = (hv[k] + lt) | (eq == 1 ? RANK_RESOLVED : 0u);
     }
   }
 #pragma unroll
@@ -1137,11 +1125,12 @@ int run_bwt(Launcher& L, const uint8_t* d_txt, const BlockDesc* d_desc, uint32_t
     cudaMemsetAsync(S.global, 0, 2 * sizeof(uint32_t), st);
     L.launch("k2_periodic_shift", k2_periodic_shift, dim3(nb), dim3(256), d_desc, S.state, S.sa, S.shift);
     // BIG-group elements go to S.A (both radix buffers are free between rounds)
+    // small groups -> per-tile lists in S.B (free until the BIG path's radix sort, which runs after the local sort);
+    // BIG-group / sparse-block elements -> S.A
     L.launch("k2_gather", k2_gather, dim3(ls_tiles, nb), dim3(G_NT), d_desc, S.rank, S.sa, S.state, S.shift, S.sparse, h,
-             S.key,
-             S.A, S.cnt, S.first_head, S.tile_active, S.ls_tiles_cap);
+             S.B, S.A, S.cnt, S.tile_meta, S.ls_tiles_cap);
     L.launch_smem("k2_local_sort", k2_local_sort, dim3(ls_tiles, nb), dim3(LS_NT), sizeof(LsSmem), d_desc, S.state,
-                  S.sa, S.key, S.rank, S.first_head, S.tile_active, S.ls_tiles_cap, S.stats);
+                  S.sparse, S.sa, S.B, S.rank, S.tile_meta, S.ls_tiles_cap, S.stats);
     const uint32_t maxbig = g[1];
     if (maxbig > 0) {
       uint64_t *s2 = S.A, *d2 = S.B;

@@ -79,9 +79,7 @@ struct BwtScratch {
   uint64_t* B;          // [M] sort elements (pong)
   uint32_t* rank;       // [M] rank[pos] = slot of the head of pos's group
   uint32_t* sa;         // [M] sa[slot] = pos | flags (rotations in the order established so far)
-  uint32_t* key;        // [M] per-slot sort key of the current round (small groups)
-  uint32_t* first_head; // [nb][ls_tiles] first group head inside each local-sort tile
-  uint32_t* tile_active;// [nb][ls_tiles]
+  uint2* tile_meta;     // [nb][ls_tiles] (entries in the tile's work list, entries before its first group head)
   uint32_t ls_tiles_cap;
   uint32_t* cnt;        // [nb] active elements per block
   uint32_t* hist;       // [nb][tiles][256] radix pass: per-tile status words (decoupled look-back)

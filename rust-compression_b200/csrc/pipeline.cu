@@ -116,7 +116,7 @@ struct bzb200_ctx {
   std::vector<uint32_t> h_crc;
 
   // ---- batch scratch ----
-  DevBuf desc, A, B, rank, sa, key, first_head, tile_active, cnt, hist, oshist, ticket, tsum, state, shift, sparse, stats, rounds, global, last, origptr;
+  DevBuf desc, A, B, rank, sa, tile_meta, cnt, hist, oshist, ticket, tsum, state, shift, sparse, stats, rounds, global, last, origptr;
   DevBuf chunk_state, chunk_zle, chunk_base, sym, freq, mtf_count;
   DevBuf lens, rfreq, sel, selmtf, codes, gbits, meta, lm_scratch, lm_list, lm_count, blockbit, bitcursor, combined;
   DevBuf stage_in, stage_out;  // bzb200_compress_host staging
@@ -238,8 +238,8 @@ static int ctx_create_impl(int device, void* stream, bool own_stream, bzb200_ctx
     if (v >= 1000) c->batch_elems_cap = v;
   }
   c->all = {&c->tile_head, &c->tile_carry, &c->tile_cnt, &c->tile_E, &c->in_off, &c->rle_off, &c->txt, &c->crc,
-            &c->inuse, &c->scal, &c->desc, &c->A, &c->B, &c->rank, &c->sa, &c->key,
-            &c->first_head, &c->tile_active, &c->cnt, &c->hist, &c->oshist, &c->ticket, &c->tsum, &c->state, &c->shift, &c->sparse,
+            &c->inuse, &c->scal, &c->desc, &c->A, &c->B, &c->rank, &c->sa,
+            &c->tile_meta, &c->cnt, &c->hist, &c->oshist, &c->ticket, &c->tsum, &c->state, &c->shift, &c->sparse,
             &c->stats, &c->rounds, &c->global, &c->last, &c->origptr, &c->chunk_state, &c->chunk_zle, &c->chunk_base,
             &c->sym, &c->freq, &c->mtf_count, &c->lens, &c->rfreq, &c->sel, &c->selmtf, &c->codes, &c->gbits, &c->meta,
             &c->lm_scratch, &c->lm_list, &c->lm_count, &c->blockbit, &c->bitcursor, &c->combined, &c->stage_in,
@@ -388,11 +388,9 @@ static int encode_batch(bzb200_ctx* c, uint32_t b0, uint32_t nb, uint8_t* d_out,
   TRY(ensure(c, c->B, M * 8));
   TRY(ensure(c, c->rank, M * 4));
   TRY(ensure(c, c->sa, M * 4));
-  TRY(ensure(c, c->key, M * 4));
   const uint32_t ls_tile = bwt_ls_tile_elems();
   const uint32_t ls_tiles = (nmax + ls_tile - 1) / ls_tile + 1;
-  TRY(ensure(c, c->first_head, (size_t)nb * ls_tiles * 4));
-  TRY(ensure(c, c->tile_active, (size_t)nb * ls_tiles * 4));
+  TRY(ensure(c, c->tile_meta, (size_t)nb * ls_tiles * 8));
   TRY(ensure(c, c->cnt, (size_t)nb * 4));
   TRY(ensure(c, c->hist, (size_t)nb * tiles * 256 * 4));
   TRY(ensure(c, c->oshist, (size_t)nb * 5 * 256 * 4));
@@ -436,9 +434,7 @@ static int encode_batch(bzb200_ctx* c, uint32_t b0, uint32_t nb, uint8_t* d_out,
   S.B = ptr<uint64_t>(c->B);
   S.rank = ptr<uint32_t>(c->rank);
   S.sa = ptr<uint32_t>(c->sa);
-  S.key = ptr<uint32_t>(c->key);
-  S.first_head = ptr<uint32_t>(c->first_head);
-  S.tile_active = ptr<uint32_t>(c->tile_active);
+  S.tile_meta = ptr<uint2>(c->tile_meta);
   S.ls_tiles_cap = ls_tiles;
   S.cnt = ptr<uint32_t>(c->cnt);
   S.hist = ptr<uint32_t>(c->hist);
