@@ -11,8 +11,9 @@
 // The block is cut into chunks of MTF_CHUNK bytes, one warp per chunk:
 //   pass A  per chunk: last occurrence of every byte + zero-run summary (lead, trail, nonzeros, interior digits)
 //   pass B  per block: running max over chunks -> state at each chunk start; output offsets of each chunk
-//   pass C  per chunk: sequential over run heads (warp-parallel count over the 256 `last` slots), RUNA/RUNB
-//           expansion by a warp scan of the digit counts, symbol histogram in shared memory.
+//   pass C  per chunk: the list at the chunk start is rebuilt from `last` (rank of every byte's previous occurrence)
+//           and kept in registers (8 per lane); run heads are looked up by ballot and moved to the front by
+//           shuffles; RUNA/RUNB expansion by a warp scan of the digit counts, symbol histogram in shared memory.
 #include <limits.h>
 
 #include "common.cuh"
@@ -20,7 +21,7 @@
 
 namespace bzb {
 
-constexpr int MTF_CHUNK = 2048;
+constexpr int MTF_CHUNK = 4096;
 constexpr int MTF_WARPS = 4;  // warps (= chunks) per CTA
 constexpr int NEG_UNUSED = -(1 << 30);
 
@@ -61,29 +62,36 @@ __global__ void __launch_bounds__(MTF_WARPS * 32) k3_chunk_scan_a(const uint8_t*
   uint32_t lead = 0, zrun = 0, emitted = 0;
   bool seen = false;
   for (uint32_t i0 = 0; i0 < len; i0 += 32) {
-    uint32_t i = i0 + lane;
-    bool valid = i < len;
-    uint8_t c = valid ? L[c0 + i] : 0;
-    uint8_t p = __shfl_up_sync(0xffffffffu, c, 1);
+    const uint32_t i = i0 + lane;
+    const bool valid = i < len;
+    const uint32_t c = valid ? L[c0 + i] : 0x100u + lane;
+    uint32_t p = __shfl_up_sync(0xffffffffu, c, 1);
     if (lane == 0) p = prev;
-    prev = __shfl_sync(0xffffffffu, c, 31);
-    if (valid) atomicMax(&s_last[w][c], (int)(c0 + i));
-    uint32_t vmask = __ballot_sync(0xffffffffu, valid);
-    uint32_t nz = __ballot_sync(0xffffffffu, valid && c != p);
-    // warp-uniform bookkeeping of runs
-    uint32_t m = nz;
-    uint32_t cur = 0;  // next unprocessed lane
-    uint32_t nvalid = __popc(vmask);
-    while (m) {
-      uint32_t l = __ffs(m) - 1;
-      uint32_t z = zrun + (l - cur);
-      if (!seen) { lead = z; seen = true; } else emitted += zle_digits(z);
-      emitted += 1;
-      zrun = 0;
-      cur = l + 1;
-      m &= m - 1;
+    prev = (uint8_t)__shfl_sync(0xffffffffu, c, 31);
+    // last occurrence inside the row: no higher lane holds the same byte; rows are visited in order
+    const uint32_t peers = __match_any_sync(0xffffffffu, c);
+    if (valid && (peers >> lane) == 1u) s_last[w][c] = (int)(c0 + i);
+    const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
+    const uint32_t nz = __ballot_sync(0xffffffffu, valid && c != p);
+    const bool is_nz = (nz >> lane) & 1u;
+    const uint32_t below = nz & lanemask_lt();
+    uint32_t z = below ? lane - (32u - __clz(below)) : zrun + lane;  // zeros in front of this run head
+    uint32_t e = 0;
+    if (is_nz) {
+      if (!seen && !below) lead = z;  // first head of the chunk: its zeros join the previous chunk's run
+      else e = zle_digits(z);
+      e += 1;
     }
-    zrun += nvalid - cur;
+    emitted += e;
+    if (nz) seen = true;
+    const uint32_t nvalid = __popc(vmask);
+    if (nz) zrun = nvalid - (32u - __clz(nz));
+    else zrun += nvalid;
+  }
+#pragma unroll
+  for (int dlt = 16; dlt > 0; dlt >>= 1) {
+    emitted += __shfl_xor_sync(0xffffffffu, emitted, dlt);
+    lead = max(lead, __shfl_xor_sync(0xffffffffu, lead, dlt));  // exactly one lane holds it
   }
   __syncwarp();
   int* cs = chunk_state + ((uint64_t)blockIdx.y * chunks_cap + chunk) * 256;
@@ -142,6 +150,35 @@ __global__ void __launch_bounds__(256) k3_chunk_scan_b(const BlockDesc* __restri
 }
 
 // ---- pass C ----
+// The warp keeps the whole MTF list in registers: list position p lives in lane p % 32, register p / 32.  A run head
+// looks its byte up with one ballot per row of 32 positions (row 0 first — BWT output mostly hits the front of the
+// list) and the entries in front of it move down by one lane (shfl_up); nothing touches memory.
+__device__ __forceinline__ uint32_t mtf_access(uint32_t (&lst)[8], uint32_t c, uint32_t lane) {
+  uint32_t hit = __ballot_sync(0xffffffffu, lst[0] == c);
+  if (hit) {  // front row
+    const uint32_t q = __ffs(hit) - 1;
+    const uint32_t up = __shfl_up_sync(0xffffffffu, lst[0], 1);
+    if (lane <= q) lst[0] = lane ? up : c;
+    return q;
+  }
+  uint32_t carry = c;  // value entering lane 0 of the current row
+  uint32_t pos = 0;
+  bool done = false;
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    if (!done) {  // warp-uniform
+      if (r) hit = __ballot_sync(0xffffffffu, lst[r] == c);
+      const uint32_t q = hit ? __ffs(hit) - 1 : 32u;  // entries 0..q-1 of this row move; q == 32: the whole row
+      const uint32_t up = __shfl_up_sync(0xffffffffu, lst[r], 1);
+      const uint32_t out = __shfl_sync(0xffffffffu, lst[r], 31);
+      if (lane <= q) lst[r] = lane ? up : carry;
+      carry = out;
+      if (hit) { pos = r * 32 + q; done = true; }
+    }
+  }
+  return pos;
+}
+
 __global__ void __launch_bounds__(MTF_WARPS * 32) k3_apply(const uint8_t* __restrict__ last,
                                                            const BlockDesc* __restrict__ desc,
                                                            const uint32_t* __restrict__ inuse,
@@ -149,6 +186,7 @@ __global__ void __launch_bounds__(MTF_WARPS * 32) k3_apply(const uint8_t* __rest
                                                            const uint2* __restrict__ chunk_base, uint32_t chunks_cap,
                                                            uint16_t* __restrict__ sym, uint32_t* __restrict__ freq) {
   __shared__ int s_last[MTF_WARPS][256];
+  __shared__ uint32_t s_list[MTF_WARPS][256];
   __shared__ uint32_t s_freq[MAX_ALPHA + 2];
   const int w = threadIdx.x >> 5;
   const uint32_t lane = lane_id();
@@ -162,45 +200,63 @@ __global__ void __launch_bounds__(MTF_WARPS * 32) k3_apply(const uint8_t* __rest
     const bool last_chunk = c0 + len == d.n;
     const uint8_t* L = last + d.off;
     const int* cs = chunk_state + ((uint64_t)blockIdx.y * chunks_cap + chunk) * 256;
-    for (int i = lane; i < 256; i += 32) s_last[w][i] = cs[i];
+    // list at the chunk start: bytes by decreasing previous occurrence (virtual occurrences for unseen in-use bytes)
+    int mine[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      mine[k] = cs[k * 32 + lane];
+      s_last[w][k * 32 + lane] = mine[k];
+      s_list[w][k * 32 + lane] = 0x1FFu;  // never matches a byte
+    }
     __syncwarp();
+    {
+      uint32_t rank[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      for (int j = 0; j < 256; ++j) {
+        const int v = s_last[w][j];
+        if (v == NEG_UNUSED) continue;  // warp-uniform
+#pragma unroll
+        for (int k = 0; k < 8; ++k) rank[k] += v > mine[k];
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        if (mine[k] != NEG_UNUSED) s_list[w][rank[k]] = k * 32 + lane;
+    }
+    __syncwarp();
+    uint32_t lst[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) lst[k] = s_list[w][k * 32 + lane];
+
     const uint2 cb = chunk_base[(uint64_t)blockIdx.y * chunks_cap + chunk];
     uint16_t* out = sym + d.symoff;
     uint32_t obase = cb.x;
     uint32_t zrun = cb.y;
     uint8_t prev = c0 > 0 ? L[c0 - 1] : smallest_inuse(inuse + blockIdx.y * 8);
     for (uint32_t i0 = 0; i0 < len; i0 += 32) {
-      uint32_t i = i0 + lane;
-      bool valid = i < len;
-      uint8_t c = valid ? L[c0 + i] : 0;
-      uint8_t p = __shfl_up_sync(0xffffffffu, c, 1);
+      const uint32_t i = i0 + lane;
+      const bool valid = i < len;
+      const uint32_t c = valid ? L[c0 + i] : 0u;
+      uint32_t p = __shfl_up_sync(0xffffffffu, c, 1);
       if (lane == 0) p = prev;
-      prev = __shfl_sync(0xffffffffu, c, 31);
+      prev = (uint8_t)__shfl_sync(0xffffffffu, c, 31);
       const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
       const uint32_t nz = __ballot_sync(0xffffffffu, valid && c != p);
       // MTF positions of the run heads, in order
       uint32_t mypos = 0;
       uint32_t m = nz;
       while (m) {
-        uint32_t l = __ffs(m) - 1;
+        const uint32_t l = __ffs(m) - 1;
         m &= m - 1;
-        uint32_t hc = __shfl_sync(0xffffffffu, (uint32_t)c, l);
-        int v = s_last[w][hc];
-        uint32_t cntl = 0;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) cntl += (s_last[w][k * 32 + lane] > v) ? 1u : 0u;
-        uint32_t pos = __reduce_add_sync(0xffffffffu, cntl);
-        __syncwarp();
-        if (lane == l) { mypos = pos; s_last[w][hc] = (int)(c0 + i0 + l); }
-        __syncwarp();
+        const uint32_t hc = __shfl_sync(0xffffffffu, c, l);
+        const uint32_t pos = mtf_access(lst, hc, lane);
+        if (lane == l) mypos = pos;
       }
       // zero-run bookkeeping and emission
       const bool is_nz = (nz >> lane) & 1u;
       uint32_t z = 0;
       if (is_nz) {
         uint32_t below = nz & lanemask_lt();
-        if (below) z = lane - (32u - __clz(below));   // zeros between the previous head in this group and me
-        else z = zrun + lane;                         // reaches back into previous groups/chunks
+        if (below) z = lane - (32u - __clz(below));   // zeros between the previous head in this row and me
+        else z = zrun + lane;                         // reaches back into previous rows/chunks
       }
       uint32_t dg = is_nz ? zle_digits(z) : 0u;
       uint32_t ecount = is_nz ? dg + 1u : 0u;

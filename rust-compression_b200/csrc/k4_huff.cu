@@ -351,52 +351,94 @@ __global__ void k4_codes(uint32_t nb, const uint8_t* __restrict__ lens, const ui
 }
 
 // ---------------------------------------------------------------- selector MTF + header size (encoder.rs:511-601)
-__global__ void k4_header_size(uint32_t nb, const uint8_t* __restrict__ lens, const uint8_t* __restrict__ sel,
-                               uint8_t* __restrict__ selmtf, const uint32_t* __restrict__ inuse,
-                               uint32_t* __restrict__ meta) {
-  const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= nb) return;
+// One CTA per block.  The selector MTF (mtf.rs:22-38 on a list of <= 6 tables) is chunked: a chunk's effect on the
+// list is "the tables it touches, most recent first, then the others in their previous order", so every thread
+// (1) runs its chunk from the identity list to get that summary, (2) thread 0 composes the summaries into the list
+// at each chunk start, (3) every thread re-runs its chunk from the true list and writes the MTF values.
+// Lists are packed 4 bits per entry.
+constexpr int HS_NT = 320;
+__device__ __forceinline__ uint32_t selmtf_step(uint32_t& list, uint32_t v) {  // returns the position of v
+  uint32_t j = 0;
+#pragma unroll
+  for (int q = 1; q < MAX_GROUPS; ++q)
+    if (((list >> (4 * q)) & 15u) == v) j = q;
+  const uint32_t low = (1u << (4 * j)) - 1u;           // entries in front of v
+  const uint32_t keep = ~((1u << (4 * (j + 1))) - 1u);  // entries behind v
+  list = (list & keep) | ((list & low) << 4) | v;
+  return j;
+}
+
+__global__ void __launch_bounds__(HS_NT) k4_header_size(uint32_t nb, const uint8_t* __restrict__ lens,
+                                                        const uint8_t* __restrict__ sel, uint8_t* __restrict__ selmtf,
+                                                        const uint32_t* __restrict__ inuse, uint32_t* __restrict__ meta) {
+  __shared__ uint32_t s_sum[HS_NT];   // chunk summary: list after the chunk run from identity | touched mask << 24
+  __shared__ uint32_t s_start[HS_NT];
+  __shared__ uint32_t s_bits;
+  const uint32_t b = blockIdx.x;
   uint32_t* m = meta + (size_t)b * META;
   const int alpha = (int)m[0], ng = (int)m[1];
   const uint32_t nsel = m[2];
-  uint32_t bits = 48 + 32 + 1 + 24;  // block magic, crc, randomised bit, origPtr
-  bits += 16;
-  for (int r = 0; r < 16; ++r) {
-    uint32_t w = inuse[b * 8 + (r >> 1)];
-    uint32_t h = (r & 1) ? (w >> 16) : (w & 0xFFFFu);
-    if (h) bits += 16;
-  }
-  bits += 3 + 15;
-  // selector MTF (mtf.rs:22-38 on a list of ng entries)
-  uint8_t list[MAX_GROUPS];
-  for (int i = 0; i < MAX_GROUPS; ++i) list[i] = (uint8_t)i;
   const uint8_t* sp = sel + (size_t)b * MAX_SELECTORS;
   uint8_t* so = selmtf + (size_t)b * MAX_SELECTORS;
-  for (uint32_t i = 0; i < nsel; ++i) {
-    const uint8_t v = sp[i];
-    int j = 0;
-    uint8_t tmp = list[0];
-    while (tmp != v) {
-      ++j;
-      uint8_t t2 = list[j];
-      list[j] = tmp;
-      tmp = t2;
+  const uint32_t per = (nsel + HS_NT - 1) / HS_NT;
+  const uint32_t lo = min(nsel, per * threadIdx.x), hi = min(nsel, lo + per);
+  const uint32_t ident = 0x543210u;
+  if (threadIdx.x == 0) s_bits = 0;
+  {
+    uint32_t list = ident, touched = 0;
+    for (uint32_t i = lo; i < hi; ++i) {
+      const uint32_t v = sp[i];
+      selmtf_step(list, v);
+      touched |= 1u << v;
     }
-    list[0] = v;
-    so[i] = (uint8_t)j;
-    bits += (uint32_t)j + 1;
+    s_sum[threadIdx.x] = list | (touched << 24);
   }
-  for (int t = 0; t < ng; ++t) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t cur = ident;
+    for (int c = 0; c < HS_NT; ++c) {
+      s_start[c] = cur;
+      const uint32_t sm = s_sum[c];
+      const uint32_t touched = sm >> 24;
+      const int k = __popc(touched);
+      // new list = first k entries of the summary, then the untouched entries of cur in order
+      uint32_t nl = sm & ((1u << (4 * k)) - 1u);
+      int o = k;
+      for (int q = 0; q < MAX_GROUPS; ++q) {
+        const uint32_t v = (cur >> (4 * q)) & 15u;
+        if (!((touched >> v) & 1u)) { nl |= v << (4 * o); ++o; }
+      }
+      cur = nl;
+    }
+  }
+  __syncthreads();
+  uint32_t bits = 0;
+  {
+    uint32_t list = s_start[threadIdx.x];
+    for (uint32_t i = lo; i < hi; ++i) {
+      const uint32_t j = selmtf_step(list, sp[i]);
+      so[i] = (uint8_t)j;
+      bits += j + 1;
+    }
+  }
+  // coding tables: 5-bit start length, then per symbol (10|11)* 0
+  for (int i = threadIdx.x; i < ng * alpha; i += HS_NT) {
+    const int t = i / alpha, sy = i - t * alpha;
     const uint8_t* l = lens + lens_index(b, LENS_SLOTS - 1, t);
-    int curr = l[0];
-    bits += 5;
-    for (int s = 0; s < alpha; ++s) {
-      int d = (int)l[s] - curr;
-      bits += 1 + 2 * (uint32_t)(d < 0 ? -d : d);
-      curr = l[s];
-    }
+    const int d = sy ? (int)l[sy] - (int)l[sy - 1] : 0;
+    bits += 1 + 2 * (uint32_t)(d < 0 ? -d : d) + (sy == 0 ? 5u : 0u);
   }
-  m[3] = bits;
+  if (threadIdx.x < 16) {
+    const uint32_t wv = inuse[b * 8 + (threadIdx.x >> 1)];
+    const uint32_t hh = (threadIdx.x & 1) ? (wv >> 16) : (wv & 0xFFFFu);
+    if (hh) bits += 16;
+  }
+  if (threadIdx.x == 0) bits += 48 + 32 + 1 + 24 + 16 + 3 + 15;  // magic, crc, randomised, origPtr, range map, nGroups, nSelectors
+#pragma unroll
+  for (int dlt = 16; dlt > 0; dlt >>= 1) bits += __shfl_xor_sync(0xffffffffu, bits, dlt);
+  if (lane_id() == 0) atomicAdd(&s_bits, bits);
+  __syncthreads();
+  if (threadIdx.x == 0) m[3] = s_bits;
 }
 
 // Per-block exclusive scan of the group bit lengths (in place) + data_bits.
@@ -440,7 +482,7 @@ void launch_huffman(Launcher& L, const uint16_t* d_sym, const BlockDesc* d_desc,
   }
   L.launch("k4_codes", k4_codes, dim3((ntab + 63) / 64), dim3(64), nb, (const uint8_t*)H.lens,
            (const uint32_t*)H.meta, H.codes);
-  L.launch("k4_header_size", k4_header_size, dim3((nb + 31) / 32), dim3(32), nb, (const uint8_t*)H.lens,
+  L.launch("k4_header_size", k4_header_size, dim3(nb), dim3(HS_NT), nb, (const uint8_t*)H.lens,
            (const uint8_t*)H.sel, H.selmtf, d_inuse, H.meta);
   L.launch("k4_cost_select", k4_cost_select, cgrid, dim3(CS_NT), d_sym, d_desc, d_mtf_count, (const uint8_t*)H.lens,
            LENS_SLOTS - 1, (const uint32_t*)H.meta, H.sel, H.rfreq, H.gbits, 1);
