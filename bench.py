@@ -25,10 +25,20 @@ LEVEL = 9
 METRIC = "bzip2 compress MB/s (uncompressed)"
 BYTES_PER_GPU = int(os.environ.get("BZB200_BENCH_BYTES", str(1 << 30)))
 CPU_SAMPLE_BYTES = int(os.environ.get("BZB200_CPU_SAMPLE_BYTES", str(128 << 20)))
-ALG_BYTES_PER_ELEM = {  # algorithmic HBM bytes per sort element and launch (DESIGN.md "Kernels")
-    "k2_rs_scatter": 16.0,  # 8 B element read + 8 B element written
-    "k2_rs_hist": 8.0,      # 8 B element read
+# Algorithmic HBM bytes per unit of work for the kernels that can top the step (DESIGN.md "Kernels").
+#   k2_rs_scatter : one radix pass over a sort element = 8 B read + 8 B written
+#   k2_local_sort : one work-list entry = 8 B entry read + 4 B SA slot written + 4 B rank written
+#   k3_apply      : one last-column byte read + 2 B per emitted symbol
+ALG_BYTES = {
+    "k2_rs_scatter": lambda st: 16.0 * st["elems_sorted_radix"],
+    "k2_local_sort": lambda st: 16.0 * st["elems_local"],
+    "k3_apply": lambda st: 1.0 * st["n_rle"] + 2.0 * st["mtf_symbols"],
 }
+
+
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures (profiles/),
+# full-size launch of the 1 GiB workload; None where no capture exists yet.
+NCU_TRAFFIC = {}
 
 
 def workload_name(n_gpus):
@@ -242,15 +252,18 @@ def main():
     if rank == 0:
         sampler.start()
     l0 = ctx.launch_count()
-    ctx.profile(True)
     ms_total, (d_stream, info) = timed(step_device, args.steps)
-    ctx.profile(False)
     launches = ctx.launch_count() - l0
     clocks = sampler.stop() if rank == 0 else None
-    recs = ctx.profile_records()
     sstats = ctx.sort_stats()
     ms_step = ms_total / args.steps
     value = total_bytes / (ms_step / 1e3) / 1e6
+    # one more step with a CUDA-event pair around every launch (same stream) for the per-kernel breakdown; it is
+    # not part of the timed region because the event traffic slows the host side of the step down
+    ctx.profile(True)
+    ms_prof, _ = timed(step_device, 1)
+    ctx.profile(False)
+    recs = ctx.profile_records()
 
     # ---- end to end with host buffers
     for _ in range(max(1, args.warmup // 2)):
@@ -279,18 +292,19 @@ def main():
         # dominant kernel by device time inside the timed region
         top = sorted(recs.items(), key=lambda kv: -kv[1][1])
         name, (nl, kms) = top[0] if top else ("none", (0, 0.0))
-        step_ms_kernels = sum(v[1] for v in recs.values()) / args.steps
-        if name in ALG_BYTES_PER_ELEM:
-            # elements sorted per step on this rank x radix passes -> launches of the pass kernel
-            alg_bytes_total = ALG_BYTES_PER_ELEM[name] * sstats["elems_sorted"] * 5 * args.steps
+        step_ms_kernels = sum(v[1] for v in recs.values())
+        if name in ALG_BYTES:
+            alg_bytes = ALG_BYTES[name](sstats)
         else:
-            alg_bytes_total = (total_bytes / world + out_bytes / world) * args.steps
-        achieved = alg_bytes_total / (kms / 1e3) / 1e9 if kms > 0 else 0.0
+            alg_bytes = total_bytes / world + out_bytes / world
+        achieved = alg_bytes / (kms / 1e3) / 1e9 if kms > 0 else 0.0
         roofline = {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                    "launches_per_step": nl / args.steps, "avg_launch_ms": kms / max(1, nl),
-                    "kernel_share_of_step": (kms / args.steps) / ms_step,
-                    "algorithmic_bytes_per_launch": alg_bytes_total / max(1, nl),
+                    "frac": achieved / peak, "traffic": NCU_TRAFFIC.get(name), "peak_source": peak_src,
+                    "launches_per_step": nl, "avg_launch_ms": kms / max(1, nl),
+                    "kernel_share_of_step": kms / ms_prof,
+                    "algorithmic_bytes_per_launch": alg_bytes / max(1, nl),
+                    "note": "achieved = algorithmic bytes of the kernel's launches in one step / their summed CUDA-event "
+                            "time (profiled step, events on the launching stream)",
                     "path": {"achieved": (total_bytes + out_bytes) / (ms_step / 1e3) / 1e9 / world, "unit": "GB/s per GPU",
                              "frac": (total_bytes + out_bytes) / (ms_step / 1e3) / 1e9 / world / peak,
                              "note": "whole path: (input + output bytes) / device time (SURVEY.md 8(d))"}}
@@ -309,7 +323,8 @@ def main():
                            "sharded.compress_host_sharded (pinned slices H2D + NCCL all-gather + C ABI + D2H)"},
             "gpu_launches": int(lsum.item()),
             "roofline": roofline,
-            "kernels_ms_per_step": {k: round(v[1] / args.steps, 3) for k, v in top[:12]},
+            "kernels_ms_per_step": {k: round(v[1], 3) for k, v in top[:14]},
+            "profiled_step_ms": round(ms_prof, 3),
             "kernel_time_ms_per_step": round(step_ms_kernels, 3),
             "cpu_baseline": cpu_baseline(raw[:CPU_SAMPLE_BYTES]),
             "clocks": clocks,

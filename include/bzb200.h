@@ -164,6 +164,11 @@ BZB200_API int bzb200_profile_get(bzb200_ctx* c, int i, const char** name, uint6
 BZB200_API uint64_t bzb200_launch_count(const bzb200_ctx* c);
 /* Sort statistics of the last encode_blocks call: doubling rounds run, radix passes run, elements sorted. */
 BZB200_API int bzb200_sort_stats(const bzb200_ctx* c, uint32_t* rounds, uint32_t* radix_passes, uint64_t* elems_sorted);
+/* Work counters of the last encode_blocks call (bench.py turns them into algorithmic bytes), out[0..7]:
+ * 0 doubling rounds, 1 radix pass launches, 2 rotations sorted (initial + unresolved entering each round),
+ * 3 elements moved by radix passes (list length x 5, summed), 4 work-list entries of the in-CTA group sort,
+ * 5 RLE1 bytes (= BWT elements), 6 MTF/RUNA/RUNB symbols emitted incl. EOB, 7 reserved. */
+BZB200_API int bzb200_path_stats(const bzb200_ctx* c, uint64_t* out, size_t cap);
 
 BZB200_API const char* bzb200_version(void);
 

@@ -20,6 +20,8 @@
 //   k2_round_finalize  per-block state machine: done / periodic fix-up pending / active
 // Fix-up   : a round that splits nothing means the block is periodic and the groups are the sets of equal
 //            rotations; one more round with key = n-1-((pos-shift) mod n) applies the reference's tie-break.
+#include <algorithm>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -608,7 +610,7 @@ __global__ void k2_round_finalize(uint32_t nb, uint32_t round_no, const BlockDes
       s = 2;
       rounds[b] = round_no;
     } else if (s == 1) {
-      atomicOr(&global[2], 1u);  // the fix-up key makes every rotation distinct; anything else is a bug
+      atomicOr(&global[3], 1u);  // the fix-up key makes every rotation distinct; anything else is a bug
       s = 2;
     } else if (created == 0) {
       s = 1;  // nothing split: the block is periodic, the groups are the sets of equal rotations
@@ -622,6 +624,7 @@ __global__ void k2_round_finalize(uint32_t nb, uint32_t round_no, const BlockDes
       sparse[b] = sp ? 1u : 0u;
       atomicAdd(&global[0], unres);
       atomicMax(&global[1], sp ? unres : big);
+      atomicAdd(&global[2], sp ? unres : big);  // rotations that take the radix path next round
     }
   }
   st[0] = 0; st[1] = 0; st[2] = 0;
@@ -1080,8 +1083,7 @@ static void regroup(Launcher& L, const uint64_t* srt, const BlockDesc* d_desc, u
 }
 
 int run_bwt(Launcher& L, const uint8_t* d_txt, const BlockDesc* d_desc, uint32_t nb, uint32_t nmax, uint64_t M,
-            BwtScratch& S, uint8_t* d_last, uint32_t* d_origptr, uint32_t* h_rounds, uint32_t* h_passes,
-            uint64_t* h_elems) {
+            BwtScratch& S, uint8_t* d_last, uint32_t* d_origptr, BwtStats* stats) {
   cudaStream_t st = L.stream;
   const uint32_t tiles_n = (nmax + RS_TILE - 1) / RS_TILE;
   const uint32_t ls_tiles = (nmax + LS_T - 1) / LS_T;
@@ -1099,7 +1101,7 @@ int run_bwt(Launcher& L, const uint8_t* d_txt, const BlockDesc* d_desc, uint32_t
     attr_set = true;
   }
   uint32_t rounds = 0, passes = 0;
-  uint64_t elems = 0;
+  uint64_t elems = 0, radix_elem_passes = 5ull * M, local_elems = 0;
   uint64_t *src = S.A, *dst = S.B;
   L.launch("k2_init_keys", k2_init_keys, dim3(tiles_n, nb), dim3(RS_NT), d_txt, d_desc, S.A, S.cnt);
   OsState os;
@@ -1119,10 +1121,10 @@ int run_bwt(Launcher& L, const uint8_t* d_txt, const BlockDesc* d_desc, uint32_t
 
   uint32_t h = 5;
   while (g[0] > 0) {
-    if (g[2]) return -5;
+    if (g[3]) return -5;
     ++rounds;
     if (rounds > 64) return -5;
-    cudaMemsetAsync(S.global, 0, 2 * sizeof(uint32_t), st);
+    cudaMemsetAsync(S.global, 0, 3 * sizeof(uint32_t), st);
     L.launch("k2_periodic_shift", k2_periodic_shift, dim3(nb), dim3(256), d_desc, S.state, S.sa, S.shift);
     // BIG-group elements go to S.A (both radix buffers are free between rounds)
     // small groups -> per-tile lists in S.B (free until the BIG path's radix sort, which runs after the local sort);
@@ -1139,6 +1141,8 @@ int run_bwt(Launcher& L, const uint8_t* d_txt, const BlockDesc* d_desc, uint32_t
       regroup(L, s2, d_desc, nb, maxbig, S, 0);
     }
     elems += g[0];
+    radix_elem_passes += 5ull * g[2];
+    local_elems += g[0] - g[2];
     L.launch("k2_round_finalize", k2_round_finalize, dim3((nb + 255) / 256), dim3(256), nb, rounds, d_desc, S.cnt,
              S.stats, S.state, S.sparse, S.rounds, S.global);
     if (L.err != cudaSuccess) return -2;
@@ -1146,12 +1150,16 @@ int run_bwt(Launcher& L, const uint8_t* d_txt, const BlockDesc* d_desc, uint32_t
     if (cudaStreamSynchronize(st) != cudaSuccess) return -2;
     if (h < (1u << 21)) h *= 2;
   }
-  if (g[2]) return -5;
+  if (g[3]) return -5;
   const uint32_t ftiles = (nmax + G_NT * 16 - 1) / (G_NT * 16);
   L.launch("k2_finish", k2_finish, dim3(ftiles, nb), dim3(G_NT), d_txt, d_desc, S.sa, d_last, d_origptr);
-  if (h_rounds) *h_rounds = rounds;
-  if (h_passes) *h_passes = passes;
-  if (h_elems) *h_elems = elems;
+  if (stats) {
+    stats->rounds = std::max(stats->rounds, rounds);
+    stats->radix_passes += passes;
+    stats->elems_sorted += elems;
+    stats->radix_elem_passes += radix_elem_passes;
+    stats->local_elems += local_elems;
+  }
   return L.err == cudaSuccess ? 0 : -2;
 }
 

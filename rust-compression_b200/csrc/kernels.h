@@ -98,9 +98,15 @@ uint32_t bwt_tile_elems();
 uint32_t bwt_ls_tile_elems();
 // Runs the whole rotation sort for a batch. txt = batch slice of the RLE1 stream, desc[nb] on device.
 // Outputs: last column L[M] (same layout as txt), origptr[nb]. Returns 0 or a negative internal error.
+struct BwtStats {
+  uint32_t rounds = 0;             // doubling rounds after the initial sort (max over batches)
+  uint32_t radix_passes = 0;       // radix pass launches
+  uint64_t elems_sorted = 0;       // rotations in the initial sort + unresolved rotations entering each round
+  uint64_t radix_elem_passes = 0;  // elements moved by radix passes (list length x 5, summed)
+  uint64_t local_elems = 0;        // work-list entries handled by k2_local_sort
+};
 int run_bwt(Launcher& L, const uint8_t* d_txt, const BlockDesc* d_desc, uint32_t nb, uint32_t nmax, uint64_t M,
-            BwtScratch& S, uint8_t* d_last, uint32_t* d_origptr, uint32_t* h_rounds, uint32_t* h_passes,
-            uint64_t* h_elems);
+            BwtScratch& S, uint8_t* d_last, uint32_t* d_origptr, BwtStats* stats);
 
 // ---- k3_mtf.cu ----
 uint32_t mtf_chunk_elems();

@@ -126,9 +126,10 @@ struct bzb200_ctx {
   uint32_t batch_b0 = 0, batch_nb = 0;
   std::vector<BlockDesc> h_desc;
   std::vector<uint64_t> h_blockbit;
+  std::vector<uint32_t> h_mtf_count;
   uint8_t* last_out = nullptr;
-  uint32_t sort_rounds = 0, sort_passes = 0;
-  uint64_t sort_elems = 0;
+  BwtStats bstats;
+  uint64_t stat_rle = 0, stat_mtf = 0;
 
   std::vector<DevBuf*> all;
 };
@@ -448,13 +449,8 @@ static int encode_batch(bzb200_ctx* c, uint32_t b0, uint32_t nb, uint8_t* d_out,
   S.rounds = ptr<uint32_t>(c->rounds);
   S.global = ptr<uint32_t>(c->global);
   S.tiles_cap = tiles;
-  uint32_t rounds = 0, passes = 0;
-  uint64_t elems = 0;
-  int r = run_bwt(c->L, d_txt, d_desc, nb, nmax, M, S, ptr<uint8_t>(c->last), ptr<uint32_t>(c->origptr), &rounds,
-                  &passes, &elems);
-  c->sort_rounds = std::max(c->sort_rounds, rounds);
-  c->sort_passes += passes;
-  c->sort_elems += elems;
+  int r = run_bwt(c->L, d_txt, d_desc, nb, nmax, M, S, ptr<uint8_t>(c->last), ptr<uint32_t>(c->origptr), &c->bstats);
+  c->stat_rle += M;
   if (r != 0) {
     TRY(check_launch(c));
     cudaError_t e = cudaGetLastError();
@@ -491,7 +487,10 @@ static int encode_batch(bzb200_ctx* c, uint32_t b0, uint32_t nb, uint8_t* d_out,
               nullptr);  // offsets only (d_out == nullptr)
   TRY(check_launch(c));
   CK(c, cudaMemcpyAsync(&cursor_after, c->bitcursor.p, 8, cudaMemcpyDeviceToHost, c->stream));
+  c->h_mtf_count.resize(nb);
+  CK(c, cudaMemcpyAsync(c->h_mtf_count.data(), c->mtf_count.p, (size_t)nb * 4, cudaMemcpyDeviceToHost, c->stream));
   CK(c, cudaStreamSynchronize(c->stream));
+  for (uint32_t i = 0; i < nb; ++i) c->stat_mtf += c->h_mtf_count[i];
   (void)cursor_before;
   if ((cursor_after + 7) / 8 + 16 > cap_bytes) {
     c->err = "output buffer too small: need " + std::to_string((cursor_after + 7) / 8 + 16) + " bytes";
@@ -522,9 +521,9 @@ int bzb200_encode_blocks(bzb200_ctx* c, uint32_t b0, uint32_t b1, uint8_t* d_out
   TRY(ensure(c, c->bitcursor, 16));
   CK(c, cudaMemcpyAsync(c->bitcursor.p, &start_bit, 8, cudaMemcpyHostToDevice, c->stream));
   CK(c, cudaStreamSynchronize(c->stream));
-  c->sort_rounds = 0;
-  c->sort_passes = 0;
-  c->sort_elems = 0;
+  c->bstats = BwtStats();
+  c->stat_rle = 0;
+  c->stat_mtf = 0;
   uint32_t b = b0;
   while (b < b1) {
     uint32_t e = b;
@@ -721,9 +720,16 @@ int bzb200_profile_get(bzb200_ctx* c, int i, const char** name, uint64_t* launch
 uint64_t bzb200_launch_count(const bzb200_ctx* c) { return c ? c->L.launches : 0; }
 int bzb200_sort_stats(const bzb200_ctx* c, uint32_t* rounds, uint32_t* radix_passes, uint64_t* elems_sorted) {
   if (!c) return BZB200_E_ARG;
-  if (rounds) *rounds = c->sort_rounds;
-  if (radix_passes) *radix_passes = c->sort_passes;
-  if (elems_sorted) *elems_sorted = c->sort_elems;
+  if (rounds) *rounds = c->bstats.rounds;
+  if (radix_passes) *radix_passes = c->bstats.radix_passes;
+  if (elems_sorted) *elems_sorted = c->bstats.elems_sorted;
+  return BZB200_OK;
+}
+int bzb200_path_stats(const bzb200_ctx* c, uint64_t* out, size_t cap) {
+  if (!c || !out) return BZB200_E_ARG;
+  const uint64_t v[8] = {c->bstats.rounds, c->bstats.radix_passes, c->bstats.elems_sorted, c->bstats.radix_elem_passes,
+                         c->bstats.local_elems, c->stat_rle, c->stat_mtf, 0};
+  for (size_t i = 0; i < cap && i < 8; ++i) out[i] = v[i];
   return BZB200_OK;
 }
 

@@ -174,7 +174,11 @@ class Context:
     def sort_stats(self):
         r, p, e = C.c_uint32(0), C.c_uint32(0), C.c_uint64(0)
         _lib.lib().bzb200_sort_stats(self._h, C.byref(r), C.byref(p), C.byref(e))
-        return {"rounds": r.value, "radix_passes": p.value, "elems_sorted": e.value}
+        v = (C.c_uint64 * 8)()
+        _lib.lib().bzb200_path_stats(self._h, v, 8)
+        return {"rounds": r.value, "radix_passes": p.value, "elems_sorted": e.value,
+                "elems_sorted_radix": int(v[3]), "elems_local": int(v[4]), "n_rle": int(v[5]),
+                "mtf_symbols": int(v[6])}
 
 
 def compress_tensor(ctx, level, d_in):
