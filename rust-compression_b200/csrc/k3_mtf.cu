@@ -11,9 +11,10 @@
 // The block is cut into chunks of MTF_CHUNK bytes, one warp per chunk:
 //   pass A  per chunk: last occurrence of every byte + zero-run summary (lead, trail, nonzeros, interior digits)
 //   pass B  per block: running max over chunks -> state at each chunk start; output offsets of each chunk
-//   pass C  per chunk: the list at the chunk start is rebuilt from `last` (rank of every byte's previous occurrence)
-//           and kept in registers (8 per lane); run heads are looked up by ballot and moved to the front by
-//           shuffles; RUNA/RUNB expansion by a warp scan of the digit counts, symbol histogram in shared memory.
+//   pass C  one lane per chunk: the list at the chunk start is rebuilt from `last` (rank of every byte's previous
+//           occurrence); its first 32 entries are packed into eight registers of the lane (SIMD byte compare +
+//           byte permute), the rest sits in shared memory; symbols are written straight to the offsets pass B
+//           assigned; symbol histogram in shared memory.
 #include <limits.h>
 
 #include "common.cuh"
@@ -150,34 +151,99 @@ __global__ void __launch_bounds__(256) k3_chunk_scan_b(const BlockDesc* __restri
 }
 
 // ---- pass C ----
-// The warp keeps the whole MTF list in registers: list position p lives in lane p % 32, register p / 32.  A run head
-// looks its byte up with one ballot per row of 32 positions (row 0 first — BWT output mostly hits the front of the
-// list) and the entries in front of it move down by one lane (shfl_up); nothing touches memory.
-__device__ __forceinline__ uint32_t mtf_access(uint32_t (&lst)[8], uint32_t c, uint32_t lane) {
-  uint32_t hit = __ballot_sync(0xffffffffu, lst[0] == c);
-  if (hit) {  // front row
-    const uint32_t q = __ffs(hit) - 1;
-    const uint32_t up = __shfl_up_sync(0xffffffffu, lst[0], 1);
-    if (lane <= q) lst[0] = lane ? up : c;
-    return q;
-  }
-  uint32_t carry = c;  // value entering lane 0 of the current row
+// One LANE per chunk: a warp runs 32 chunks side by side, each lane a scalar move-to-front coder of its own.
+// The first 32 list entries of a lane live in eight packed registers (lookup = one SIMD byte compare per word,
+// move-to-front = one byte permute per word); entries 32..255 live as packed words in a lane-interleaved
+// shared-memory column and are only touched when a byte is found that deep (rare on BWT output, bounded work
+// otherwise).  The list of each
+// chunk at its start is rebuilt by the whole warp from the chunk's `last occurrence` state (rank of every byte's
+// previous occurrence).
+constexpr int MTF_FRONT = 32;                      // list entries held in registers (8 packed words)
+constexpr int MTF_DEEP_WORDS = (256 - MTF_FRONT) / 4;  // the rest: packed words in shared memory, one column per lane
+
+struct MtfLane {
+  uint32_t f[8];
+};
+
+// hit in word `f` at byte p: [carry, b0..b(p-1), b(p+1)..b3]
+__device__ __forceinline__ uint32_t mtf_word_hit(uint32_t f, uint32_t carry, uint32_t p) {
+  const uint32_t sel = (uint32_t)(0x2104310432043214ull >> (16 * p)) & 0xFFFFu;
+  return __byte_perm(f, carry, sel);
+}
+
+// Moves byte c (not at the front) to the front of the lane's list, returns its previous position.  The register
+// part is branch-free (lanes of a warp sit at different depths; a branch per word would serialise them).
+__device__ __forceinline__ uint32_t mtf_lane_access(MtfLane& l, uint32_t c, uint32_t* deep /* column, stride 32 */) {
+  const uint32_t x = c * 0x01010101u;
+  uint32_t carry = c;
   uint32_t pos = 0;
   bool done = false;
 #pragma unroll
-  for (int r = 0; r < 8; ++r) {
-    if (!done) {  // warp-uniform
-      if (r) hit = __ballot_sync(0xffffffffu, lst[r] == c);
-      const uint32_t q = hit ? __ffs(hit) - 1 : 32u;  // entries 0..q-1 of this row move; q == 32: the whole row
-      const uint32_t up = __shfl_up_sync(0xffffffffu, lst[r], 1);
-      const uint32_t out = __shfl_sync(0xffffffffu, lst[r], 31);
-      if (lane <= q) lst[r] = lane ? up : carry;
-      carry = out;
-      if (hit) { pos = r * 32 + q; done = true; }
+  for (int k = 0; k < 8; ++k) {
+    const uint32_t f = l.f[k];
+    const uint32_t m = __vcmpeq4(f, x);
+    const uint32_t p = (__ffs(m) - 1) >> 3;               // garbage when m == 0
+    const uint32_t sel = m ? ((uint32_t)(0x2104310432043214ull >> (16 * (p & 3u))) & 0xFFFFu) : 0x2104u;
+    const uint32_t nf = __byte_perm(f, carry, sel);       // m == 0: (f << 8) | carry
+    l.f[k] = done ? f : nf;
+    if (!done && m) pos = 4 * k + p;
+    carry = f >> 24;
+    done = done || (m != 0);
+  }
+  if (done) return pos;
+  for (uint32_t k = 0; k < (uint32_t)MTF_DEEP_WORDS; ++k) {  // every entry in front of c moves down by one
+    const uint32_t f = deep[k * 32];
+    const uint32_t m = __vcmpeq4(f, x);
+    if (m) {
+      const uint32_t p = (__ffs(m) - 1) >> 3;
+      deep[k * 32] = mtf_word_hit(f, carry, p);
+      return MTF_FRONT + 4 * k + p;
+    }
+    deep[k * 32] = (f << 8) | carry;
+    carry = f >> 24;
+  }
+  return 255;
+}
+
+struct MtfOut {
+  uint16_t* out;
+  uint32_t o;        // next symbol index
+  uint32_t pend;     // symbol waiting for its pair (stores are 32-bit where aligned)
+  bool have;
+  unsigned long long hot;  // counts of symbols 0..3, 16 bits each
+  uint32_t* freq;          // shared-memory histogram
+  __device__ __forceinline__ void put(uint32_t sv) {
+    if (sv < 4) hot += 1ull << (16 * sv);
+    else atomicAdd(&freq[sv], 1u);
+    if (have) {
+      *reinterpret_cast<uint32_t*>(out + o - 1) = pend | (sv << 16);
+      have = false;
+    } else if ((o & 1u) == 0) {
+      pend = sv;
+      have = true;
+    } else {
+      out[o] = (uint16_t)sv;
+    }
+    ++o;
+  }
+  __device__ __forceinline__ void zero_run(uint32_t z) {  // RUNA/RUNB digits of a run of z zeros (encoder.rs:653-669)
+    uint32_t zz = z + 1;
+    while (zz > 1) {
+      put(zz & 1u);
+      zz >>= 1;
     }
   }
-  return pos;
-}
+  __device__ __forceinline__ void flush() {
+    if (have) out[o - 1] = (uint16_t)pend;
+    have = false;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const uint32_t v = (uint32_t)(hot >> (16 * k)) & 0xFFFFu;
+      if (v) atomicAdd(&freq[k], v);
+    }
+    hot = 0;
+  }
+};
 
 __global__ void __launch_bounds__(MTF_WARPS * 32) k3_apply(const uint8_t* __restrict__ last,
                                                            const BlockDesc* __restrict__ desc,
@@ -187,32 +253,34 @@ __global__ void __launch_bounds__(MTF_WARPS * 32) k3_apply(const uint8_t* __rest
                                                            uint16_t* __restrict__ sym, uint32_t* __restrict__ freq) {
   __shared__ int s_last[MTF_WARPS][256];
   __shared__ uint32_t s_list[MTF_WARPS][256];
+  __shared__ uint32_t s_deep[MTF_WARPS][MTF_DEEP_WORDS][32];
   __shared__ uint32_t s_freq[MAX_ALPHA + 2];
   const int w = threadIdx.x >> 5;
   const uint32_t lane = lane_id();
   const BlockDesc d = desc[blockIdx.y];
   for (int i = threadIdx.x; i < MAX_ALPHA + 2; i += MTF_WARPS * 32) s_freq[i] = 0;
   __syncthreads();
-  const uint32_t chunk = blockIdx.x * MTF_WARPS + w;
-  const uint32_t c0 = chunk * MTF_CHUNK;
-  if (c0 < d.n) {
-    const uint32_t len = min((uint32_t)MTF_CHUNK, d.n - c0);
-    const bool last_chunk = c0 + len == d.n;
-    const uint8_t* L = last + d.off;
-    const int* cs = chunk_state + ((uint64_t)blockIdx.y * chunks_cap + chunk) * 256;
-    // list at the chunk start: bytes by decreasing previous occurrence (virtual occurrences for unseen in-use bytes)
-    int mine[8];
+  const uint32_t nch = (d.n + MTF_CHUNK - 1) / MTF_CHUNK;
+  const uint32_t cbase = (blockIdx.x * MTF_WARPS + w) * 32;  // first chunk of this warp
+  if (cbase < nch) {
+    // ---- the list of every lane's chunk at the chunk start
+    MtfLane ml;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      mine[k] = cs[k * 32 + lane];
-      s_last[w][k * 32 + lane] = mine[k];
-      s_list[w][k * 32 + lane] = 0x1FFu;  // never matches a byte
-    }
-    __syncwarp();
-    {
+    for (int k = 0; k < 8; ++k) ml.f[k] = 0;
+    const uint32_t nmine = min(32u, nch - cbase);
+    for (uint32_t j = 0; j < nmine; ++j) {
+      const int* cs = chunk_state + ((uint64_t)blockIdx.y * chunks_cap + cbase + j) * 256;
+      int mine[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        mine[k] = cs[k * 32 + lane];
+        s_last[w][k * 32 + lane] = mine[k];
+        s_list[w][k * 32 + lane] = 0xFFu;  // filler behind the in-use bytes; a real 0xFF always sits in front of it
+      }
+      __syncwarp();
       uint32_t rank[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-      for (int j = 0; j < 256; ++j) {
-        const int v = s_last[w][j];
+      for (int q = 0; q < 256; ++q) {
+        const int v = s_last[w][q];
         if (v == NEG_UNUSED) continue;  // warp-uniform
 #pragma unroll
         for (int k = 0; k < 8; ++k) rank[k] += v > mine[k];
@@ -220,80 +288,68 @@ __global__ void __launch_bounds__(MTF_WARPS * 32) k3_apply(const uint8_t* __rest
 #pragma unroll
       for (int k = 0; k < 8; ++k)
         if (mine[k] != NEG_UNUSED) s_list[w][rank[k]] = k * 32 + lane;
-    }
-    __syncwarp();
-    uint32_t lst[8];
+      __syncwarp();
+      if (lane == j) {
 #pragma unroll
-    for (int k = 0; k < 8; ++k) lst[k] = s_list[w][k * 32 + lane];
-
-    const uint2 cb = chunk_base[(uint64_t)blockIdx.y * chunks_cap + chunk];
-    uint16_t* out = sym + d.symoff;
-    uint32_t obase = cb.x;
-    uint32_t zrun = cb.y;
-    uint8_t prev = c0 > 0 ? L[c0 - 1] : smallest_inuse(inuse + blockIdx.y * 8);
-    for (uint32_t i0 = 0; i0 < len; i0 += 32) {
-      const uint32_t i = i0 + lane;
-      const bool valid = i < len;
-      const uint32_t c = valid ? L[c0 + i] : 0u;
-      uint32_t p = __shfl_up_sync(0xffffffffu, c, 1);
-      if (lane == 0) p = prev;
-      prev = (uint8_t)__shfl_sync(0xffffffffu, c, 31);
-      const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
-      const uint32_t nz = __ballot_sync(0xffffffffu, valid && c != p);
-      // MTF positions of the run heads, in order
-      uint32_t mypos = 0;
-      uint32_t m = nz;
-      while (m) {
-        const uint32_t l = __ffs(m) - 1;
-        m &= m - 1;
-        const uint32_t hc = __shfl_sync(0xffffffffu, c, l);
-        const uint32_t pos = mtf_access(lst, hc, lane);
-        if (lane == l) mypos = pos;
+        for (int k = 0; k < 8; ++k)
+          ml.f[k] = s_list[w][4 * k] | (s_list[w][4 * k + 1] << 8) | (s_list[w][4 * k + 2] << 16) |
+                    (s_list[w][4 * k + 3] << 24);
       }
-      // zero-run bookkeeping and emission
-      const bool is_nz = (nz >> lane) & 1u;
-      uint32_t z = 0;
-      if (is_nz) {
-        uint32_t below = nz & lanemask_lt();
-        if (below) z = lane - (32u - __clz(below));   // zeros between the previous head in this row and me
-        else z = zrun + lane;                         // reaches back into previous rows/chunks
+      for (int q = lane; q < MTF_DEEP_WORDS; q += 32) {
+        const uint32_t* e = &s_list[w][MTF_FRONT + 4 * q];
+        s_deep[w][q][j] = e[0] | (e[1] << 8) | (e[2] << 16) | (e[3] << 24);
       }
-      uint32_t dg = is_nz ? zle_digits(z) : 0u;
-      uint32_t ecount = is_nz ? dg + 1u : 0u;
-      uint32_t inc = warp_incl_scan_add(ecount);
-      uint32_t total = __shfl_sync(0xffffffffu, inc, 31);
-      if (is_nz) {
-        uint32_t o = obase + inc - ecount;
-        uint32_t zz = z + 1;
-        for (uint32_t k = 0; k < dg; ++k) {
-          uint32_t bit = zz & 1u;
-          out[o++] = (uint16_t)bit;
-          atomicAdd(&s_freq[bit], 1u);
-          zz >>= 1;
-        }
-        uint32_t sv = mypos + 1u;  // position p>0 is written as p+1 (encoder.rs:340)
-        out[o] = (uint16_t)sv;
-        atomicAdd(&s_freq[sv], 1u);
-      }
-      obase += total;
-      const uint32_t nvalid = __popc(vmask);
-      if (nz) zrun = nvalid - (32u - __clz(nz));
-      else zrun += nvalid;
+      __syncwarp();
     }
-    if (last_chunk && lane == 0) {
-      // final zero run + EOB (encoder.rs:355-358); EOB = in_use_count + 1
-      uint32_t o = obase;
-      uint32_t zz = zrun + 1;
-      for (uint32_t k = 0, dg = zle_digits(zrun); k < dg; ++k) {
-        uint32_t bit = zz & 1u;
-        out[o++] = (uint16_t)bit;
-        atomicAdd(&s_freq[bit], 1u);
-        zz >>= 1;
+
+    // ---- every lane codes its own chunk
+    const uint32_t chunk = cbase + lane;
+    if (chunk < nch) {
+      const uint32_t c0 = chunk * MTF_CHUNK;
+      const uint32_t len = min((uint32_t)MTF_CHUNK, d.n - c0);
+      const uint8_t* L = last + d.off + c0;
+      const uint2 cb = chunk_base[(uint64_t)blockIdx.y * chunks_cap + chunk];
+      MtfOut mo;
+      mo.out = sym + d.symoff;
+      mo.o = cb.x;
+      mo.pend = 0;
+      mo.have = false;
+      mo.hot = 0;
+      mo.freq = s_freq;
+      uint32_t zrun = cb.y;
+      uint32_t prev = c0 > 0 ? L[-1] : smallest_inuse(inuse + blockIdx.y * 8);
+      uint32_t* deep = &s_deep[w][0][lane];
+      auto step = [&](uint32_t c) {
+        if (c == prev) {
+          ++zrun;
+        } else {
+          mo.zero_run(zrun);
+          zrun = 0;
+          mo.put(mtf_lane_access(ml, c, deep) + 1u);  // position p > 0 is written as p+1 (encoder.rs:340)
+          prev = c;
+        }
+      };
+      uint32_t i = 0;
+      const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(L) & 15u);
+      const uint32_t headn = min(len, mis ? 16u - mis : 0u);
+      for (; i < headn; ++i) step(L[i]);
+      for (; i + 16 <= len; i += 16) {
+        const uint4 q = *reinterpret_cast<const uint4*>(L + i);
+        unsigned long long lo = q.x | ((unsigned long long)q.y << 32), hi = q.z | ((unsigned long long)q.w << 32);
+#pragma unroll 1
+        for (int k = 0; k < 8; ++k) { step((uint32_t)lo & 255u); lo >>= 8; }
+#pragma unroll 1
+        for (int k = 0; k < 8; ++k) { step((uint32_t)hi & 255u); hi >>= 8; }
       }
-      uint32_t k = 0;
-      for (int ww = 0; ww < 8; ++ww) k += __popc(inuse[blockIdx.y * 8 + ww]);
-      out[o] = (uint16_t)(k + 1);
-      atomicAdd(&s_freq[k + 1], 1u);
+      for (; i < len; ++i) step(L[i]);
+      if (c0 + len == d.n) {
+        // final zero run + EOB (encoder.rs:355-358); EOB = in_use_count + 1
+        mo.zero_run(zrun);
+        uint32_t k = 0;
+        for (int ww = 0; ww < 8; ++ww) k += __popc(inuse[blockIdx.y * 8 + ww]);
+        mo.put(k + 1);
+      }
+      mo.flush();
     }
   }
   __syncthreads();
@@ -314,7 +370,8 @@ void launch_mtf(Launcher& L, const uint8_t* d_last, const BlockDesc* d_desc, con
            d_chunk_state, d_chunk_zle, chunks_cap);
   L.launch("k3_chunk_scan_b", k3_chunk_scan_b, dim3(nb), dim3(256), d_desc, d_inuse, d_chunk_state,
            (const uint4*)d_chunk_zle, d_chunk_base, chunks_cap, d_mtf_count);
-  L.launch("k3_apply", k3_apply, dim3(gx, nb), dim3(MTF_WARPS * 32), d_last, d_desc, d_inuse,
+  const uint32_t gxc = (nch + MTF_WARPS * 32 - 1) / (MTF_WARPS * 32);  // one lane per chunk
+  L.launch("k3_apply", k3_apply, dim3(gxc, nb), dim3(MTF_WARPS * 32), d_last, d_desc, d_inuse,
            (const int*)d_chunk_state, (const uint2*)d_chunk_base, chunks_cap, d_sym, d_freq);
 }
 
