@@ -92,8 +92,13 @@ BZB200_API int bzb200_plan(bzb200_ctx* c, int level, const uint8_t* d_in, size_t
 /* Number of blocks of the current plan (0 before any plan). */
 BZB200_API uint32_t bzb200_num_blocks(const bzb200_ctx* c);
 /* Block table of the current plan: in_off[nblocks+1] (input byte offsets), rle_off[nblocks+1] (offsets into the
- * RLE1 stream), crc[nblocks].  Any pointer may be NULL. */
+ * RLE1 stream), crc[nblocks].  Any pointer may be NULL.  The RLE1 bytes, CRCs and in-use maps of a block are
+ * produced when the block is encoded (bzb200_encode_blocks); asking for crc here computes the CRCs of the blocks
+ * this context has not encoded as well (one K5 launch over the whole input). */
 BZB200_API int bzb200_block_table(bzb200_ctx* c, uint64_t* in_off, uint64_t* rle_off, uint32_t* crc);
+/* CRCs as they stand: valid for the blocks encoded by this context, 0 elsewhere; no device work.  A sharded caller
+ * exchanges these slices between ranks instead of recomputing them (rust-compression_b200/sharded.py). */
+BZB200_API int bzb200_block_crcs(const bzb200_ctx* c, uint32_t* crc, size_t cap);
 
 /* K2-K6 for blocks [b0,b1) of the current plan: BWT (prefix-doubling rotation sort), MTF + RUNA/RUNB,
  * Huffman table selection/refinement, header + symbol bit packing.  replaces write_blockdata

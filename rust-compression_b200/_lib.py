@@ -42,6 +42,7 @@ SIGNATURES = {
     "bzb200_launch_count": (C.c_uint64, [_P]),
     "bzb200_sort_stats": (C.c_int, [_P, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)]),
     "bzb200_path_stats": (C.c_int, [_P, C.POINTER(C.c_uint64), C.c_size_t]),
+    "bzb200_block_crcs": (C.c_int, [_P, C.c_void_p, C.c_size_t]),
     "bzb200_version": (C.c_char_p, []),
 }
 

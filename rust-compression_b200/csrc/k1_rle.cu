@@ -197,14 +197,16 @@ __global__ void __launch_bounds__(K1_NT) k1_tile_counts(const uint8_t* __restric
 // ---- kernel F: scatter the RLE1 byte stream ----
 __global__ void __launch_bounds__(K1_NT) k1_scatter(const uint8_t* __restrict__ in, uint64_t N,
                                                     const long long* __restrict__ tile_carry,
-                                                    const uint64_t* __restrict__ tile_E, uint8_t* __restrict__ out) {
+                                                    const uint64_t* __restrict__ tile_E, uint64_t tile0,
+                                                    uint8_t* __restrict__ out) {
   __shared__ long long ws64[K1_NT / 32];
   __shared__ uint32_t ws32[K1_NT / 32 + 1];
   ThreadBytes tb;
   ThreadEval ev;
   uint32_t q[K1_BPT];
-  uint32_t ex = tile_eval_cta(in, N, blockIdx.x, tile_carry[blockIdx.x], tb, ev, q, ws64, ws32, nullptr);
-  uint64_t o = tile_E[blockIdx.x] + ex;
+  const uint64_t tile = tile0 + blockIdx.x;
+  uint32_t ex = tile_eval_cta(in, N, tile, tile_carry[tile], tb, ev, q, ws64, ws32, nullptr);
+  uint64_t o = tile_E[tile] + ex;
 #pragma unroll
   for (int j = 0; j < K1_BPT; ++j) {
     if (j < tb.cnt) {
@@ -214,114 +216,152 @@ __global__ void __launch_bounds__(K1_NT) k1_scatter(const uint8_t* __restrict__ 
   }
 }
 
-// ---- kernel E: greedy cut chain (one CTA) ----
-// cuts: in_off[k], rle_off[k] for k=0..nblocks; nblocks_out. max_blocks bounds the arrays (nblocks+1 <= max_blocks).
-__global__ void __launch_bounds__(K1_NT) k1_cut_chain(const uint8_t* __restrict__ in, uint64_t N,
-                                                      const long long* __restrict__ tile_carry,
-                                                      const uint64_t* __restrict__ tile_E, uint64_t ntiles, uint32_t T,
-                                                      uint64_t* __restrict__ in_off, uint64_t* __restrict__ rle_off,
-                                                      uint32_t max_blocks, uint32_t* __restrict__ nblocks_out,
-                                                      uint32_t* __restrict__ max_block_len) {
+// ---- kernel E': the cut chain as parallel windows + a pointer walk ----
+// A block that starts at emitted offset S ends at f(S + T), f(x) = emitted offset of the first piece end at or
+// after x; f(x) - x <= 4.  With center_j = x0 + (j+1) T and drift d_j = S_j - (x0 + j T) the chain is
+// d_{j+1} = f(center_j + d_j) - center_j.  k1_cut_windows tabulates F[j][w] = f(center_j + w) - center_j for
+// w < CW_W for every j at once (one CTA per window: locate the tile, evaluate it, every piece end fills the <= 5
+// offsets it covers); k1_cut_walk then follows the chain through the table, 32 windows per step as long as the drift
+// does not change.  A drift that leaves the window ends the phase; the host starts the next one at that cut.
+constexpr int CW_W = 256;
+constexpr uint64_t CW_LAST = 1ull << 63;  // the piece is the last piece of the input: no cut (encoder.rs:729-739)
+
+__global__ void __launch_bounds__(K1_NT) k1_cut_windows(const uint8_t* __restrict__ in, uint64_t N,
+                                                        const long long* __restrict__ tile_carry,
+                                                        const uint64_t* __restrict__ tile_E, uint64_t ntiles, uint32_t T,
+                                                        const uint64_t* __restrict__ state, uint64_t* __restrict__ F) {
   __shared__ long long ws64[K1_NT / 32];
   __shared__ uint32_t ws32[K1_NT / 32 + 1];
-  __shared__ uint64_t s_lo, s_hi, s_S, s_cut_i, s_cut_E;
-  __shared__ uint32_t s_first, s_k, s_done, s_maxlen;
+  __shared__ uint64_t s_lo, s_hi;
+  __shared__ uint32_t s_first;
+  if (state[2]) return;  // chain already finished
+  const uint64_t x0 = state[1];
   const uint64_t Etot = tile_E[ntiles];
-  if (threadIdx.x == 0) {
-    s_S = 0; s_k = 0; s_done = 0; s_lo = 0; s_maxlen = 0;
-    in_off[0] = 0; rle_off[0] = 0;
-  }
+  const uint64_t center = x0 + (uint64_t)(blockIdx.x + 1) * T;
+  if (center > Etot) return;
+  // first tile t with tile_E[t+1] >= center (256-ary search)
+  if (threadIdx.x == 0) { s_lo = 0; s_hi = ntiles - 1; }
   __syncthreads();
   while (true) {
-    const uint64_t S = s_S;
-    const uint64_t target = S + T;
-    if (target > Etot || s_k + 2 > max_blocks) break;  // remaining bytes fit in the last block
-    // -- 256-ary search: smallest tile t in [lo, ntiles-1] with tile_E[t+1] >= target
-    if (threadIdx.x == 0) s_hi = ntiles - 1;
+    const uint64_t lo = s_lo, hi = s_hi;
+    if (lo >= hi) break;
+    const uint64_t span = hi - lo + 1;
+    const uint64_t step = (span + K1_NT - 1) / K1_NT;
+    const uint64_t p = min(lo + (uint64_t)threadIdx.x * step, hi);
+    const bool ok = tile_E[p + 1] >= center;
+    if (threadIdx.x == 0) s_first = K1_NT;
     __syncthreads();
-    while (true) {
-      uint64_t lo = s_lo, hi = s_hi;
-      if (lo >= hi) break;
-      uint64_t span = hi - lo + 1;
-      uint64_t step = (span + K1_NT - 1) / K1_NT;
-      uint64_t p = min(lo + (uint64_t)threadIdx.x * step, hi);
-      bool ok = tile_E[p + 1] >= target;
-      if (threadIdx.x == 0) s_first = K1_NT;
-      __syncthreads();
-      if (ok) atomicMin(&s_first, (uint32_t)threadIdx.x);
-      __syncthreads();
-      uint32_t f = s_first;
-      __syncthreads();
-      if (threadIdx.x == 0) {
-        uint64_t pf = min(lo + (uint64_t)f * step, hi);
-        uint64_t pl = f > 0 ? min(lo + (uint64_t)(f - 1) * step, hi) + 1 : lo;
-        s_hi = pf;
-        s_lo = pl;
-      }
-      __syncthreads();
+    if (ok) atomicMin(&s_first, (uint32_t)threadIdx.x);
+    __syncthreads();
+    const uint32_t f = s_first;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      s_hi = min(lo + (uint64_t)f * step, hi);
+      s_lo = f > 0 ? min(lo + (uint64_t)(f - 1) * step, hi) + 1 : lo;
     }
-    const uint64_t t = s_lo;
-    // -- evaluate tile t, find first byte with E(i) >= target
+    __syncthreads();
+  }
+  uint64_t* Fj = F + (uint64_t)blockIdx.x * CW_W;
+  for (uint64_t t = s_lo; t < ntiles; ++t) {
     ThreadBytes tb;
     ThreadEval ev;
     uint32_t q[K1_BPT];
-    uint32_t ex = tile_eval_cta(in, N, t, tile_carry[t], tb, ev, q, ws64, ws32, nullptr);
+    const uint32_t ex = tile_eval_cta(in, N, t, tile_carry[t], tb, ev, q, ws64, ws32, nullptr);
     uint64_t E = tile_E[t] + ex;
-    int cand = -1;
-    uint64_t candE = 0;
 #pragma unroll
     for (int j = 0; j < K1_BPT; ++j) {
       if (j < tb.cnt) {
         E += ((ev.lit_mask >> j) & 1u) + ((ev.cb_mask >> j) & 1u);
-        if (cand < 0 && E >= target) { cand = j; candE = E; }
+        const uint64_t i = tb.i0 + j;
+        const uint8_t nb = (j + 1 < tb.cnt) ? tb.b[j + 1] : tb.next;
+        const bool pe = (i == N - 1) || (nb != tb.b[j]) || q[j] == 254u;
+        if (pe && E >= center) {
+          const uint32_t piece = min(q[j] + 1u, 4u) + (q[j] >= 3u ? 1u : 0u);  // bytes this piece emits
+          const uint64_t eprev = E - piece;                                    // previous piece end
+          if (eprev + 1 < center + CW_W) {
+            const uint64_t wlo = eprev + 1 > center ? eprev + 1 - center : 0;
+            const uint64_t whi = min((uint64_t)CW_W - 1, E - center);
+            const uint64_t v = (E - center) | ((i + 1) << 16) | (i == N - 1 ? CW_LAST : 0ull);
+            for (uint64_t w = wlo; w <= whi; ++w) Fj[w] = v;
+          }
+        }
       }
     }
-    if (threadIdx.x == 0) s_first = 0xFFFFFFFFu;
+    if (tile_E[t + 1] >= center + CW_W + 4) break;  // every piece that covers an offset of the window ends by here
     __syncthreads();
-    if (cand >= 0) atomicMin(&s_first, (uint32_t)(threadIdx.x * K1_BPT + cand));
-    __syncthreads();
-    if (cand >= 0 && s_first == (uint32_t)(threadIdx.x * K1_BPT + cand)) {
-      // walk to the end of the piece that contains byte i
-      uint64_t i = tb.i0 + cand;
-      uint32_t qq = q[cand];
-      uint8_t c = tb.b[cand];
-      bool tail = (i == N - 1) || (((cand + 1 < tb.cnt) ? tb.b[cand + 1] : tb.next) != c);
-      bool pe = tail || qq == 254u;
-      uint64_t EE = candE;
-      while (!pe) {
-        ++i;
-        ++qq;  // same run, qq <= 254
-        tail = (i == N - 1) || (in[i + 1] != c);
-        pe = tail || qq == 254u;
-        EE += (qq < 4u ? 1u : 0u) + ((pe && qq >= 3u) ? 1u : 0u);
-      }
-      s_cut_i = i;
-      s_cut_E = EE;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      if (s_cut_i == N - 1) {
-        s_done = 1;  // the piece that reaches T is the last piece of the input: no cut (encoder.rs:729-739)
-      } else {
-        uint32_t k = s_k + 1;
-        in_off[k] = s_cut_i + 1;
-        rle_off[k] = s_cut_E;
-        s_maxlen = max(s_maxlen, (uint32_t)(s_cut_E - S));
-        s_k = k;
-        s_S = s_cut_E;
-        s_lo = t;  // next search starts at this tile (E is monotone)
-      }
-    }
-    __syncthreads();
-    if (s_done) break;
   }
-  if (threadIdx.x == 0) {
-    uint32_t nb = s_k + 1;
-    in_off[nb] = N;
-    rle_off[nb] = Etot;
-    s_maxlen = max(s_maxlen, (uint32_t)min((uint64_t)0xFFFFFFFFu, Etot - s_S));
-    *nblocks_out = nb;
-    *max_block_len = s_maxlen;
+}
+
+// state[0] = blocks cut so far (k), [1] = emitted offset where the current block starts (S), [2] = done,
+// [3] = longest block so far.  One warp.
+__global__ void __launch_bounds__(32) k1_cut_walk(const uint64_t* __restrict__ F, uint32_t K, uint32_t T,
+                                                  const uint64_t* __restrict__ tile_E, uint64_t ntiles, uint64_t N,
+                                                  uint64_t* __restrict__ in_off, uint64_t* __restrict__ rle_off,
+                                                  uint32_t max_blocks, uint64_t* __restrict__ state,
+                                                  uint32_t* __restrict__ nblocks_out, uint32_t* __restrict__ max_block_len) {
+  if (state[2]) return;
+  const uint32_t lane = lane_id();
+  const uint64_t Etot = tile_E[ntiles];
+  const uint64_t x0 = state[1];
+  uint64_t k = state[0], S = x0, maxlen = state[3];
+  uint64_t d = 0;
+  uint32_t j = 0;
+  bool done = false;
+  if (k == 0 && lane == 0) { in_off[0] = 0; rle_off[0] = 0; }
+  while (true) {
+    const uint32_t jj = j + lane;
+    const uint64_t center = x0 + (uint64_t)(jj + 1) * T;
+    const bool in_table = jj < K;
+    const bool reach = center + d <= Etot && k + lane + 2 <= max_blocks;  // otherwise the rest is the last block
+    const uint64_t v = (in_table && reach) ? F[(uint64_t)jj * CW_W + d] : 0ull;
+    const uint64_t rel = v & 0xFFFFull;
+    const bool good = in_table && reach && !(v & CW_LAST) && rel == d;
+    const uint32_t bad = __ballot_sync(0xffffffffu, !good);
+    const uint32_t nb_good = bad ? (uint32_t)(__ffs(bad) - 1) : 32u;
+    if (lane < nb_good) {  // cuts with unchanged drift: every block is exactly T long
+      in_off[k + 1 + lane] = (v >> 16) & 0x7FFFFFFFFFFFull;
+      rle_off[k + 1 + lane] = center + rel;
+    }
+    if (nb_good) {
+      maxlen = max(maxlen, (uint64_t)T);
+      k += nb_good;
+      j += nb_good;
+      S = x0 + (uint64_t)j * T + d;
+    }
+    if (nb_good == 32) continue;
+    // the first lane that breaks the pattern decides what happens next (all lanes follow it)
+    const uint32_t src = nb_good;
+    const uint64_t bv = __shfl_sync(0xffffffffu, v, src);
+    const bool b_in = __shfl_sync(0xffffffffu, (int)in_table, src);
+    const bool b_reach = __shfl_sync(0xffffffffu, (int)reach, src);
+    const uint64_t b_center = x0 + (uint64_t)(j + 1) * T;
+    if (!b_in) break;                                   // table exhausted: the host starts another phase at S
+    if (!b_reach || (bv & CW_LAST)) { done = true; break; }
+    const uint64_t brel = bv & 0xFFFFull;               // a cut that changes the drift
+    k += 1;
+    if (lane == 0) {
+      in_off[k] = (bv >> 16) & 0x7FFFFFFFFFFFull;
+      rle_off[k] = b_center + brel;
+    }
+    maxlen = max(maxlen, b_center + brel - S);
+    S = b_center + brel;
+    j += 1;
+    if (brel >= (uint64_t)CW_W) break;                  // drift left the window: next phase starts at S
+    d = brel;
+  }
+  if (lane == 0) {
+    state[0] = k;
+    state[1] = S;
+    state[3] = maxlen;
+    if (done) {
+      state[2] = 1;
+      const uint32_t nb = (uint32_t)k + 1;
+      in_off[nb] = N;
+      rle_off[nb] = Etot;
+      maxlen = max(maxlen, Etot - S);
+      *nblocks_out = nb;
+      *max_block_len = (uint32_t)min((uint64_t)0xFFFFFFFFu, maxlen);
+    }
   }
 }
 
@@ -409,9 +449,8 @@ __global__ void __launch_bounds__(256) k1_inuse(const uint8_t* __restrict__ txt,
 // =========================== host launchers ===========================
 uint64_t k1_num_tiles(uint64_t N) { return (N + K1_TILE - 1) / K1_TILE; }
 
-void launch_k1_plan(Launcher& L, const uint8_t* d_in, uint64_t N, uint32_t T, long long* d_tile_head,
-                    long long* d_tile_carry, uint32_t* d_tile_cnt, uint64_t* d_tile_E, uint64_t* d_in_off,
-                    uint64_t* d_rle_off, uint32_t max_blocks, uint32_t* d_nblocks, uint32_t* d_maxlen) {
+void launch_k1_plan(Launcher& L, const uint8_t* d_in, uint64_t N, long long* d_tile_head, long long* d_tile_carry,
+                    uint32_t* d_tile_cnt, uint64_t* d_tile_E) {
   uint64_t nt = k1_num_tiles(N);
   L.launch("k1_tile_heads", k1_tile_heads, dim3((unsigned)nt), dim3(K1_NT), d_in, N, d_tile_head);
   L.launch("k_scan_max64_excl", k_scan_max64_excl, dim3(1), dim3(SC_NT), (const long long*)d_tile_head,
@@ -420,14 +459,28 @@ void launch_k1_plan(Launcher& L, const uint8_t* d_in, uint64_t N, uint32_t T, lo
            (const long long*)d_tile_carry, d_tile_cnt);
   L.launch("k_scan_add64_excl", k_scan_add64_excl, dim3(1), dim3(SC_NT), (const uint32_t*)d_tile_cnt,
            d_tile_E, nt);
-  L.launch("k1_cut_chain", k1_cut_chain, dim3(1), dim3(K1_NT), d_in, N, (const long long*)d_tile_carry,
-           (const uint64_t*)d_tile_E, nt, T, d_in_off, d_rle_off, max_blocks, d_nblocks, d_maxlen);
 }
 
-void launch_k1_scatter(Launcher& L, const uint8_t* d_in, uint64_t N, const long long* d_tile_carry,
-                       const uint64_t* d_tile_E, uint8_t* d_txt) {
+uint32_t k1_cut_window() { return CW_W; }
+
+// One phase of the cut chain: K windows from the chain state in d_state, then the walk.
+void launch_k1_cut_phase(Launcher& L, const uint8_t* d_in, uint64_t N, uint32_t T, const long long* d_tile_carry,
+                         const uint64_t* d_tile_E, uint32_t K, uint64_t* d_F, uint64_t* d_state, uint64_t* d_in_off,
+                         uint64_t* d_rle_off, uint32_t max_blocks, uint32_t* d_nblocks, uint32_t* d_maxlen) {
   uint64_t nt = k1_num_tiles(N);
-  L.launch("k1_scatter", k1_scatter, dim3((unsigned)nt), dim3(K1_NT), d_in, N, d_tile_carry, d_tile_E,
+  if (K)
+    L.launch("k1_cut_windows", k1_cut_windows, dim3(K), dim3(K1_NT), d_in, N, d_tile_carry, d_tile_E, nt, T,
+             (const uint64_t*)d_state, d_F);
+  L.launch("k1_cut_walk", k1_cut_walk, dim3(1), dim3(32), (const uint64_t*)d_F, K, T, d_tile_E, nt, N, d_in_off,
+           d_rle_off, max_blocks, d_state, d_nblocks, d_maxlen);
+}
+
+// RLE1 bytes of the input range [in_lo, in_hi) (whole tiles; the bytes land at their global emitted offsets).
+void launch_k1_scatter(Launcher& L, const uint8_t* d_in, uint64_t N, uint64_t in_lo, uint64_t in_hi,
+                       const long long* d_tile_carry, const uint64_t* d_tile_E, uint8_t* d_txt) {
+  if (in_hi <= in_lo) return;
+  const uint64_t t0 = in_lo / K1_TILE, t1 = (in_hi + K1_TILE - 1) / K1_TILE;
+  L.launch("k1_scatter", k1_scatter, dim3((unsigned)(t1 - t0)), dim3(K1_NT), d_in, N, d_tile_carry, d_tile_E, t0,
            d_txt);
 }
 

@@ -65,11 +65,14 @@ struct Launcher {
 
 // ---- k1_rle.cu ----
 uint64_t k1_num_tiles(uint64_t N);
-void launch_k1_plan(Launcher& L, const uint8_t* d_in, uint64_t N, uint32_t T, long long* d_tile_head,
-                    long long* d_tile_carry, uint32_t* d_tile_cnt, uint64_t* d_tile_E, uint64_t* d_in_off,
-                    uint64_t* d_rle_off, uint32_t max_blocks, uint32_t* d_nblocks, uint32_t* d_maxlen);
-void launch_k1_scatter(Launcher& L, const uint8_t* d_in, uint64_t N, const long long* d_tile_carry,
-                       const uint64_t* d_tile_E, uint8_t* d_txt);
+uint32_t k1_cut_window();
+void launch_k1_plan(Launcher& L, const uint8_t* d_in, uint64_t N, long long* d_tile_head, long long* d_tile_carry,
+                    uint32_t* d_tile_cnt, uint64_t* d_tile_E);
+void launch_k1_cut_phase(Launcher& L, const uint8_t* d_in, uint64_t N, uint32_t T, const long long* d_tile_carry,
+                         const uint64_t* d_tile_E, uint32_t K, uint64_t* d_F, uint64_t* d_state, uint64_t* d_in_off,
+                         uint64_t* d_rle_off, uint32_t max_blocks, uint32_t* d_nblocks, uint32_t* d_maxlen);
+void launch_k1_scatter(Launcher& L, const uint8_t* d_in, uint64_t N, uint64_t in_lo, uint64_t in_hi,
+                       const long long* d_tile_carry, const uint64_t* d_tile_E, uint8_t* d_txt);
 void launch_k5_crc(Launcher& L, const uint8_t* d_in, const uint64_t* d_in_off, uint32_t nblocks, uint32_t* d_crc);
 void launch_k1_inuse(Launcher& L, const uint8_t* d_txt, const uint64_t* d_rle_off, uint32_t nblocks, uint32_t* d_inuse);
 

@@ -111,7 +111,9 @@ struct bzb200_ctx {
   uint32_t nblocks = 0;
   uint32_t max_block_len = 0;
   bool planned = false;
-  DevBuf tile_head, tile_carry, tile_cnt, tile_E, in_off, rle_off, txt, crc, inuse, scal;
+  DevBuf tile_head, tile_carry, tile_cnt, tile_E, in_off, rle_off, txt, crc, inuse, scal, cut_state, cut_F;
+  uint32_t prep_lo = 0, prep_hi = 0;  // blocks whose RLE1 bytes, CRC and in-use map are on the device
+  bool crc_all = false;
   std::vector<uint64_t> h_in_off, h_rle_off;
   std::vector<uint32_t> h_crc;
 
@@ -239,7 +241,7 @@ static int ctx_create_impl(int device, void* stream, bool own_stream, bzb200_ctx
     if (v >= 1000) c->batch_elems_cap = v;
   }
   c->all = {&c->tile_head, &c->tile_carry, &c->tile_cnt, &c->tile_E, &c->in_off, &c->rle_off, &c->txt, &c->crc,
-            &c->inuse, &c->scal, &c->desc, &c->A, &c->B, &c->rank, &c->sa,
+            &c->inuse, &c->scal, &c->cut_state, &c->cut_F, &c->desc, &c->A, &c->B, &c->rank, &c->sa,
             &c->tile_meta, &c->cnt, &c->hist, &c->oshist, &c->ticket, &c->tsum, &c->state, &c->shift, &c->sparse,
             &c->stats, &c->rounds, &c->global, &c->last, &c->origptr, &c->chunk_state, &c->chunk_zle, &c->chunk_base,
             &c->sym, &c->freq, &c->mtf_count, &c->lens, &c->rfreq, &c->sel, &c->selmtf, &c->codes, &c->gbits, &c->meta,
@@ -314,16 +316,28 @@ int bzb200_plan(bzb200_ctx* c, int level, const uint8_t* d_in, size_t n, uint32_
   TRY(ensure(c, c->rle_off, ((size_t)max_blocks + 1) * 8));
   TRY(ensure(c, c->scal, 64));
   TRY(ensure(c, c->txt, emax));
-  launch_k1_plan(c->L, d_in, n, c->T, ptr<long long>(c->tile_head), ptr<long long>(c->tile_carry),
-                 ptr<uint32_t>(c->tile_cnt), ptr<uint64_t>(c->tile_E), ptr<uint64_t>(c->in_off),
-                 ptr<uint64_t>(c->rle_off), max_blocks, ptr<uint32_t>(c->scal), ptr<uint32_t>(c->scal) + 1);
-  launch_k1_scatter(c->L, d_in, n, ptr<long long>(c->tile_carry), ptr<uint64_t>(c->tile_E), ptr<uint8_t>(c->txt));
-  TRY(check_launch(c));
+  launch_k1_plan(c->L, d_in, n, ptr<long long>(c->tile_head), ptr<long long>(c->tile_carry),
+                 ptr<uint32_t>(c->tile_cnt), ptr<uint64_t>(c->tile_E));
+  // cut chain: phases of (windows, walk) until the walk reports done (one phase unless the drift leaves a window)
+  TRY(ensure(c, c->cut_state, 64));
+  CK(c, cudaMemsetAsync(c->cut_state.p, 0, 64, c->stream));
   uint32_t sc[2] = {0, 0};
-  CK(c, cudaMemcpyAsync(sc, c->scal.p, sizeof(sc), cudaMemcpyDeviceToHost, c->stream));
-  CK(c, cudaStreamSynchronize(c->stream));
+  uint64_t st[4] = {0, 0, 0, 0};
+  for (int phase = 0; phase < 1 << 20; ++phase) {
+    const uint64_t left = emax - std::min<uint64_t>(emax, st[1]);
+    const uint32_t K = (uint32_t)std::min<uint64_t>(left / c->T + 2, 1u << 20);
+    TRY(ensure(c, c->cut_F, (size_t)K * k1_cut_window() * 8));
+    launch_k1_cut_phase(c->L, d_in, n, c->T, ptr<long long>(c->tile_carry), ptr<uint64_t>(c->tile_E), K,
+                        ptr<uint64_t>(c->cut_F), ptr<uint64_t>(c->cut_state), ptr<uint64_t>(c->in_off),
+                        ptr<uint64_t>(c->rle_off), max_blocks, ptr<uint32_t>(c->scal), ptr<uint32_t>(c->scal) + 1);
+    TRY(check_launch(c));
+    CK(c, cudaMemcpyAsync(st, c->cut_state.p, sizeof(st), cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaMemcpyAsync(sc, c->scal.p, sizeof(sc), cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    if (st[2]) break;
+  }
   const uint32_t nb = sc[0];
-  if (nb == 0 || nb > max_blocks) {
+  if (!st[2] || nb == 0 || nb > max_blocks) {
     c->err = "cut chain produced an invalid block count";
     return BZB200_E_INTERNAL;
   }
@@ -331,15 +345,13 @@ int bzb200_plan(bzb200_ctx* c, int level, const uint8_t* d_in, size_t n, uint32_
   c->max_block_len = sc[1];
   c->h_in_off.resize((size_t)nb + 1);
   c->h_rle_off.resize((size_t)nb + 1);
-  c->h_crc.resize(nb);
+  c->h_crc.assign(nb, 0);
+  c->prep_lo = c->prep_hi = 0;
+  c->crc_all = false;
   TRY(ensure(c, c->crc, (size_t)nb * 4));
   TRY(ensure(c, c->inuse, (size_t)nb * 32));
-  launch_k5_crc(c->L, d_in, ptr<uint64_t>(c->in_off), nb, ptr<uint32_t>(c->crc));
-  launch_k1_inuse(c->L, ptr<uint8_t>(c->txt), ptr<uint64_t>(c->rle_off), nb, ptr<uint32_t>(c->inuse));
-  TRY(check_launch(c));
   CK(c, cudaMemcpyAsync(c->h_in_off.data(), c->in_off.p, ((size_t)nb + 1) * 8, cudaMemcpyDeviceToHost, c->stream));
   CK(c, cudaMemcpyAsync(c->h_rle_off.data(), c->rle_off.p, ((size_t)nb + 1) * 8, cudaMemcpyDeviceToHost, c->stream));
-  CK(c, cudaMemcpyAsync(c->h_crc.data(), c->crc.p, (size_t)nb * 4, cudaMemcpyDeviceToHost, c->stream));
   CK(c, cudaStreamSynchronize(c->stream));
   if (c->max_block_len > (uint32_t)level * 100000u || c->max_block_len > MAX_BLOCK) {
     c->err = "block longer than level*100000";
@@ -356,7 +368,40 @@ int bzb200_block_table(bzb200_ctx* c, uint64_t* in_off, uint64_t* rle_off, uint3
   if (!c || !c->planned) return BZB200_E_STATE;
   if (in_off) memcpy(in_off, c->h_in_off.data(), c->h_in_off.size() * 8);
   if (rle_off) memcpy(rle_off, c->h_rle_off.data(), c->h_rle_off.size() * 8);
-  if (crc && c->nblocks) memcpy(crc, c->h_crc.data(), (size_t)c->nblocks * 4);
+  if (crc && c->nblocks) {
+    if (!c->crc_all && !(c->prep_lo == 0 && c->prep_hi == c->nblocks)) {  // CRCs of blocks this context did not encode
+      TRY(set_device(c));
+      launch_k5_crc(c->L, c->d_in, ptr<uint64_t>(c->in_off), c->nblocks, ptr<uint32_t>(c->crc));
+      TRY(check_launch(c));
+      CK(c, cudaMemcpyAsync(c->h_crc.data(), c->crc.p, (size_t)c->nblocks * 4, cudaMemcpyDeviceToHost, c->stream));
+      CK(c, cudaStreamSynchronize(c->stream));
+      c->crc_all = true;
+    }
+    memcpy(crc, c->h_crc.data(), (size_t)c->nblocks * 4);
+  }
+  return BZB200_OK;
+}
+
+int bzb200_block_crcs(const bzb200_ctx* c, uint32_t* crc, size_t cap) {
+  if (!c || !c->planned || !crc) return BZB200_E_STATE;
+  for (size_t i = 0; i < cap && i < c->h_crc.size(); ++i) crc[i] = c->h_crc[i];
+  return BZB200_OK;
+}
+
+// RLE1 bytes, CRCs and in-use maps of blocks [b0, b1) (K1 scatter, K5, in-use) — only what this context encodes.
+static int prepare_blocks(bzb200_ctx* c, uint32_t b0, uint32_t b1) {
+  if (b0 >= b1 || (b0 >= c->prep_lo && b1 <= c->prep_hi)) return BZB200_OK;
+  launch_k1_scatter(c->L, c->d_in, c->n_in, c->h_in_off[b0], c->h_in_off[b1], ptr<long long>(c->tile_carry),
+                    ptr<uint64_t>(c->tile_E), ptr<uint8_t>(c->txt));
+  launch_k5_crc(c->L, c->d_in, ptr<uint64_t>(c->in_off) + b0, b1 - b0, ptr<uint32_t>(c->crc) + b0);
+  launch_k1_inuse(c->L, ptr<uint8_t>(c->txt), ptr<uint64_t>(c->rle_off) + b0, b1 - b0,
+                  ptr<uint32_t>(c->inuse) + (size_t)b0 * 8);
+  TRY(check_launch(c));
+  CK(c, cudaMemcpyAsync(c->h_crc.data() + b0, ptr<uint32_t>(c->crc) + b0, (size_t)(b1 - b0) * 4, cudaMemcpyDeviceToHost,
+                        c->stream));
+  CK(c, cudaStreamSynchronize(c->stream));
+  c->prep_lo = b0;
+  c->prep_hi = b1;
   return BZB200_OK;
 }
 
@@ -518,6 +563,7 @@ int bzb200_encode_blocks(bzb200_ctx* c, uint32_t b0, uint32_t b1, uint8_t* d_out
     return BZB200_E_ARG;
   }
   TRY(set_device(c));
+  TRY(prepare_blocks(c, b0, b1));
   TRY(ensure(c, c->bitcursor, 16));
   CK(c, cudaMemcpyAsync(c->bitcursor.p, &start_bit, 8, cudaMemcpyHostToDevice, c->stream));
   CK(c, cudaStreamSynchronize(c->stream));

@@ -82,13 +82,18 @@ class Context:
         self.nblocks = nb.value
         return nb.value
 
-    def block_table(self):
+    def block_table(self, with_crc=True):
+        """(in_off, rle_off, crc) of the planned blocks.  CRCs are computed for the blocks this context encodes;
+        with_crc=True asks for all of them (the missing ones are computed on demand), with_crc=False returns the
+        array as it stands (zeros for blocks not encoded here) without touching the device."""
         nb = self.nblocks = int(_lib.lib().bzb200_num_blocks(self._h))
         in_off = np.zeros(nb + 1, dtype=np.uint64)
         rle_off = np.zeros(nb + 1, dtype=np.uint64)
         crc = np.zeros(max(nb, 1), dtype=np.uint32)
-        self._check(_lib.lib().bzb200_block_table(self._h, in_off.ctypes.data, rle_off.ctypes.data, crc.ctypes.data),
-                    "bzb200_block_table")
+        self._check(_lib.lib().bzb200_block_table(self._h, in_off.ctypes.data, rle_off.ctypes.data,
+                                                  crc.ctypes.data if with_crc else None), "bzb200_block_table")
+        if not with_crc and nb:
+            self._check(_lib.lib().bzb200_block_crcs(self._h, crc.ctypes.data, nb), "bzb200_block_crcs")
         return in_off, rle_off, crc[:nb]
 
     def encode_blocks(self, b0, b1, d_out, start_bit):

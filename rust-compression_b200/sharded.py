@@ -28,7 +28,7 @@ def compress_sharded(ctx, level, d_in, group=None, gather=True):
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     dev = d_in.device
     nb = ctx.plan(level, d_in)
-    in_off, rle_off, crc = ctx.block_table()
+    in_off, rle_off, _ = ctx.block_table(with_crc=False)
     b0, b1 = block_range(nb, rank, world)
     my_in = int(in_off[b1] - in_off[b0]) if nb else 0
     cap = (max_output_bytes(level, my_in) + 64 + 3) & ~3
@@ -38,17 +38,27 @@ def compress_sharded(ctx, level, d_in, group=None, gather=True):
         ctx.write_stream_header(level, d_out)
     end = ctx.encode_blocks(b0, b1, d_out, start) if b1 > b0 else start
     info = {"nblocks": nb, "b0": b0, "b1": b1, "bits": end - start, "rank": rank, "world": world}
+    crc = ctx.block_table(with_crc=False)[2]  # valid for [b0, b1)
     if world == 1:
         total = ctx.write_stream_trailer(d_out, end, ctx.combine_crc(crc))
         return d_out[:total], info
     if not gather:
         return None, info
 
-    # gather (nbits) then payloads to rank 0
-    nbits = torch.tensor([end - start], dtype=torch.int64, device=dev)
-    allbits = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
-    dist.all_gather(allbits, nbits, group=group)
-    bits = [int(t.item()) for t in allbits]
+    # all-gather (nbits, block CRCs of the rank's range), then payloads to rank 0
+    per = (nb + world - 1) // world + 1
+    meta = np.zeros(1 + per, dtype=np.int64)
+    meta[0] = end - start
+    meta[1:1 + (b1 - b0)] = crc[b0:b1]
+    t_meta = torch.from_numpy(meta).to(dev)
+    t_all = torch.empty(world * (1 + per), dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(t_all, t_meta, group=group)
+    h_all = t_all.cpu().numpy().reshape(world, 1 + per)
+    bits = [int(h_all[r, 0]) for r in range(world)]
+    crc = np.zeros(nb, dtype=np.uint32)
+    for r in range(world):
+        lo, hi = block_range(nb, r, world)
+        crc[lo:hi] = h_all[r, 1:1 + (hi - lo)].astype(np.uint32)
     if rank == 0:
         total_bits = 32 + sum(bits)
         need = ((total_bits + 80 + 31) // 32) * 4 + 64

@@ -26,14 +26,21 @@ class OracleBackedContext:
         self.run = orc.Run(d_in.numpy().tobytes(), level)
         self.nblocks = self.run.nblocks
         self.bits = np.unpackbits(np.frombuffer(self.run.out, dtype=np.uint8))
+        self.encoded = (0, 0)
         return self.nblocks
 
-    def block_table(self):
+    def block_table(self, with_crc=True):
+        """Like device.Context.block_table: with_crc=False returns CRCs only for the blocks this rank encoded
+        (zeros elsewhere), so the test exercises the CRC exchange between ranks."""
         nb = self.nblocks
         infos = [self.run.info(b) for b in range(nb)]
         in_off = np.array([i["in_start"] for i in infos] + [infos[-1]["in_end"] if nb else 0], dtype=np.uint64)
         rle = np.zeros(nb + 1, dtype=np.uint64)
         crc = np.array([i["crc"] for i in infos], dtype=np.uint32)
+        if not with_crc:
+            keep = np.zeros(nb, dtype=bool)
+            keep[self.encoded[0]:self.encoded[1]] = True
+            crc = np.where(keep, crc, 0).astype(np.uint32)
         return in_off, rle, crc
 
     @staticmethod
@@ -44,6 +51,7 @@ class OracleBackedContext:
         dst[:nbytes] = torch.from_numpy(np.packbits(cur))
 
     def encode_blocks(self, b0, b1, d_out, start_bit):
+        self.encoded = (b0, b1)
         s = self.run.info(b0)["bit_start"]
         e = self.run.info(b1 - 1)["bit_end"]
         self._or_bits(d_out, start_bit, self.bits[s:e])
