@@ -21,7 +21,10 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
-LEVEL = 9
+# The headline workload is BASELINE.json configs[2] (level 9, text).  BZB200_BENCH_LEVEL / BZB200_BENCH_GEN=mixed
+# switch to the other throughput case of BASELINE.json (configs[3]: level 1 on mixed binary/text) for side runs.
+LEVEL = int(os.environ.get("BZB200_BENCH_LEVEL", "9"))
+GEN = os.environ.get("BZB200_BENCH_GEN", "text")
 METRIC = "bzip2 compress MB/s (uncompressed)"
 BYTES_PER_GPU = int(os.environ.get("BZB200_BENCH_BYTES", str(1 << 30)))
 CPU_SAMPLE_BYTES = int(os.environ.get("BZB200_CPU_SAMPLE_BYTES", str(128 << 20)))
@@ -43,8 +46,9 @@ NCU_TRAFFIC = {}
 
 def workload_name(n_gpus):
     gib = BYTES_PER_GPU / float(1 << 30)
-    return (f"{gib:g} GiB synthetic English-like text per GPU, level {LEVEL} (~{int(BYTES_PER_GPU / 899981)} blocks of "
-            f"900 kB per GPU), one .bz2 stream sharded block-wise over {n_gpus} GPU(s)")
+    kind = "English-like text" if GEN == "text" else "mixed binary/text (64 KiB segments)"
+    return (f"{gib:g} GiB synthetic {kind} per GPU, level {LEVEL} (~{int(BYTES_PER_GPU / (LEVEL * 100000 - 19))} blocks "
+            f"of {LEVEL}00 kB per GPU), one .bz2 stream sharded block-wise over {n_gpus} GPU(s)")
 
 
 class ClockSampler:
@@ -96,7 +100,7 @@ class ClockSampler:
 
 def gen_slice(rank, nbytes):
     import gen
-    return gen.text(1 + rank, nbytes)
+    return gen.text(1 + rank, nbytes) if GEN == "text" else gen.mixed(1 + rank, nbytes)
 
 
 def run_reference(args, rank):
@@ -139,7 +143,7 @@ def _ref_worker(a):
     seed, n = a
     import gen
     from oracle import orc
-    data = gen.text(seed, n)
+    data = gen.text(seed, n) if GEN == "text" else gen.mixed(seed, n)
     return len(orc.compress(data, LEVEL))
 
 

@@ -499,15 +499,27 @@ __global__ void __launch_bounds__(RS_NT) k2_rg_apply(const uint64_t* __restrict_
   uint32_t* so = sa + off;
   const int4 carry = tsum[(uint64_t)blockIdx.y * tiles_cap + blockIdx.x];
 
-  // blocked arrangement: thread t owns elements base + t*16 .. +15
+  // The tile is loaded coalesced into shared memory and read back in a blocked arrangement (thread t owns elements
+  // base + t*16 .. +15; index i sits at i + i/16, which keeps both access patterns conflict-free).
+  extern __shared__ __align__(16) uint8_t rg_raw[];
+  uint64_t* stg = reinterpret_cast<uint64_t*>(rg_raw);
+#pragma unroll 4
+  for (int k = 0; k < RS_IPT; ++k) {
+    const uint32_t i = threadIdx.x + k * RS_NT;
+    stg[i + (i >> 4)] = (base + i < c) ? s[base + i] : ~0ull;
+  }
+  __syncthreads();
   const uint32_t a0 = base + threadIdx.x * RS_IPT;
   uint64_t e[RS_IPT];
   uint64_t prv = ~0ull;
   if (a0 < c) {
-    if (a0 > 0) prv = s[a0 - 1] >> KEY_LO;
+    if (threadIdx.x > 0) prv = stg[threadIdx.x * 17 - 2] >> KEY_LO;  // element 16t-1 sits at 17t-2
+    else if (a0 > 0) prv = s[a0 - 1] >> KEY_LO;
 #pragma unroll
-    for (int j = 0; j < RS_IPT; ++j) e[j] = (a0 + j < c) ? s[a0 + j] : ~0ull;
+    for (int j = 0; j < RS_IPT; ++j) e[j] = stg[threadIdx.x * 17 + j];
   }
+  __syncthreads();
+  uint32_t* sa_stage = reinterpret_cast<uint32_t*>(rg_raw);  // initial round: SA slots leave through shared memory
   int lh = -1, lg = -1, fh = 0x7FFFFFFF;
   uint32_t hmask = 0, gmask = 0;
   if (a0 < c) {
@@ -572,8 +584,17 @@ __global__ void __launch_bounds__(RS_NT) k2_rg_apply(const uint64_t* __restrict_
           if (size > (uint32_t)LOCAL_MAX) { fl |= SA_BIG; ++n_big; }
         }
         rk[pos] = nr | (size == 1 ? RANK_RESOLVED : 0u);
-        so[slot] = pos | fl;
+        if (initial) sa_stage[threadIdx.x * 17 + j] = pos | fl;  // slot == a
+        else so[slot] = pos | fl;
       }
+    }
+  }
+  if (initial) {
+    __syncthreads();
+#pragma unroll 4
+    for (int k = 0; k < RS_IPT; ++k) {
+      const uint32_t i = threadIdx.x + k * RS_NT;
+      if (base + i < c) so[base + i] = sa_stage[i + (i >> 4)];
     }
   }
 #pragma unroll
@@ -1078,8 +1099,8 @@ static void regroup(Launcher& L, const uint64_t* srt, const BlockDesc* d_desc, u
   const uint32_t tiles = (maxcnt + RS_TILE - 1) / RS_TILE;
   L.launch("k2_rg_flags", k2_rg_flags, dim3(tiles, nb), dim3(RS_NT), srt, d_desc, S.cnt, S.tsum, S.tiles_cap, initial);
   L.launch("k2_rg_scan", k2_rg_scan, dim3(nb), dim3(32), S.cnt, S.tsum, S.tiles_cap);
-  L.launch("k2_rg_apply", k2_rg_apply, dim3(tiles, nb), dim3(RS_NT), srt, d_desc, S.cnt, S.tsum, S.tiles_cap, initial,
-           S.rank, S.sa, S.stats);
+  L.launch_smem("k2_rg_apply", k2_rg_apply, dim3(tiles, nb), dim3(RS_NT), (size_t)(RS_TILE + RS_TILE / 16) * 8, srt,
+                d_desc, S.cnt, S.tsum, S.tiles_cap, initial, S.rank, S.sa, S.stats);
 }
 
 int run_bwt(Launcher& L, const uint8_t* d_txt, const BlockDesc* d_desc, uint32_t nb, uint32_t nmax, uint64_t M,

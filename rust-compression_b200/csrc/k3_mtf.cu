@@ -175,21 +175,28 @@ __device__ __forceinline__ uint32_t mtf_word_hit(uint32_t f, uint32_t carry, uin
 // part is branch-free (lanes of a warp sit at different depths; a branch per word would serialise them).
 __device__ __forceinline__ uint32_t mtf_lane_access(MtfLane& l, uint32_t c, uint32_t* deep /* column, stride 32 */) {
   const uint32_t x = c * 0x01010101u;
-  uint32_t carry = c;
+  // every word's new value depends only on OLD values (the byte entering word k is the top byte of old word k-1),
+  // so the eight updates are independent instructions
+  uint32_t m[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) m[k] = __vcmpeq4(l.f[k], x);
+  uint32_t before = 0xFFFFFFFFu;  // all ones while no earlier word has matched
   uint32_t pos = 0;
-  bool done = false;
+  uint32_t carry = c;
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
     const uint32_t f = l.f[k];
-    const uint32_t m = __vcmpeq4(f, x);
-    const uint32_t p = (__ffs(m) - 1) >> 3;               // garbage when m == 0
-    const uint32_t sel = m ? ((uint32_t)(0x2104310432043214ull >> (16 * (p & 3u))) & 0xFFFFu) : 0x2104u;
-    const uint32_t nf = __byte_perm(f, carry, sel);       // m == 0: (f << 8) | carry
-    l.f[k] = done ? f : nf;
-    if (!done && m) pos = 4 * k + p;
+    const uint32_t p = (__ffs(m[k]) - 1) >> 3;  // garbage when m[k] == 0
+    // selector: hit at byte p -> [carry, b0..b(p-1), b(p+1)..b3]; no hit -> [carry, b0, b1, b2]
+    const uint32_t pc = m[k] ? (p & 3u) : 3u;
+    const uint32_t sel = 0x3214u - (0x1110u & ((16u << (4 * pc)) - 1u));
+    const uint32_t nf = __byte_perm(f, carry, sel);
+    l.f[k] = before ? nf : f;
+    if (before && m[k]) pos = 4 * k + p;
     carry = f >> 24;
-    done = done || (m != 0);
+    before = m[k] ? 0u : before;
   }
+  const bool done = before == 0;
   if (done) return pos;
   for (uint32_t k = 0; k < (uint32_t)MTF_DEEP_WORDS; ++k) {  // every entry in front of c moves down by one
     const uint32_t f = deep[k * 32];
@@ -250,18 +257,24 @@ __global__ void __launch_bounds__(MTF_WARPS * 32) k3_apply(const uint8_t* __rest
                                                            const uint32_t* __restrict__ inuse,
                                                            const int* __restrict__ chunk_state,
                                                            const uint2* __restrict__ chunk_base, uint32_t chunks_cap,
+                                                           uint32_t nb, uint32_t groups_cap,
                                                            uint16_t* __restrict__ sym, uint32_t* __restrict__ freq) {
   __shared__ int s_last[MTF_WARPS][256];
   __shared__ uint32_t s_list[MTF_WARPS][256];
   __shared__ uint32_t s_deep[MTF_WARPS][MTF_DEEP_WORDS][32];
-  __shared__ uint32_t s_freq[MAX_ALPHA + 2];
+  __shared__ uint32_t s_freqw[MTF_WARPS][MAX_ALPHA + 2];
   const int w = threadIdx.x >> 5;
   const uint32_t lane = lane_id();
-  const BlockDesc d = desc[blockIdx.y];
-  for (int i = threadIdx.x; i < MAX_ALPHA + 2; i += MTF_WARPS * 32) s_freq[i] = 0;
-  __syncthreads();
+  // warp task = (block, group of 32 chunks); the warps of a CTA may belong to different blocks
+  const uint32_t task = blockIdx.x * MTF_WARPS + w;
+  const uint32_t blk = task / groups_cap;
+  if (blk >= nb) return;
+  const BlockDesc d = desc[blk];
+  uint32_t* s_freq = s_freqw[w];
+  for (int i = lane; i < MAX_ALPHA + 2; i += 32) s_freq[i] = 0;
+  __syncwarp();
   const uint32_t nch = (d.n + MTF_CHUNK - 1) / MTF_CHUNK;
-  const uint32_t cbase = (blockIdx.x * MTF_WARPS + w) * 32;  // first chunk of this warp
+  const uint32_t cbase = (task % groups_cap) * 32;  // first chunk of this warp
   if (cbase < nch) {
     // ---- the list of every lane's chunk at the chunk start
     MtfLane ml;
@@ -269,7 +282,7 @@ __global__ void __launch_bounds__(MTF_WARPS * 32) k3_apply(const uint8_t* __rest
     for (int k = 0; k < 8; ++k) ml.f[k] = 0;
     const uint32_t nmine = min(32u, nch - cbase);
     for (uint32_t j = 0; j < nmine; ++j) {
-      const int* cs = chunk_state + ((uint64_t)blockIdx.y * chunks_cap + cbase + j) * 256;
+      const int* cs = chunk_state + ((uint64_t)blk * chunks_cap + cbase + j) * 256;
       int mine[8];
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
@@ -308,7 +321,7 @@ __global__ void __launch_bounds__(MTF_WARPS * 32) k3_apply(const uint8_t* __rest
       const uint32_t c0 = chunk * MTF_CHUNK;
       const uint32_t len = min((uint32_t)MTF_CHUNK, d.n - c0);
       const uint8_t* L = last + d.off + c0;
-      const uint2 cb = chunk_base[(uint64_t)blockIdx.y * chunks_cap + chunk];
+      const uint2 cb = chunk_base[(uint64_t)blk * chunks_cap + chunk];
       MtfOut mo;
       mo.out = sym + d.symoff;
       mo.o = cb.x;
@@ -317,7 +330,7 @@ __global__ void __launch_bounds__(MTF_WARPS * 32) k3_apply(const uint8_t* __rest
       mo.hot = 0;
       mo.freq = s_freq;
       uint32_t zrun = cb.y;
-      uint32_t prev = c0 > 0 ? L[-1] : smallest_inuse(inuse + blockIdx.y * 8);
+      uint32_t prev = c0 > 0 ? L[-1] : smallest_inuse(inuse + blk * 8);
       uint32_t* deep = &s_deep[w][0][lane];
       auto step = [&](uint32_t c) {
         if (c == prev) {
@@ -346,15 +359,15 @@ __global__ void __launch_bounds__(MTF_WARPS * 32) k3_apply(const uint8_t* __rest
         // final zero run + EOB (encoder.rs:355-358); EOB = in_use_count + 1
         mo.zero_run(zrun);
         uint32_t k = 0;
-        for (int ww = 0; ww < 8; ++ww) k += __popc(inuse[blockIdx.y * 8 + ww]);
+        for (int ww = 0; ww < 8; ++ww) k += __popc(inuse[blk * 8 + ww]);
         mo.put(k + 1);
       }
       mo.flush();
     }
   }
-  __syncthreads();
-  uint32_t* f = freq + (uint64_t)blockIdx.y * MAX_ALPHA;
-  for (int i = threadIdx.x; i < MAX_ALPHA; i += MTF_WARPS * 32) {
+  __syncwarp();
+  uint32_t* f = freq + (uint64_t)blk * MAX_ALPHA;
+  for (int i = lane; i < MAX_ALPHA; i += 32) {
     uint32_t v = s_freq[i];
     if (v) atomicAdd(&f[i], v);
   }
@@ -370,9 +383,10 @@ void launch_mtf(Launcher& L, const uint8_t* d_last, const BlockDesc* d_desc, con
            d_chunk_state, d_chunk_zle, chunks_cap);
   L.launch("k3_chunk_scan_b", k3_chunk_scan_b, dim3(nb), dim3(256), d_desc, d_inuse, d_chunk_state,
            (const uint4*)d_chunk_zle, d_chunk_base, chunks_cap, d_mtf_count);
-  const uint32_t gxc = (nch + MTF_WARPS * 32 - 1) / (MTF_WARPS * 32);  // one lane per chunk
-  L.launch("k3_apply", k3_apply, dim3(gxc, nb), dim3(MTF_WARPS * 32), d_last, d_desc, d_inuse,
-           (const int*)d_chunk_state, (const uint2*)d_chunk_base, chunks_cap, d_sym, d_freq);
+  const uint32_t groups_cap = (nch + 31) / 32;  // warp tasks per block: one lane per chunk
+  const uint32_t ntask = groups_cap * nb;
+  L.launch("k3_apply", k3_apply, dim3((ntask + MTF_WARPS - 1) / MTF_WARPS), dim3(MTF_WARPS * 32), d_last, d_desc,
+           d_inuse, (const int*)d_chunk_state, (const uint2*)d_chunk_base, chunks_cap, nb, groups_cap, d_sym, d_freq);
 }
 
 }  // namespace bzb

@@ -448,7 +448,7 @@ static int encode_batch(bzb200_ctx* c, uint32_t b0, uint32_t nb, uint8_t* d_out,
   TRY(ensure(c, c->stats, (size_t)nb * 16));
   TRY(ensure(c, c->rounds, (size_t)nb * 4));
   TRY(ensure(c, c->global, 64));
-  TRY(ensure(c, c->last, M));
+  TRY(ensure(c, c->last, M + 16));  // K3 reads the last column through aligned 32-bit words
   TRY(ensure(c, c->origptr, (size_t)nb * 4));
   TRY(ensure(c, c->chunk_state, (size_t)nb * chunks * 256 * 4));
   TRY(ensure(c, c->chunk_zle, (size_t)nb * chunks * sizeof(uint4)));

@@ -143,6 +143,36 @@ def test_all_a_fills_exactly_one_block():
     assert not {k: v for k, v in res.items() if v}, res
 
 
+def test_cut_chain_drift_leaves_window():
+    """'aaaab' repeated: every cut lands inside a 5-byte piece, so every block is 3 bytes longer than T and the drift
+    of the cut positions leaves k1_cut_windows' 256-offset window several times (multi-phase cut chain)."""
+    data = b"aaaab" * 3_000_000
+    res = parity.compare(data, 1, orc, keep_sa=False, check_blocks=[0, 1, 84, 85, 86, 87, 170, 179, 180])
+    assert not {k: v for k, v in res.items() if v}, res
+
+
+def test_cut_chain_long_runs_and_last_piece():
+    """Runs far longer than a tile (cut candidates many tiles apart) and an input whose last piece is the one that
+    reaches T (no cut there: encoder.rs:729-739)."""
+    parity.assert_parity(b"x" * 3_000_000 + gen.text(5, 150000) + b"y" * 2_000_000, 1, keep_sa=False)
+    T = 99981
+    d = gen.text(6, T - 3) + b"zzzz"          # the run of 4 'z' ends the input and crosses T
+    parity.assert_parity(d, 1, keep_sa=False)
+
+
+def test_doubling_rounds_group_sizes():
+    """Group-size classes of the rotation sort: enumeration (<= 16), bucket split (17..1535), BIG groups (radix
+    path), sparse blocks, and a block that needs many rounds."""
+    rng = np.random.default_rng(7)
+    words = [bytes(rng.integers(97, 101, size=int(rng.integers(3, 9))).tolist()) for _ in range(40)]
+    d1 = b" ".join(words[int(i)] for i in rng.integers(0, 40, size=40000))            # few distinct words: BIG + buckets
+    parity.assert_parity(d1, 9)
+    d2 = (gen.text(9, 30000) * 12)[:350000]                                            # long repeats: many rounds
+    parity.assert_parity(d2, 9)
+    d3 = bytes(rng.integers(0, 4, size=300000, dtype=np.uint8))                        # 4-letter alphabet
+    parity.assert_parity(d3, 9)
+
+
 def test_multi_batch_equals_single_batch(monkeypatch):
     d = gen.mixed(5, 1200000)
     monkeypatch.setenv("BZB200_BATCH_ELEMS", "250000")
