@@ -89,6 +89,19 @@ BZB200_API int bzb200_sync(bzb200_ctx* c);
  * over the whole input.  replaces EncoderInner::next/write_rle (encoder.rs:671-716), the cut test
  * (:692-696) and crc32::Digest (crc32.rs:82-84,129-131).  Synchronises once (block count -> host). */
 BZB200_API int bzb200_plan(bzb200_ctx* c, int level, const uint8_t* d_in, size_t n, uint32_t* nblocks);
+/* The same plan in four steps, for a sharded caller: K1's per-tile summaries (last run head, emitted bytes) are
+ * computed by the rank that owns the tile range [t0,t1) into CALLER-owned device arrays of `ntiles` entries, the
+ * caller exchanges the ranges between ranks (rust-compression_b200/sharded.py: NCCL all-gather), and every rank
+ * finishes with the cheap global part (prefix sum + cut chain).  A tile is bzb200_plan_tile_bytes() input bytes.
+ *   begin  : binds level/input, sizes the buffers, returns ntiles
+ *   heads  : d_tile_head[t0..t1) = index of the last run head inside the tile (-1: none)
+ *   counts : needs d_tile_head complete; d_tile_cnt[t0..t1) = RLE1 bytes the tile emits
+ *   finish : needs d_tile_cnt complete; block cuts -> host; afterwards identical to bzb200_plan */
+BZB200_API size_t bzb200_plan_tile_bytes(void);
+BZB200_API int bzb200_plan_begin(bzb200_ctx* c, int level, const uint8_t* d_in, size_t n, uint64_t* ntiles);
+BZB200_API int bzb200_plan_heads(bzb200_ctx* c, uint64_t t0, uint64_t t1, int64_t* d_tile_head);
+BZB200_API int bzb200_plan_counts(bzb200_ctx* c, const int64_t* d_tile_head, uint64_t t0, uint64_t t1, uint32_t* d_tile_cnt);
+BZB200_API int bzb200_plan_finish(bzb200_ctx* c, const uint32_t* d_tile_cnt, uint32_t* nblocks);
 /* Number of blocks of the current plan (0 before any plan). */
 BZB200_API uint32_t bzb200_num_blocks(const bzb200_ctx* c);
 /* Block table of the current plan: in_off[nblocks+1] (input byte offsets), rle_off[nblocks+1] (offsets into the

@@ -43,6 +43,11 @@ SIGNATURES = {
     "bzb200_sort_stats": (C.c_int, [_P, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)]),
     "bzb200_path_stats": (C.c_int, [_P, C.POINTER(C.c_uint64), C.c_size_t]),
     "bzb200_block_crcs": (C.c_int, [_P, C.c_void_p, C.c_size_t]),
+    "bzb200_plan_tile_bytes": (C.c_size_t, []),
+    "bzb200_plan_begin": (C.c_int, [_P, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_uint64)]),
+    "bzb200_plan_heads": (C.c_int, [_P, C.c_uint64, C.c_uint64, C.c_void_p]),
+    "bzb200_plan_counts": (C.c_int, [_P, C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]),
+    "bzb200_plan_finish": (C.c_int, [_P, C.c_void_p, C.POINTER(C.c_uint32)]),
     "bzb200_version": (C.c_char_p, []),
 }
 

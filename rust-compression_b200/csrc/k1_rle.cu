@@ -96,11 +96,12 @@ __device__ __forceinline__ void eval_thread(const ThreadBytes& tb, uint64_t N, l
 }
 
 // ---- kernel A: last head per tile ----
-__global__ void __launch_bounds__(K1_NT) k1_tile_heads(const uint8_t* __restrict__ in, uint64_t N,
+__global__ void __launch_bounds__(K1_NT) k1_tile_heads(const uint8_t* __restrict__ in, uint64_t N, uint64_t tile0,
                                                        long long* __restrict__ tile_last_head) {
   __shared__ long long ws[K1_NT / 32];
   ThreadBytes tb;
-  load_thread_bytes(in, N, (uint64_t)blockIdx.x * K1_TILE, tb);
+  const uint64_t tile = tile0 + blockIdx.x;
+  load_thread_bytes(in, N, tile * K1_TILE, tb);
   long long lh = thread_last_head(tb);
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) lh = max(lh, __shfl_xor_sync(0xffffffffu, lh, d));
@@ -109,7 +110,7 @@ __global__ void __launch_bounds__(K1_NT) k1_tile_heads(const uint8_t* __restrict
   if (threadIdx.x == 0) {
     long long m = -1;
     for (int w = 0; w < K1_NT / 32; ++w) m = max(m, ws[w]);
-    tile_last_head[blockIdx.x] = m;
+    tile_last_head[tile] = m;
   }
 }
 
@@ -182,7 +183,7 @@ __device__ __forceinline__ uint32_t tile_eval_cta(const uint8_t* __restrict__ in
 }
 
 // ---- kernel C: emitted bytes per tile ----
-__global__ void __launch_bounds__(K1_NT) k1_tile_counts(const uint8_t* __restrict__ in, uint64_t N,
+__global__ void __launch_bounds__(K1_NT) k1_tile_counts(const uint8_t* __restrict__ in, uint64_t N, uint64_t tile0,
                                                         const long long* __restrict__ tile_carry,
                                                         uint32_t* __restrict__ tile_cnt) {
   __shared__ long long ws64[K1_NT / 32];
@@ -190,8 +191,9 @@ __global__ void __launch_bounds__(K1_NT) k1_tile_counts(const uint8_t* __restric
   ThreadBytes tb;
   ThreadEval ev;
   uint32_t total;
-  tile_eval_cta(in, N, blockIdx.x, tile_carry[blockIdx.x], tb, ev, nullptr, ws64, ws32, &total);
-  if (threadIdx.x == 0) tile_cnt[blockIdx.x] = total;
+  const uint64_t tile = tile0 + blockIdx.x;
+  tile_eval_cta(in, N, tile, tile_carry[tile], tb, ev, nullptr, ws64, ws32, &total);
+  if (threadIdx.x == 0) tile_cnt[tile] = total;
 }
 
 // ---- kernel F: scatter the RLE1 byte stream ----
@@ -449,16 +451,24 @@ __global__ void __launch_bounds__(256) k1_inuse(const uint8_t* __restrict__ txt,
 // =========================== host launchers ===========================
 uint64_t k1_num_tiles(uint64_t N) { return (N + K1_TILE - 1) / K1_TILE; }
 
-void launch_k1_plan(Launcher& L, const uint8_t* d_in, uint64_t N, long long* d_tile_head, long long* d_tile_carry,
-                    uint32_t* d_tile_cnt, uint64_t* d_tile_E) {
+// K1 in four steps so that a sharded caller can compute the per-tile summaries of its own tile range and exchange
+// them between ranks: heads [t0,t1) -> (exchange) -> carry scan + counts [t0,t1) -> (exchange) -> prefix sum.
+uint32_t k1_tile_bytes() { return K1_TILE; }
+void launch_k1_heads(Launcher& L, const uint8_t* d_in, uint64_t N, uint64_t t0, uint64_t t1, long long* d_tile_head) {
+  if (t1 > t0)
+    L.launch("k1_tile_heads", k1_tile_heads, dim3((unsigned)(t1 - t0)), dim3(K1_NT), d_in, N, t0, d_tile_head);
+}
+void launch_k1_counts(Launcher& L, const uint8_t* d_in, uint64_t N, uint64_t t0, uint64_t t1,
+                      const long long* d_tile_head, long long* d_tile_carry, uint32_t* d_tile_cnt) {
   uint64_t nt = k1_num_tiles(N);
-  L.launch("k1_tile_heads", k1_tile_heads, dim3((unsigned)nt), dim3(K1_NT), d_in, N, d_tile_head);
-  L.launch("k_scan_max64_excl", k_scan_max64_excl, dim3(1), dim3(SC_NT), (const long long*)d_tile_head,
-           d_tile_carry, nt);
-  L.launch("k1_tile_counts", k1_tile_counts, dim3((unsigned)nt), dim3(K1_NT), d_in, N,
-           (const long long*)d_tile_carry, d_tile_cnt);
-  L.launch("k_scan_add64_excl", k_scan_add64_excl, dim3(1), dim3(SC_NT), (const uint32_t*)d_tile_cnt,
-           d_tile_E, nt);
+  L.launch("k_scan_max64_excl", k_scan_max64_excl, dim3(1), dim3(SC_NT), d_tile_head, d_tile_carry, nt);
+  if (t1 > t0)
+    L.launch("k1_tile_counts", k1_tile_counts, dim3((unsigned)(t1 - t0)), dim3(K1_NT), d_in, N, t0,
+             (const long long*)d_tile_carry, d_tile_cnt);
+}
+void launch_k1_prefix(Launcher& L, uint64_t N, const uint32_t* d_tile_cnt, uint64_t* d_tile_E) {
+  uint64_t nt = k1_num_tiles(N);
+  L.launch("k_scan_add64_excl", k_scan_add64_excl, dim3(1), dim3(SC_NT), d_tile_cnt, d_tile_E, nt);
 }
 
 uint32_t k1_cut_window() { return CW_W; }

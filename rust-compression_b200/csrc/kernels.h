@@ -66,8 +66,11 @@ struct Launcher {
 // ---- k1_rle.cu ----
 uint64_t k1_num_tiles(uint64_t N);
 uint32_t k1_cut_window();
-void launch_k1_plan(Launcher& L, const uint8_t* d_in, uint64_t N, long long* d_tile_head, long long* d_tile_carry,
-                    uint32_t* d_tile_cnt, uint64_t* d_tile_E);
+uint32_t k1_tile_bytes();
+void launch_k1_heads(Launcher& L, const uint8_t* d_in, uint64_t N, uint64_t t0, uint64_t t1, long long* d_tile_head);
+void launch_k1_counts(Launcher& L, const uint8_t* d_in, uint64_t N, uint64_t t0, uint64_t t1,
+                      const long long* d_tile_head, long long* d_tile_carry, uint32_t* d_tile_cnt);
+void launch_k1_prefix(Launcher& L, uint64_t N, const uint32_t* d_tile_cnt, uint64_t* d_tile_E);
 void launch_k1_cut_phase(Launcher& L, const uint8_t* d_in, uint64_t N, uint32_t T, const long long* d_tile_carry,
                          const uint64_t* d_tile_E, uint32_t K, uint64_t* d_F, uint64_t* d_state, uint64_t* d_in_off,
                          uint64_t* d_rle_off, uint32_t max_blocks, uint32_t* d_nblocks, uint32_t* d_maxlen);

@@ -111,6 +111,7 @@ struct bzb200_ctx {
   uint32_t nblocks = 0;
   uint32_t max_block_len = 0;
   bool planned = false;
+  bool plan_open = false;  // between plan_begin and plan_finish
   DevBuf tile_head, tile_carry, tile_cnt, tile_E, in_off, rle_off, txt, crc, inuse, scal, cut_state, cut_F;
   uint32_t prep_lo = 0, prep_hi = 0;  // blocks whose RLE1 bytes, CRC and in-use map are on the device
   bool crc_all = false;
@@ -192,6 +193,8 @@ T* ptr(DevBuf& b) {
     int r__ = (x);            \
     if (r__ != BZB200_OK) return r__; \
   } while (0)
+
+int level_of(const bzb200_ctx* c) { return c->level; }
 
 int set_device(bzb200_ctx* c) {
   CK(c, cudaSetDevice(c->device));
@@ -278,8 +281,10 @@ size_t bzb200_max_output_bytes(int level, size_t n) {
   return (bytes + 7) & ~(size_t)7;
 }
 
-// ------------------------------------------------------------------ plan (K1 + K5)
-int bzb200_plan(bzb200_ctx* c, int level, const uint8_t* d_in, size_t n, uint32_t* nblocks) {
+// ------------------------------------------------------------------ plan (K1: run pieces, emitted-length prefix, cuts)
+size_t bzb200_plan_tile_bytes(void) { return k1_tile_bytes(); }
+
+int bzb200_plan_begin(bzb200_ctx* c, int level, const uint8_t* d_in, size_t n, uint64_t* ntiles) {
   if (!c) return BZB200_E_ARG;
   if (level < 1 || level > 9) {
     c->err = "invalid level";
@@ -288,6 +293,7 @@ int bzb200_plan(bzb200_ctx* c, int level, const uint8_t* d_in, size_t n, uint32_
   if (!d_in && n) return BZB200_E_ARG;
   TRY(set_device(c));
   c->planned = false;
+  c->plan_open = false;
   c->level = level;
   c->T = (uint32_t)level * 100000u - 19u;  // encoder.rs:186
   c->d_in = d_in;
@@ -298,12 +304,12 @@ int bzb200_plan(bzb200_ctx* c, int level, const uint8_t* d_in, size_t n, uint32_
   c->h_rle_off.assign(1, 0);
   c->h_crc.clear();
   c->batch_nb = 0;
-  if (n == 0) {
-    c->planned = true;
-    if (nblocks) *nblocks = 0;
-    return BZB200_OK;
-  }
-  const uint64_t nt = k1_num_tiles(n);
+  c->prep_lo = c->prep_hi = 0;
+  c->crc_all = false;
+  const uint64_t nt = n ? k1_num_tiles(n) : 0;
+  if (ntiles) *ntiles = nt;
+  c->plan_open = true;
+  if (n == 0) return BZB200_OK;
   const uint64_t emax = (uint64_t)n + n / 4 + 64;
   const uint64_t max_blocks64 = emax / c->T + 2;
   if (max_blocks64 > 0x7FFFFFF0ull) return BZB200_E_ARG;
@@ -316,8 +322,44 @@ int bzb200_plan(bzb200_ctx* c, int level, const uint8_t* d_in, size_t n, uint32_
   TRY(ensure(c, c->rle_off, ((size_t)max_blocks + 1) * 8));
   TRY(ensure(c, c->scal, 64));
   TRY(ensure(c, c->txt, emax));
-  launch_k1_plan(c->L, d_in, n, ptr<long long>(c->tile_head), ptr<long long>(c->tile_carry),
-                 ptr<uint32_t>(c->tile_cnt), ptr<uint64_t>(c->tile_E));
+  return BZB200_OK;
+}
+
+int bzb200_plan_heads(bzb200_ctx* c, uint64_t t0, uint64_t t1, int64_t* d_tile_head) {
+  if (!c || !c->plan_open) return BZB200_E_STATE;
+  const uint64_t nt = c->n_in ? k1_num_tiles(c->n_in) : 0;
+  if (t0 > t1 || t1 > nt || (!d_tile_head && nt)) return BZB200_E_ARG;
+  TRY(set_device(c));
+  launch_k1_heads(c->L, c->d_in, c->n_in, t0, t1, reinterpret_cast<long long*>(d_tile_head));
+  return check_launch(c);
+}
+
+int bzb200_plan_counts(bzb200_ctx* c, const int64_t* d_tile_head, uint64_t t0, uint64_t t1, uint32_t* d_tile_cnt) {
+  if (!c || !c->plan_open) return BZB200_E_STATE;
+  const uint64_t nt = c->n_in ? k1_num_tiles(c->n_in) : 0;
+  if (t0 > t1 || t1 > nt || ((!d_tile_head || !d_tile_cnt) && nt)) return BZB200_E_ARG;
+  if (nt == 0) return BZB200_OK;
+  TRY(set_device(c));
+  launch_k1_counts(c->L, c->d_in, c->n_in, t0, t1, reinterpret_cast<const long long*>(d_tile_head),
+                   ptr<long long>(c->tile_carry), d_tile_cnt);
+  return check_launch(c);
+}
+
+int bzb200_plan_finish(bzb200_ctx* c, const uint32_t* d_tile_cnt, uint32_t* nblocks) {
+  if (!c || !c->plan_open) return BZB200_E_STATE;
+  c->plan_open = false;
+  const size_t n = c->n_in;
+  if (n == 0) {
+    c->planned = true;
+    if (nblocks) *nblocks = 0;
+    return BZB200_OK;
+  }
+  if (!d_tile_cnt) return BZB200_E_ARG;
+  TRY(set_device(c));
+  const uint8_t* d_in = c->d_in;
+  const uint64_t emax = (uint64_t)n + n / 4 + 64;
+  const uint32_t max_blocks = (uint32_t)(emax / c->T + 2);
+  launch_k1_prefix(c->L, n, d_tile_cnt, ptr<uint64_t>(c->tile_E));
   // cut chain: phases of (windows, walk) until the walk reports done (one phase unless the drift leaves a window)
   TRY(ensure(c, c->cut_state, 64));
   CK(c, cudaMemsetAsync(c->cut_state.p, 0, 64, c->stream));
@@ -346,20 +388,28 @@ int bzb200_plan(bzb200_ctx* c, int level, const uint8_t* d_in, size_t n, uint32_
   c->h_in_off.resize((size_t)nb + 1);
   c->h_rle_off.resize((size_t)nb + 1);
   c->h_crc.assign(nb, 0);
-  c->prep_lo = c->prep_hi = 0;
-  c->crc_all = false;
   TRY(ensure(c, c->crc, (size_t)nb * 4));
   TRY(ensure(c, c->inuse, (size_t)nb * 32));
   CK(c, cudaMemcpyAsync(c->h_in_off.data(), c->in_off.p, ((size_t)nb + 1) * 8, cudaMemcpyDeviceToHost, c->stream));
   CK(c, cudaMemcpyAsync(c->h_rle_off.data(), c->rle_off.p, ((size_t)nb + 1) * 8, cudaMemcpyDeviceToHost, c->stream));
   CK(c, cudaStreamSynchronize(c->stream));
-  if (c->max_block_len > (uint32_t)level * 100000u || c->max_block_len > MAX_BLOCK) {
+  if (c->max_block_len > (uint32_t)level_of(c) * 100000u || c->max_block_len > MAX_BLOCK) {
     c->err = "block longer than level*100000";
     return BZB200_E_INTERNAL;
   }
   c->planned = true;
   if (nblocks) *nblocks = nb;
   return BZB200_OK;
+}
+
+int bzb200_plan(bzb200_ctx* c, int level, const uint8_t* d_in, size_t n, uint32_t* nblocks) {
+  uint64_t nt = 0;
+  TRY(bzb200_plan_begin(c, level, d_in, n, &nt));
+  if (nt) {
+    TRY(bzb200_plan_heads(c, 0, nt, ptr<int64_t>(c->tile_head)));
+    TRY(bzb200_plan_counts(c, ptr<int64_t>(c->tile_head), 0, nt, ptr<uint32_t>(c->tile_cnt)));
+  }
+  return bzb200_plan_finish(c, ptr<uint32_t>(c->tile_cnt), nblocks);
 }
 
 uint32_t bzb200_num_blocks(const bzb200_ctx* c) { return (c && c->planned) ? c->nblocks : 0; }

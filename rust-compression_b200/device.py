@@ -82,6 +82,32 @@ class Context:
         self.nblocks = nb.value
         return nb.value
 
+    # ---- the plan in four steps (sharded.py: per-tile summaries are computed per rank and all-gathered)
+    def plan_begin(self, level, d_in):
+        self._u8(d_in)
+        nt = C.c_uint64(0)
+        self._check(_lib.lib().bzb200_plan_begin(self._h, level, C.c_void_p(d_in.data_ptr()), d_in.numel(), C.byref(nt)),
+                    "bzb200_plan_begin")
+        self._keep_in = d_in
+        self.level = level
+        return int(nt.value)
+
+    def plan_heads(self, t0, t1, t_head):
+        assert t_head.is_cuda and t_head.dtype == torch.int64 and t_head.is_contiguous()
+        self._check(_lib.lib().bzb200_plan_heads(self._h, t0, t1, C.c_void_p(t_head.data_ptr())), "bzb200_plan_heads")
+
+    def plan_counts(self, t_head, t0, t1, t_cnt):
+        assert t_cnt.is_cuda and t_cnt.dtype == torch.int32 and t_cnt.is_contiguous()
+        self._check(_lib.lib().bzb200_plan_counts(self._h, C.c_void_p(t_head.data_ptr()), t0, t1,
+                                                  C.c_void_p(t_cnt.data_ptr())), "bzb200_plan_counts")
+
+    def plan_finish(self, t_cnt):
+        nb = C.c_uint32(0)
+        self._check(_lib.lib().bzb200_plan_finish(self._h, C.c_void_p(t_cnt.data_ptr()), C.byref(nb)),
+                    "bzb200_plan_finish")
+        self.nblocks = nb.value
+        return nb.value
+
     def block_table(self, with_crc=True):
         """(in_off, rle_off, crc) of the planned blocks.  CRCs are computed for the blocks this context encodes;
         with_crc=True asks for all of them (the missing ones are computed on demand), with_crc=False returns the

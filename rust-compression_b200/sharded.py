@@ -1,9 +1,13 @@
 """Block-wise sharding of one .bz2 stream across the GPUs of a box (one process per GPU, torch.distributed).
 
-bzip2 blocks are independent once the RLE1 cut points are known, so the path partitions: every rank runs the cheap
-K1/K5 plan over the whole input (replicated; ~1 ms/GiB), compresses only its contiguous range of blocks
-(K2-K6), and the compressed bit strings are gathered to rank 0 over NCCL (NVLink P2P send/recv) where K7 joins them
-at bit granularity and the stream trailer is appended.  No collective touches the data path of a block.
+bzip2 blocks are independent once the RLE1 cut points are known, so the path partitions:
+  1. plan: every rank evaluates K1's per-tile summaries (last run head, emitted bytes; 12 bytes per 4 KiB tile) for
+     its 1/W of the tiles; two small all-gathers make them complete everywhere and every rank runs the cheap global
+     part (prefix sum + cut chain), so all ranks hold the same block table;
+  2. every rank compresses only its contiguous range of blocks (RLE1 scatter, CRC, K2-K6 for those blocks);
+  3. the block CRCs (all-gather) and the compressed bit strings (NCCL P2P send/recv over NVLink) go to rank 0, where
+     K7 joins them at bit granularity and the stream trailer with the folded CRC is appended.
+No collective touches the data path of a block.
 """
 import numpy as np
 import torch
@@ -19,6 +23,25 @@ def block_range(nblocks, rank, world):
     return lo, hi
 
 
+def plan_sharded(ctx, level, d_in, rank, world, group=None):
+    """The K1 plan with the per-tile work split over the ranks (see the module docstring). Returns nblocks."""
+    if world == 1 or not hasattr(ctx, "plan_begin"):
+        return ctx.plan(level, d_in)
+    dev = d_in.device
+    nt = ctx.plan_begin(level, d_in)
+    per = max(1, (nt + world - 1) // world)
+    t0, t1 = min(nt, rank * per), min(nt, (rank + 1) * per)
+    t_head = torch.full((world * per,), -1, dtype=torch.int64, device=dev)
+    ctx.plan_heads(t0, t1, t_head)
+    mine = t_head[rank * per:(rank + 1) * per].clone()
+    dist.all_gather_into_tensor(t_head, mine, group=group)
+    t_cnt = torch.zeros(world * per, dtype=torch.int32, device=dev)
+    ctx.plan_counts(t_head, t0, t1, t_cnt)
+    mine = t_cnt[rank * per:(rank + 1) * per].clone()
+    dist.all_gather_into_tensor(t_cnt, mine, group=group)
+    return ctx.plan_finish(t_cnt)
+
+
 def compress_sharded(ctx, level, d_in, group=None, gather=True):
     """Returns (d_stream or None, info). On rank 0 d_stream holds the complete .bz2 stream (device uint8 tensor).
 
@@ -27,7 +50,7 @@ def compress_sharded(ctx, level, d_in, group=None, gather=True):
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     dev = d_in.device
-    nb = ctx.plan(level, d_in)
+    nb = plan_sharded(ctx, level, d_in, rank, world, group)
     in_off, rle_off, _ = ctx.block_table(with_crc=False)
     b0, b1 = block_range(nb, rank, world)
     my_in = int(in_off[b1] - in_off[b0]) if nb else 0

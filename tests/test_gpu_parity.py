@@ -173,6 +173,38 @@ def test_doubling_rounds_group_sizes():
     parity.assert_parity(d3, 9)
 
 
+def test_plan_in_steps_equals_plan():
+    """bzb200_plan_begin/heads/counts/finish over two tile ranges (what sharded.py does per rank) == bzb200_plan."""
+    import torch
+    from rust_compression_b200 import device as dv
+    data = gen.g2(5, 3_000_000) + gen.text(8, 700_000)
+    d_in = torch.frombuffer(bytearray(data), dtype=torch.uint8).cuda()
+    a = dv.Context()
+    nb = a.plan(1, d_in)
+    want = a.block_table(with_crc=False)
+    b = dv.Context()
+    nt = b.plan_begin(1, d_in)
+    half = nt // 3
+    t_head = torch.full((nt,), -1, dtype=torch.int64, device="cuda")
+    t_cnt = torch.zeros(nt, dtype=torch.int32, device="cuda")
+    b.plan_heads(half, nt, t_head)
+    b.plan_heads(0, half, t_head)
+    b.plan_counts(t_head, 0, half, t_cnt)
+    b.plan_counts(t_head, half, nt, t_cnt)
+    assert b.plan_finish(t_cnt) == nb
+    got = b.block_table(with_crc=False)
+    assert (got[0] == want[0]).all() and (got[1] == want[1]).all()
+    # and the blocks encode identically from either plan
+    cap = dv.max_output_bytes(1, len(data))
+    o1 = torch.zeros(cap, dtype=torch.uint8, device="cuda")
+    o2 = torch.zeros(cap, dtype=torch.uint8, device="cuda")
+    e1 = a.encode_blocks(0, nb, o1, 0)
+    e2 = b.encode_blocks(0, nb, o2, 0)
+    assert e1 == e2 and torch.equal(o1, o2)
+    a.close()
+    b.close()
+
+
 def test_multi_batch_equals_single_batch(monkeypatch):
     d = gen.mixed(5, 1200000)
     monkeypatch.setenv("BZB200_BATCH_ELEMS", "250000")

@@ -29,6 +29,23 @@ class OracleBackedContext:
         self.encoded = (0, 0)
         return self.nblocks
 
+    # the plan in four steps: the stand-in checks that sharded.py hands every rank the COMPLETE tile arrays
+    def plan_begin(self, level, d_in):
+        self._level, self._d_in = level, d_in
+        self.nt = (d_in.numel() + 4095) // 4096
+        return self.nt
+
+    def plan_heads(self, t0, t1, t_head):
+        t_head[t0:t1] = torch.arange(t0, t1, dtype=torch.int64) * 3 + 1
+
+    def plan_counts(self, t_head, t0, t1, t_cnt):
+        assert torch.equal(t_head[:self.nt], torch.arange(self.nt, dtype=torch.int64) * 3 + 1), "tile heads incomplete"
+        t_cnt[t0:t1] = torch.arange(t0, t1, dtype=torch.int32) + 7
+
+    def plan_finish(self, t_cnt):
+        assert torch.equal(t_cnt[:self.nt], torch.arange(self.nt, dtype=torch.int32) + 7), "tile counts incomplete"
+        return self.plan(self._level, self._d_in)
+
     def block_table(self, with_crc=True):
         """Like device.Context.block_table: with_crc=False returns CRCs only for the blocks this rank encoded
         (zeros elsewhere), so the test exercises the CRC exchange between ranks."""
