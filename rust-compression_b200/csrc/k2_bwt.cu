@@ -20,6 +20,8 @@
 //   k2_round_finalize  per-block state machine: done / periodic fix-up pending / active
 // Fix-up   : a round that splits nothing means the block is periodic and the groups are the sets of equal
 //            rotations; one more round with key = n-1-((pos-shift) mod n) applies the reference's tie-break.
+#include <stdlib.h>
+
 #include <algorithm>
 
 #include "common.cuh"
@@ -195,20 +197,17 @@ __global__ void __launch_bounds__(RS_NT) k2_rs_scatter(const uint64_t* __restric
 // those tiles, and scatters through shared memory.  Tiles of a block are numbered by a ticket, so a tile only ever
 // waits for tiles that are already running.  The grid is (block, tile): CTAs in flight belong to different blocks,
 // which keeps the look-back chains short.
-constexpr int OS_NT = 512;
-constexpr int OS_IPT = 8;
-constexpr int OS_TILE = OS_NT * OS_IPT;   // 4096
-constexpr int OS_WARPS = OS_NT / 32;      // 16
-constexpr int OS_WCH = OS_TILE / OS_WARPS;  // 256 elements per warp
-static_assert(OS_TILE == RS_TILE, "hist/status arrays are sized by RS_TILE tiles");
 constexpr uint32_t ST_AGG = 1u << 20, ST_PREFIX = 2u << 20, ST_VAL = 0xFFFFFu;
 
-struct OsSmem {
-  uint64_t stage[OS_TILE];
-  uint32_t wcnt[OS_WARPS][256];
+template <int NT, int IPT>
+struct OsSmemT {
+  static constexpr int TILE = NT * IPT;
+  static constexpr int WARPS = NT / 32;
+  uint64_t stage[TILE];
+  uint32_t wcnt[WARPS][256];
   uint32_t dstart[256];
   int goff[256];
-  uint32_t ws[OS_NT / 32 + 1];
+  uint32_t ws[NT / 32 + 1];
   uint32_t tile;
 };
 
@@ -283,7 +282,8 @@ __device__ __forceinline__ void st_status(uint32_t* p, uint32_t v) {
   asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-__global__ void __launch_bounds__(OS_NT, 2) k2_os_scatter(const uint64_t* __restrict__ src, uint64_t* __restrict__ dst,
+template <int OS_NT, int OS_IPT, int OS_MINB>
+__global__ void __launch_bounds__(OS_NT, OS_MINB) k2_os_scatter(const uint64_t* __restrict__ src, uint64_t* __restrict__ dst,
                                                           const BlockDesc* __restrict__ desc,
                                                           const uint32_t* __restrict__ cnt,
                                                           const uint32_t* __restrict__ bucket_off,
@@ -291,6 +291,8 @@ __global__ void __launch_bounds__(OS_NT, 2) k2_os_scatter(const uint64_t* __rest
                                                           uint32_t ticket_base, uint32_t tiles_cap, uint32_t epoch,
                                                           int pass) {
   extern __shared__ __align__(16) uint8_t os_raw[];
+  using OsSmem = OsSmemT<OS_NT, OS_IPT>;
+  constexpr int OS_TILE = OS_NT * OS_IPT, OS_WARPS = OS_NT / 32, OS_WCH = OS_TILE / OS_WARPS;
   OsSmem& sm = *reinterpret_cast<OsSmem*>(os_raw);
   const uint32_t b = blockIdx.x;
   const uint32_t c = cnt[b];
@@ -316,17 +318,27 @@ __global__ void __launch_bounds__(OS_NT, 2) k2_os_scatter(const uint64_t* __rest
     const uint32_t li = w * OS_WCH + it * 32 + lane;
     e[it] = li < tcount ? s[li] : ~0ull;
   }
+  // three separate sweeps so that the eight matches, the eight leader atomics and the eight broadcasts of a thread
+  // are independent instructions the scheduler can overlap
+  uint32_t peers[OS_IPT];
 #pragma unroll
   for (int it = 0; it < OS_IPT; ++it) {
     const uint32_t li = w * OS_WCH + it * 32 + lane;
-    const bool valid = li < tcount;
-    const uint32_t dgt = valid ? (uint32_t)(e[it] >> shift) & 255u : 0xFFFFu;
-    const uint32_t peers = __match_any_sync(0xffffffffu, dgt);
-    const int leader = __ffs(peers) - 1;
-    uint32_t old = 0;
-    if (valid && (int)lane == leader) old = atomicAdd(&sm.wcnt[w][dgt], (uint32_t)__popc(peers));
-    old = __shfl_sync(0xffffffffu, old, leader);
-    rk[it] = old + __popc(peers & lanemask_lt());
+    const uint32_t dgt = li < tcount ? (uint32_t)(e[it] >> shift) & 255u : 0xFFFFu;
+    peers[it] = __match_any_sync(0xffffffffu, dgt);
+  }
+#pragma unroll
+  for (int it = 0; it < OS_IPT; ++it) {
+    const uint32_t li = w * OS_WCH + it * 32 + lane;
+    const uint32_t dgt = (uint32_t)(e[it] >> shift) & 255u;
+    rk[it] = 0;
+    if (li < tcount && (peers[it] & lanemask_lt()) == 0)  // lowest lane of the peer group
+      rk[it] = atomicAdd(&sm.wcnt[w][dgt], (uint32_t)__popc(peers[it]));
+  }
+#pragma unroll
+  for (int it = 0; it < OS_IPT; ++it) {
+    const int leader = __ffs(peers[it]) - 1;
+    rk[it] = __shfl_sync(0xffffffffu, rk[it], leader) + __popc(peers[it] & lanemask_lt());
   }
   __syncthreads();
 
@@ -807,7 +819,7 @@ __global__ void __launch_bounds__(G_NT) k2_gather(const BlockDesc* __restrict__ 
 // entries, dense (resolved slots are not in the lists).  Elements live in registers; shared memory holds, per
 // window index, the composite (group start << 20 | key) of the element currently placed there.
 //   * split levels: a group larger than ENUM_MAX whose keys are not all equal is partitioned into key-range
-//     buckets (range [min,max] of its keys, ~2-4 entries per bucket, counting pass with shared-memory atomics);
+//     buckets (range [min,max] of its keys, ~1-2 entries per bucket, counting pass with shared-memory atomics);
 //     the buckets are groups of their own from then on; repeated until every group is small or flat (all keys
 //     equal — nothing to sort, which is what heavy duplicates end as);
 //   * enumeration: final index of an element = group start + #{smaller keys} + #{equal keys placed earlier};
@@ -916,7 +928,7 @@ __global__ void __launch_bounds__(LS_NT, 2) k2_local_sort(const BlockDesc* __res
           gp[k] &= 0x7FFFFFFFu;
           if (((gp[k] >> 12) & 0xFFFu) == gs) sm.gsz[gs] = size | GS_FLAT;
         } else {
-          const int lnb = 31 - __clz(size >> 1);       // buckets = largest power of two <= size/2
+          const int lnb = 31 - __clz(size);            // buckets = largest power of two <= size
           const int rb = 32 - __clz(mx - mn);           // bits of the key range
           const int sh = max(rb - lnb, 0);
           const uint32_t bs = gs + ((kv[k] - mn) >> sh);
@@ -1071,10 +1083,27 @@ struct OsState {
 
 static void radix_sort40(Launcher& L, uint64_t*& src, uint64_t*& dst, const uint8_t* d_txt, const BlockDesc* d_desc,
                          uint32_t nb, uint32_t maxcnt, BwtScratch& S, OsState& os) {
-  const uint32_t tiles = (maxcnt + OS_TILE - 1) / OS_TILE;
+  // tile geometry of the pass kernel (BZB200_OS_VARIANT picks another one for experiments)
+  static int variant = -1;
+  if (variant < 0) {
+    const char* v = getenv("BZB200_OS_VARIANT");
+    variant = v ? atoi(v) : 0;
+    cudaFuncSetAttribute((const void*)k2_os_scatter<512, 8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)sizeof(OsSmemT<512, 8>));
+    cudaFuncSetAttribute((const void*)k2_os_scatter<256, 16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)sizeof(OsSmemT<256, 16>));
+    cudaFuncSetAttribute((const void*)k2_os_scatter<1024, 8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)sizeof(OsSmemT<1024, 8>));
+    cudaFuncSetAttribute((const void*)k2_os_scatter<512, 16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)sizeof(OsSmemT<512, 16>));
+    cudaFuncSetAttribute((const void*)k2_os_scatter<384, 12, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)sizeof(OsSmemT<384, 12>));
+  }
+  const uint32_t tile_elems = variant == 2 || variant == 3 ? 8192u : variant == 4 ? 4608u : 4096u;
+  const uint32_t tiles = (maxcnt + tile_elems - 1) / tile_elems;
   if (tiles == 0) return;
   cudaMemsetAsync(S.oshist, 0, (size_t)nb * 5 * 256 * sizeof(uint32_t), L.stream);
-  const uint32_t chunk = 16 * OS_TILE;
+  const uint32_t chunk = 16 * 4096;
   const uint32_t chunks = (maxcnt + chunk - 1) / chunk;
   if (d_txt)
     L.launch("k2_os_hist_txt", k2_os_hist_txt, dim3(chunks, nb), dim3(256), d_txt, d_desc, S.oshist, chunk);
@@ -1087,8 +1116,17 @@ static void radix_sort40(Launcher& L, uint64_t*& src, uint64_t*& dst, const uint
       os.epoch = 0;
     }
     ++os.epoch;
-    L.launch_smem("k2_rs_scatter", k2_os_scatter, dim3(nb, tiles), dim3(OS_NT), sizeof(OsSmem), src, dst, d_desc, S.cnt,
-                  S.oshist, S.hist, S.ticket, os.ticket_base, S.tiles_cap, os.epoch, p);
+#define OS_LAUNCH(NT, IPT, MB)                                                                                     \
+  L.launch_smem("k2_rs_scatter", k2_os_scatter<NT, IPT, MB>, dim3(nb, tiles), dim3(NT), sizeof(OsSmemT<NT, IPT>), src, \
+                dst, d_desc, S.cnt, S.oshist, S.hist, S.ticket, os.ticket_base, S.tiles_cap, os.epoch, p)
+    switch (variant) {
+      case 1: OS_LAUNCH(256, 16, 2); break;
+      case 2: OS_LAUNCH(1024, 8, 1); break;
+      case 3: OS_LAUNCH(512, 16, 1); break;
+      case 4: OS_LAUNCH(384, 12, 2); break;
+      default: OS_LAUNCH(512, 8, 2); break;
+    }
+#undef OS_LAUNCH
     os.ticket_base += tiles;
     uint64_t* t = src; src = dst; dst = t;
   }
@@ -1118,7 +1156,6 @@ int run_bwt(Launcher& L, const uint8_t* d_txt, const BlockDesc* d_desc, uint32_t
   static bool attr_set = false;
   if (!attr_set) {
     cudaFuncSetAttribute((const void*)k2_local_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LsSmem));
-    cudaFuncSetAttribute((const void*)k2_os_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(OsSmem));
     attr_set = true;
   }
   uint32_t rounds = 0, passes = 0;
