@@ -35,9 +35,29 @@ __device__ __forceinline__ void load_thread_bytes(const uint8_t* __restrict__ in
   int cnt = (int)min((uint64_t)K1_BPT, N - i0);
   tb.cnt = cnt;
   const uint8_t* p = in + i0;
-  if (cnt == K1_BPT && ((reinterpret_cast<uintptr_t>(p) & 15) == 0)) {
+  const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(p) & 15);
+  if (cnt == K1_BPT && mis == 0) {
     uint4 v = __ldg(reinterpret_cast<const uint4*>(p));
     uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int j = 0; j < K1_BPT; ++j) tb.b[j] = (uint8_t)(w[j >> 2] >> ((j & 3) * 8));
+  } else if (cnt == K1_BPT && i0 + 2 * K1_BPT <= N) {
+    // unaligned input (a plan over a sub-range of a buffer): two aligned 128-bit loads + funnel shifts; the second
+    // load stays inside the input because at least 16 more bytes follow
+    const uint4* q = reinterpret_cast<const uint4*>(p - mis);
+    const uint4 v0 = __ldg(q), v1 = __ldg(q + 1);
+    const uint32_t bs = (mis & 3) * 8;
+    uint32_t w[4];
+    switch (mis >> 2) {  // the same for every thread of the grid
+      case 0: w[0] = __funnelshift_r(v0.x, v0.y, bs); w[1] = __funnelshift_r(v0.y, v0.z, bs);
+              w[2] = __funnelshift_r(v0.z, v0.w, bs); w[3] = __funnelshift_r(v0.w, v1.x, bs); break;
+      case 1: w[0] = __funnelshift_r(v0.y, v0.z, bs); w[1] = __funnelshift_r(v0.z, v0.w, bs);
+              w[2] = __funnelshift_r(v0.w, v1.x, bs); w[3] = __funnelshift_r(v1.x, v1.y, bs); break;
+      case 2: w[0] = __funnelshift_r(v0.z, v0.w, bs); w[1] = __funnelshift_r(v0.w, v1.x, bs);
+              w[2] = __funnelshift_r(v1.x, v1.y, bs); w[3] = __funnelshift_r(v1.y, v1.z, bs); break;
+      default: w[0] = __funnelshift_r(v0.w, v1.x, bs); w[1] = __funnelshift_r(v1.x, v1.y, bs);
+               w[2] = __funnelshift_r(v1.y, v1.z, bs); w[3] = __funnelshift_r(v1.z, v1.w, bs); break;
+    }
 #pragma unroll
     for (int j = 0; j < K1_BPT; ++j) tb.b[j] = (uint8_t)(w[j >> 2] >> ((j & 3) * 8));
   } else {

@@ -296,17 +296,21 @@ __global__ void __launch_bounds__(HB_NT) k4_build_tables(uint32_t nb, uint32_t* 
   }
 }
 
-// Length-limited fallback for the queued tables; slot s works on items s, s+nslots, ...
+// Length-limited fallback for the queued tables: CTA s works on items s, s+nslots, ...  The package-merge lists
+// (17 levels x <= 516 entries) live in shared memory — the algorithm is a serial chain of dependent reads, so it
+// runs at shared-memory latency on one thread; parallelism comes from the tables in flight.
 __global__ void __launch_bounds__(32) k4_lm_fallback(uint32_t nslots, uint32_t* __restrict__ rfreq,
                                                      uint8_t* __restrict__ lens, int slot_out,
                                                      uint32_t* __restrict__ meta, const uint32_t* __restrict__ lm_list,
                                                      const uint32_t* __restrict__ lm_count,
                                                      uint8_t* __restrict__ scratch) {
-  const uint32_t s = blockIdx.x * 32 + threadIdx.x;
-  if (s >= nslots) return;
+  extern __shared__ __align__(16) uint8_t lm_raw[];
+  (void)scratch;
+  if (threadIdx.x != 0) return;
+  const uint32_t s = blockIdx.x;
   const uint32_t cnt = *lm_count;
-  uint32_t* val = reinterpret_cast<uint32_t*>(scratch + (size_t)s * LM_BYTES);
-  uint16_t* ty = reinterpret_cast<uint16_t*>(scratch + (size_t)s * LM_BYTES + (size_t)LM_LEVELS * LM_ROW * 4);
+  uint32_t* val = reinterpret_cast<uint32_t*>(lm_raw);
+  uint16_t* ty = reinterpret_cast<uint16_t*>(lm_raw + (size_t)LM_LEVELS * LM_ROW * 4);
   for (uint32_t k = s; k < cnt; k += nslots) {
     const uint32_t id = lm_list[k];
     const uint32_t b = id / MAX_GROUPS;
@@ -467,6 +471,11 @@ void launch_huffman(Launcher& L, const uint16_t* d_sym, const BlockDesc* d_desc,
                     const uint32_t* d_freq, const uint32_t* d_inuse, uint32_t nb, uint32_t max_groups_per_block,
                     HuffBuffers& H) {
   uint32_t* lm_list = reinterpret_cast<uint32_t*>(H.lm_list);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute((const void*)k4_lm_fallback, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LM_BYTES);
+    attr_set = true;
+  }
   L.launch("k4_init", k4_init, dim3((nb + 63) / 64), dim3(64), nb, d_mtf_count, d_freq, d_inuse, H.lens, H.meta,
            H.rfreq);
   const dim3 cgrid((max_groups_per_block + CS_NT - 1) / CS_NT, nb);
@@ -477,8 +486,8 @@ void launch_huffman(Launcher& L, const uint16_t* d_sym, const BlockDesc* d_desc,
              (const uint8_t*)H.lens, it, (const uint32_t*)H.meta, H.sel, H.rfreq, H.gbits, 0);
     L.launch("k4_build_tables", k4_build_tables, dim3((ntab + HB_NT - 1) / HB_NT), dim3(HB_NT), nb, H.rfreq, H.lens,
              it + 1, H.meta, lm_list, H.lm_count);
-    L.launch("k4_lm_fallback", k4_lm_fallback, dim3((H.lm_slots + 31) / 32), dim3(32), H.lm_slots, H.rfreq, H.lens,
-             it + 1, H.meta, (const uint32_t*)lm_list, (const uint32_t*)H.lm_count, H.lm_scratch);
+    L.launch_smem("k4_lm_fallback", k4_lm_fallback, dim3(H.lm_slots), dim3(32), LM_BYTES, H.lm_slots, H.rfreq, H.lens,
+                  it + 1, H.meta, (const uint32_t*)lm_list, (const uint32_t*)H.lm_count, H.lm_scratch);
   }
   L.launch("k4_codes", k4_codes, dim3((ntab + 63) / 64), dim3(64), nb, (const uint8_t*)H.lens,
            (const uint32_t*)H.meta, H.codes);

@@ -94,56 +94,99 @@ __global__ void __launch_bounds__(BO_NT) k6_block_offsets(uint32_t nb, const uin
   }
 }
 
-// ---- block header: one thread per block ----
-__global__ void k6_pack_header(uint32_t nb, const uint32_t* __restrict__ meta, const uint32_t* __restrict__ inuse,
-                               const uint32_t* __restrict__ crc, const uint32_t* __restrict__ origptr,
-                               const uint8_t* __restrict__ selmtf, const uint8_t* __restrict__ lens_final_base,
-                               size_t lens_block_stride, size_t lens_final_off,
-                               const uint64_t* __restrict__ blockbit, uint32_t* __restrict__ out_words) {
-  const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= nb) return;
+// ---- block header: one CTA per block ----
+// Thread 0 writes the fixed part; the selector codes are cut into one chunk per thread (bit offsets by a CTA scan of
+// the code lengths); the coding tables are written by one thread each.  Every writer ORs into the stream with
+// atomics, so chunks may share boundary words.
+constexpr int PH_NT = 256;
+__global__ void __launch_bounds__(PH_NT) k6_pack_header(uint32_t nb, const uint32_t* __restrict__ meta,
+                                                        const uint32_t* __restrict__ inuse,
+                                                        const uint32_t* __restrict__ crc,
+                                                        const uint32_t* __restrict__ origptr,
+                                                        const uint8_t* __restrict__ selmtf,
+                                                        const uint8_t* __restrict__ lens_final_base,
+                                                        size_t lens_block_stride, size_t lens_final_off,
+                                                        const uint64_t* __restrict__ blockbit,
+                                                        uint32_t* __restrict__ out_words) {
+  __shared__ uint32_t ws[PH_NT / 32 + 1];
+  __shared__ uint32_t s_tab[MAX_GROUPS + 1];
+  const uint32_t b = blockIdx.x;
   const uint32_t* m = meta + (size_t)b * META;
   const int alpha = (int)m[0], ng = (int)m[1];
   const uint32_t nsel = m[2];
-  SeqBits<false> bw;
-  bw.init(out_words, blockbit[b]);
-  bw.put(0x314159u, 24);  // block magic 0x314159265359 (encoder.rs:254-259)
-  bw.put(0x265359u, 24);
-  bw.put(crc[b], 32);     // (:262)
-  bw.put(0, 1);           // randomised bit (:273)
-  bw.put(origptr[b], 24); // (:333)
-  // mapping table (:528-554; bitset.rs:186-199)
-  uint32_t used16 = 0;
+  const uint64_t base = blockbit[b];
+  uint32_t used16 = 0, nused = 0;
   for (int r = 0; r < 16; ++r) {
     uint32_t wv = inuse[b * 8 + (r >> 1)];
     uint32_t h = (r & 1) ? (wv >> 16) : (wv & 0xFFFFu);
     used16 = (used16 << 1) | (h ? 1u : 0u);
+    nused += h ? 1u : 0u;
   }
-  bw.put(used16, 16);
-  for (int r = 0; r < 16; ++r) {
-    uint32_t wv = inuse[b * 8 + (r >> 1)];
-    uint32_t h = (r & 1) ? (wv >> 16) : (wv & 0xFFFFu);
-    if (h) bw.put(__brev(h) >> 16, 16);  // symbol 16r+j is bit j of h; it is written j-th, i.e. MSB first
+  const uint32_t fixed_bits = 48 + 32 + 1 + 24 + 16 + 16 * nused + 3 + 15;
+  if (threadIdx.x == 0) {
+    SeqBits<false> bw;
+    bw.init(out_words, base);
+    bw.put(0x314159u, 24);  // block magic 0x314159265359 (encoder.rs:254-259)
+    bw.put(0x265359u, 24);
+    bw.put(crc[b], 32);     // (:262)
+    bw.put(0, 1);           // randomised bit (:273)
+    bw.put(origptr[b], 24); // (:333)
+    bw.put(used16, 16);     // mapping table (:528-554; bitset.rs:186-199)
+    for (int r = 0; r < 16; ++r) {
+      uint32_t wv = inuse[b * 8 + (r >> 1)];
+      uint32_t h = (r & 1) ? (wv >> 16) : (wv & 0xFFFFu);
+      if (h) bw.put(__brev(h) >> 16, 16);  // symbol 16r+j is bit j of h; it is written j-th, i.e. MSB first
+    }
+    bw.put((uint32_t)ng, 3);   // (:569)
+    bw.put(nsel, 15);          // (:570)
+    bw.finish();
   }
-  bw.put((uint32_t)ng, 3);   // (:569)
-  bw.put(nsel, 15);          // (:570)
+  // selector MTF values j as j ones and a zero (:572-574)
   const uint8_t* sm = selmtf + (size_t)b * MAX_SELECTORS;
-  for (uint32_t i = 0; i < nsel; ++i) {
-    uint32_t j = sm[i];
-    bw.put((1u << (j + 1)) - 2u, (int)j + 1);  // (:572-574)
+  const uint32_t per = (nsel + PH_NT - 1) / PH_NT;
+  const uint32_t lo = min(nsel, per * threadIdx.x), hi = min(nsel, lo + per);
+  uint32_t mybits = 0;
+  for (uint32_t i = lo; i < hi; ++i) mybits += (uint32_t)sm[i] + 1u;
+  uint32_t selbits;
+  const uint32_t ex = cta_excl_scan_add<PH_NT>(mybits, ws, &selbits);
+  if (hi > lo) {
+    SeqBits<false> bw;
+    bw.init(out_words, base + fixed_bits + ex);
+    for (uint32_t i = lo; i < hi; ++i) {
+      const uint32_t j = sm[i];
+      bw.put((1u << (j + 1)) - 2u, (int)j + 1);
+    }
+    bw.finish();
   }
-  for (int t = 0; t < ng; ++t) {  // (:585-601)
-    const uint8_t* l = lens_final_base + (size_t)b * lens_block_stride + lens_final_off + (size_t)t * MAX_ALPHA;
+  // coding tables (:585-601): 5-bit start length, then per symbol (10 | 11)* 0
+  if (threadIdx.x < (uint32_t)ng) {
+    const uint8_t* l = lens_final_base + (size_t)b * lens_block_stride + lens_final_off + (size_t)threadIdx.x * MAX_ALPHA;
+    uint32_t bits = 5;
+    int curr = l[0];
+    for (int sy = 0; sy < alpha; ++sy) {
+      const int d = (int)l[sy] - curr;
+      bits += 1 + 2 * (uint32_t)(d < 0 ? -d : d);
+      curr = l[sy];
+    }
+    s_tab[threadIdx.x] = bits;
+  }
+  __syncthreads();
+  if (threadIdx.x < (uint32_t)ng) {
+    uint32_t off = 0;
+    for (uint32_t t = 0; t < threadIdx.x; ++t) off += s_tab[t];
+    const uint8_t* l = lens_final_base + (size_t)b * lens_block_stride + lens_final_off + (size_t)threadIdx.x * MAX_ALPHA;
+    SeqBits<false> bw;
+    bw.init(out_words, base + fixed_bits + selbits + off);
     int curr = l[0];
     bw.put((uint32_t)curr, 5);
-    for (int s = 0; s < alpha; ++s) {
-      const int li = l[s];
+    for (int sy = 0; sy < alpha; ++sy) {
+      const int li = l[sy];
       while (curr < li) { bw.put(2, 2); ++curr; }
       while (curr > li) { bw.put(3, 2); --curr; }
       bw.put(0, 1);
     }
+    bw.finish();
   }
-  bw.finish();
 }
 
 // ---- block data: one thread per 50-symbol group ----
@@ -240,7 +283,7 @@ void launch_pack(Launcher& L, const uint16_t* d_sym, const BlockDesc* d_desc, co
   uint32_t* words = reinterpret_cast<uint32_t*>(d_out);
   const size_t lens_block_stride = (size_t)5 * MAX_GROUPS * MAX_ALPHA;
   const size_t lens_final_off = (size_t)4 * MAX_GROUPS * MAX_ALPHA;
-  L.launch("k6_pack_header", k6_pack_header, dim3((nb + 31) / 32), dim3(32), nb, (const uint32_t*)H.meta, d_inuse, d_crc,
+  L.launch("k6_pack_header", k6_pack_header, dim3(nb), dim3(PH_NT), nb, (const uint32_t*)H.meta, d_inuse, d_crc,
            d_origptr, (const uint8_t*)H.selmtf, (const uint8_t*)H.lens, lens_block_stride, lens_final_off,
            (const uint64_t*)d_blockbit, words);
   L.launch("k6_pack_symbols", k6_pack_symbols, dim3((max_groups_per_block + PS_NT - 1) / PS_NT, nb), dim3(PS_NT), d_sym,

@@ -123,6 +123,8 @@ struct bzb200_ctx {
   DevBuf chunk_state, chunk_zle, chunk_base, sym, freq, mtf_count;
   DevBuf lens, rfreq, sel, selmtf, codes, gbits, meta, lm_scratch, lm_list, lm_count, blockbit, bitcursor, combined;
   DevBuf stage_in, stage_out;  // bzb200_compress_host staging
+  cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
+  std::vector<cudaEvent_t> seg_events;
   uint64_t batch_elems_cap = (uint64_t)1400 * 1000 * 1000;
 
   // ---- last batch (debug) ----
@@ -262,6 +264,9 @@ void bzb200_ctx_destroy(bzb200_ctx* c) {
   for (DevBuf* b : c->all)
     if (b->p) cudaFree(b->p);
   if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+  if (c->h2d_stream) cudaStreamDestroy(c->h2d_stream);
+  if (c->d2h_stream) cudaStreamDestroy(c->d2h_stream);
+  for (cudaEvent_t ev : c->seg_events) cudaEventDestroy(ev);
   delete c;
 }
 
@@ -696,6 +701,11 @@ int bzb200_compress_device(bzb200_ctx* c, int level, const uint8_t* d_in, size_t
   return BZB200_OK;
 }
 
+// Host buffers in, host buffers out.  The input is copied in segments on a copy stream; as soon as a segment has
+// landed, the bytes from the last block cut up to the end of that segment are planned as a stream of their own and
+// all of their blocks but the (still open) last one are encoded, while the next segments are still in flight —
+// a block cut is a piece boundary, so RLE1 restarts there exactly as in the one-pass plan.  Finished output bytes
+// go back to the host on a second copy stream while the next segment is compressed.
 int bzb200_compress_host(bzb200_ctx* c, int level, const uint8_t* h_in, size_t n, uint8_t* h_out, size_t cap_bytes,
                          size_t* out_n) {
   if (!c || !h_out || !out_n || (!h_in && n)) return BZB200_E_ARG;
@@ -707,16 +717,81 @@ int bzb200_compress_host(bzb200_ctx* c, int level, const uint8_t* h_in, size_t n
   const size_t cap = bzb200_max_output_bytes(level, n);
   TRY(ensure(c, c->stage_in, n + 16));
   TRY(ensure(c, c->stage_out, cap));
-  if (n) CK(c, cudaMemcpyAsync(c->stage_in.p, h_in, n, cudaMemcpyHostToDevice, c->stream));
-  CK(c, cudaMemsetAsync(c->stage_out.p, 0, cap, c->stream));
+  size_t seg = (size_t)512 << 20;  // measured on B200: each extra segment costs ~5 ms of fixed per-batch latency
+  if (const char* e = getenv("BZB200_HOST_SEGMENT")) {
+    unsigned long long v = strtoull(e, nullptr, 10);
+    if (v >= (1u << 20)) seg = (size_t)v;
+  }
+  if (n <= seg) {  // small input: one copy, one plan
+    if (n) CK(c, cudaMemcpyAsync(c->stage_in.p, h_in, n, cudaMemcpyHostToDevice, c->stream));
+    CK(c, cudaMemsetAsync(c->stage_out.p, 0, cap, c->stream));
+    size_t got = 0;
+    TRY(bzb200_compress_device(c, level, ptr<uint8_t>(c->stage_in), n, ptr<uint8_t>(c->stage_out), cap, &got));
+    if (got > cap_bytes) {
+      c->err = "compress_host: output buffer too small: need " + std::to_string(got) + " bytes";
+      return BZB200_E_ARG;
+    }
+    CK(c, cudaMemcpyAsync(h_out, c->stage_out.p, got, cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    *out_n = got;
+    return BZB200_OK;
+  }
+  if (!c->h2d_stream) CK(c, cudaStreamCreateWithFlags(&c->h2d_stream, cudaStreamNonBlocking));
+  if (!c->d2h_stream) CK(c, cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking));
+  // segment ends: a half-size first segment (compute starts early), then full segments
+  std::vector<size_t> ends;
+  for (size_t e = seg / 2; e < n; e += seg) ends.push_back(e);
+  if (ends.size() && n - ends.back() < seg / 4) ends.pop_back();  // no tiny tail segment
+  ends.push_back(n);
+  const size_t nseg = ends.size();
+  while (c->seg_events.size() < nseg + 1) {
+    cudaEvent_t ev;
+    CK(c, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    c->seg_events.push_back(ev);
+  }
+  uint8_t* d_in = ptr<uint8_t>(c->stage_in);
+  uint8_t* d_out = ptr<uint8_t>(c->stage_out);
+  for (size_t s = 0; s < nseg; ++s) {
+    const size_t lo = s ? ends[s - 1] : 0, len = ends[s] - lo;
+    CK(c, cudaMemcpyAsync(d_in + lo, h_in + lo, len, cudaMemcpyHostToDevice, c->h2d_stream));
+    CK(c, cudaEventRecord(c->seg_events[s], c->h2d_stream));
+  }
+  CK(c, cudaMemsetAsync(d_out, 0, cap, c->stream));
+  TRY(bzb200_write_stream_header(c, level, d_out, cap));
+  size_t pos = 0, copied = 0;
+  uint64_t bit = 32;
+  uint32_t combined = 0;
+  for (size_t s = 0; s < nseg; ++s) {
+    const size_t avail = ends[s];
+    const bool last = s + 1 == nseg;
+    CK(c, cudaStreamWaitEvent(c->stream, c->seg_events[s], 0));
+    uint32_t nb = 0;
+    TRY(bzb200_plan(c, level, d_in + pos, avail - pos, &nb));
+    const uint32_t nenc = last ? nb : (nb ? nb - 1 : 0);  // the last block of a segment is still open
+    if (nenc) {
+      TRY(bzb200_encode_blocks(c, 0, nenc, d_out, cap, bit, &bit));
+      combined = bzb200_combine_crc(combined, c->h_crc.data(), nenc);
+      pos += (size_t)c->h_in_off[nenc];
+    }
+    const size_t fin = (size_t)(bit / 8);  // bytes below `bit` are final (later blocks only OR at >= bit)
+    if (fin > cap_bytes) {
+      c->err = "compress_host: output buffer too small";
+      return BZB200_E_ARG;
+    }
+    if (!last && fin > copied) {  // encode_blocks has synchronised: those bytes are in place
+      CK(c, cudaMemcpyAsync(h_out + copied, d_out + copied, fin - copied, cudaMemcpyDeviceToHost, c->d2h_stream));
+      copied = fin;
+    }
+  }
   size_t got = 0;
-  TRY(bzb200_compress_device(c, level, ptr<uint8_t>(c->stage_in), n, ptr<uint8_t>(c->stage_out), cap, &got));
+  TRY(bzb200_write_stream_trailer(c, d_out, cap, bit, combined, &got));
   if (got > cap_bytes) {
     c->err = "compress_host: output buffer too small: need " + std::to_string(got) + " bytes";
     return BZB200_E_ARG;
   }
-  CK(c, cudaMemcpyAsync(h_out, c->stage_out.p, got, cudaMemcpyDeviceToHost, c->stream));
+  CK(c, cudaMemcpyAsync(h_out + copied, d_out + copied, got - copied, cudaMemcpyDeviceToHost, c->stream));
   CK(c, cudaStreamSynchronize(c->stream));
+  CK(c, cudaStreamSynchronize(c->d2h_stream));
   *out_n = got;
   return BZB200_OK;
 }

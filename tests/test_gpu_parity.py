@@ -205,6 +205,25 @@ def test_plan_in_steps_equals_plan():
     b.close()
 
 
+def test_host_path_segmented_pipeline(monkeypatch):
+    """bzb200_compress_host with the input copied in segments and every segment planned from the previous block cut
+    (H2D / compute / D2H overlap): the stream must not depend on the segment size.  g2 has long runs, so cuts fall
+    inside maximal runs and segments start at unaligned offsets."""
+    import torch
+    from rust_compression_b200 import device as dv
+    data = gen.g2(11, 5_000_000) + gen.text(12, 3_000_000) + b"q" * 700_000 + gen.mixed(13, 2_000_000)
+    want = orc.compress(data, 1)
+    h_in = torch.frombuffer(bytearray(data), dtype=torch.uint8).pin_memory()
+    h_out = torch.empty(dv.max_output_bytes(1, len(data)), dtype=torch.uint8).pin_memory()
+    for seg in (1 << 20, 3_333_333):
+        monkeypatch.setenv("BZB200_HOST_SEGMENT", str(seg))
+        ctx = dv.Context()
+        n = ctx.compress_host(1, h_in, h_out)
+        assert h_out[:n].numpy().tobytes() == want, f"segment size {seg}"
+        ctx.close()
+    monkeypatch.delenv("BZB200_HOST_SEGMENT")
+
+
 def test_multi_batch_equals_single_batch(monkeypatch):
     d = gen.mixed(5, 1200000)
     monkeypatch.setenv("BZB200_BATCH_ELEMS", "250000")
