@@ -194,6 +194,9 @@ def main():
     from rust_compression_b200 import device as dv
     from rust_compression_b200 import sharded
 
+    # rank 0 prints exactly one line on stdout: keep NCCL's version banner (NCCL_DEBUG=VERSION/INFO) off it
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO") and not os.environ.get("BZB200_KEEP_NCCL_DEBUG"):
+        os.environ["NCCL_DEBUG"] = "WARN"
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:

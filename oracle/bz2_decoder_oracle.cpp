@@ -1,0 +1,357 @@
+// bz2_decoder_oracle.cpp — CPU restatement of the reference's bzip2 DEcoder, for validation only.
+//
+// TEST INFRASTRUCTURE: linked into liborc.so next to bz2_oracle.cpp; only tests/, __graft_entry__.smoke() and
+// bench.py's baseline legs may load it.  north_star asks that the GPU stream "round-trips through the reference
+// BZip2Decoder"; the Rust crate cannot be built here, so this file restates that decoder with its own acceptance
+// limits and is pinned on the reference's decoder fixtures (data/sample{1..4}.bz2 -> .ref, src/bzip2/mod.rs:84-148).
+//
+// Follows /root/reference/src/bzip2/decoder.rs:
+//   init_block           :163-525  stream/block headers, mapping table, selectors, coding tables, MTF/RUNA/RUNB
+//                                  decode into tt, cftab checks, T^(-1) vector, multi-stream restart (:510-520)
+//   get_next_lfm         :527-542  position check against 100000*level, inverse-BWT step
+//   BitDecodeService::next :545-581  RLE1 undo (4 equal bytes + count), block CRC digest
+// and src/bzip2/mtf.rs:41-65 (MtfPositionDecoder), src/crc32.rs (IEEE_NORMAL, MSB first), src/bitio/reader.rs with
+// direction Left (MSB-first bit reads), src/huffman/decoder.rs + huffman/mod.rs:22-67 (canonical codes by
+// (length, symbol); a code that is not in the table is a DataError, decoder.rs:376-379).
+//
+// Deviations, malformed input only: block_randomised streams (decoder.rs:70-120 table) are rejected as DataError
+// (the encoder never sets the bit, encoder.rs:273); an over-subscribed coding table is rejected as DataError where
+// the reference's tree builder may accept or overwrite (huffman/decoder.rs:43-88).
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <vector>
+
+namespace {
+
+enum Err { OK = 0, DataError = 1, DataErrorMagicFirst = 2, DataErrorMagic = 3, UnexpectedEof = 4, Unexpected = 5 };
+
+struct BitReader {  // bitio/reader.rs, Left direction
+  const uint8_t* p;
+  size_t n;
+  size_t bit = 0;
+  bool read(int len, uint32_t& v) {
+    if (bit + (size_t)len > n * 8) return false;
+    uint32_t r = 0;
+    for (int i = 0; i < len; ++i, ++bit) r = (r << 1) | ((p[bit >> 3] >> (7 - (bit & 7))) & 1u);
+    v = r;
+    return true;
+  }
+  void skip_to_next_byte() { bit = (bit + 7) & ~(size_t)7; }
+  size_t bits_left() const { return n * 8 - bit; }
+};
+
+struct Crc {  // crc32.rs: IEEE_NORMAL = poly 0x04C11DB7, MSB first, init/xorout 0xFFFFFFFF
+  uint32_t tab[256];
+  Crc() {
+    for (uint32_t i = 0; i < 256; ++i) {
+      uint32_t v = i << 24;
+      for (int k = 0; k < 8; ++k) v = (v & 0x80000000u) ? (v << 1) ^ 0x04C11DB7u : (v << 1);
+      tab[i] = v;
+    }
+  }
+};
+const Crc g_crc;
+
+struct Huff {  // canonical codes, huffman/mod.rs:22-67; lookup by (length, code)
+  int max_len = 0;
+  std::vector<uint32_t> first_code, count;  // per length
+  std::vector<std::vector<uint16_t>> syms;  // per length, in code order
+  bool build(const std::vector<uint8_t>& len) {
+    max_len = 0;
+    for (uint8_t l : len) max_len = l > max_len ? l : max_len;
+    if (max_len >= 32) return false;  // huffman/decoder.rs:113-115
+    first_code.assign(max_len + 2, 0);
+    count.assign(max_len + 2, 0);
+    syms.assign(max_len + 2, {});
+    for (size_t s = 0; s < len.size(); ++s)
+      if (len[s]) syms[len[s]].push_back((uint16_t)s);  // stable by symbol inside a length (bucket_sort.rs:43-75)
+    uint64_t code = 0;
+    int prev = 0;
+    for (int l = 1; l <= max_len; ++l) {
+      if (syms[l].empty()) continue;
+      code <<= (l - prev);
+      prev = l;
+      first_code[l] = (uint32_t)code;
+      count[l] = (uint32_t)syms[l].size();
+      code += syms[l].size();
+      if (code > (1ull << l)) return false;  // over-subscribed (see header)
+    }
+    return true;
+  }
+  // returns symbol or -1 (code not in the table) or -2 (eof)
+  int dec(BitReader& r) const {
+    uint32_t code = 0;
+    for (int l = 1; l <= max_len; ++l) {
+      uint32_t b;
+      if (!r.read(1, b)) return -2;
+      code = (code << 1) | b;
+      if (count[l] && code >= first_code[l] && code - first_code[l] < count[l]) return syms[l][code - first_code[l]];
+    }
+    return -1;
+  }
+};
+
+struct MtfDec {  // mtf.rs:41-65
+  std::vector<size_t> data;
+  explicit MtfDec(size_t k) : data(k) {
+    for (size_t i = 0; i < k; ++i) data[i] = i;
+  }
+  size_t pop(size_t v) {
+    if (v == 0) return data[0];
+    size_t t = data[v];
+    for (size_t i = v; i > 0; --i) data[i] = data[i - 1];
+    data[0] = t;
+    return t;
+  }
+};
+
+struct Decoder {
+  BitReader rd;
+  std::vector<uint8_t> out;
+  size_t block_size_100k = 0, block_no = 0, stream_no = 1;
+  uint32_t block_crc = 0, combined_crc = 0, digest = 0xFFFFFFFFu;
+  std::vector<uint32_t> tt;
+  uint32_t t_pos = 0;
+  size_t n_block_used = 0;
+  uint8_t result_char = 0;
+  size_t result_count = 0, result_wrote = 0;
+
+  bool read_u8(uint32_t& v) { return rd.read(8, v); }
+
+  // decoder.rs:163-525. ret: 1 block ready, 0 end of data, <0 error (-Err)
+  int init_block() {
+    for (;;) {
+      if (block_no == 0) {
+        const int magic_err = stream_no == 1 ? DataErrorMagicFirst : DataErrorMagic;
+        uint32_t b;
+        const uint8_t want[3] = {'B', 'Z', 'h'};
+        for (int i = 0; i < 3; ++i) {
+          if (!read_u8(b) || b != want[i]) return -magic_err;  // check_u8(..).map_err(|_| magic_err)
+        }
+        if (!read_u8(b)) return -UnexpectedEof;
+        if (b < 1 + '0' || b > 9 + '0') return -magic_err;
+        block_size_100k = b - '0';
+      } else {
+        const uint32_t data_crc = ~digest;
+        if (data_crc != block_crc) return -DataError;
+        combined_crc = ((combined_crc << 1) | (combined_crc >> 31)) ^ block_crc;
+        digest = 0xFFFFFFFFu;
+      }
+      uint32_t head;
+      if (!read_u8(head)) return -UnexpectedEof;
+      if (head == 0x31) {
+        const uint8_t rest[5] = {0x41, 0x59, 0x26, 0x53, 0x59};
+        uint32_t b;
+        for (int i = 0; i < 5; ++i)
+          if (!read_u8(b) || b != rest[i]) return -DataError;
+        block_no += 1;
+        if (!rd.read(32, block_crc)) return -UnexpectedEof;
+        uint32_t randomised, orig_pos;
+        if (!rd.read(1, randomised)) return -UnexpectedEof;
+        if (!rd.read(24, orig_pos)) return -UnexpectedEof;
+        if (orig_pos > 10 + 100000 * block_size_100k) return -DataError;  // :238
+        if (randomised) return -DataError;                                 // see header (deviation)
+        // mapping table (:243-275)
+        uint32_t in_use16;
+        if (!rd.read(16, in_use16)) return -UnexpectedEof;
+        std::vector<size_t> seq2unseq;
+        for (int i = 0; i < 16; ++i) {
+          if (!((in_use16 >> (15 - i)) & 1u)) continue;
+          uint32_t m;
+          if (!rd.read(16, m)) return -UnexpectedEof;
+          for (int j = 0; j < 16; ++j)
+            if ((m >> (15 - j)) & 1u) seq2unseq.push_back((size_t)i * 16 + j);
+        }
+        if (seq2unseq.empty()) return -DataError;
+        const size_t alpha_size = seq2unseq.size() + 2;
+        // selectors (:283-318)
+        uint32_t n_groups, n_selectors;
+        if (!rd.read(3, n_groups)) return -UnexpectedEof;
+        if (n_groups < 2 || n_groups > 6) return -DataError;
+        if (!rd.read(15, n_selectors)) return -UnexpectedEof;
+        if (n_selectors < 1) return -DataError;
+        std::vector<size_t> selector;
+        selector.reserve(n_selectors);
+        {
+          MtfDec sm(n_groups);
+          for (uint32_t s = 0; s < n_selectors; ++s) {
+            uint32_t j = 0, bit;
+            for (;;) {
+              if (!rd.read(1, bit)) return -UnexpectedEof;
+              if (!bit) break;
+              j += 1;
+              if (j >= n_groups) return -DataError;
+            }
+            selector.push_back(sm.pop(j));
+          }
+        }
+        // coding tables (:320-349)
+        std::vector<std::vector<uint8_t>> len(n_groups, std::vector<uint8_t>(alpha_size, 0));
+        for (auto& t : len) {
+          uint32_t curr;
+          if (!rd.read(5, curr)) return -UnexpectedEof;
+          for (auto& li : t) {
+            for (;;) {
+              uint32_t bit;
+              if (!rd.read(1, bit)) return -UnexpectedEof;
+              if (!bit) break;
+              if (curr < 1 || curr > 20) return -DataError;
+              if (!rd.read(1, bit)) return -UnexpectedEof;
+              if (bit == 0) curr += 1; else curr -= 1;
+            }
+            li = (uint8_t)curr;
+          }
+        }
+        std::vector<Huff> code(n_groups);
+        for (uint32_t t = 0; t < n_groups; ++t)
+          if (!code[t].build(len[t])) return -DataError;
+        // MTF values (:360-444)
+        const uint32_t eob = (uint32_t)alpha_size - 1;
+        const size_t nblock_max = 100000 * block_size_100k;
+        std::vector<size_t> unzftab(257, 0);
+        tt.clear();
+        tt.reserve(nblock_max);
+        {
+          size_t group_no = 0, group_pos = 0, nn = 1, es = 0;
+          MtfDec md(seq2unseq.size());
+          for (;;) {
+            if (group_pos == 0) {
+              group_no += 1;
+              if (group_no > n_selectors) return -DataError;
+              group_pos = 50;
+            }
+            group_pos -= 1;
+            const int sym = code[selector[group_no - 1]].dec(rd);
+            if (sym < 0) return -DataError;  // both "not in table" and read failure map to DataError (:376-379)
+            const uint32_t next_sym = (uint32_t)sym;
+            if (es > 0 && next_sym != 0 && next_sym != 1) {
+              const size_t uc = seq2unseq[md.pop(0)];
+              unzftab[uc + 1] += es;
+              for (size_t k = 0; k < es; ++k) tt.push_back((uint32_t)uc);
+              if (tt.size() >= nblock_max) return -DataError;  // :399
+              nn = 1;
+              es = 0;
+            }
+            if (next_sym == eob) break;
+            if (nn >= 2 * 1024 * 1024) return -DataError;  // :416
+            if (next_sym == 0) {
+              es += nn;
+              nn <<= 1;
+            } else if (next_sym == 1) {
+              nn <<= 1;
+              es += nn;
+            } else {
+              if (tt.size() >= nblock_max) return -DataError;  // :427
+              if ((size_t)next_sym - 1 >= seq2unseq.size()) return -DataError;  // (a Rust index panic in the reference)
+              const size_t uc = seq2unseq[md.pop(next_sym - 1)];
+              unzftab[uc + 1] += 1;
+              tt.push_back((uint32_t)uc);
+            }
+          }
+        }
+        if (orig_pos >= tt.size()) return -DataError;  // :446-450
+        if (unzftab[0] != 0) return -DataError;
+        for (size_t i = 1; i < unzftab.size(); ++i) {
+          unzftab[i] += unzftab[i - 1];
+          if (unzftab[i - 1] > unzftab[i]) return -DataError;
+        }
+        if (unzftab[256] != tt.size()) return -DataError;
+        for (size_t i = 0; i < tt.size(); ++i) {  // T^(-1) (:479-484)
+          const size_t uc = tt[i] & 0xFF;
+          tt[unzftab[uc]] |= (uint32_t)i << 8;
+          unzftab[uc] += 1;
+        }
+        t_pos = tt[orig_pos] >> 8;
+        n_block_used = 0;
+        result_count = 0;
+        result_wrote = 0;
+        return 1;
+      } else if (head == 0x17) {
+        const uint8_t rest[5] = {0x72, 0x45, 0x38, 0x50, 0x90};
+        uint32_t b;
+        for (int i = 0; i < 5; ++i)
+          if (!read_u8(b) || b != rest[i]) return -DataError;
+        uint32_t stored;
+        if (!rd.read(32, stored)) return -UnexpectedEof;
+        if (stored != combined_crc) return -DataError;
+        rd.skip_to_next_byte();
+        if (rd.bits_left() >= 8) {  // another stream follows (:510-517)
+          block_no = 0;
+          combined_crc = 0;
+          stream_no += 1;
+        } else {
+          return 0;
+        }
+      } else {
+        return -DataError;
+      }
+    }
+  }
+
+  int get_next_lfm(uint8_t& k0) {  // :527-542
+    uint32_t position = t_pos;
+    if (position >= 100000 * block_size_100k) return -DataError;
+    if (position >= tt.size()) return -Unexpected;  // (index panic in the reference)
+    position = tt[position];
+    k0 = (uint8_t)position;
+    t_pos = position >> 8;
+    n_block_used += 1;
+    return 0;
+  }
+
+  int run() {  // BitDecodeService::next (:545-581), looped
+    for (;;) {
+      if (result_count == result_wrote) {
+        if (n_block_used == tt.size()) {
+          const int r = init_block();
+          if (r < 0) return -r;
+          if (r == 0) return OK;
+        }
+        uint8_t buffer;
+        int e = get_next_lfm(buffer);
+        if (e) return -e;
+        if (buffer == result_char && result_count < 4) {
+          result_count += 1;
+          result_wrote += 1;
+        } else {
+          result_char = buffer;
+          result_count = 1;
+          result_wrote = 1;
+        }
+        if (result_count == 4) {
+          uint8_t cnt;
+          e = get_next_lfm(cnt);
+          if (e) return -e;
+          result_count += cnt;
+        }
+      } else {
+        result_wrote += 1;
+      }
+      digest = g_crc.tab[((digest >> 24) ^ result_char) & 0xFF] ^ (digest << 8);
+      out.push_back(result_char);
+    }
+  }
+};
+
+}  // namespace
+
+extern "C" {
+
+// Decodes a (possibly multi-stream) .bz2 buffer. Returns 0 or the BZip2Error ordinal + 1 (1 DataError,
+// 2 DataErrorMagicFirst, 3 DataErrorMagic, 4 UnexpectedEof, 5 Unexpected). *out is malloc'ed even on error (bytes
+// decoded so far); free with orc_decode_free.
+int orc_decode(const uint8_t* in, size_t n, uint8_t** out, size_t* out_n) {
+  Decoder d;
+  d.rd.p = in;
+  d.rd.n = n;
+  const int e = d.run();
+  *out_n = d.out.size();
+  *out = (uint8_t*)malloc(d.out.size() ? d.out.size() : 1);
+  if (*out && d.out.size()) memcpy(*out, d.out.data(), d.out.size());
+  return e;
+}
+void orc_decode_free(uint8_t* p) { free(p); }
+
+}  // extern "C"

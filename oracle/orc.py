@@ -16,8 +16,8 @@ _LIB = None
 
 def build(force=False):
     so = os.path.join(_HERE, "liborc.so")
-    src = os.path.join(_HERE, "bz2_oracle.cpp")
-    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+    srcs = [os.path.join(_HERE, "bz2_oracle.cpp"), os.path.join(_HERE, "bz2_decoder_oracle.cpp")]
+    if force or not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(s) for s in srcs):
         subprocess.check_call(["make", "-C", _HERE, "-B", "liborc.so"], stdout=subprocess.DEVNULL)
     return so
 
@@ -53,6 +53,9 @@ def lib():
         L.orc_crc32_bzip2.restype = C.c_uint32
         L.orc_crc32_bzip2.argtypes = [C.c_void_p, C.c_size_t]
         L.orc_mtf_positions.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p]
+        L.orc_decode.restype = C.c_int
+        L.orc_decode.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
+        L.orc_decode_free.argtypes = [C.c_void_p]
         _LIB = L
     return _LIB
 
@@ -176,3 +179,26 @@ def mtf_positions(syms, k):
     o = np.zeros(a.size, dtype=np.uint8)
     lib().orc_mtf_positions(a.ctypes.data, a.size, k, o.ctypes.data)
     return o
+
+
+class DecodeError(Exception):
+    """BZip2Error of the restated reference decoder (bzip2/error.rs:13-19)."""
+    KINDS = {1: "DataError", 2: "DataErrorMagicFirst", 3: "DataErrorMagic", 4: "UnexpectedEof", 5: "Unexpected"}
+
+    def __init__(self, code, partial):
+        super().__init__(self.KINDS.get(code, str(code)))
+        self.kind = self.KINDS.get(code, str(code))
+        self.partial = partial
+
+
+def decode(data):
+    """Restatement of BZip2Decoder (oracle/bz2_decoder_oracle.cpp): multi-stream .bz2 bytes -> original bytes."""
+    b = _buf(data)
+    out = C.c_void_p()
+    n = C.c_size_t(0)
+    rc = lib().orc_decode(b.ctypes.data if b.size else None, b.size, C.byref(out), C.byref(n))
+    res = C.string_at(out, n.value) if n.value else b""
+    lib().orc_decode_free(out)
+    if rc != 0:
+        raise DecodeError(rc, res)
+    return res

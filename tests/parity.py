@@ -22,7 +22,7 @@ def gpu_run(data, level, batch_elems=None):
 
 
 STAGES = ["blocks", "crc", "rle", "inuse", "order", "last", "origptr", "mtf", "freq", "len0", "len1", "len2", "len3",
-          "len4", "sel", "bits", "stream", "libbz2"]
+          "len4", "sel", "bits", "stream", "libbz2", "refdec"]
 
 
 def compare(data, level, orc, keep_sa=True, check_blocks=None):
@@ -100,6 +100,13 @@ def compare(data, level, orc, keep_sa=True, check_blocks=None):
                 res["libbz2"] = "decodes to different bytes"
         except Exception as e:
             res["libbz2"] = f"libbz2 rejects the stream: {e}"
+        # ... and through the restated reference BZip2Decoder with its own acceptance limits (origPtr bound,
+        # tt.len() < 100000*level; oracle/bz2_decoder_oracle.cpp)
+        try:
+            if O.decode(out) != bytes(data):
+                res["refdec"] = "reference decoder restatement decodes to different bytes"
+        except O.DecodeError as e:
+            res["refdec"] = f"reference decoder restatement rejects the stream: {e.kind}"
     finally:
         ref.close()
         ctx.close()

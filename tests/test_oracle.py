@@ -5,6 +5,7 @@ CPU-only; runs in seconds.
 """
 import bz2
 import hashlib
+import os
 import random
 
 import numpy as np
@@ -269,6 +270,38 @@ def test_stage_agreement_with_libbz2_on_text():
 
     assert header(r.out) == header(ref)
     assert r.out[-4:] != b"" and r.info(0)["crc"] == header(ref)[0]
+
+
+# ---- the restated reference DEcoder (oracle/bz2_decoder_oracle.cpp), pinned on the reference's decoder fixtures ----
+
+@pytest.mark.parametrize("idx", [1, 2, 3, 4])
+def test_decoder_reference_fixtures(sample_data, idx):
+    """bzip2/mod.rs:84-148 test_sample1..4 (decode half): data/sampleN.bz2 -> sampleN.ref; sample4.bz2 is two
+    concatenated streams (multi-stream restart, decoder.rs:510-520)."""
+    z = open(os.path.join(os.path.dirname(__file__), "golden", "data", f"sample{idx}.bz2"), "rb").read()
+    assert orc.decode(z) == sample_data[idx]
+    assert bz2.decompress(z) == sample_data[idx]
+
+
+def test_decoder_accepts_encoder_output_at_the_block_limits(sample_data):
+    """The encoder's largest block (level*100000-15 bytes) is inside the decoder's limits (decoder.rs:238,399,427):
+    round trip of a full block and of the reference's own round-trip inputs (mod.rs:84-172, lib.rs:13-33)."""
+    for data, level in ((gen.text(31, 100200), 1), (b"a" * 1000, 9), (b"aabbaabbaabbaabb\n", 9), (b"", 9),
+                        (sample_data[2], 2), (gen.g2(4, 400000), 1)):
+        assert orc.decode(orc.compress(data, level)) == data
+
+
+def test_decoder_error_kinds():
+    """BZip2Error mapping (bzip2/error.rs:13-19; decoder.rs:170-188,197,470-475)."""
+    z = orc.compress(gen.text(32, 60000), 9)
+    for bad, kind in ((b"XZh9" + z[4:], "DataErrorMagicFirst"), (z[:3] + b"0" + z[4:], "DataErrorMagicFirst"),
+                      (z[:-3], "UnexpectedEof"), (z + b"BZx9", "DataErrorMagic"),
+                      (z[:len(z) // 2] + bytes([z[len(z) // 2] ^ 0x10]) + z[len(z) // 2 + 1:], "DataError"),
+                      (z[:-1] + bytes([z[-1] ^ 1]) if False else z[:-5] + bytes([z[-5] ^ 0x80]) + z[-4:], "DataError")):
+        with pytest.raises(orc.DecodeError) as e:
+            orc.decode(bad)
+        assert e.value.kind == kind, (kind, e.value.kind)
+    assert orc.decode(z + z) == gen.text(32, 60000) * 2   # multi-stream
 
 
 def test_invalid_level():
