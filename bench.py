@@ -39,9 +39,13 @@ ALG_BYTES = {
 }
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures (profiles/),
-# full-size launch of the 1 GiB workload; None where no capture exists yet.
-NCU_TRAFFIC = {}
+# DRAM traffic per algorithmic byte, from the committed `ncu --set full` capture (profiles/r1b_ncu_kernels.csv:
+# (dram__bytes_read.sum + dram__bytes_write.sum) of the kernel's full-size launch on the 256 MiB slice of the same corpus
+# / the algorithmic bytes of that launch).  roofline.traffic = ratio x algorithmic bytes per launch.
+#   k2_rs_scatter : (2.155 + 2.175) GB / (268.5 M elements x 16 B)
+#   k2_local_sort : (2.911 + 2.146) GB / (230.7 M entries x 16 B)   (round 1)
+#   k3_apply      : (0.380 + 0.317) GB / (268.5 M bytes + 2 B x 164.3 M symbols)
+NCU_TRAFFIC_RATIO = {"k2_rs_scatter": 1.008, "k2_local_sort": 1.370, "k3_apply": 1.168}
 
 
 def workload_name(n_gpus):
@@ -52,21 +56,60 @@ def workload_name(n_gpus):
 
 
 class ClockSampler:
-    """nvidia-smi clocks/throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock and throttle reasons sampled DURING the timed region (B200_PROFILING.md).  In-process NVML
+    (nvidia_ml_py) every 100 ms: a looping `nvidia-smi --query-gpu` was measured to stretch the timed steps by up to
+    15 % on some boxes (each query stalls launches and synchronisations); nvidia-smi remains the fallback."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, gpu_index):
         self.gpu = gpu_index
-        self.rows = []
+        self.rows = []      # nvidia-smi fallback rows
+        self.samples = []   # (sm_mhz, sm_max_mhz, reason_bits)
         self.p = None
+        self.t = None
+        self.stop_flag = False
+        self.how = None
+
+    def _nvml_handle(self):
+        import pynvml
+        import torch
+        pynvml.nvmlInit()
+        try:
+            uuid = str(torch.cuda.get_device_properties(self.gpu).uuid)
+            if not uuid.startswith("GPU-"):
+                uuid = "GPU-" + uuid
+            return pynvml, pynvml.nvmlDeviceGetHandleByUUID(uuid.encode())
+        except Exception:
+            return pynvml, pynvml.nvmlDeviceGetHandleByIndex(self.gpu)
 
     def start(self):
+        try:
+            nv, h = self._nvml_handle()
+            mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+                nv.nvmlDeviceGetCurrentClocksThrottleReasons
+
+            def loop():
+                while not self.stop_flag:
+                    try:
+                        self.samples.append((nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM), mx, int(get_reasons(h))))
+                    except Exception:
+                        pass
+                    time.sleep(0.1)
+            self.how = "nvml"
+            self.t = threading.Thread(target=loop, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            pass
         try:
             self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms",
                                        "200", "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL,
                                       text=True)
+            self.how = "nvidia-smi"
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
@@ -79,6 +122,17 @@ class ClockSampler:
                 self.rows.append(f)
 
     def stop(self):
+        if self.how == "nvml":
+            self.stop_flag = True
+            self.t.join(timeout=1)
+            sm = [s[0] for s in self.samples]
+            bits = 0
+            for s in self.samples:
+                bits |= s[2]
+            return {"sm_mhz": statistics.median(sm) if sm else None,
+                    "sm_max_mhz": self.samples[0][1] if self.samples else None,
+                    "reasons": sorted(n for b, n in self.REASONS.items() if bits & b), "samples": len(self.samples),
+                    "source": "nvml, 100 ms period, during the timed region"}
         if not self.p:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.p.terminate()
@@ -95,7 +149,7 @@ class ClockSampler:
                 if r[5 + k].lower().startswith("active"):
                     reasons.add(nm)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(self.rows)}
+                "reasons": sorted(reasons), "samples": len(self.rows), "source": "nvidia-smi -lms 200"}
 
 
 def gen_slice(rank, nbytes):
@@ -306,7 +360,11 @@ def main():
             alg_bytes = total_bytes / world + out_bytes / world
         achieved = alg_bytes / (kms / 1e3) / 1e9 if kms > 0 else 0.0
         roofline = {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": achieved / peak, "traffic": NCU_TRAFFIC.get(name), "peak_source": peak_src,
+                    "frac": achieved / peak,
+                    "traffic": (NCU_TRAFFIC_RATIO[name] * alg_bytes / max(1, nl)) if name in NCU_TRAFFIC_RATIO else None,
+                    "traffic_source": "profiles/r1b_ncu_kernels.csv (ncu --set full, dram bytes / algorithmic bytes of "
+                                      "the full-size launch) x algorithmic bytes per launch",
+                    "peak_source": peak_src,
                     "launches_per_step": nl, "avg_launch_ms": kms / max(1, nl),
                     "kernel_share_of_step": kms / ms_prof,
                     "algorithmic_bytes_per_launch": alg_bytes / max(1, nl),

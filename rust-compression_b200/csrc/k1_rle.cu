@@ -452,11 +452,25 @@ __global__ void __launch_bounds__(256) k1_inuse(const uint8_t* __restrict__ txt,
   __syncthreads();
   const uint64_t lo = rle_off[blockIdx.x], hi = rle_off[blockIdx.x + 1];
   uint32_t loc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  for (uint64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
-    uint8_t c = __ldg(txt + i);
+  auto mark = [&](uint32_t c) {
 #pragma unroll
-    for (int w = 0; w < 8; ++w) loc[w] |= ((c >> 5) == w) ? (1u << (c & 31)) : 0u;
+    for (int w = 0; w < 8; ++w) loc[w] |= ((c >> 5) == (uint32_t)w) ? (1u << (c & 31)) : 0u;
+  };
+  // unaligned head and tail byte-wise, the body as 128-bit loads
+  const uint64_t alo = min(hi, (uint64_t)((lo + 15) & ~15ull)), ahi = max(alo, (uint64_t)(hi & ~15ull));
+  for (uint64_t i = lo + threadIdx.x; i < alo; i += blockDim.x) mark(__ldg(txt + i));
+  for (uint64_t i = alo + (uint64_t)threadIdx.x * 16; i < ahi; i += (uint64_t)blockDim.x * 16) {
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(txt + i));
+    const uint32_t wv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      mark(wv[k] & 255u);
+      mark((wv[k] >> 8) & 255u);
+      mark((wv[k] >> 16) & 255u);
+      mark(wv[k] >> 24);
+    }
   }
+  for (uint64_t i = ahi + threadIdx.x; i < hi; i += blockDim.x) mark(__ldg(txt + i));
 #pragma unroll
   for (int w = 0; w < 8; ++w) {
     uint32_t v = loc[w];

@@ -1060,15 +1060,23 @@ __global__ void __launch_bounds__(G_NT) k2_finish(const uint8_t* __restrict__ tx
   if (base >= n) return;
   const uint8_t* t = txt + d.off;
   const uint32_t* s = sa + d.off;
-  // 4 consecutive slots per thread and step: one 128-bit SA load, one 32-bit store of the last column
-  // (d.off is not 4-aligned in general, so the vector path is taken only where both addresses are aligned)
-#pragma unroll 4
+  // two sweeps (all SA loads, then all text gathers) keep 16 independent loads per thread in flight: the kernel is
+  // bound by the latency of the gather
+  uint32_t pos[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    const uint32_t i = base + threadIdx.x + k * G_NT;
+    pos[k] = i < n ? (s[i] & RANK_MASK) : 1u;
+  }
+  uint8_t c[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) c[k] = t[pos[k] == 0 ? n - 1 : pos[k] - 1];
+#pragma unroll
   for (int k = 0; k < 16; ++k) {
     const uint32_t i = base + threadIdx.x + k * G_NT;
     if (i < n) {
-      const uint32_t pos = s[i] & RANK_MASK;
-      last[d.off + i] = t[pos == 0 ? n - 1 : pos - 1];
-      if (pos == 0) origptr[blockIdx.y] = i;
+      last[d.off + i] = c[k];
+      if (pos[k] == 0) origptr[blockIdx.y] = i;
     }
   }
 }

@@ -756,6 +756,10 @@ int bzb200_compress_host(bzb200_ctx* c, int level, const uint8_t* h_in, size_t n
     CK(c, cudaMemcpyAsync(d_in + lo, h_in + lo, len, cudaMemcpyHostToDevice, c->h2d_stream));
     CK(c, cudaEventRecord(c->seg_events[s], c->h2d_stream));
   }
+  {  // size the RLE1 buffer for the longest sub-stream up front (a segment plus the open block carried into it)
+    const size_t longest = std::min(n, seg + ((size_t)64 << 20));
+    TRY(ensure(c, c->txt, longest + longest / 4 + 64));
+  }
   CK(c, cudaMemsetAsync(d_out, 0, cap, c->stream));
   TRY(bzb200_write_stream_header(c, level, d_out, cap));
   size_t pos = 0, copied = 0;
