@@ -91,6 +91,8 @@ class ClockSampler:
             mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
             get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
                 nv.nvmlDeviceGetCurrentClocksThrottleReasons
+            nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)   # first calls initialise NVML state: keep that out of
+            get_reasons(h)                                    # the timed region
 
             def loop():
                 while not self.stop_flag:

@@ -37,7 +37,7 @@ constexpr int RS_WCH = RS_TILE / RS_WARPS;  // 512 elements per warp
 constexpr int KEY_LO = 20;                  // key field = bits 20..59
 constexpr uint64_t POS_MASK = 0xFFFFFull;
 
-uint32_t bwt_tile_elems() { return RS_TILE; }
+uint32_t bwt_tile_elems() { return RS_TILE / 2; }  // sizing unit of the per-tile arrays (smallest tile of any pass variant)
 
 // ------------------------------------------------------------------ round 0 keys
 __global__ void __launch_bounds__(RS_NT) k2_init_keys(const uint8_t* __restrict__ txt, const BlockDesc* __restrict__ desc,
@@ -406,7 +406,8 @@ constexpr int G_NT = 256;        // k2_gather / k2_finish threads
 constexpr int LS_NT = 512;       // k2_local_sort threads
 constexpr int LS_T = 2048;       // slots per tile (k2_gather, k2_local_sort)
 constexpr int LOCAL_MAX = 1535;  // largest group sorted inside a CTA
-constexpr int ENUM_MAX = 16;     // largest group sorted by plain enumeration (larger ones are bucketed first)
+constexpr int ENUM_MAX_DEFAULT = 48;  // largest group sorted by plain enumeration (larger ones are bucketed first)
+constexpr int ENUM_MAX_CAP = 64;
 constexpr int LS_CAP = LS_T + LOCAL_MAX;
 constexpr int LS_IPT = (LS_CAP + LS_NT - 1) / LS_NT;  // 7 (odd: blocked shared-memory access is conflict-free)
 static_assert(LS_CAP < 4095, "group start must fit the 12 bits above the 20-bit key (4095 = sentinel)");
@@ -827,7 +828,7 @@ __global__ void __launch_bounds__(G_NT) k2_gather(const BlockDesc* __restrict__ 
 // A group occupies consecutive slots, so window index i of a group maps to slot (head slot + i - group start);
 // SA and rank are written in place.
 constexpr uint32_t GS_FLAT = 0x8000u;
-constexpr int LS_PAD = ENUM_MAX + 8;
+constexpr int LS_PAD = ENUM_MAX_CAP + 8;
 struct LsSmem {
   uint32_t ck[LS_CAP + LS_PAD];
   uint32_t cnt[LS_CAP + 8];
@@ -839,6 +840,7 @@ struct LsSmem {
 };
 size_t bwt_ls_smem_bytes() { return sizeof(LsSmem); }
 
+template <int ENUM_MAX>
 __global__ void __launch_bounds__(LS_NT, 2) k2_local_sort(const BlockDesc* __restrict__ desc,
                                                           const uint32_t* __restrict__ state,
                                                           const uint32_t* __restrict__ sparse,
@@ -1095,7 +1097,7 @@ static void radix_sort40(Launcher& L, uint64_t*& src, uint64_t*& dst, const uint
   static int variant = -1;
   if (variant < 0) {
     const char* v = getenv("BZB200_OS_VARIANT");
-    variant = v ? atoi(v) : 0;
+    variant = v ? atoi(v) : 5;  // measured on B200: 256 threads x 8 elements (2 048-element tiles, 4 CTAs/SM) is fastest
     cudaFuncSetAttribute((const void*)k2_os_scatter<512, 8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          (int)sizeof(OsSmemT<512, 8>));
     cudaFuncSetAttribute((const void*)k2_os_scatter<256, 16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1106,8 +1108,10 @@ static void radix_sort40(Launcher& L, uint64_t*& src, uint64_t*& dst, const uint
                          (int)sizeof(OsSmemT<512, 16>));
     cudaFuncSetAttribute((const void*)k2_os_scatter<384, 12, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          (int)sizeof(OsSmemT<384, 12>));
+    cudaFuncSetAttribute((const void*)k2_os_scatter<256, 8, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)sizeof(OsSmemT<256, 8>));
   }
-  const uint32_t tile_elems = variant == 2 || variant == 3 ? 8192u : variant == 4 ? 4608u : 4096u;
+  const uint32_t tile_elems = variant == 2 || variant == 3 ? 8192u : variant == 4 ? 4608u : (variant == 0 || variant == 1) ? 4096u : 2048u;
   const uint32_t tiles = (maxcnt + tile_elems - 1) / tile_elems;
   if (tiles == 0) return;
   cudaMemsetAsync(S.oshist, 0, (size_t)nb * 5 * 256 * sizeof(uint32_t), L.stream);
@@ -1132,7 +1136,8 @@ static void radix_sort40(Launcher& L, uint64_t*& src, uint64_t*& dst, const uint
       case 2: OS_LAUNCH(1024, 8, 1); break;
       case 3: OS_LAUNCH(512, 16, 1); break;
       case 4: OS_LAUNCH(384, 12, 2); break;
-      default: OS_LAUNCH(512, 8, 2); break;
+      case 0: OS_LAUNCH(512, 8, 2); break;
+      default: OS_LAUNCH(256, 8, 4); break;
     }
 #undef OS_LAUNCH
     os.ticket_base += tiles;
@@ -1162,8 +1167,15 @@ int run_bwt(Launcher& L, const uint8_t* d_txt, const BlockDesc* d_desc, uint32_t
   cudaMemsetAsync(S.global, 0, 4 * sizeof(uint32_t), st);
 
   static bool attr_set = false;
+  static int ls_enum = ENUM_MAX_DEFAULT;
   if (!attr_set) {
-    cudaFuncSetAttribute((const void*)k2_local_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LsSmem));
+    cudaFuncSetAttribute((const void*)k2_local_sort<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LsSmem));
+    cudaFuncSetAttribute((const void*)k2_local_sort<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LsSmem));
+    cudaFuncSetAttribute((const void*)k2_local_sort<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LsSmem));
+    cudaFuncSetAttribute((const void*)k2_local_sort<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LsSmem));
+    cudaFuncSetAttribute((const void*)k2_local_sort<48>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LsSmem));
+    cudaFuncSetAttribute((const void*)k2_local_sort<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LsSmem));
+    if (const char* e = getenv("BZB200_LS_ENUM")) ls_enum = atoi(e);
     attr_set = true;
   }
   uint32_t rounds = 0, passes = 0;
@@ -1197,8 +1209,32 @@ int run_bwt(Launcher& L, const uint8_t* d_txt, const BlockDesc* d_desc, uint32_t
     // BIG-group / sparse-block elements -> S.A
     L.launch("k2_gather", k2_gather, dim3(ls_tiles, nb), dim3(G_NT), d_desc, S.rank, S.sa, S.state, S.shift, S.sparse, h,
              S.B, S.A, S.cnt, S.tile_meta, S.ls_tiles_cap);
-    L.launch_smem("k2_local_sort", k2_local_sort, dim3(ls_tiles, nb), dim3(LS_NT), sizeof(LsSmem), d_desc, S.state,
-                  S.sparse, S.sa, S.B, S.rank, S.tile_meta, S.ls_tiles_cap, S.stats);
+    switch (ls_enum) {
+      case 8:
+        L.launch_smem("k2_local_sort", k2_local_sort<8>, dim3(ls_tiles, nb), dim3(LS_NT), sizeof(LsSmem), d_desc, S.state,
+                      S.sparse, S.sa, S.B, S.rank, S.tile_meta, S.ls_tiles_cap, S.stats);
+        break;
+      case 24:
+        L.launch_smem("k2_local_sort", k2_local_sort<24>, dim3(ls_tiles, nb), dim3(LS_NT), sizeof(LsSmem), d_desc, S.state,
+                      S.sparse, S.sa, S.B, S.rank, S.tile_meta, S.ls_tiles_cap, S.stats);
+        break;
+      case 16:
+        L.launch_smem("k2_local_sort", k2_local_sort<16>, dim3(ls_tiles, nb), dim3(LS_NT), sizeof(LsSmem), d_desc, S.state,
+                      S.sparse, S.sa, S.B, S.rank, S.tile_meta, S.ls_tiles_cap, S.stats);
+        break;
+      case 64:
+        L.launch_smem("k2_local_sort", k2_local_sort<64>, dim3(ls_tiles, nb), dim3(LS_NT), sizeof(LsSmem), d_desc, S.state,
+                      S.sparse, S.sa, S.B, S.rank, S.tile_meta, S.ls_tiles_cap, S.stats);
+        break;
+      case 32:
+        L.launch_smem("k2_local_sort", k2_local_sort<32>, dim3(ls_tiles, nb), dim3(LS_NT), sizeof(LsSmem), d_desc, S.state,
+                      S.sparse, S.sa, S.B, S.rank, S.tile_meta, S.ls_tiles_cap, S.stats);
+        break;
+      default:
+        L.launch_smem("k2_local_sort", k2_local_sort<ENUM_MAX_DEFAULT>, dim3(ls_tiles, nb), dim3(LS_NT), sizeof(LsSmem),
+                      d_desc, S.state, S.sparse, S.sa, S.B, S.rank, S.tile_meta, S.ls_tiles_cap, S.stats);
+        break;
+    }
     const uint32_t maxbig = g[1];
     if (maxbig > 0) {
       uint64_t *s2 = S.A, *d2 = S.B;

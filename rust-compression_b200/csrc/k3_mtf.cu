@@ -259,8 +259,7 @@ __global__ void __launch_bounds__(MTF_WARPS * 32) k3_apply(const uint8_t* __rest
                                                            const uint2* __restrict__ chunk_base, uint32_t chunks_cap,
                                                            uint32_t nb, uint32_t groups_cap,
                                                            uint16_t* __restrict__ sym, uint32_t* __restrict__ freq) {
-  __shared__ int s_last[MTF_WARPS][256];
-  __shared__ uint32_t s_list[MTF_WARPS][256];
+  __shared__ uint8_t s_front[MTF_WARPS][MTF_FRONT];
   __shared__ uint32_t s_deep[MTF_WARPS][MTF_DEEP_WORDS][32];
   __shared__ uint32_t s_freqw[MTF_WARPS][MAX_ALPHA + 2];
   const int w = threadIdx.x >> 5;
@@ -285,32 +284,37 @@ __global__ void __launch_bounds__(MTF_WARPS * 32) k3_apply(const uint8_t* __rest
       const int* cs = chunk_state + ((uint64_t)blk * chunks_cap + cbase + j) * 256;
       int mine[8];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        mine[k] = cs[k * 32 + lane];
-        s_last[w][k * 32 + lane] = mine[k];
-        s_list[w][k * 32 + lane] = 0xFFu;  // filler behind the in-use bytes; a real 0xFF always sits in front of it
+      for (int k = 0; k < 8; ++k) mine[k] = cs[k * 32 + lane];
+      // filler behind the in-use bytes (a real 0xFF always sits in front of it)
+      s_front[w][lane] = 0xFFu;
+      for (int q = lane; q < MTF_DEEP_WORDS; q += 32) s_deep[w][q][j] = 0xFFFFFFFFu;
+      // rank of every byte's previous occurrence among the in-use bytes = its list position; the 256 values are
+      // broadcast from the registers that hold them
+      uint32_t rank[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+      for (int k2 = 0; k2 < 8; ++k2) {
+        for (int l = 0; l < 32; ++l) {
+          const int v = __shfl_sync(0xffffffffu, mine[k2], l);
+          if (v == NEG_UNUSED) continue;  // warp-uniform
+#pragma unroll
+          for (int k = 0; k < 8; ++k) rank[k] += v > mine[k];
+        }
       }
       __syncwarp();
-      uint32_t rank[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-      for (int q = 0; q < 256; ++q) {
-        const int v = s_last[w][q];
-        if (v == NEG_UNUSED) continue;  // warp-uniform
 #pragma unroll
-        for (int k = 0; k < 8; ++k) rank[k] += v > mine[k];
+      for (int k = 0; k < 8; ++k) {
+        if (mine[k] != NEG_UNUSED) {
+          const uint32_t p = rank[k];
+          if (p < (uint32_t)MTF_FRONT) s_front[w][p] = (uint8_t)(k * 32 + lane);
+          else reinterpret_cast<uint8_t*>(&s_deep[w][(p - MTF_FRONT) >> 2][j])[(p - MTF_FRONT) & 3u] = (uint8_t)(k * 32 + lane);
+        }
       }
-#pragma unroll
-      for (int k = 0; k < 8; ++k)
-        if (mine[k] != NEG_UNUSED) s_list[w][rank[k]] = k * 32 + lane;
       __syncwarp();
       if (lane == j) {
 #pragma unroll
         for (int k = 0; k < 8; ++k)
-          ml.f[k] = s_list[w][4 * k] | (s_list[w][4 * k + 1] << 8) | (s_list[w][4 * k + 2] << 16) |
-                    (s_list[w][4 * k + 3] << 24);
-      }
-      for (int q = lane; q < MTF_DEEP_WORDS; q += 32) {
-        const uint32_t* e = &s_list[w][MTF_FRONT + 4 * q];
-        s_deep[w][q][j] = e[0] | (e[1] << 8) | (e[2] << 16) | (e[3] << 24);
+          ml.f[k] = s_front[w][4 * k] | (s_front[w][4 * k + 1] << 8) | (s_front[w][4 * k + 2] << 16) |
+                    ((uint32_t)s_front[w][4 * k + 3] << 24);
       }
       __syncwarp();
     }
