@@ -214,11 +214,13 @@ struct OsSmemT {
 // Byte histogram of a block's text = digit histogram of every pass of the initial sort (every byte of the block is
 // digit p of exactly one rotation).  grid (chunks, nb); hist[b][p][d] accumulated with global atomics.
 __global__ void __launch_bounds__(256) k2_os_hist_txt(const uint8_t* __restrict__ txt, const BlockDesc* __restrict__ desc,
-                                                      uint32_t* __restrict__ hist, uint32_t chunk) {
+                                                      uint32_t* __restrict__ hist, uint32_t* __restrict__ cnt,
+                                                      uint32_t chunk) {
   __shared__ uint32_t h[8][256];
   const BlockDesc d = desc[blockIdx.y];
   const uint32_t lo = blockIdx.x * chunk;
   if (lo >= d.n) return;
+  if (blockIdx.x == 0 && threadIdx.x == 0) cnt[blockIdx.y] = d.n;  // list length of the initial sort
   const uint32_t hi = min(d.n, lo + chunk);
   for (int i = threadIdx.x; i < 8 * 256; i += 256) (&h[0][0])[i] = 0;
   __syncthreads();
@@ -282,7 +284,9 @@ __device__ __forceinline__ void st_status(uint32_t* p, uint32_t v) {
   asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-template <int OS_NT, int OS_IPT, int OS_MINB>
+// FROM_TEXT: pass 0 of the initial sort builds its elements (first 5 bytes of the rotation | pos) from the block's
+// text instead of reading a materialised key array.
+template <int OS_NT, int OS_IPT, int OS_MINB, bool FROM_TEXT>
 __global__ void __launch_bounds__(OS_NT, OS_MINB) k2_os_scatter(const uint64_t* __restrict__ src, uint64_t* __restrict__ dst,
                                                           const BlockDesc* __restrict__ desc,
                                                           const uint32_t* __restrict__ cnt,
@@ -316,7 +320,24 @@ __global__ void __launch_bounds__(OS_NT, OS_MINB) k2_os_scatter(const uint64_t* 
 #pragma unroll
   for (int it = 0; it < OS_IPT; ++it) {
     const uint32_t li = w * OS_WCH + it * 32 + lane;
-    e[it] = li < tcount ? s[li] : ~0ull;
+    if (FROM_TEXT) {
+      e[it] = ~0ull;
+      if (li < tcount) {
+        const uint8_t* t = reinterpret_cast<const uint8_t*>(src) + off;  // src carries the text pointer
+        const uint32_t pos = base + li;
+        uint64_t key = 0;
+        uint32_t idx = pos;
+#pragma unroll
+        for (int j = 0; j < 5; ++j) {
+          key = (key << 8) | t[idx];
+          ++idx;
+          if (idx == c) idx = 0;  // c == block length in pass 0
+        }
+        e[it] = (key << KEY_LO) | pos;
+      }
+    } else {
+      e[it] = li < tcount ? s[li] : ~0ull;
+    }
   }
   // three separate sweeps so that the eight matches, the eight leader atomics and the eight broadcasts of a thread
   // are independent instructions the scheduler can overlap
@@ -1098,27 +1119,34 @@ static void radix_sort40(Launcher& L, uint64_t*& src, uint64_t*& dst, const uint
   if (variant < 0) {
     const char* v = getenv("BZB200_OS_VARIANT");
     variant = v ? atoi(v) : 5;  // measured on B200: 256 threads x 8 elements (2 048-element tiles, 4 CTAs/SM) is fastest
-    cudaFuncSetAttribute((const void*)k2_os_scatter<512, 8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaFuncSetAttribute((const void*)k2_os_scatter<512, 8, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          (int)sizeof(OsSmemT<512, 8>));
-    cudaFuncSetAttribute((const void*)k2_os_scatter<256, 16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaFuncSetAttribute((const void*)k2_os_scatter<256, 16, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          (int)sizeof(OsSmemT<256, 16>));
-    cudaFuncSetAttribute((const void*)k2_os_scatter<1024, 8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaFuncSetAttribute((const void*)k2_os_scatter<1024, 8, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          (int)sizeof(OsSmemT<1024, 8>));
-    cudaFuncSetAttribute((const void*)k2_os_scatter<512, 16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaFuncSetAttribute((const void*)k2_os_scatter<512, 16, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          (int)sizeof(OsSmemT<512, 16>));
-    cudaFuncSetAttribute((const void*)k2_os_scatter<384, 12, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaFuncSetAttribute((const void*)k2_os_scatter<384, 12, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          (int)sizeof(OsSmemT<384, 12>));
-    cudaFuncSetAttribute((const void*)k2_os_scatter<256, 8, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaFuncSetAttribute((const void*)k2_os_scatter<256, 8, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)sizeof(OsSmemT<256, 8>));
+    cudaFuncSetAttribute((const void*)k2_os_scatter<256, 8, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          (int)sizeof(OsSmemT<256, 8>));
   }
   const uint32_t tile_elems = variant == 2 || variant == 3 ? 8192u : variant == 4 ? 4608u : (variant == 0 || variant == 1) ? 4096u : 2048u;
   const uint32_t tiles = (maxcnt + tile_elems - 1) / tile_elems;
   if (tiles == 0) return;
+  const bool fuse_keys = d_txt && variant >= 5;  // default geometry: pass 0 reads the text, no key array
+  if (d_txt && !fuse_keys) {
+    const uint32_t tiles_n = (maxcnt + RS_TILE - 1) / RS_TILE;
+    L.launch("k2_init_keys", k2_init_keys, dim3(tiles_n, nb), dim3(RS_NT), d_txt, d_desc, src, S.cnt);
+  }
   cudaMemsetAsync(S.oshist, 0, (size_t)nb * 5 * 256 * sizeof(uint32_t), L.stream);
   const uint32_t chunk = 16 * 4096;
   const uint32_t chunks = (maxcnt + chunk - 1) / chunk;
   if (d_txt)
-    L.launch("k2_os_hist_txt", k2_os_hist_txt, dim3(chunks, nb), dim3(256), d_txt, d_desc, S.oshist, chunk);
+    L.launch("k2_os_hist_txt", k2_os_hist_txt, dim3(chunks, nb), dim3(256), d_txt, d_desc, S.oshist, S.cnt, chunk);
   else
     L.launch("k2_os_hist", k2_os_hist, dim3(chunks, nb), dim3(256), src, d_desc, S.cnt, S.oshist, chunk);
   L.launch("k2_os_offsets", k2_os_offsets, dim3(nb), dim3(256), S.oshist);
@@ -1129,15 +1157,23 @@ static void radix_sort40(Launcher& L, uint64_t*& src, uint64_t*& dst, const uint
     }
     ++os.epoch;
 #define OS_LAUNCH(NT, IPT, MB)                                                                                     \
-  L.launch_smem("k2_rs_scatter", k2_os_scatter<NT, IPT, MB>, dim3(nb, tiles), dim3(NT), sizeof(OsSmemT<NT, IPT>), src, \
-                dst, d_desc, S.cnt, S.oshist, S.hist, S.ticket, os.ticket_base, S.tiles_cap, os.epoch, p)
+  L.launch_smem("k2_rs_scatter", k2_os_scatter<NT, IPT, MB, false>, dim3(nb, tiles), dim3(NT),                     \
+                sizeof(OsSmemT<NT, IPT>), src, dst, d_desc, S.cnt, S.oshist, S.hist, S.ticket, os.ticket_base,     \
+                S.tiles_cap, os.epoch, p)
     switch (variant) {
       case 1: OS_LAUNCH(256, 16, 2); break;
       case 2: OS_LAUNCH(1024, 8, 1); break;
       case 3: OS_LAUNCH(512, 16, 1); break;
       case 4: OS_LAUNCH(384, 12, 2); break;
       case 0: OS_LAUNCH(512, 8, 2); break;
-      default: OS_LAUNCH(256, 8, 4); break;
+      default:
+        if (p == 0 && fuse_keys)  // elements built from the text on the fly
+          L.launch_smem("k2_rs_scatter", k2_os_scatter<256, 8, 4, true>, dim3(nb, tiles), dim3(256),
+                        sizeof(OsSmemT<256, 8>), reinterpret_cast<const uint64_t*>(d_txt), dst, d_desc, S.cnt, S.oshist,
+                        S.hist, S.ticket, os.ticket_base, S.tiles_cap, os.epoch, p);
+        else
+          OS_LAUNCH(256, 8, 4);
+        break;
     }
 #undef OS_LAUNCH
     os.ticket_base += tiles;
@@ -1181,7 +1217,6 @@ int run_bwt(Launcher& L, const uint8_t* d_txt, const BlockDesc* d_desc, uint32_t
   uint32_t rounds = 0, passes = 0;
   uint64_t elems = 0, radix_elem_passes = 5ull * M, local_elems = 0;
   uint64_t *src = S.A, *dst = S.B;
-  L.launch("k2_init_keys", k2_init_keys, dim3(tiles_n, nb), dim3(RS_NT), d_txt, d_desc, S.A, S.cnt);
   OsState os;
   cudaMemsetAsync(S.hist, 0, (size_t)nb * S.tiles_cap * 256 * sizeof(uint32_t), st);
   cudaMemsetAsync(S.ticket, 0, nb * sizeof(uint32_t), st);
