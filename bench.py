@@ -29,11 +29,12 @@ METRIC = "bzip2 compress MB/s (uncompressed)"
 BYTES_PER_GPU = int(os.environ.get("BZB200_BENCH_BYTES", str(1 << 30)))
 CPU_SAMPLE_BYTES = int(os.environ.get("BZB200_CPU_SAMPLE_BYTES", str(128 << 20)))
 # Algorithmic HBM bytes per unit of work for the kernels that can top the step (DESIGN.md "Kernels").
-#   k2_rs_scatter : one radix pass over a sort element = 8 B read + 8 B written
+#   k2_rs_scatter : one radix pass over a sort element = 8 B read + 8 B written; pass 0 of the initial sort reads
+#                   the text instead (1 B per element, the 5-byte windows overlap)
 #   k2_local_sort : one work-list entry = 8 B entry read + 4 B SA slot written + 4 B rank written
 #   k3_apply      : one last-column byte read + 2 B per emitted symbol
 ALG_BYTES = {
-    "k2_rs_scatter": lambda st: 16.0 * st["elems_sorted_radix"],
+    "k2_rs_scatter": lambda st: 16.0 * st["elems_sorted_radix"] - 7.0 * st["n_rle"],
     "k2_local_sort": lambda st: 16.0 * st["elems_local"],
     "k3_apply": lambda st: 1.0 * st["n_rle"] + 2.0 * st["mtf_symbols"],
 }

@@ -9,15 +9,17 @@
 // State per block:  SA[slot] = pos | HEAD | BIG | SINGLE   (rotations in the order established so far; a *group* is
 //                                a maximal run of slots whose rotations are still tied; HEAD marks its first slot)
 //                   rank[pos] = slot of the head of pos's group (| RESOLVED once the group is a singleton)
-// Round 0  : 64-bit elements [59:20] first 5 bytes | [19:0] pos, LSD radix sort (5 passes of 8 bits, per-block
-//            segments), regroup -> SA, rank.
+// Round 0  : 64-bit elements [59:20] first 5 bytes | [19:0] pos, LSD radix sort (5 one-sweep passes of 8 bits, per-block
+//            segments; pass 0 builds the elements from the text, the digit histograms are the block's byte
+//            histogram), regroup -> SA, rank.
 // Round r  : step h = 5, 10, 20, ...  key of a tied rotation = rank[(pos + h) mod n]:
-//   k2_gather      every unresolved slot fetches its key (slot order, coalesced SA read, L2-resident rank gather);
-//                  members of BIG groups (> LOCAL_MAX slots) are emitted as [59:40] g | [39:20] key | [19:0] pos
-//   k2_local_sort  one CTA per 2048-slot tile sorts every small group it owns inside shared memory (enumeration
-//                  sort on (group, key)), splits it, writes SA and rank in place
+//   k2_gather      every unresolved slot fetches its key and its group head (slot order, coalesced SA read,
+//                  L2-resident rank gathers) and is appended to its tile's dense work list; members of BIG groups
+//                  (> LOCAL_MAX slots) and of sparse blocks are emitted as [59:40] g | [39:20] key | [19:0] pos
+//   k2_local_sort  one CTA per 2048-slot tile sorts every group it owns inside shared memory (key-range bucket
+//                  split for larger groups, then enumeration sort on (group, key)), writes SA and rank in place
 //   BIG groups     LSD radix sort of the emitted elements + regroup (the round-0 machinery on a shorter list)
-//   k2_round_finalize  per-block state machine: done / periodic fix-up pending / active
+//   k2_round_finalize  per-block state machine: done / periodic fix-up pending / active / sparse
 // Fix-up   : a round that splits nothing means the block is periodic and the groups are the sets of equal
 //            rotations; one more round with key = n-1-((pos-shift) mod n) applies the reference's tie-break.
 #include <stdlib.h>
@@ -33,7 +35,6 @@ constexpr int RS_NT = 256;
 constexpr int RS_IPT = 16;
 constexpr int RS_TILE = RS_NT * RS_IPT;  // 4096 elements per CTA
 constexpr int RS_WARPS = RS_NT / 32;
-constexpr int RS_WCH = RS_TILE / RS_WARPS;  // 512 elements per warp
 constexpr int KEY_LO = 20;                  // key field = bits 20..59
 constexpr uint64_t POS_MASK = 0xFFFFFull;
 
@@ -64,131 +65,6 @@ __global__ void __launch_bounds__(RS_NT) k2_init_keys(const uint8_t* __restrict_
     }
   }
 }
-
-// ------------------------------------------------------------------ LSD radix pass (per-block segments)
-__device__ __forceinline__ uint32_t match_digit(uint32_t dgt, bool valid) {
-  uint32_t m = __ballot_sync(0xffffffffu, valid);
-#pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    uint32_t bit = (dgt >> k) & 1u;
-    uint32_t bk = __ballot_sync(0xffffffffu, bit);
-    m &= bit ? bk : ~bk;
-  }
-  return m;
-}
-
-__global__ void __launch_bounds__(RS_NT) k2_rs_hist(const uint64_t* __restrict__ src, const BlockDesc* __restrict__ desc,
-                                                    const uint32_t* __restrict__ cnt, uint32_t* __restrict__ hist,
-                                                    uint32_t tiles_cap, int shift) {
-  __shared__ uint32_t h[256];
-  const uint32_t c = cnt[blockIdx.y];
-  const uint32_t base = blockIdx.x * RS_TILE;
-  if (base >= c) return;
-  h[threadIdx.x] = 0;
-  __syncthreads();
-  const uint64_t* s = src + desc[blockIdx.y].off;
-#pragma unroll 4
-  for (int k = 0; k < RS_IPT; ++k) {
-    uint32_t i = base + threadIdx.x + k * RS_NT;
-    bool valid = i < c;
-    uint32_t dgt = valid ? (uint32_t)(s[i] >> shift) & 255u : 0u;
-    uint32_t peers = match_digit(dgt, valid);
-    if (valid && (peers & lanemask_lt()) == 0) atomicAdd(&h[dgt], __popc(peers));
-  }
-  __syncthreads();
-  hist[((uint64_t)blockIdx.y * tiles_cap + blockIdx.x) * 256 + threadIdx.x] = h[threadIdx.x];
-}
-
-// One CTA per block: turns per-(tile,digit) counts into exclusive offsets in (digit, tile) order.
-__global__ void __launch_bounds__(256) k2_rs_scan(const uint32_t* __restrict__ cnt, uint32_t* __restrict__ hist,
-                                                  uint32_t tiles_cap) {
-  __shared__ uint32_t ws[256 / 32 + 1];
-  const uint32_t c = cnt[blockIdx.x];
-  if (c == 0) return;
-  const uint32_t nt = (c + RS_TILE - 1) / RS_TILE;
-  uint32_t* hb = hist + (uint64_t)blockIdx.x * tiles_cap * 256;
-  uint32_t tot = 0;
-  for (uint32_t t = 0; t < nt; ++t) tot += hb[t * 256 + threadIdx.x];
-  uint32_t run = cta_excl_scan_add<256>(tot, ws, nullptr);
-  for (uint32_t t = 0; t < nt; ++t) {
-    uint32_t v = hb[t * 256 + threadIdx.x];
-    hb[t * 256 + threadIdx.x] = run;
-    run += v;
-  }
-}
-
-__global__ void __launch_bounds__(RS_NT) k2_rs_scatter(const uint64_t* __restrict__ src, uint64_t* __restrict__ dst,
-                                                       const BlockDesc* __restrict__ desc,
-                                                       const uint32_t* __restrict__ cnt,
-                                                       const uint32_t* __restrict__ hist, uint32_t tiles_cap, int shift) {
-  __shared__ uint32_t wcnt[RS_WARPS][256];
-  __shared__ uint64_t stage[RS_TILE];
-  __shared__ uint32_t dstart[256];
-  __shared__ int goff[256];
-  __shared__ uint32_t ws[RS_NT / 32 + 1];
-  const uint32_t c = cnt[blockIdx.y];
-  const uint32_t base = blockIdx.x * RS_TILE;
-  if (base >= c) return;
-  const uint32_t tcount = min((uint32_t)RS_TILE, c - base);
-  const uint32_t off = desc[blockIdx.y].off;
-  const uint64_t* s = src + off;
-  const int w = threadIdx.x >> 5;
-  const uint32_t lane = lane_id();
-  for (int i = lane; i < 256; i += 32) wcnt[w][i] = 0;
-  __syncwarp();
-
-  uint64_t e[RS_IPT];
-  uint16_t rk[RS_IPT];
-#pragma unroll
-  for (int it = 0; it < RS_IPT; ++it) {
-    uint32_t li = w * RS_WCH + it * 32 + lane;  // index inside the tile; memory order == (warp, it, lane)
-    bool valid = li < tcount;
-    e[it] = valid ? s[base + li] : 0ull;
-    uint32_t dgt = (uint32_t)(e[it] >> shift) & 255u;
-    uint32_t peers = match_digit(dgt, valid);
-    uint32_t old = valid ? wcnt[w][dgt] : 0u;
-    __syncwarp();
-    if (valid && (peers & lanemask_lt()) == 0) wcnt[w][dgt] = old + __popc(peers);
-    __syncwarp();
-    rk[it] = (uint16_t)(old + __popc(peers & lanemask_lt()));
-  }
-  __syncthreads();
-  // thread d: exclusive prefix over warps for digit d, and the tile total
-  {
-    const int dgt = threadIdx.x;
-    uint32_t run = 0;
-#pragma unroll
-    for (int ww = 0; ww < RS_WARPS; ++ww) {
-      uint32_t t = wcnt[ww][dgt];
-      wcnt[ww][dgt] = run;
-      run += t;
-    }
-    uint32_t ds = cta_excl_scan_add<RS_NT>(run, ws, nullptr);
-    dstart[dgt] = ds;
-    goff[dgt] = (int)hist[((uint64_t)blockIdx.y * tiles_cap + blockIdx.x) * 256 + dgt] - (int)ds;
-  }
-  __syncthreads();
-#pragma unroll
-  for (int it = 0; it < RS_IPT; ++it) {
-    uint32_t li = w * RS_WCH + it * 32 + lane;
-    if (li < tcount) {
-      uint32_t dgt = (uint32_t)(e[it] >> shift) & 255u;
-      stage[dstart[dgt] + wcnt[w][dgt] + rk[it]] = e[it];
-    }
-  }
-  __syncthreads();
-  uint64_t* o = dst + off;
-#pragma unroll 4
-  for (int k = 0; k < RS_IPT; ++k) {
-    uint32_t i = threadIdx.x + k * RS_NT;
-    if (i < tcount) {
-      uint64_t v = stage[i];
-      uint32_t dgt = (uint32_t)(v >> shift) & 255u;
-      o[goff[dgt] + (int)i] = v;
-    }
-  }
-}
-
 
 // ------------------------------------------------------------------ one-sweep LSD radix pass (per-block segments)
 // Digit histograms of all five passes are taken once (k2_os_hist*), turned into bucket offsets (k2_os_offsets), and
@@ -518,9 +394,10 @@ __global__ void __launch_bounds__(32) k2_rg_scan(const uint32_t* __restrict__ cn
 // New ranks, SA slots with flags, per-block statistics.  For the element at index a of the sorted list:
 //   fa = start of its g-run, ha = start of its (g,k2)-run, he = end of that run
 //   slot = g + (a - fa)        new rank = g + (ha - fa)        run size = he - ha
+template <bool initial>
 __global__ void __launch_bounds__(RS_NT) k2_rg_apply(const uint64_t* __restrict__ srt, const BlockDesc* __restrict__ desc,
                                                      const uint32_t* __restrict__ cnt, const int4* __restrict__ tsum,
-                                                     uint32_t tiles_cap, int initial, uint32_t* __restrict__ rank,
+                                                     uint32_t tiles_cap, uint32_t* __restrict__ rank,
                                                      uint32_t* __restrict__ sa, uint32_t* __restrict__ stats) {
   __shared__ int wsh[RS_WARPS], wsg[RS_WARPS], wsf[RS_WARPS];
   __shared__ uint32_t red[3][RS_WARPS];
@@ -570,8 +447,8 @@ __global__ void __launch_bounds__(RS_NT) k2_rg_apply(const uint64_t* __restrict_
     }
     if (hmask) fh = (int)a0 + __ffs(hmask) - 1;
   }
-  // CTA exclusive max-scan of (lh, lg); exclusive reverse min-scan of fh
-  int ih = warp_incl_scan_max(lh), ig = warp_incl_scan_max(lg);
+  // CTA exclusive max-scan of (lh, lg); exclusive reverse min-scan of fh  (initial round: one g-run, lg scan skipped)
+  int ih = warp_incl_scan_max(lh), ig = initial ? 0 : warp_incl_scan_max(lg);
   int rf = fh;
 #pragma unroll
   for (int d = 1; d < 32; d <<= 1) {
@@ -582,11 +459,11 @@ __global__ void __launch_bounds__(RS_NT) k2_rg_apply(const uint64_t* __restrict_
   if (lane_id() == 31) { wsh[w] = ih; wsg[w] = ig; }
   if (lane_id() == 0) wsf[w] = rf;
   __syncthreads();
-  int eh = __shfl_up_sync(0xffffffffu, ih, 1), eg = __shfl_up_sync(0xffffffffu, ig, 1);
-  if (lane_id() == 0) { eh = -1; eg = -1; }
-  for (int ww = 0; ww < w; ++ww) { eh = max(eh, wsh[ww]); eg = max(eg, wsg[ww]); }
+  int eh = __shfl_up_sync(0xffffffffu, ih, 1), eg = initial ? 0 : __shfl_up_sync(0xffffffffu, ig, 1);
+  if (lane_id() == 0) { eh = -1; if (!initial) eg = -1; }
+  for (int ww = 0; ww < w; ++ww) { eh = max(eh, wsh[ww]); if (!initial) eg = max(eg, wsg[ww]); }
   eh = max(eh, carry.x);
-  eg = max(eg, carry.y);
+  if (!initial) eg = max(eg, carry.y);
   int nh = __shfl_down_sync(0xffffffffu, rf, 1);
   if (lane_id() == 31) nh = 0x7FFFFFFF;
   for (int ww = w + 1; ww < RS_WARPS; ++ww) nh = min(nh, wsf[ww]);
@@ -1186,14 +1063,17 @@ static void regroup(Launcher& L, const uint64_t* srt, const BlockDesc* d_desc, u
   const uint32_t tiles = (maxcnt + RS_TILE - 1) / RS_TILE;
   L.launch("k2_rg_flags", k2_rg_flags, dim3(tiles, nb), dim3(RS_NT), srt, d_desc, S.cnt, S.tsum, S.tiles_cap, initial);
   L.launch("k2_rg_scan", k2_rg_scan, dim3(nb), dim3(32), S.cnt, S.tsum, S.tiles_cap);
-  L.launch_smem("k2_rg_apply", k2_rg_apply, dim3(tiles, nb), dim3(RS_NT), (size_t)(RS_TILE + RS_TILE / 16) * 8, srt,
-                d_desc, S.cnt, S.tsum, S.tiles_cap, initial, S.rank, S.sa, S.stats);
+  if (initial)
+    L.launch_smem("k2_rg_apply", k2_rg_apply<true>, dim3(tiles, nb), dim3(RS_NT), (size_t)(RS_TILE + RS_TILE / 16) * 8,
+                  srt, d_desc, S.cnt, S.tsum, S.tiles_cap, S.rank, S.sa, S.stats);
+  else
+    L.launch_smem("k2_rg_apply", k2_rg_apply<false>, dim3(tiles, nb), dim3(RS_NT), (size_t)(RS_TILE + RS_TILE / 16) * 8,
+                  srt, d_desc, S.cnt, S.tsum, S.tiles_cap, S.rank, S.sa, S.stats);
 }
 
 int run_bwt(Launcher& L, const uint8_t* d_txt, const BlockDesc* d_desc, uint32_t nb, uint32_t nmax, uint64_t M,
             BwtScratch& S, uint8_t* d_last, uint32_t* d_origptr, BwtStats* stats) {
   cudaStream_t st = L.stream;
-  const uint32_t tiles_n = (nmax + RS_TILE - 1) / RS_TILE;
   const uint32_t ls_tiles = (nmax + LS_T - 1) / LS_T;
   cudaMemsetAsync(S.state, 0, nb * sizeof(uint32_t), st);
   cudaMemsetAsync(S.shift, 0xFF, nb * sizeof(uint32_t), st);
