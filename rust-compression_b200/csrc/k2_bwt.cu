@@ -817,6 +817,7 @@ __global__ void __launch_bounds__(LS_NT, 2) k2_local_sort(const BlockDesc* __res
       }
     __syncthreads();
     uint32_t bi[LS_IPT];  // bucket index | arrival index << 12
+    uint32_t flat_heads = 0;
 #pragma unroll
     for (int k = 0; k < LS_IPT; ++k) {
       bi[k] = NONE;
@@ -826,7 +827,7 @@ __global__ void __launch_bounds__(LS_NT, 2) k2_local_sort(const BlockDesc* __res
         const uint32_t size = sm.gsz[gs] & 0xFFFu;
         if (mn == mx) {  // all keys equal: nothing to sort
           gp[k] &= 0x7FFFFFFFu;
-          if (((gp[k] >> 12) & 0xFFFu) == gs) sm.gsz[gs] = size | GS_FLAT;
+          if (((gp[k] >> 12) & 0xFFFu) == gs) flat_heads |= 1u << k;  // flag written after the barrier (others read gsz)
         } else {
           const int lnb = 31 - __clz(size);            // buckets = largest power of two <= size
           const int rb = 32 - __clz(mx - mn);           // bits of the key range
@@ -837,6 +838,9 @@ __global__ void __launch_bounds__(LS_NT, 2) k2_local_sort(const BlockDesc* __res
       }
     }
     __syncthreads();
+#pragma unroll
+    for (int k = 0; k < LS_IPT; ++k)
+      if (flat_heads & (1u << k)) sm.gsz[gp[k] & 0xFFFu] |= GS_FLAT;
     {  // exclusive prefix sum of the bucket counters over indices 0..count (blocked), in place
       const uint32_t r0 = threadIdx.x * LS_IPT;
       uint32_t loc[LS_IPT];

@@ -72,6 +72,7 @@ __global__ void __launch_bounds__(MTF_WARPS * 32) k3_chunk_scan_a(const uint8_t*
     // last occurrence inside the row: no higher lane holds the same byte; rows are visited in order
     const uint32_t peers = __match_any_sync(0xffffffffu, c);
     if (valid && (peers >> lane) == 1u) s_last[w][c] = (int)(c0 + i);
+    __syncwarp();  // the next row may store to the same byte's slot from another lane: keep the stores ordered
     const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
     const uint32_t nz = __ballot_sync(0xffffffffu, valid && c != p);
     const bool is_nz = (nz >> lane) & 1u;
