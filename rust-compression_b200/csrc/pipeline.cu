@@ -717,12 +717,15 @@ int bzb200_compress_host(bzb200_ctx* c, int level, const uint8_t* h_in, size_t n
   const size_t cap = bzb200_max_output_bytes(level, n);
   TRY(ensure(c, c->stage_in, n + 16));
   TRY(ensure(c, c->stage_out, cap));
-  size_t seg = (size_t)512 << 20;  // measured on B200: each extra segment costs ~5 ms of fixed per-batch latency
+  // Segment schedule: a small first segment (compute starts after ~2.5 ms of copying), then 1 GiB segments — every
+  // extra segment costs ~5 ms of fixed per-batch latency on a B200, more than the copy time it hides.
+  size_t seg = (size_t)1 << 30, first = (size_t)128 << 20;
   if (const char* e = getenv("BZB200_HOST_SEGMENT")) {
     unsigned long long v = strtoull(e, nullptr, 10);
     if (v >= (1u << 20)) seg = (size_t)v;
   }
-  if (n <= seg) {  // small input: one copy, one plan
+  first = std::min(first, seg / 2);
+  if (n <= 2 * first) {  // small input: one copy, one plan
     if (n) CK(c, cudaMemcpyAsync(c->stage_in.p, h_in, n, cudaMemcpyHostToDevice, c->stream));
     CK(c, cudaMemsetAsync(c->stage_out.p, 0, cap, c->stream));
     size_t got = 0;
@@ -738,9 +741,8 @@ int bzb200_compress_host(bzb200_ctx* c, int level, const uint8_t* h_in, size_t n
   }
   if (!c->h2d_stream) CK(c, cudaStreamCreateWithFlags(&c->h2d_stream, cudaStreamNonBlocking));
   if (!c->d2h_stream) CK(c, cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking));
-  // segment ends: a half-size first segment (compute starts early), then full segments
   std::vector<size_t> ends;
-  for (size_t e = seg / 2; e < n; e += seg) ends.push_back(e);
+  for (size_t e = first; e < n; e += seg) ends.push_back(e);
   if (ends.size() && n - ends.back() < seg / 4) ends.pop_back();  // no tiny tail segment
   ends.push_back(n);
   const size_t nseg = ends.size();
