@@ -38,6 +38,15 @@ extern "C" {
 #define BZB200_E_ARG (-3)      /* null pointer / bad range / output capacity too small */
 #define BZB200_E_STATE (-4)    /* call order violated (e.g. write after finish) */
 #define BZB200_E_INTERNAL (-5) /* device-side invariant failed (reported, never silently ignored) */
+#define BZB200_E_DATA (-6)     /* decoder: the input is not a valid .bz2 stream; the BZip2Error kind is reported next to it */
+
+/* BZip2Error of the reference decoder (src/bzip2/error.rs:4-11), as reported by the decoder entry points. */
+#define BZB200_BZ_OK 0
+#define BZB200_BZ_DATA_ERROR 1             /* -> CompressionError::DataError   (error.rs:44-52) */
+#define BZB200_BZ_DATA_ERROR_MAGIC_FIRST 2 /* -> CompressionError::DataError */
+#define BZB200_BZ_DATA_ERROR_MAGIC 3       /* -> CompressionError::DataError */
+#define BZB200_BZ_UNEXPECTED_EOF 4         /* -> CompressionError::UnexpectedEof */
+#define BZB200_BZ_UNEXPECTED 5             /* -> CompressionError::Unexpected */
 
 /* ------------------------------------------------------------------------
  * 1. Streaming encoder — what the Rust shim's `BZip2Encoder` binds.
@@ -51,17 +60,23 @@ typedef struct bzb200_enc bzb200_enc;
 
 /* level 1..9 (else BZB200_E_LEVEL); device = CUDA ordinal, -1 = current device. */
 BZB200_API int bzb200_enc_create(int level, int device, bzb200_enc** out);
-/* Action::Run: append n input bytes (copied into pinned host staging). */
+/* Action::Run: append n input bytes.  Input accumulates in a window (256 MiB, env BZB200_ENC_WINDOW); whenever the
+ * window is full, every block that is already closed is compressed on the GPU and its bytes become readable, while
+ * the still-open last block stays buffered (the reference also yields a block as soon as it
+ * closes, encoder.rs:91-107).  Only the concatenation of all bytes read is defined, not which call yields which. */
 BZB200_API int bzb200_enc_write(bzb200_enc* e, const uint8_t* p, size_t n);
-/* Action::Finish: compress everything written so far into one .bz2 stream. */
+/* Action::Finish: compress the remaining blocks and append the stream trailer. */
 BZB200_API int bzb200_enc_finish(bzb200_enc* e);
-/* Drain output bytes; returns the number copied, 0 after the last byte (-> `None`). */
+/* Drain output bytes; returns the number copied.  Before finish, 0 means "nothing ready yet, feed more input"
+ * (-> `None` under Action::Run); after finish, 0 means the stream is complete (-> `None` under Action::Finish). */
 BZB200_API size_t bzb200_enc_read(bzb200_enc* e, uint8_t* dst, size_t cap);
-/* Total size of the finished stream (valid after finish). */
+/* Output bytes ready to be read right now (after finish and before any read: the size of the whole remainder). */
 BZB200_API size_t bzb200_enc_output_size(const bzb200_enc* e);
 /* Re-arm for a new stream at the same level (the reference resets its latches when it returns None,
  * encoder.rs:87-90,130-133). */
 BZB200_API int bzb200_enc_reset(bzb200_enc* e);
+/* out[0..3]: blocks encoded so far, windows compressed, input bytes still buffered, output bytes ready. */
+BZB200_API int bzb200_enc_stats(const bzb200_enc* e, uint64_t* out, size_t cap);
 BZB200_API void bzb200_enc_destroy(bzb200_enc* e);
 BZB200_API const char* bzb200_enc_last_error(const bzb200_enc* e);
 
@@ -150,7 +165,48 @@ BZB200_API int bzb200_compress_host(bzb200_ctx* c, int level, const uint8_t* h_i
                          size_t* out_n);
 
 /* ------------------------------------------------------------------------
- * 3. Instrumentation (parity tests, bench roofline).  Not needed by a shim.
+ * 3. Decoder — block-parallel bzip2 decompression of whole buffers.
+ *    replaces: BZip2Decoder::new / Decoder::next  src/bzip2/decoder.rs:584-615
+ *              BZip2DecoderBase::init_block       src/bzip2/decoder.rs:163-525
+ *              get_next_lfm, BitDecodeService     src/bzip2/decoder.rs:527-581
+ *              DecodeExt::decode                  src/traits/decoder.rs:14-43
+ *    Accepts what the reference accepts (multi-stream buffers, any level, its limits decoder.rs:238,285,292,399,416,427)
+ *    and reports what it reports: the bytes the reference would have yielded before an error, then the BZip2Error kind.
+ *    Deviations, malformed input only: randomised blocks and over-subscribed coding tables are DataError (as in the
+ *    restated reference decoder under oracle/); a block that ends in four equal bytes with no count byte is DataError.
+ * ------------------------------------------------------------------------ */
+/* Device in -> device out on the context's stream; synchronises.  Returns BZB200_OK (*bz_error = 0, *out_n bytes
+ * written), BZB200_E_DATA (*bz_error = kind, the first *out_n bytes are what the reference yields before the error), or
+ * BZB200_E_ARG when cap_bytes is too small (*out_n = bytes required; nothing useful was written). */
+BZB200_API int bzb200_decompress_device(bzb200_ctx* c, const uint8_t* d_in, size_t n, uint8_t* d_out, size_t cap_bytes,
+                             size_t* out_n, int* bz_error);
+/* HOST in -> HOST out: H2D copy, decode, D2H copy of *out_n bytes; same return convention. */
+BZB200_API int bzb200_decompress_host(bzb200_ctx* c, const uint8_t* h_in, size_t n, uint8_t* h_out, size_t cap_bytes,
+                           size_t* out_n, int* bz_error);
+/* Counters of the last decode, out[0..7]: 0 streams, 1 blocks on the chain, 2 magic candidates found, 3 batches,
+ * 4 Huffman symbols decoded, 5 bytes before RLE1 undo (inverse-BWT elements), 6 output bytes, 7 reserved. */
+BZB200_API int bzb200_dec_stats(const bzb200_ctx* c, uint64_t* out, size_t cap);
+
+/* Streaming decoder object — what a Rust shim's `BZip2Decoder` binds (input is buffered; the blocks are decoded on
+ * the GPU when the input iterator is exhausted). */
+typedef struct bzb200_dec bzb200_dec;
+BZB200_API int bzb200_dec_create(int device, bzb200_dec** out);
+BZB200_API int bzb200_dec_write(bzb200_dec* d, const uint8_t* p, size_t n);
+/* Decodes everything written so far.  BZB200_OK, or BZB200_E_DATA: the bytes before the error can still be read, and
+ * bzb200_dec_error_kind() gives the BZip2Error the shim returns after them. */
+BZB200_API int bzb200_dec_finish(bzb200_dec* d);
+BZB200_API int bzb200_dec_error_kind(const bzb200_dec* d);
+BZB200_API size_t bzb200_dec_read(bzb200_dec* d, uint8_t* dst, size_t cap);
+BZB200_API size_t bzb200_dec_output_size(const bzb200_dec* d);
+BZB200_API int bzb200_dec_reset(bzb200_dec* d);
+BZB200_API void bzb200_dec_destroy(bzb200_dec* d);
+BZB200_API const char* bzb200_dec_last_error(const bzb200_dec* d);
+/* One-shot host->host: `bytes.decode(&mut BZip2Decoder::new()).collect()`.  *out is malloc'ed (also on
+ * BZB200_E_DATA: the bytes before the error); free with bzb200_free. */
+BZB200_API int bzb200_decompress(int device, const uint8_t* in, size_t n, uint8_t** out, size_t* out_n, int* bz_error);
+
+/* ------------------------------------------------------------------------
+ * 4. Instrumentation (parity tests, bench roofline).  Not needed by a shim.
  * ------------------------------------------------------------------------ */
 /* Stage dump of block b (absolute index in the current plan; must be inside the most recent
  * bzb200_encode_blocks batch).  field: */

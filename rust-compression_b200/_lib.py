@@ -5,7 +5,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libbzb200.so")
 
-OK, E_LEVEL, E_CUDA, E_ARG, E_STATE, E_INTERNAL = 0, -1, -2, -3, -4, -5
+OK, E_LEVEL, E_CUDA, E_ARG, E_STATE, E_INTERNAL, E_DATA = 0, -1, -2, -3, -4, -5, -6
 
 # every symbol include/bzb200.h declares: (restype, argtypes)
 _P = C.c_void_p
@@ -16,6 +16,7 @@ SIGNATURES = {
     "bzb200_enc_read": (C.c_size_t, [_P, _P, C.c_size_t]),
     "bzb200_enc_output_size": (C.c_size_t, [_P]),
     "bzb200_enc_reset": (C.c_int, [_P]),
+    "bzb200_enc_stats": (C.c_int, [_P, _P, C.c_size_t]),
     "bzb200_enc_destroy": (None, [_P]),
     "bzb200_enc_last_error": (C.c_char_p, [_P]),
     "bzb200_compress": (C.c_int, [C.c_int, C.c_int, _P, C.c_size_t, C.POINTER(_P), C.POINTER(C.c_size_t)]),
@@ -49,6 +50,19 @@ SIGNATURES = {
     "bzb200_plan_counts": (C.c_int, [_P, C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]),
     "bzb200_plan_finish": (C.c_int, [_P, C.c_void_p, C.POINTER(C.c_uint32)]),
     "bzb200_version": (C.c_char_p, []),
+    "bzb200_decompress_device": (C.c_int, [_P, _P, C.c_size_t, _P, C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(C.c_int)]),
+    "bzb200_decompress_host": (C.c_int, [_P, _P, C.c_size_t, _P, C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(C.c_int)]),
+    "bzb200_dec_stats": (C.c_int, [_P, _P, C.c_size_t]),
+    "bzb200_dec_create": (C.c_int, [C.c_int, C.POINTER(_P)]),
+    "bzb200_dec_write": (C.c_int, [_P, _P, C.c_size_t]),
+    "bzb200_dec_finish": (C.c_int, [_P]),
+    "bzb200_dec_error_kind": (C.c_int, [_P]),
+    "bzb200_dec_read": (C.c_size_t, [_P, _P, C.c_size_t]),
+    "bzb200_dec_output_size": (C.c_size_t, [_P]),
+    "bzb200_dec_reset": (C.c_int, [_P]),
+    "bzb200_dec_destroy": (None, [_P]),
+    "bzb200_dec_last_error": (C.c_char_p, [_P]),
+    "bzb200_decompress": (C.c_int, [C.c_int, _P, C.c_size_t, C.POINTER(_P), C.POINTER(C.c_size_t), C.POINTER(C.c_int)]),
 }
 
 _lib = None

@@ -1,0 +1,630 @@
+// dec_core.cuh — per-thread bodies of the block-parallel bzip2 DEcoder kernels.
+//
+// replaces, block by block and in parallel, the reference's BZip2Decoder:
+//   init_block             /root/reference/src/bzip2/decoder.rs:163-525  (block header, mapping table, selectors,
+//                                                                         coding tables, MTF/RUNA/RUNB, T^-1 vector)
+//   get_next_lfm           decoder.rs:527-542                            (inverse-BWT step)
+//   BitDecodeService::next decoder.rs:545-581                            (RLE1 undo, block CRC)
+//   MtfPositionDecoder     bzip2/mtf.rs:41-65
+//   canonical codes        huffman/mod.rs:22-67 (codes by (length, symbol)); a code that is not in the table is a
+//                          DataError (decoder.rs:376-379)
+//
+// Every kernel body is a plain function of (thread coordinates, pointers).  decoder.cu wraps each body in a
+// __global__ kernel; tests/cpp/dec_emu.cpp compiles the SAME bodies for the host (BZB_EMU) and runs them thread by
+// thread, so the algorithm can be checked against the restated reference decoder without a GPU.  The emulation is
+// test infrastructure; libbzb200.so contains device code only.
+//
+// Stages (one .bz2 buffer, all of its blocks at once):
+//   D1 d1_scan      every bit offset is tested for the 48-bit block magic 0x314159265359 and the end-of-stream magic
+//                   0x177245385090 -> candidate list (the host later keeps the candidates that lie on the chain
+//                   "block i ends where block i+1 starts", which is what a sequential parse would have visited)
+//   D2 d2_decode    one warp per candidate, lane 0 decodes: header, tables, Huffman symbols, MTF, RUNA/RUNB ->
+//                   last column L[i], occurrence index occ[i] = #{j < i : L[j] == L[i]}, byte counts -> cftab
+//   D3 d3_scatter   V[cftab[L[i]] + occ[i]] = i << 8 | L[i]   (the reference's tt after decoder.rs:479-484, with the
+//                   first-column byte in the low bits so that one load per step yields the output byte)
+//   D4 d4_walk_a    list ranking of the walk p -> V[p] >> 8: every SEG-th slot (and origPtr) is a splitter; a thread
+//                   walks from its splitter to the next one (length, successor)
+//      d4_schedule  one thread per block follows the splitters from origPtr and assigns output offsets; a periodic
+//                   block revisits its cycle (cycle length recorded)
+//      d4_walk_c    every scheduled splitter re-walks its segment and stores the bytes (the block before RLE1 undo)
+//   D5 d5_count     RLE1 undo as a 5-state machine (k equal bytes seen so far, k = 4: the next byte is a count): per
+//                   chunk and entry state -> exit state and expanded length
+//      d5_compose   one thread per block composes the chunk maps -> entry state and output offset of every chunk
+//      d5_expand    every chunk re-runs the machine from its entry state and writes the original bytes
+//   CRC             k5_crc_blocks (the encoder's kernel) over the output ranges of the blocks, compared on the host
+#pragma once
+#include <stdint.h>
+
+#ifdef BZB_EMU
+#define BZB_DEV inline
+#define BZB_HD inline
+#else
+#define BZB_DEV __device__ __forceinline__
+#define BZB_HD __host__ __device__ __forceinline__
+#endif
+
+namespace bzb {
+namespace dec {
+
+constexpr uint32_t SEG = 1024;          // splitter spacing of the inverse-BWT walks (slots)
+constexpr uint32_t RLE_CHUNK = 1024;    // bytes of the pre-RLE1 block per d5 thread
+constexpr uint32_t LUT_BITS = 10;       // primary Huffman lookup width
+constexpr uint32_t MAX_SEL = 32768;     // n_selectors is a 15-bit field (decoder.rs:285)
+constexpr uint64_t KIND_END = 1ull << 63;
+constexpr uint64_t MAGIC_BLOCK = 0x314159265359ull;
+constexpr uint64_t MAGIC_END = 0x177245385090ull;
+
+// BZip2Error ordinals + 1 (bzip2/error.rs:4-11), 0 = no error
+enum : uint32_t { E_OK = 0, E_DATA = 1, E_MAGIC_FIRST = 2, E_MAGIC = 3, E_EOF = 4, E_UNEXPECTED = 5 };
+
+struct CandInfo {       // one per candidate, written by d2_decode / d4_schedule / d5_compose, read by the host
+  uint64_t start_bit;   // position of the 48-bit magic
+  uint64_t end_bit;     // block: first bit after the EOB code; end of stream: first bit after the stored CRC
+  uint32_t kind;        // 0 block, 1 end of stream
+  uint32_t err;         // E_* raised while parsing (0: parsed through)
+  uint32_t err_early;   // 1: err was raised before origPtr had been read (decoder.rs:231-237)
+  uint32_t stored_crc;  // block CRC / combined CRC as stored in the stream
+  uint32_t orig_pos;
+  uint32_t randomised;
+  uint32_t nblock;      // tt.len(): bytes of the block before RLE1 undo
+  uint32_t need_max;    // smallest 100000*level that passes decoder.rs:399,427: nblock, +1 if a run was pushed last
+  uint32_t cyc;         // 0, or the length of the walk's cycle when it is shorter than nblock (periodic block)
+  uint32_t rle_len;     // bytes after RLE1 undo
+  uint32_t rle_dangling;  // 1: the block ends with four equal bytes and no count byte
+  uint32_t nsym;        // Huffman symbols decoded (incl. EOB), instrumentation
+  uint8_t tail[4];      // end of stream: the bytes after the padding (next stream's "BZh" + level, if any)
+  uint32_t tail_n;      // how many of them exist
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// Bit input, MSB first (bitio/reader.rs with direction Left).  Bytes beyond n read as zero; `read` refuses to go
+// beyond n*8 like the reference's reader does.
+BZB_DEV uint32_t load_be32(const uint8_t* p, uint64_t n, uint64_t w) {
+  const uint64_t o = w * 4;
+  if (o + 4 <= n && (((uintptr_t)p) & 3u) == 0) {
+    const uint32_t v = *reinterpret_cast<const uint32_t*>(p + o);
+    return (v >> 24) | ((v >> 8) & 0xFF00u) | ((v << 8) & 0xFF0000u) | (v << 24);
+  }
+  uint32_t r = 0;
+  for (int k = 0; k < 4; ++k) r = (r << 8) | (o + k < n ? (uint32_t)p[o + k] : 0u);
+  return r;
+}
+
+struct Reader {
+  const uint8_t* p;
+  uint64_t n, nbits;
+  uint64_t pos;    // next unread bit
+  uint64_t buf;    // unread bits, left aligned
+  uint32_t cnt;    // valid bits in buf (kept > 32 after refill)
+  uint64_t w;      // next 32-bit word to append
+  uint32_t ahead;  // word w, loaded one refill early so that its latency overlaps decoding
+
+  BZB_DEV void init(const uint8_t* p_, uint64_t n_, uint64_t pos_) {
+    p = p_;
+    n = n_;
+    nbits = n_ * 8;
+    pos = pos_;
+    w = pos_ >> 5;
+    const uint32_t sh = (uint32_t)(pos_ & 31);
+    buf = ((uint64_t)load_be32(p, n, w)) << 32;
+    buf <<= sh;
+    cnt = 32 - sh;
+    ++w;
+    ahead = load_be32(p, n, w);
+    refill();
+  }
+  BZB_DEV void refill() {
+    if (cnt <= 32) {
+      buf |= ((uint64_t)ahead) << (32 - cnt);
+      cnt += 32;
+      ++w;
+      ahead = load_be32(p, n, w);
+    }
+  }
+  // the next k (1..32) bits without consuming them; bits beyond the end of the input are zero
+  BZB_DEV uint32_t peek(uint32_t k) const { return (uint32_t)(buf >> (64 - k)); }
+  BZB_DEV void skip(uint32_t k) {
+    buf <<= k;
+    cnt -= k;
+    pos += k;
+    refill();
+  }
+  BZB_DEV bool read(uint32_t k, uint32_t& v) {
+    if (pos + k > nbits) return false;
+    v = peek(k);
+    skip(k);
+    return true;
+  }
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// D1: magic scan.  Thread x tests the 32 bit offsets of input word x.
+BZB_DEV void d1_scan_body(uint64_t x, const uint8_t* in, uint64_t n, uint64_t* cand, uint32_t* cand_count, uint32_t cap) {
+  const uint64_t nbits = n * 8;
+  if (x * 32 + 48 > nbits) return;
+  const uint64_t hi = ((uint64_t)load_be32(in, n, x) << 32) | load_be32(in, n, x + 1);
+  const uint32_t lo = load_be32(in, n, x + 2);
+  for (uint32_t s = 0; s < 32; ++s) {
+    const uint64_t win = s ? ((hi << s) | ((uint64_t)lo >> (32 - s))) : hi;
+    const uint64_t v = win >> 16;
+    if (v != MAGIC_BLOCK && v != MAGIC_END) continue;
+    const uint64_t bit = x * 32 + s;
+    if (bit + 48 > nbits) continue;
+#ifdef BZB_EMU
+    const uint32_t idx = (*cand_count)++;
+#else
+    const uint32_t idx = atomicAdd(cand_count, 1u);
+#endif
+    if (idx < cap) cand[idx] = bit | (v == MAGIC_END ? KIND_END : 0ull);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// D2: one candidate -> header, coding tables, symbols, MTF, RUNA/RUNB.
+struct D2Scratch {
+  uint16_t lut[6][1u << LUT_BITS];  // len << 9 | sym for codes of at most LUT_BITS bits, 0 = longer or invalid
+  uint32_t first_code[6][32];       // per length 1..31 (huffman/mod.rs:22-67)
+  uint16_t count[6][32];
+  uint16_t offs[6][32];             // start of the length's symbols inside perm
+  uint16_t perm[6][258];            // symbols by (length, symbol)
+  uint8_t max_len[6];
+  uint8_t len[258];
+  uint8_t mtf[256];                 // MTF list holding the block's bytes (seq2unseq applied)
+  uint32_t cnt[256];                // occurrences so far per byte
+};
+
+// Canonical codes of one table into scratch; false: over-subscribed (rejected as DataError, as the oracle does).
+BZB_DEV bool d2_build_table(D2Scratch* s, uint32_t t, uint32_t alpha) {
+  for (uint32_t l = 0; l < 32; ++l) {
+    s->count[t][l] = 0;
+    s->first_code[t][l] = 0;
+    s->offs[t][l] = 0;
+  }
+  uint32_t maxl = 0;
+  for (uint32_t i = 0; i < alpha; ++i) {
+    const uint32_t l = s->len[i];
+    if (l) s->count[t][l]++;
+    maxl = l > maxl ? l : maxl;
+  }
+  s->max_len[t] = (uint8_t)maxl;
+  uint64_t code = 0;
+  uint32_t prev = 0, off = 0;
+  for (uint32_t l = 1; l <= maxl; ++l) {
+    if (!s->count[t][l]) continue;
+    code <<= (l - prev);
+    prev = l;
+    s->first_code[t][l] = (uint32_t)code;
+    s->offs[t][l] = (uint16_t)off;
+    off += s->count[t][l];
+    code += s->count[t][l];
+    if (code > (1ull << l)) return false;
+  }
+  // symbols by (length, symbol): a counting sort, stable in the symbol (bucket_sort.rs:43-75)
+  {
+    uint16_t next[32];
+    for (uint32_t l = 0; l < 32; ++l) next[l] = s->offs[t][l];
+    for (uint32_t i = 0; i < alpha; ++i) {
+      const uint32_t l = s->len[i];
+      if (l) s->perm[t][next[l]++] = (uint16_t)i;
+    }
+  }
+  for (uint32_t e = 0; e < (1u << LUT_BITS); ++e) s->lut[t][e] = 0;
+  for (uint32_t l = 1; l <= maxl && l <= LUT_BITS; ++l) {
+    for (uint32_t j = 0; j < s->count[t][l]; ++j) {
+      const uint32_t c = s->first_code[t][l] + j;
+      const uint16_t v = (uint16_t)((l << 9) | s->perm[t][s->offs[t][l] + j]);
+      const uint32_t lo = c << (LUT_BITS - l), hi = (c + 1) << (LUT_BITS - l);
+      for (uint32_t e = lo; e < hi; ++e) s->lut[t][e] = v;
+    }
+  }
+  return true;
+}
+
+// One Huffman symbol of table t: returns the symbol, or -1 (no such code / input exhausted -> DataError).
+BZB_DEV int d2_symbol(const D2Scratch* s, uint32_t t, Reader& r) {
+  const uint32_t e = s->lut[t][r.peek(LUT_BITS)];
+  if (e) {
+    const uint32_t l = e >> 9;
+    if (r.pos + l > r.nbits) return -1;
+    r.skip(l);
+    return (int)(e & 511u);
+  }
+  const uint32_t maxl = s->max_len[t];
+  for (uint32_t l = LUT_BITS + 1; l <= maxl; ++l) {
+    if (!s->count[t][l]) continue;
+    const uint32_t c = r.peek(l);
+    const uint32_t f = s->first_code[t][l];
+    if (c >= f && c - f < s->count[t][l]) {
+      if (r.pos + l > r.nbits) return -1;
+      r.skip(l);
+      return (int)s->perm[t][s->offs[t][l] + (c - f)];
+    }
+  }
+  return -1;
+}
+
+// c: candidate index inside the batch.  cap = 100000 * (largest level of any stream in the buffer): the most a block
+// of this buffer may hold; stride >= cap is the per-candidate pitch of L / occ.
+BZB_DEV void d2_decode_body(uint32_t c, D2Scratch* s, const uint8_t* in, uint64_t n, const uint64_t* cand, uint32_t cap,
+                            uint64_t stride, uint8_t* Lbuf, uint32_t* occbuf, uint8_t* selbuf, uint32_t* cftab,
+                            CandInfo* infos) {
+  CandInfo I;
+  I.start_bit = cand[c] & ~KIND_END;
+  I.end_bit = 0;
+  I.kind = (cand[c] & KIND_END) ? 1u : 0u;
+  I.err = E_OK;
+  I.err_early = 0;
+  I.stored_crc = 0;
+  I.orig_pos = 0;
+  I.randomised = 0;
+  I.nblock = 0;
+  I.need_max = 0;
+  I.cyc = 0;
+  I.rle_len = 0;
+  I.rle_dangling = 0;
+  I.nsym = 0;
+  I.tail_n = 0;
+  for (int k = 0; k < 4; ++k) I.tail[k] = 0;
+
+  Reader r;
+  r.init(in, n, I.start_bit + 48);
+  uint8_t* L = Lbuf + (uint64_t)c * stride;
+  uint32_t* occ = occbuf + (uint64_t)c * stride;
+  uint8_t* sel = selbuf + (uint64_t)c * MAX_SEL;
+  uint32_t* cf = cftab + (uint64_t)c * 257;
+
+  do {
+    if (I.kind == 1) {  // end of stream (decoder.rs:494-520)
+      if (!r.read(32, I.stored_crc)) { I.err = E_EOF; break; }
+      I.end_bit = r.pos;
+      const uint64_t nb = ((r.pos + 7) >> 3);
+      for (uint32_t k = 0; k < 4 && nb + k < n; ++k) {
+        I.tail[k] = in[nb + k];
+        I.tail_n = k + 1;
+      }
+      break;
+    }
+    // ---- block header (decoder.rs:226-241)
+    I.err_early = 1;
+    if (!r.read(32, I.stored_crc)) { I.err = E_EOF; break; }
+    if (!r.read(1, I.randomised)) { I.err = E_EOF; break; }
+    if (!r.read(24, I.orig_pos)) { I.err = E_EOF; break; }
+    I.err_early = 0;
+    // (origPtr > 10 + 100000*level is checked by the host, which knows the stream's level)
+    if (I.randomised) { I.err = E_DATA; break; }  // deviation shared with the oracle: never produced by the encoder
+    // ---- mapping table (decoder.rs:243-281)
+    uint32_t in_use16;
+    if (!r.read(16, in_use16)) { I.err = E_EOF; break; }
+    uint32_t nsyms = 0;
+    bool fail = false;
+    for (uint32_t i = 0; i < 16 && !fail; ++i) {
+      if (!((in_use16 >> (15 - i)) & 1u)) continue;
+      uint32_t m;
+      if (!r.read(16, m)) { I.err = E_EOF; fail = true; break; }
+      for (uint32_t j = 0; j < 16; ++j)
+        if ((m >> (15 - j)) & 1u) s->mtf[nsyms++] = (uint8_t)(i * 16 + j);
+    }
+    if (fail) break;
+    if (nsyms == 0) { I.err = E_DATA; break; }
+    const uint32_t alpha = nsyms + 2;
+    // ---- selectors (decoder.rs:283-318)
+    uint32_t n_groups, n_sel;
+    if (!r.read(3, n_groups)) { I.err = E_EOF; break; }
+    if (n_groups < 2 || n_groups > 6) { I.err = E_DATA; break; }
+    if (!r.read(15, n_sel)) { I.err = E_EOF; break; }
+    if (n_sel < 1) { I.err = E_DATA; break; }
+    {
+      uint8_t sm[6] = {0, 1, 2, 3, 4, 5};
+      for (uint32_t k = 0; k < n_sel && !fail; ++k) {
+        uint32_t j = 0;
+        for (;;) {
+          uint32_t bit;
+          if (!r.read(1, bit)) { I.err = E_EOF; fail = true; break; }
+          if (!bit) break;
+          if (++j >= n_groups) { I.err = E_DATA; fail = true; break; }
+        }
+        if (fail) break;
+        const uint8_t t = sm[j];
+        for (uint32_t q = j; q > 0; --q) sm[q] = sm[q - 1];
+        sm[0] = t;
+        sel[k] = t;
+      }
+    }
+    if (fail) break;
+    // ---- coding tables (decoder.rs:320-358)
+    for (uint32_t t = 0; t < n_groups && !fail; ++t) {
+      uint32_t curr;
+      if (!r.read(5, curr)) { I.err = E_EOF; fail = true; break; }
+      for (uint32_t i = 0; i < alpha && !fail; ++i) {
+        for (;;) {
+          uint32_t bit;
+          if (!r.read(1, bit)) { I.err = E_EOF; fail = true; break; }
+          if (!bit) break;
+          if (curr < 1 || curr > 20) { I.err = E_DATA; fail = true; break; }
+          if (!r.read(1, bit)) { I.err = E_EOF; fail = true; break; }
+          if (bit == 0) curr += 1; else curr -= 1;
+        }
+        s->len[i] = (uint8_t)curr;
+      }
+      if (fail) break;
+      if (!d2_build_table(s, t, alpha)) { I.err = E_DATA; fail = true; break; }
+    }
+    if (fail) break;
+    // ---- symbols (decoder.rs:360-444)
+    for (uint32_t k = 0; k < 256; ++k) s->cnt[k] = 0;
+    const uint32_t eob = alpha - 1;
+    uint32_t group_no = 0, group_pos = 0, tbl = 0;
+    uint64_t nn = 1, es = 0;
+    uint32_t size = 0, need = 0, nsym = 0;
+    for (;;) {
+      if (group_pos == 0) {
+        group_no += 1;
+        if (group_no > n_sel) { I.err = E_DATA; break; }
+        group_pos = 50;
+        tbl = sel[group_no - 1];
+      }
+      group_pos -= 1;
+      const int sym = d2_symbol(s, tbl, r);
+      if (sym < 0) { I.err = E_DATA; break; }
+      ++nsym;
+      const uint32_t next_sym = (uint32_t)sym;
+      if (es > 0 && next_sym != 0 && next_sym != 1) {  // flush the zero run: es copies of the list front
+        const uint8_t uc = s->mtf[0];
+        if ((uint64_t)size + es >= (uint64_t)cap) { I.err = E_DATA; break; }  // decoder.rs:399 at the largest level
+        const uint32_t base = s->cnt[uc];
+        for (uint32_t k = 0; k < (uint32_t)es; ++k) {
+          L[size + k] = uc;
+          occ[size + k] = base + k;
+        }
+        s->cnt[uc] = base + (uint32_t)es;
+        size += (uint32_t)es;
+        need = size + 1;
+        nn = 1;
+        es = 0;
+      }
+      if (next_sym == eob) break;
+      if (nn >= 2u * 1024u * 1024u) { I.err = E_DATA; break; }  // decoder.rs:416
+      if (next_sym == 0) {
+        es += nn;
+        nn <<= 1;
+      } else if (next_sym == 1) {
+        nn <<= 1;
+        es += nn;
+      } else {
+        if (size >= cap) { I.err = E_DATA; break; }              // decoder.rs:427 at the largest level
+        const uint32_t v = next_sym - 1;
+        if (v >= nsyms) { I.err = E_DATA; break; }
+        const uint8_t uc = s->mtf[v];
+        for (uint32_t q = v; q > 0; --q) s->mtf[q] = s->mtf[q - 1];
+        s->mtf[0] = uc;
+        L[size] = uc;
+        occ[size] = s->cnt[uc]++;
+        size += 1;
+        need = size;
+      }
+    }
+    I.nsym = nsym;
+    if (I.err) break;
+    I.end_bit = r.pos;
+    I.nblock = size;
+    I.need_max = need;
+    if (I.orig_pos >= size) { I.err = E_DATA; break; }  // decoder.rs:446-450
+    uint32_t acc = 0;
+    for (uint32_t k = 0; k < 256; ++k) {  // cftab (decoder.rs:452-476)
+      cf[k] = acc;
+      acc += s->cnt[k];
+    }
+    cf[256] = acc;
+  } while (0);
+  infos[c] = I;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// D3: x = position inside the block, y = candidate.
+BZB_DEV void d3_scatter_body(uint32_t x, uint32_t y, const CandInfo* infos, uint64_t stride, const uint8_t* Lbuf,
+                             const uint32_t* occbuf, const uint32_t* cftab, uint32_t* Vbuf) {
+  const CandInfo& I = infos[y];
+  if (I.kind != 0 || I.err != 0 || x >= I.nblock) return;
+  const uint64_t base = (uint64_t)y * stride;
+  const uint32_t b = Lbuf[base + x];
+  const uint32_t slot = cftab[(uint64_t)y * 257 + b] + occbuf[base + x];
+  Vbuf[base + slot] = (x << 8) | b;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// D4: list ranking.  Splitter ids: x < nseg0 = ceil(nblock / SEG) is slot x*SEG; id nseg0 is slot origPtr (unused
+// when origPtr is a multiple of SEG).  segs_pitch = splitters per candidate the arrays were sized for.
+BZB_HD uint32_t d4_nseg0(uint32_t nblock) { return (nblock + SEG - 1) / SEG; }
+
+BZB_DEV void d4_walk_a_body(uint32_t x, uint32_t y, const CandInfo* infos, uint64_t stride, const uint32_t* Vbuf,
+                            uint32_t segs_pitch, uint32_t* seg_len, uint32_t* seg_next) {
+  const CandInfo& I = infos[y];
+  if (I.kind != 0 || I.err != 0) return;
+  const uint32_t n0 = d4_nseg0(I.nblock);
+  const uint32_t orig = I.orig_pos;
+  const bool orig_on_grid = (orig % SEG) == 0;
+  uint32_t pos;
+  if (x < n0) pos = x * SEG;
+  else if (x == n0 && !orig_on_grid) pos = orig;
+  else return;
+  const uint32_t* V = Vbuf + (uint64_t)y * stride;
+  uint32_t len = 0;
+  do {
+    pos = V[pos] >> 8;
+    ++len;
+  } while ((pos % SEG) != 0 && pos != orig);
+  const uint64_t o = (uint64_t)y * segs_pitch + x;
+  seg_len[o] = len;
+  seg_next[o] = (pos == orig && !orig_on_grid) ? n0 : pos / SEG;
+}
+
+// one thread per candidate; seg_off must be filled with 0xFFFFFFFF beforehand
+BZB_DEV void d4_schedule_body(uint32_t y, CandInfo* infos, uint32_t segs_pitch, const uint32_t* seg_len,
+                              const uint32_t* seg_next, uint32_t* seg_off) {
+  CandInfo& I = infos[y];
+  if (I.kind != 0 || I.err != 0) return;
+  const uint32_t n0 = d4_nseg0(I.nblock);
+  const uint64_t base = (uint64_t)y * segs_pitch;
+  uint32_t cur = (I.orig_pos % SEG) == 0 ? I.orig_pos / SEG : n0;
+  uint32_t off = 0;
+  uint32_t cyc = 0;
+  while (off < I.nblock) {
+    if (seg_off[base + cur] != 0xFFFFFFFFu) {  // back at the start: the walk is a cycle shorter than the block
+      cyc = off;
+      break;
+    }
+    seg_off[base + cur] = off;
+    off += seg_len[base + cur];
+    cur = seg_next[base + cur];
+  }
+  I.cyc = cyc;
+}
+
+BZB_DEV void d4_walk_c_body(uint32_t x, uint32_t y, const CandInfo* infos, uint64_t stride, const uint32_t* Vbuf,
+                            uint32_t segs_pitch, const uint32_t* seg_len, const uint32_t* seg_off, uint8_t* Wbuf) {
+  const CandInfo& I = infos[y];
+  if (I.kind != 0 || I.err != 0) return;
+  const uint32_t n0 = d4_nseg0(I.nblock);
+  if (x > n0) return;
+  const uint64_t so = (uint64_t)y * segs_pitch + x;
+  const uint32_t off = seg_off[so];
+  if (off == 0xFFFFFFFFu) return;
+  const uint32_t len = seg_len[so];
+  const uint32_t n = I.nblock;
+  const uint32_t* V = Vbuf + (uint64_t)y * stride;
+  uint8_t* W = Wbuf + (uint64_t)y * stride;
+  uint32_t pos = x < n0 ? x * SEG : I.orig_pos;
+  if (I.cyc == 0) {
+    // bytes off .. off+len-1 (clipped to n): head byte-wise up to a 4-byte boundary, then whole words
+    uint32_t k = 0;
+    const uint32_t end = off + len < n ? len : n - off;
+    uint32_t acc = 0, have = 0;
+    for (; k < end; ++k) {
+      const uint32_t v = V[pos];
+      pos = v >> 8;
+      const uint32_t o = off + k;
+      if (have == 0 && ((o & 3u) != 0 || end - k < 4)) {
+        W[o] = (uint8_t)v;
+        continue;
+      }
+      acc |= (v & 255u) << (8 * have);
+      if (++have == 4) {
+        *reinterpret_cast<uint32_t*>(W + (o - 3)) = acc;
+        acc = 0;
+        have = 0;
+      }
+    }
+  } else {
+    const uint32_t cyc = I.cyc;
+    for (uint32_t k = 0; k < len; ++k) {
+      const uint32_t v = V[pos];
+      pos = v >> 8;
+      for (uint64_t o = (uint64_t)off + k; o < n; o += cyc) W[o] = (uint8_t)v;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// D5: RLE1 undo.  State k = number of equal bytes seen so far in the current run (0 fresh, 1..3; 4: the next byte
+// is a count).  For k in 1..3 the run's byte is the byte before the chunk.
+struct RleStep {
+  uint32_t k;
+  uint32_t prev;
+};
+
+BZB_HD uint32_t d5_nchunks(uint32_t nblock) { return (nblock + RLE_CHUNK - 1) / RLE_CHUNK; }
+
+// map entry: exit state in bits 29..31, expanded length in bits 0..28
+BZB_DEV void d5_count_body(uint32_t x, uint32_t y, const CandInfo* infos, uint64_t stride, const uint8_t* Wbuf,
+                           uint32_t chunks_pitch, uint32_t* rle_map /*[cand][chunk][5]*/) {
+  const CandInfo& I = infos[y];
+  if (I.kind != 0 || I.err != 0) return;
+  const uint32_t n = I.nblock;
+  if (x >= d5_nchunks(n)) return;
+  const uint8_t* W = Wbuf + (uint64_t)y * stride;
+  const uint32_t lo = x * RLE_CHUNK, hi = lo + RLE_CHUNK < n ? lo + RLE_CHUNK : n;
+  const uint32_t before = lo ? W[lo - 1] : 0x100u;
+  for (uint32_t k0 = 0; k0 < 5; ++k0) {
+    uint32_t k = k0, prev = before, len = 0;
+    if (k0 >= 1 && k0 <= 3) {  // the state is only reachable if the k0 bytes before the chunk are equal
+      bool ok = lo >= k0;
+      for (uint32_t q = 1; ok && q < k0; ++q) ok = W[lo - 1 - q] == before;
+      if (!ok) {
+        rle_map[((uint64_t)y * chunks_pitch + x) * 5 + k0] = 0;
+        continue;
+      }
+    }
+    if (k0 == 4 && lo < 4) {
+      rle_map[((uint64_t)y * chunks_pitch + x) * 5 + k0] = 0;
+      continue;
+    }
+    for (uint32_t i = lo; i < hi; ++i) {
+      const uint32_t b = W[i];
+      if (k == 4) {
+        len += b;
+        k = 0;
+      } else if (k > 0 && b == prev) {
+        ++k;
+        ++len;
+      } else {
+        k = 1;
+        ++len;
+      }
+      prev = b;
+    }
+    rle_map[((uint64_t)y * chunks_pitch + x) * 5 + k0] = (k << 29) | len;
+  }
+}
+
+BZB_DEV void d5_compose_body(uint32_t y, CandInfo* infos, uint32_t chunks_pitch, const uint32_t* rle_map,
+                             uint32_t* chunk_entry /*[cand][chunk]: state << 29 ... */, uint64_t* chunk_off) {
+  CandInfo& I = infos[y];
+  if (I.kind != 0 || I.err != 0) return;
+  const uint32_t nc = d5_nchunks(I.nblock);
+  uint32_t k = 0;
+  uint64_t off = 0;
+  for (uint32_t ch = 0; ch < nc; ++ch) {
+    const uint64_t o = (uint64_t)y * chunks_pitch + ch;
+    chunk_entry[o] = k;
+    chunk_off[o] = off;
+    const uint32_t m = rle_map[o * 5 + k];
+    k = m >> 29;
+    off += m & 0x1FFFFFFFu;
+  }
+  I.rle_len = (uint32_t)(off > 0xFFFFFFFFull ? 0xFFFFFFFFull : off);
+  I.rle_dangling = k == 4 ? 1u : 0u;
+}
+
+// out_off[y] = byte offset of the block's original bytes in the output, or ~0 when the block is not on the chain
+BZB_DEV void d5_expand_body(uint32_t x, uint32_t y, const CandInfo* infos, uint64_t stride, const uint8_t* Wbuf,
+                            uint32_t chunks_pitch, const uint32_t* chunk_entry, const uint64_t* chunk_off,
+                            const uint64_t* out_off, uint8_t* out) {
+  const CandInfo& I = infos[y];
+  if (I.kind != 0 || I.err != 0) return;
+  if (out_off[y] == ~0ull) return;
+  const uint32_t n = I.nblock;
+  if (x >= d5_nchunks(n)) return;
+  const uint8_t* W = Wbuf + (uint64_t)y * stride;
+  const uint32_t lo = x * RLE_CHUNK, hi = lo + RLE_CHUNK < n ? lo + RLE_CHUNK : n;
+  const uint64_t co = (uint64_t)y * chunks_pitch + x;
+  uint32_t k = chunk_entry[co];
+  uint8_t* o = out + out_off[y] + chunk_off[co];
+  uint32_t prev = lo ? W[lo - 1] : 0x100u;
+  for (uint32_t i = lo; i < hi; ++i) {
+    const uint32_t b = W[i];
+    if (k == 4) {
+      for (uint32_t q = 0; q < b; ++q) o[q] = (uint8_t)prev;
+      o += b;
+      k = 0;
+      // `prev` keeps the run's byte, but the next byte starts a new run whatever it is (result_count >= 4)
+      continue;
+    }
+    if (k > 0 && b == prev) ++k;
+    else k = 1;
+    *o++ = (uint8_t)b;
+    prev = b;
+  }
+}
+
+}  // namespace dec
+}  // namespace bzb

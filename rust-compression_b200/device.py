@@ -170,6 +170,39 @@ class Context:
                     "bzb200_compress_host")
         return n.value
 
+    # ---- decoder (include/bzb200.h section 3) ----
+    def decompress_device(self, d_in, d_out):
+        """Device tensor holding a .bz2 buffer -> original bytes in d_out.  Returns (bytes written, BZip2Error code
+        or 0); raises ValueError(needed) when d_out is too small."""
+        self._u8(d_in)
+        self._u8(d_out)
+        n, kind = C.c_size_t(0), C.c_int(0)
+        rc = _lib.lib().bzb200_decompress_device(self._h, C.c_void_p(d_in.data_ptr()), d_in.numel(),
+                                                 C.c_void_p(d_out.data_ptr()), d_out.numel(), C.byref(n), C.byref(kind))
+        if rc == _lib.E_ARG and n.value > d_out.numel():
+            raise ValueError(n.value)
+        if rc not in (_lib.OK, _lib.E_DATA):
+            self._check(rc, "bzb200_decompress_device")
+        return n.value, kind.value
+
+    def decompress_host(self, h_in, h_out):
+        """Host tensor in -> host tensor out through bzb200_decompress_host; same return convention."""
+        assert (not h_in.is_cuda) and (not h_out.is_cuda) and h_in.dtype == torch.uint8 and h_out.dtype == torch.uint8
+        n, kind = C.c_size_t(0), C.c_int(0)
+        rc = _lib.lib().bzb200_decompress_host(self._h, C.c_void_p(h_in.data_ptr()), h_in.numel(),
+                                               C.c_void_p(h_out.data_ptr()), h_out.numel(), C.byref(n), C.byref(kind))
+        if rc == _lib.E_ARG and n.value > h_out.numel():
+            raise ValueError(n.value)
+        if rc not in (_lib.OK, _lib.E_DATA):
+            self._check(rc, "bzb200_decompress_host")
+        return n.value, kind.value
+
+    def dec_stats(self):
+        v = (C.c_uint64 * 8)()
+        _lib.lib().bzb200_dec_stats(self._h, v, 8)
+        keys = ["streams", "blocks", "candidates", "batches", "symbols", "pre_rle_bytes", "out_bytes"]
+        return {k: int(v[i]) for i, k in enumerate(keys)}
+
     # ---- instrumentation ----
     def debug_stage(self, block, name):
         fid, dt = FIELDS[name]

@@ -10,7 +10,8 @@ Reference (chalharu/rust-compression):
 Semantics kept: with Action.Finish, `next` yields every byte of the .bz2 stream and then None, after which the
 encoder is re-armed (encoder.rs:87-90,130-133); with Action.Run, None means "input drained, feed more".
 Action.Flush is out of contract and behaves like Run.  Only the concatenated byte sequence is
-guaranteed, not the call at which each byte appears: blocks are compressed on the GPU when Finish arrives.
+guaranteed, not the call at which each byte appears: closed blocks are compressed on the GPU whenever a window of
+input (256 MiB, env BZB200_ENC_WINDOW) has accumulated, the rest when Finish arrives.
 All compute happens in libbzb200.so (CUDA, sm_100a); there is no CPU path.
 """
 import ctypes as C
@@ -83,6 +84,21 @@ class BZip2Encoder:
         L.bzb200_enc_reset(self._h)
         return buf.raw[:got]
 
+    def stats(self):
+        v = (C.c_uint64 * 4)()
+        _lib.lib().bzb200_enc_stats(self._h, v, 4)
+        return {"blocks": int(v[0]), "windows": int(v[1]), "buffered_in": int(v[2]), "ready_out": int(v[3])}
+
+    def read_available(self):
+        """Output bytes that are ready now (closed blocks of full windows under Action.Run; everything after finish)."""
+        L = _lib.lib()
+        n = L.bzb200_enc_output_size(self._h)
+        if not n:
+            return b""
+        buf = C.create_string_buffer(n)
+        got = L.bzb200_enc_read(self._h, buf, n)
+        return buf.raw[:got]
+
     def next(self, it, action):
         """Encoder::next (encoder.rs:120-158): returns the next output byte (int) or None."""
         L = _lib.lib()
@@ -90,32 +106,31 @@ class BZip2Encoder:
             b = self._chunk[self._pos]
             self._pos += 1
             return b
-        if self._finished:
-            # stream fully drained: reset the latches like the reference and report None once
-            self._finished = False
-            self._chunk, self._pos = b"", 0
-            L.bzb200_enc_reset(self._h)
-            return None
-        # drain the input iterator (the reference pulls one byte at a time, encoder.rs:79-85)
-        pending = bytearray()
-        for x in it:
-            pending.append(x)
-            if len(pending) >= (1 << 20):
+        if not self._finished:
+            # drain the input iterator (the reference pulls one byte at a time, encoder.rs:79-85)
+            pending = bytearray()
+            for x in it:
+                pending.append(x)
+                if len(pending) >= (1 << 20):
+                    self.write(pending)
+                    pending.clear()
+            if pending:
                 self.write(pending)
-                pending.clear()
-        if pending:
-            self.write(pending)
-        if action is not Action.Finish:
-            return None  # Run/Flush: input drained, nothing to hand out yet
-        rc = L.bzb200_enc_finish(self._h)
-        if rc != _lib.OK:
-            raise self._err("bzb200_enc_finish", rc)
-        n = L.bzb200_enc_output_size(self._h)
-        buf = C.create_string_buffer(n)
-        got = L.bzb200_enc_read(self._h, buf, n)
-        self._chunk, self._pos = buf.raw[:got], 0
-        self._finished = True
-        return self.next(it, action)
+            if action is Action.Finish:
+                rc = L.bzb200_enc_finish(self._h)
+                if rc != _lib.OK:
+                    raise self._err("bzb200_enc_finish", rc)
+                self._finished = True
+        chunk = self.read_available()  # under Run: the blocks that closed so far; after Finish: the rest
+        if chunk:
+            self._chunk, self._pos = chunk, 0
+            return self.next(it, action)
+        self._chunk, self._pos = b"", 0
+        if self._finished:
+            # stream fully drained: reset the latches like the reference (encoder.rs:87-90,130-133)
+            self._finished = False
+            L.bzb200_enc_reset(self._h)
+        return None  # Run/Flush: input drained, nothing (more) to hand out yet
 
 
 class EncodeIterator:

@@ -1,4 +1,4 @@
-// The reference's own bzip2 encoder tests (src/bzip2/mod.rs:41-172, src/lib.rs:13-33), restated against the C++
+// The reference's own bzip2 encoder and decoder tests (src/bzip2/mod.rs:41-172, src/lib.rs:13-33), restated against the C++
 // mirror of its API (rust-compression_b200/csrc/bzb200.hpp).  Expected streams come from the CPU oracle (linked
 // here as the CHECKER only) and from the reference's golden vector.  Needs a CUDA device.
 //   usage: test_bzip2 <dir with sample1-3.ref>
@@ -11,6 +11,8 @@
 #include "../../rust-compression_b200/csrc/bzb200.hpp"
 
 extern "C" long long orc_compress(int level, const uint8_t* in, size_t n, uint8_t* out, size_t cap);
+extern "C" int orc_decode(const uint8_t* in, size_t n, uint8_t** out, size_t* out_n);
+extern "C" void orc_decode_free(uint8_t* p);
 
 using namespace compression;
 
@@ -95,6 +97,82 @@ static void test_run_then_finish() {  // Action::Run semantics, encoder.rs:91-10
   CHECK(again == oracle(in, 9));
 }
 
+// bzip2/mod.rs:72-82 check_unzip: actual.decode(&mut BZip2Decoder::new()).collect() == Ok(expected)
+static void check_unzip(const std::vector<uint8_t>& actual, const std::vector<uint8_t>& expected) {
+  BZip2Decoder dec;
+  std::vector<uint8_t> ret;
+  BZip2Error e = BZip2Error::Unexpected;
+  CHECK(decode_collect(actual, dec, ret, &e));
+  CHECK(ret == expected);
+}
+
+static void test_decode_samples(const std::string& dir) {  // bzip2/mod.rs:84-148 (the .bz2 halves), :150-172
+  for (int idx = 1; idx <= 4; ++idx) {
+    auto ref = read_file(dir + "/sample" + std::to_string(idx) + ".ref");
+    auto bz = read_file(dir + "/sample" + std::to_string(idx) + ".bz2");
+    CHECK(!ref.empty() && !bz.empty());
+    check_unzip(bz, ref);
+    if (idx <= 3) {  // encode at level idx, then unzip (the first halves of test_sample1..3)
+      BZip2Encoder encoder(idx);
+      std::vector<uint8_t> ret;
+      CHECK(encode_collect(ref, encoder, Action::Finish, ret));
+      check_unzip(ret, ref);
+    }
+  }
+  std::vector<uint8_t> data(1000, 'a'), comp;
+  BZip2Encoder enc(9);
+  CHECK(encode_collect(data, enc, Action::Finish, comp));
+  check_unzip(comp, data);
+}
+
+static void test_decode_errors(const std::string& dir) {  // same bytes and BZip2Error kind as the restated reference
+  auto bz = read_file(dir + "/sample1.bz2");
+  std::vector<std::vector<uint8_t>> bad;
+  bad.push_back({});                                                              // DataErrorMagicFirst
+  bad.push_back(std::vector<uint8_t>(bz.begin(), bz.begin() + bz.size() / 2));    // cut inside the block
+  bad.push_back(std::vector<uint8_t>(bz.begin(), bz.end() - 2));                  // cut inside the combined CRC
+  { auto t = bz; t[bz.size() / 2] ^= 0x04; bad.push_back(t); }                    // flipped bit
+  { auto t = bz; t.push_back('x'); t.push_back('y'); bad.push_back(t); }          // trailing garbage: DataErrorMagic
+  for (const auto& b : bad) {
+    uint8_t* o = nullptr;
+    size_t on = 0;
+    const int want = orc_decode(b.data(), b.size(), &o, &on);
+    std::vector<uint8_t> want_bytes(o, o + on);
+    orc_decode_free(o);
+    BZip2Decoder dec;
+    std::vector<uint8_t> ret;
+    BZip2Error e = BZip2Error::Unexpected;
+    const bool ok = decode_collect(b, dec, ret, &e);
+    CHECK(ok == (want == 0));
+    CHECK(ok || (int)e == want);
+    CHECK(ret == want_bytes);
+  }
+}
+
+static void test_run_streams_blocks_early() {  // closed blocks become readable under Action::Run
+  setenv("BZB200_ENC_WINDOW", "300000", 1);
+  std::vector<uint8_t> all;
+  for (int i = 0; i < 1000000; ++i) all.push_back((uint8_t)("the quick brown fox jumps over the lazy dog. "[(i * 7 + i / 13) % 45]));
+  BZip2Encoder enc(1);
+  unsetenv("BZB200_ENC_WINDOW");
+  std::vector<uint8_t> ret;
+  size_t early = 0;
+  for (size_t lo = 0; lo < all.size(); lo += 250000) {
+    std::vector<uint8_t> part(all.begin() + lo, all.begin() + std::min(all.size(), lo + 250000));
+    auto it = part.begin();
+    while (auto r = enc.next(it, part.end(), Action::Run)) {
+      CHECK(r->ok);
+      ret.push_back(r->value);
+    }
+    early = ret.size();
+  }
+  CHECK(early > 0);  // bytes were handed out before Finish
+  std::vector<uint8_t> none, rest;
+  CHECK(encode_collect(none, enc, Action::Finish, rest));
+  ret.insert(ret.end(), rest.begin(), rest.end());
+  CHECK(ret == oracle(all, 1));
+}
+
 int main(int argc, char** argv) {
   std::string dir = argc > 1 ? argv[1] : "tests/golden/data";
   test_invalid_level();
@@ -105,6 +183,9 @@ int main(int argc, char** argv) {
   test_long();
   test_doc();
   test_run_then_finish();
+  test_run_streams_blocks_early();
+  test_decode_samples(dir);
+  test_decode_errors(dir);
   printf(failures ? "FAILED (%d)\n" : "all C++ mirror tests passed\n", failures);
   return failures ? 1 : 0;
 }

@@ -1,0 +1,73 @@
+"""Decoder test cases shared by the CPU emulation test (test_dec_emu.py) and the GPU parity test
+(test_gpu_decoder.py): (name, .bz2 buffer) pairs, valid and malformed, all deterministic.  The expected result of a
+case is whatever the restated reference decoder (oracle.orc.decode) does with it: bytes, or bytes + BZip2Error kind."""
+import bz2
+import os
+
+import numpy as np
+
+import gen
+from oracle import orc
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+DATA = os.path.join(ROOT, "tests", "golden", "data")
+
+
+def expected(buf):
+    """(error code 0..5, bytes yielded before the error) from the restated reference decoder."""
+    try:
+        return 0, orc.decode(buf)
+    except orc.DecodeError as ex:
+        code = {v: k for k, v in orc.DecodeError.KINDS.items()}[ex.kind]
+        return code, ex.partial
+
+
+def valid_cases(big=False):
+    cases = []
+    for i in range(1, 5):  # the reference's decoder fixtures (bzip2/mod.rs:84-148); sample4 = two streams
+        with open(os.path.join(DATA, f"sample{i}.bz2"), "rb") as f:
+            cases.append((f"sample{i}.bz2", f.read()))
+    txt = gen.text(3, 250000)
+    for lvl in (1, 2, 9):
+        cases.append((f"oracle-encoded text level {lvl}", orc.compress(txt, lvl)))
+        cases.append((f"libbz2-encoded text level {lvl}", bz2.compress(txt, lvl)))
+    cases.append(("empty stream", orc.compress(b"", 9)))
+    cases.append(("test_unit a\\n", orc.compress(b"a\n", 9)))
+    cases.append(("test_long a*1000", orc.compress(b"a" * 1000, 9)))
+    cases.append(("all a, 3 blocks", orc.compress(b"a" * 300000, 1)))
+    cases.append(("period 2", orc.compress(b"ab" * 60000, 1)))
+    cases.append(("period 4 + tail", orc.compress(b"aabb" * 30000 + b"x", 1)))
+    cases.append(("runs g2", orc.compress(gen.g2(5, 200000), 1)))
+    cases.append(("random bytes", orc.compress(np.random.default_rng(1).integers(0, 256, 150000, dtype=np.uint8)
+                                               .tobytes(), 1)))
+    cases.append(("run lengths 4,5,255,259 and every byte value",
+                  orc.compress(bytes(range(256)) * 40 + b"\xff" * 1000 + b"\x00" * 259 + b"\x00" * 4 + b"\x01" * 5, 9)))
+    cases.append(("three streams, levels 1/3/5, one empty",
+                  orc.compress(txt[:50000], 1) + orc.compress(b"", 3) + bz2.compress(txt[50000:120000], 5)))
+    cases.append(("mixed level 1, 14 blocks", orc.compress(gen.mixed(1, 1_500_000), 1)))
+    if big:
+        t2 = gen.text(7, 2_000_000)
+        cases.append(("text 2 MB level 9", orc.compress(t2, 9)))
+        cases.append(("all-a exactly one full block", orc.compress(b"a" * 45_899_235, 9)))
+        cases.append(("period 2, full block", orc.compress(b"ab" * 500_000, 9)))
+        cases.append(("period 4 + tail, full block", orc.compress(b"aabb" * 230_000 + b"q", 9)))
+    return cases
+
+
+def malformed_cases():
+    """Truncations, bit flips and trailing bytes of one two-block stream.  Positions were chosen to hit every header
+    field, the selector/table area, the symbol area of both blocks, the end magic and the combined CRC; each was run
+    through the restated reference decoder when the list was written (none sends it into its endless-read case, a block
+    that ends in four equal bytes without a count)."""
+    s = orc.compress(gen.text(3, 120000), 1)
+    n = len(s)
+    cases = [("empty input", b"")]
+    for cut in (1, 2, 3, 4, 5, 9, 10, 13, 14, 17, 18, 20, 40, 100, n // 2, n - 11, n - 10, n - 5, n - 4, n - 1):
+        cases.append((f"truncated to {cut}", s[:cut]))
+    for pos in (0, 1, 2, 3, 4, 5, 10, 11, 14, 15, 17, 18, 19, 20, 25, 30, 60, 200, n // 2, n - 12, n - 8, n - 3, n - 1):
+        b = bytearray(s)
+        b[pos] ^= 0x10
+        cases.append((f"bit flip in byte {pos}", bytes(b)))
+    for tail in (b"xyz", b"B", b"BZh", b"BZh9", b"BZh0"):
+        cases.append((f"trailing {tail!r}", s + tail))
+    return cases

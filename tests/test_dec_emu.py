@@ -1,0 +1,68 @@
+"""CPU check of the GPU decoder's ALGORITHM: tests/cpp/dec_emu.cpp compiles the kernel bodies of
+rust-compression_b200/csrc/dec_core.cuh and the orchestration of decoder.cu for the host (every launch becomes a
+loop over the same per-thread bodies) and the result is compared with the restated reference decoder
+(oracle/bz2_decoder_oracle.cpp) — bytes and BZip2Error kinds.  The emulation library is test infrastructure: it is
+built here, under tests/, and is not part of libbzb200.so (the GPU parity proper is tests/test_gpu_decoder.py)."""
+import ctypes as C
+import os
+import subprocess
+
+import pytest
+
+import dec_cases
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SRC = os.path.join(ROOT, "tests", "cpp", "dec_emu.cpp")
+LIB = os.path.join(ROOT, "tests", "cpp", "libdecemu.so")
+
+
+@pytest.fixture(scope="module")
+def emu():
+    deps = [SRC] + [os.path.join(ROOT, "rust-compression_b200", "csrc", f) for f in
+                    ("decoder.cu", "decoder.h", "dec_core.cuh")]
+    if not os.path.exists(LIB) or any(os.path.getmtime(d) > os.path.getmtime(LIB) for d in deps):
+        subprocess.check_call(["g++", "-std=c++17", "-O2", "-shared", "-fPIC", SRC, "-o", LIB])
+    lib = C.CDLL(LIB)
+    lib.emu_decode.restype = C.c_int
+    lib.emu_decode.argtypes = [C.c_char_p, C.c_size_t, C.c_size_t, C.c_size_t, C.POINTER(C.c_void_p),
+                               C.POINTER(C.c_size_t), C.POINTER(C.c_uint32), C.c_void_p]
+    lib.emu_free.argtypes = [C.c_void_p]
+
+    def run(data, first_cap=1 << 20, batch_bytes=1 << 34):
+        out, n, e, info = C.c_void_p(), C.c_size_t(0), C.c_uint32(0), (C.c_uint64 * 8)()
+        rc = lib.emu_decode(bytes(data), len(data), first_cap, batch_bytes, C.byref(out), C.byref(n), C.byref(e), info)
+        res = C.string_at(out, n.value) if n.value else b""
+        lib.emu_free(out)
+        assert rc == 0
+        return e.value, res, dict(streams=info[0], blocks=info[1], candidates=info[2], batches=info[3],
+                                  launches=info[4], retried=info[5])
+
+    return run
+
+
+def test_valid_streams(emu):
+    for name, buf in dec_cases.valid_cases():
+        want = dec_cases.expected(buf)
+        assert want[0] == 0, name
+        err, out, info = emu(buf)
+        assert (err, out) == want, name
+
+
+def test_malformed_streams_report_what_the_reference_reports(emu):
+    for name, buf in dec_cases.malformed_cases():
+        want = dec_cases.expected(buf)
+        err, out, info = emu(buf)
+        assert err == want[0], f"{name}: kind {err} != {want[0]}"
+        assert out == want[1], f"{name}: {len(out)} bytes before the error, reference {len(want[1])}"
+
+
+def test_batches_and_output_retry(emu):
+    name, buf = [c for c in dec_cases.valid_cases() if c[0].startswith("mixed level 1")][0]
+    want = dec_cases.expected(buf)
+    err, out, info = emu(buf, batch_bytes=2_500_000)       # a few blocks per batch
+    assert (err, out) == want and info["batches"] > 3
+    err, out, info = emu(buf, first_cap=1000)              # too small: dry pass for the size, then a second run
+    assert (err, out) == want and info["retried"] == 1
+    name, buf = [c for c in dec_cases.valid_cases() if c[0].startswith("three streams")][0]
+    err, out, info = emu(buf, batch_bytes=1)               # one candidate per batch, chain crosses streams
+    assert (err, out) == dec_cases.expected(buf) and info["streams"] == 3

@@ -84,6 +84,46 @@ def test_run_then_finish_and_reuse(rc):
     assert again == orc.compress(b"a\n", 9)
 
 
+def test_run_streams_closed_blocks_before_finish(rc, monkeypatch):
+    """with Action.Run the encoder compresses the blocks that have closed whenever a window of
+    input has accumulated and hands their bytes out early; the concatenation is the oracle's stream bit for bit —
+    including the partial byte carried from window to window, a run that straddles a window edge, and multi-stream
+    reuse of the same encoder object."""
+    for level, window, piece in ((1, 250_000, 70_001), (1, 99_981, 33_333), (2, 1, 500_000), (9, 2_000_000, 1 << 20)):
+        monkeypatch.setenv("BZB200_ENC_WINDOW", str(window))
+        enc = rc.BZip2Encoder(level)
+        monkeypatch.delenv("BZB200_ENC_WINDOW")
+        data = gen.mixed(5, 1_200_000) + b"q" * 300_000 + gen.text(6, 900_000)
+        got = bytearray()
+        early = 0
+        for lo in range(0, len(data), piece):
+            enc.write(data[lo:lo + piece])
+            got += enc.read_available()
+            early = len(got)
+        st = enc.stats()
+        got += enc.finish()
+        assert bytes(got) == orc.compress(data, level), (level, window, piece)
+        assert early > 0 and st["windows"] >= 2, (level, window, st)
+        # the same object starts a second, independent stream (multi-stream container: SURVEY.md section 8(f).3)
+        second = bytes(rc.encode(b"second stream", enc, rc.Action.Finish))
+        assert second == orc.compress(b"second stream", level)
+        assert rc.decompress(bytes(got) + second) == data + b"second stream"
+    # through the iterator adapter: bytes appear under Run, None means "feed more"
+    monkeypatch.setenv("BZB200_ENC_WINDOW", "150000")
+    enc = rc.BZip2Encoder(1)
+    data = gen.text(8, 400_000)
+    out = bytearray()
+    for lo in range(0, len(data), 100_000):
+        it = iter(data[lo:lo + 100_000])
+        while (b := enc.next(it, rc.Action.Run)) is not None:
+            out.append(b)
+    assert len(out) > 0
+    it = iter(b"")
+    while (b := enc.next(it, rc.Action.Finish)) is not None:
+        out.append(b)
+    assert bytes(out) == orc.compress(data, 1)
+
+
 def test_empty_input(rc):
     assert rc.compress(b"", 9).hex() == "425a683917724538509000000000"
     assert bytes(rc.encode(b"", rc.BZip2Encoder(1), rc.Action.Finish)) == orc.compress(b"", 1)
