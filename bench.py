@@ -246,6 +246,126 @@ def check_prefix(stream, corpus_prefix):
     return f"{r.nblocks - 1} leading blocks ({bits} bits) bit-exact vs oracle" if ok else "MISMATCH"
 
 
+DEC_METRIC = "bzip2 decompress MB/s (uncompressed)"
+# Algorithmic HBM bytes of the decoder's kernels (DESIGN.md "Decoder"): st = bzb200_dec_stats + compressed size
+DEC_ALG_BYTES = {
+    "d2_decode": lambda st: st["comp_bytes"] + 5.0 * st["pre_rle_bytes"],   # bits in; L (1 B) + occ (4 B) out
+    "d3_scatter": lambda st: 9.0 * st["pre_rle_bytes"],                     # L + occ in, V (4 B) scattered
+    "d4_walk_a": lambda st: 4.0 * st["pre_rle_bytes"],                      # one V entry per step
+    "d4_walk_c": lambda st: 5.0 * st["pre_rle_bytes"],                      # one V entry per step + the byte out
+    "d5_count": lambda st: 1.0 * st["pre_rle_bytes"],
+    "d5_expand": lambda st: 1.0 * st["pre_rle_bytes"] + st["out_bytes"],
+    "k5_crc_blocks": lambda st: 1.0 * st["out_bytes"],
+}
+
+
+def run_decode(args):
+    """Side case, BZB200_BENCH_MODE=decode: the block-parallel GPU decoder on the stream the
+    encoder produces for the headline corpus.  Same JSON contract; one GPU (replicas only at N > 1, not launched)."""
+    import torch
+
+    import rust_compression_b200  # noqa: F401
+    from oracle import orc
+    from rust_compression_b200 import device as dv
+
+    torch.cuda.set_device(0)
+    dev = torch.device("cuda", 0)
+    raw = gen_slice(0, BYTES_PER_GPU)
+    h_raw = torch.frombuffer(bytearray(raw), dtype=torch.uint8)
+    d_raw = h_raw.to(dev)
+    ctx = dv.Context()
+    d_comp = dv.compress_tensor(ctx, LEVEL, d_raw).clone()
+    h_comp = d_comp.cpu().pin_memory()
+    n, nc = d_raw.numel(), d_comp.numel()
+    d_out = torch.empty(n, dtype=torch.uint8, device=dev)
+    h_out = torch.empty(n, dtype=torch.uint8).pin_memory()
+
+    def step_device():
+        return ctx.decompress_device(d_comp, d_out)
+
+    def step_e2e():
+        return ctx.decompress_host(h_comp, h_out)
+
+    def timed(fn, steps):
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            res = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1), res
+
+    for _ in range(args.warmup):
+        step_device()
+    sampler = ClockSampler(0)
+    sampler.start()
+    l0 = ctx.launch_count()
+    ms_total, res = timed(step_device, args.steps)
+    launches = ctx.launch_count() - l0
+    clocks = sampler.stop()
+    assert res == (n, 0), res
+    same = bool(torch.equal(d_out, d_raw))
+    ms_step = ms_total / args.steps
+    st = ctx.dec_stats()
+    st["comp_bytes"] = nc
+    ctx.profile(True)
+    ms_prof, _ = timed(step_device, 1)
+    ctx.profile(False)
+    recs = ctx.profile_records()
+    for _ in range(max(1, args.warmup // 2)):
+        step_e2e()
+    e2e_steps = max(2, args.steps // 2)
+    ms_e2e, res = timed(step_e2e, e2e_steps)
+    same_e2e = res == (n, 0) and bool(torch.equal(h_out, h_raw))
+    # CPU beside it: the restated reference decoder, one thread, on the stream of a prefix of the corpus
+    sample = d_raw[:min(n, CPU_SAMPLE_BYTES)]
+    s_comp = dv.compress_tensor(ctx, LEVEL, sample).cpu().numpy().tobytes()
+    t = time.perf_counter()
+    back = orc.decode(s_comp)
+    dt = time.perf_counter() - t
+    ok_cpu = back == raw[:sample.numel()]
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    top = sorted(recs.items(), key=lambda kv: -kv[1][1])
+    name, (nl, kms) = top[0]
+    alg = DEC_ALG_BYTES.get(name, lambda s_: nc + n)(st)
+    achieved = alg / (kms / 1e3) / 1e9
+    line = {
+        "metric": DEC_METRIC, "value": n / (ms_step / 1e3) / 1e6, "unit": "MB/s", "n_gpus": 1, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u8", "data": "synthetic",
+        "config": {"workload": "decode of the level-%d stream of: %s" % (LEVEL, workload_name(1)), "level": LEVEL,
+                   "compressed_bytes": nc, "stats": st,
+                   "l2": "compressed input (0.3 GB) and all per-block arrays (10 GB) exceed the 126 MB L2; no flush",
+                   "verified": ("device output == corpus; " if same else "DEVICE OUTPUT DIFFERS; ") +
+                               ("e2e output == corpus; " if same_e2e else "E2E OUTPUT DIFFERS; ") +
+                               ("block and stream CRCs verified by the decoder; oracle decoder agrees on the sample"
+                                if ok_cpu else "ORACLE DECODER DISAGREES")},
+        "e2e": {"value": n / (ms_e2e / e2e_steps / 1e3) / 1e6, "unit": "MB/s", "h2d_bytes_per_step": nc,
+                "d2h_bytes_per_step": n, "steps": e2e_steps, "api": "bzb200_decompress_host (C ABI, pinned host in/out)"},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": None, "launches_per_step": nl, "avg_launch_ms": kms / max(1, nl),
+                     "kernel_share_of_step": kms / ms_prof, "algorithmic_bytes_per_launch": alg / max(1, nl),
+                     "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback",
+                     "path": {"achieved": (n + nc) / (ms_step / 1e3) / 1e9, "unit": "GB/s",
+                              "frac": (n + nc) / (ms_step / 1e3) / 1e9 / peak,
+                              "note": "whole path: (compressed in + bytes out) / device time"}},
+        "kernels_ms_per_step": {k: round(v[1], 3) for k, v in top[:12]},
+        "profiled_step_ms": round(ms_prof, 3),
+        "cpu_baseline": {"value": sample.numel() / dt / 1e6, "unit": "MB/s", "cores": 1, "kind": "port",
+                         "sample": f"stream of the first {sample.numel() >> 20} MiB of the corpus, single thread, restated "
+                                   "reference BZip2Decoder (oracle/bz2_decoder_oracle.cpp)"},
+        "clocks": clocks,
+    }
+    print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -258,6 +378,10 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         run_reference(args, rank)
+        return
+    if os.environ.get("BZB200_BENCH_MODE") == "decode":
+        if rank == 0:
+            run_decode(args)
         return
 
     import torch

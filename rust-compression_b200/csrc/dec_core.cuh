@@ -169,8 +169,11 @@ struct D2Scratch {
   uint16_t perm[6][258];            // symbols by (length, symbol)
   uint8_t max_len[6];
   uint8_t len[258];
-  uint8_t mtf[256];                 // MTF list holding the block's bytes (seq2unseq applied)
-  uint32_t cnt[256];                // occurrences so far per byte
+  uint8_t mtf[256];                 // MTF start list holding the block's bytes (seq2unseq applied)
+  uint32_t cnt[256];                // occurrences per byte (filled from the lanes' registers after the symbol loop)
+  CandInfo info;                    // lane 0's result record
+  uint64_t pos;                     // bit position after the header
+  uint32_t nsyms, n_sel, go;        // header results handed to all lanes
 };
 
 // Canonical codes of one table into scratch; false: over-subscribed (rejected as DataError, as the oracle does).
@@ -243,15 +246,95 @@ BZB_DEV int d2_symbol(const D2Scratch* s, uint32_t t, Reader& r) {
   return -1;
 }
 
-// c: candidate index inside the batch.  cap = 100000 * (largest level of any stream in the buffer): the most a block
-// of this buffer may hold; stride >= cap is the per-candidate pitch of L / occ.
-BZB_DEV void d2_decode_body(uint32_t c, D2Scratch* s, const uint8_t* in, uint64_t n, const uint64_t* cand, uint32_t cap,
-                            uint64_t stride, uint8_t* Lbuf, uint32_t* occbuf, uint8_t* selbuf, uint32_t* cftab,
-                            CandInfo* infos) {
-  CandInfo I;
-  I.start_bit = cand[c] & ~KIND_END;
+// ---- warp-resident decoder state: the MTF list and the per-byte occurrence counters live in registers, entry
+// 32*q + lane in register q of `lane`; every lane runs the (uniform) symbol loop, so v and uc below are the same in
+// all lanes.  The host emulation keeps the same state in plain arrays (one "lane").
+#ifdef BZB_EMU
+struct LaneState {
+  uint8_t list[256];
+  uint32_t cnt[256];
+  void init(const uint8_t* mtf0, uint32_t) {
+    for (int i = 0; i < 256; ++i) {
+      list[i] = mtf0[i];
+      cnt[i] = 0;
+    }
+  }
+  uint32_t front() const { return list[0]; }
+  uint32_t pop(uint32_t v) {  // MtfPositionDecoder::pop (mtf.rs:52-64)
+    const uint8_t t = list[v];
+    for (uint32_t q = v; q > 0; --q) list[q] = list[q - 1];
+    list[0] = t;
+    return t;
+  }
+  uint32_t count_add(uint32_t uc, uint32_t add) {
+    const uint32_t old = cnt[uc];
+    cnt[uc] = old + add;
+    return old;
+  }
+  void counts_to(uint32_t* dst, uint32_t) const {
+    for (int i = 0; i < 256; ++i) dst[i] = cnt[i];
+  }
+};
+BZB_DEV void warp_sync() {}
+#else
+struct LaneState {
+  uint32_t row[8];
+  uint32_t c[8];
+  __device__ __forceinline__ void init(const uint8_t* mtf0, uint32_t lane) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      row[q] = mtf0[32 * q + lane];
+      c[q] = 0;
+    }
+  }
+  __device__ __forceinline__ uint32_t front() const { return __shfl_sync(0xffffffffu, row[0], 0); }
+  __device__ __forceinline__ uint32_t pop(uint32_t v) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t q = v >> 5, l = v & 31u;
+    uint32_t pick = row[0];
+#pragma unroll
+    for (int k = 1; k < 8; ++k) pick = ((uint32_t)k == q) ? row[k] : pick;
+    const uint32_t t = __shfl_sync(0xffffffffu, pick, l);
+    if (v == 0) return t;
+    uint32_t carry = t;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      if ((uint32_t)k <= q) {  // uniform
+        const uint32_t up = __shfl_up_sync(0xffffffffu, row[k], 1);
+        const uint32_t last = __shfl_sync(0xffffffffu, row[k], 31);
+        const uint32_t limit = ((uint32_t)k < q) ? 31u : l;
+        row[k] = lane == 0 ? carry : (lane <= limit ? up : row[k]);
+        carry = last;
+      }
+    }
+    return t;
+  }
+  __device__ __forceinline__ uint32_t count_add(uint32_t uc, uint32_t add) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t q = uc >> 5, l = uc & 31u;
+    uint32_t pick = c[0];
+#pragma unroll
+    for (int k = 1; k < 8; ++k) pick = ((uint32_t)k == q) ? c[k] : pick;
+    const uint32_t old = __shfl_sync(0xffffffffu, pick, l);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) c[k] += ((uint32_t)k == q && lane == l) ? add : 0u;
+    return old;
+  }
+  __device__ __forceinline__ void counts_to(uint32_t* dst, uint32_t lane) const {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) dst[32 * q + lane] = c[q];
+  }
+};
+BZB_DEV void warp_sync() { __syncwarp(); }
+#endif
+
+// Header phase, one lane: stream position, block header, mapping table, selectors, coding tables.  Leaves the MTF
+// start list in s->mtf and the tables in s; s->go = 1 when the symbol phase should run.
+BZB_DEV void d2_header(D2Scratch* s, const uint8_t* in, uint64_t n, uint64_t cand, uint8_t* sel) {
+  CandInfo& I = s->info;
+  I.start_bit = cand & ~KIND_END;
   I.end_bit = 0;
-  I.kind = (cand[c] & KIND_END) ? 1u : 0u;
+  I.kind = (cand & KIND_END) ? 1u : 0u;
   I.err = E_OK;
   I.err_early = 0;
   I.stored_crc = 0;
@@ -265,157 +348,188 @@ BZB_DEV void d2_decode_body(uint32_t c, D2Scratch* s, const uint8_t* in, uint64_
   I.nsym = 0;
   I.tail_n = 0;
   for (int k = 0; k < 4; ++k) I.tail[k] = 0;
+  s->go = 0;
 
   Reader r;
   r.init(in, n, I.start_bit + 48);
+  if (I.kind == 1) {  // end of stream (decoder.rs:494-520)
+    if (!r.read(32, I.stored_crc)) { I.err = E_EOF; return; }
+    I.end_bit = r.pos;
+    const uint64_t nb = ((r.pos + 7) >> 3);
+    for (uint32_t k = 0; k < 4 && nb + k < n; ++k) {
+      I.tail[k] = in[nb + k];
+      I.tail_n = k + 1;
+    }
+    return;
+  }
+  // ---- block header (decoder.rs:226-241)
+  I.err_early = 1;
+  if (!r.read(32, I.stored_crc)) { I.err = E_EOF; return; }
+  if (!r.read(1, I.randomised)) { I.err = E_EOF; return; }
+  if (!r.read(24, I.orig_pos)) { I.err = E_EOF; return; }
+  I.err_early = 0;
+  // (origPtr > 10 + 100000*level is checked by the host, which knows the stream's level)
+  if (I.randomised) { I.err = E_DATA; return; }  // deviation shared with the oracle: never produced by the encoder
+  // ---- mapping table (decoder.rs:243-281)
+  uint32_t in_use16;
+  if (!r.read(16, in_use16)) { I.err = E_EOF; return; }
+  uint32_t nsyms = 0;
+  for (uint32_t i = 0; i < 16; ++i) {
+    if (!((in_use16 >> (15 - i)) & 1u)) continue;
+    uint32_t m;
+    if (!r.read(16, m)) { I.err = E_EOF; return; }
+    for (uint32_t j = 0; j < 16; ++j)
+      if ((m >> (15 - j)) & 1u) s->mtf[nsyms++] = (uint8_t)(i * 16 + j);
+  }
+  if (nsyms == 0) { I.err = E_DATA; return; }
+  const uint32_t alpha = nsyms + 2;
+  // ---- selectors (decoder.rs:283-318)
+  uint32_t n_groups, n_sel;
+  if (!r.read(3, n_groups)) { I.err = E_EOF; return; }
+  if (n_groups < 2 || n_groups > 6) { I.err = E_DATA; return; }
+  if (!r.read(15, n_sel)) { I.err = E_EOF; return; }
+  if (n_sel < 1) { I.err = E_DATA; return; }
+  {
+    uint8_t sm[6] = {0, 1, 2, 3, 4, 5};
+    for (uint32_t k = 0; k < n_sel; ++k) {
+      uint32_t j = 0;
+      for (;;) {
+        uint32_t bit;
+        if (!r.read(1, bit)) { I.err = E_EOF; return; }
+        if (!bit) break;
+        if (++j >= n_groups) { I.err = E_DATA; return; }
+      }
+      const uint8_t t = sm[j];
+      for (uint32_t q = j; q > 0; --q) sm[q] = sm[q - 1];
+      sm[0] = t;
+      sel[k] = t;
+    }
+  }
+  // ---- coding tables (decoder.rs:320-358)
+  for (uint32_t t = 0; t < n_groups; ++t) {
+    uint32_t curr;
+    if (!r.read(5, curr)) { I.err = E_EOF; return; }
+    for (uint32_t i = 0; i < alpha; ++i) {
+      for (;;) {
+        uint32_t bit;
+        if (!r.read(1, bit)) { I.err = E_EOF; return; }
+        if (!bit) break;
+        if (curr < 1 || curr > 20) { I.err = E_DATA; return; }
+        if (!r.read(1, bit)) { I.err = E_EOF; return; }
+        if (bit == 0) curr += 1; else curr -= 1;
+      }
+      s->len[i] = (uint8_t)curr;
+    }
+    if (!d2_build_table(s, t, alpha)) { I.err = E_DATA; return; }
+  }
+  s->pos = r.pos;
+  s->nsyms = nsyms;
+  s->n_sel = n_sel;
+  s->go = 1;
+}
+
+// c: candidate index inside the batch.  cap = 100000 * (largest level of any stream in the buffer): the most a block
+// of this buffer may hold; stride >= cap is the per-candidate pitch of L / occ.  Called by all 32 lanes of the
+// candidate's warp (the emulation calls it once with lane 0): lane 0 parses the header, then every lane runs the
+// symbol loop in lock step — the bit reader and Huffman lookups are replicated, the MTF list and the occurrence
+// counters are spread over the lanes' registers, runs are stored by all lanes.
+BZB_DEV void d2_decode_body(uint32_t c, uint32_t lane, D2Scratch* s, const uint8_t* in, uint64_t n, const uint64_t* cand,
+                            uint32_t cap, uint64_t stride, uint8_t* Lbuf, uint32_t* occbuf, uint8_t* selbuf,
+                            uint32_t* cftab, CandInfo* infos) {
   uint8_t* L = Lbuf + (uint64_t)c * stride;
   uint32_t* occ = occbuf + (uint64_t)c * stride;
   uint8_t* sel = selbuf + (uint64_t)c * MAX_SEL;
   uint32_t* cf = cftab + (uint64_t)c * 257;
-
-  do {
-    if (I.kind == 1) {  // end of stream (decoder.rs:494-520)
-      if (!r.read(32, I.stored_crc)) { I.err = E_EOF; break; }
-      I.end_bit = r.pos;
-      const uint64_t nb = ((r.pos + 7) >> 3);
-      for (uint32_t k = 0; k < 4 && nb + k < n; ++k) {
-        I.tail[k] = in[nb + k];
-        I.tail_n = k + 1;
-      }
-      break;
+  if (lane == 0) d2_header(s, in, n, cand[c], sel);
+  warp_sync();
+  if (!s->go) {
+    if (lane == 0) infos[c] = s->info;
+    return;
+  }
+  const uint32_t nsyms = s->nsyms, n_sel = s->n_sel;
+  const uint32_t eob = nsyms + 1;
+  Reader r;
+  r.init(in, n, s->pos);
+  LaneState st;
+  st.init(s->mtf, lane);
+  // ---- symbols (decoder.rs:360-444)
+  uint32_t err = 0;
+  uint32_t group_no = 0, group_pos = 0, tbl = 0;
+  uint64_t nn = 1, es = 0;
+  uint32_t size = 0, need = 0, nsym = 0;
+  for (;;) {
+    if (group_pos == 0) {
+      group_no += 1;
+      if (group_no > n_sel) { err = E_DATA; break; }
+      group_pos = 50;
+      tbl = sel[group_no - 1];
     }
-    // ---- block header (decoder.rs:226-241)
-    I.err_early = 1;
-    if (!r.read(32, I.stored_crc)) { I.err = E_EOF; break; }
-    if (!r.read(1, I.randomised)) { I.err = E_EOF; break; }
-    if (!r.read(24, I.orig_pos)) { I.err = E_EOF; break; }
-    I.err_early = 0;
-    // (origPtr > 10 + 100000*level is checked by the host, which knows the stream's level)
-    if (I.randomised) { I.err = E_DATA; break; }  // deviation shared with the oracle: never produced by the encoder
-    // ---- mapping table (decoder.rs:243-281)
-    uint32_t in_use16;
-    if (!r.read(16, in_use16)) { I.err = E_EOF; break; }
-    uint32_t nsyms = 0;
-    bool fail = false;
-    for (uint32_t i = 0; i < 16 && !fail; ++i) {
-      if (!((in_use16 >> (15 - i)) & 1u)) continue;
-      uint32_t m;
-      if (!r.read(16, m)) { I.err = E_EOF; fail = true; break; }
-      for (uint32_t j = 0; j < 16; ++j)
-        if ((m >> (15 - j)) & 1u) s->mtf[nsyms++] = (uint8_t)(i * 16 + j);
+    group_pos -= 1;
+    const int sym = d2_symbol(s, tbl, r);
+    if (sym < 0) { err = E_DATA; break; }
+    ++nsym;
+    const uint32_t next_sym = (uint32_t)sym;
+    if (es > 0 && next_sym != 0 && next_sym != 1) {  // flush the zero run: es copies of the list front
+      const uint32_t uc = st.front();
+      if ((uint64_t)size + es >= (uint64_t)cap) { err = E_DATA; break; }  // decoder.rs:399 at the largest level
+      const uint32_t base = st.count_add(uc, (uint32_t)es);
+#ifdef BZB_EMU
+      for (uint32_t k = 0; k < (uint32_t)es; ++k) {
+#else
+      for (uint32_t k = lane; k < (uint32_t)es; k += 32) {
+#endif
+        L[size + k] = (uint8_t)uc;
+        occ[size + k] = base + k;
+      }
+      size += (uint32_t)es;
+      need = size + 1;
+      nn = 1;
+      es = 0;
     }
-    if (fail) break;
-    if (nsyms == 0) { I.err = E_DATA; break; }
-    const uint32_t alpha = nsyms + 2;
-    // ---- selectors (decoder.rs:283-318)
-    uint32_t n_groups, n_sel;
-    if (!r.read(3, n_groups)) { I.err = E_EOF; break; }
-    if (n_groups < 2 || n_groups > 6) { I.err = E_DATA; break; }
-    if (!r.read(15, n_sel)) { I.err = E_EOF; break; }
-    if (n_sel < 1) { I.err = E_DATA; break; }
-    {
-      uint8_t sm[6] = {0, 1, 2, 3, 4, 5};
-      for (uint32_t k = 0; k < n_sel && !fail; ++k) {
-        uint32_t j = 0;
-        for (;;) {
-          uint32_t bit;
-          if (!r.read(1, bit)) { I.err = E_EOF; fail = true; break; }
-          if (!bit) break;
-          if (++j >= n_groups) { I.err = E_DATA; fail = true; break; }
-        }
-        if (fail) break;
-        const uint8_t t = sm[j];
-        for (uint32_t q = j; q > 0; --q) sm[q] = sm[q - 1];
-        sm[0] = t;
-        sel[k] = t;
+    if (next_sym == eob) break;
+    if (nn >= 2u * 1024u * 1024u) { err = E_DATA; break; }  // decoder.rs:416
+    if (next_sym == 0) {
+      es += nn;
+      nn <<= 1;
+    } else if (next_sym == 1) {
+      nn <<= 1;
+      es += nn;
+    } else {
+      if (size >= cap) { err = E_DATA; break; }              // decoder.rs:427 at the largest level
+      const uint32_t v = next_sym - 1;
+      if (v >= nsyms) { err = E_DATA; break; }
+      const uint32_t uc = st.pop(v);
+      const uint32_t o = st.count_add(uc, 1);
+      if (lane == 0) {
+        L[size] = (uint8_t)uc;
+        occ[size] = o;
       }
+      size += 1;
+      need = size;
     }
-    if (fail) break;
-    // ---- coding tables (decoder.rs:320-358)
-    for (uint32_t t = 0; t < n_groups && !fail; ++t) {
-      uint32_t curr;
-      if (!r.read(5, curr)) { I.err = E_EOF; fail = true; break; }
-      for (uint32_t i = 0; i < alpha && !fail; ++i) {
-        for (;;) {
-          uint32_t bit;
-          if (!r.read(1, bit)) { I.err = E_EOF; fail = true; break; }
-          if (!bit) break;
-          if (curr < 1 || curr > 20) { I.err = E_DATA; fail = true; break; }
-          if (!r.read(1, bit)) { I.err = E_EOF; fail = true; break; }
-          if (bit == 0) curr += 1; else curr -= 1;
-        }
-        s->len[i] = (uint8_t)curr;
-      }
-      if (fail) break;
-      if (!d2_build_table(s, t, alpha)) { I.err = E_DATA; fail = true; break; }
-    }
-    if (fail) break;
-    // ---- symbols (decoder.rs:360-444)
-    for (uint32_t k = 0; k < 256; ++k) s->cnt[k] = 0;
-    const uint32_t eob = alpha - 1;
-    uint32_t group_no = 0, group_pos = 0, tbl = 0;
-    uint64_t nn = 1, es = 0;
-    uint32_t size = 0, need = 0, nsym = 0;
-    for (;;) {
-      if (group_pos == 0) {
-        group_no += 1;
-        if (group_no > n_sel) { I.err = E_DATA; break; }
-        group_pos = 50;
-        tbl = sel[group_no - 1];
-      }
-      group_pos -= 1;
-      const int sym = d2_symbol(s, tbl, r);
-      if (sym < 0) { I.err = E_DATA; break; }
-      ++nsym;
-      const uint32_t next_sym = (uint32_t)sym;
-      if (es > 0 && next_sym != 0 && next_sym != 1) {  // flush the zero run: es copies of the list front
-        const uint8_t uc = s->mtf[0];
-        if ((uint64_t)size + es >= (uint64_t)cap) { I.err = E_DATA; break; }  // decoder.rs:399 at the largest level
-        const uint32_t base = s->cnt[uc];
-        for (uint32_t k = 0; k < (uint32_t)es; ++k) {
-          L[size + k] = uc;
-          occ[size + k] = base + k;
-        }
-        s->cnt[uc] = base + (uint32_t)es;
-        size += (uint32_t)es;
-        need = size + 1;
-        nn = 1;
-        es = 0;
-      }
-      if (next_sym == eob) break;
-      if (nn >= 2u * 1024u * 1024u) { I.err = E_DATA; break; }  // decoder.rs:416
-      if (next_sym == 0) {
-        es += nn;
-        nn <<= 1;
-      } else if (next_sym == 1) {
-        nn <<= 1;
-        es += nn;
-      } else {
-        if (size >= cap) { I.err = E_DATA; break; }              // decoder.rs:427 at the largest level
-        const uint32_t v = next_sym - 1;
-        if (v >= nsyms) { I.err = E_DATA; break; }
-        const uint8_t uc = s->mtf[v];
-        for (uint32_t q = v; q > 0; --q) s->mtf[q] = s->mtf[q - 1];
-        s->mtf[0] = uc;
-        L[size] = uc;
-        occ[size] = s->cnt[uc]++;
-        size += 1;
-        need = size;
-      }
-    }
-    I.nsym = nsym;
-    if (I.err) break;
+  }
+  st.counts_to(s->cnt, lane);
+  warp_sync();
+  if (lane != 0) return;
+  CandInfo& I = s->info;
+  I.nsym = nsym;
+  if (err) {
+    I.err = err;
+  } else {
     I.end_bit = r.pos;
     I.nblock = size;
     I.need_max = need;
-    if (I.orig_pos >= size) { I.err = E_DATA; break; }  // decoder.rs:446-450
-    uint32_t acc = 0;
-    for (uint32_t k = 0; k < 256; ++k) {  // cftab (decoder.rs:452-476)
-      cf[k] = acc;
-      acc += s->cnt[k];
+    if (I.orig_pos >= size) {  // decoder.rs:446-450
+      I.err = E_DATA;
+    } else {
+      uint32_t acc = 0;
+      for (uint32_t k = 0; k < 256; ++k) {  // cftab (decoder.rs:452-476)
+        cf[k] = acc;
+        acc += s->cnt[k];
+      }
+      cf[256] = acc;
     }
-    cf[256] = acc;
-  } while (0);
+  }
   infos[c] = I;
 }
 
@@ -534,7 +648,8 @@ struct RleStep {
 
 BZB_HD uint32_t d5_nchunks(uint32_t nblock) { return (nblock + RLE_CHUNK - 1) / RLE_CHUNK; }
 
-// map entry: exit state in bits 29..31, expanded length in bits 0..28
+// map entry: exit state in bits 29..31, expanded length in bits 0..28.  All five entry states are advanced in one
+// pass over the chunk (states that cannot occur at this chunk boundary are computed too and never used).
 BZB_DEV void d5_count_body(uint32_t x, uint32_t y, const CandInfo* infos, uint64_t stride, const uint8_t* Wbuf,
                            uint32_t chunks_pitch, uint32_t* rle_map /*[cand][chunk][5]*/) {
   const CandInfo& I = infos[y];
@@ -543,37 +658,28 @@ BZB_DEV void d5_count_body(uint32_t x, uint32_t y, const CandInfo* infos, uint64
   if (x >= d5_nchunks(n)) return;
   const uint8_t* W = Wbuf + (uint64_t)y * stride;
   const uint32_t lo = x * RLE_CHUNK, hi = lo + RLE_CHUNK < n ? lo + RLE_CHUNK : n;
-  const uint32_t before = lo ? W[lo - 1] : 0x100u;
-  for (uint32_t k0 = 0; k0 < 5; ++k0) {
-    uint32_t k = k0, prev = before, len = 0;
-    if (k0 >= 1 && k0 <= 3) {  // the state is only reachable if the k0 bytes before the chunk are equal
-      bool ok = lo >= k0;
-      for (uint32_t q = 1; ok && q < k0; ++q) ok = W[lo - 1 - q] == before;
-      if (!ok) {
-        rle_map[((uint64_t)y * chunks_pitch + x) * 5 + k0] = 0;
-        continue;
-      }
-    }
-    if (k0 == 4 && lo < 4) {
-      rle_map[((uint64_t)y * chunks_pitch + x) * 5 + k0] = 0;
-      continue;
-    }
-    for (uint32_t i = lo; i < hi; ++i) {
-      const uint32_t b = W[i];
-      if (k == 4) {
-        len += b;
-        k = 0;
-      } else if (k > 0 && b == prev) {
-        ++k;
-        ++len;
+  uint32_t prev = lo ? W[lo - 1] : 0x100u;
+  uint32_t k[5] = {0, 1, 2, 3, 4}, len[5] = {0, 0, 0, 0, 0};
+  for (uint32_t i = lo; i < hi; ++i) {
+    const uint32_t b = W[i];
+#pragma unroll
+    for (int s = 0; s < 5; ++s) {
+      if (k[s] == 4) {
+        len[s] += b;
+        k[s] = 0;
+      } else if (k[s] > 0 && b == prev) {
+        ++k[s];
+        ++len[s];
       } else {
-        k = 1;
-        ++len;
+        k[s] = 1;
+        ++len[s];
       }
-      prev = b;
     }
-    rle_map[((uint64_t)y * chunks_pitch + x) * 5 + k0] = (k << 29) | len;
+    prev = b;
   }
+  uint32_t* m = rle_map + ((uint64_t)y * chunks_pitch + x) * 5;
+#pragma unroll
+  for (int s = 0; s < 5; ++s) m[s] = (k[s] << 29) | len[s];
 }
 
 BZB_DEV void d5_compose_body(uint32_t y, CandInfo* infos, uint32_t chunks_pitch, const uint32_t* rle_map,

@@ -34,7 +34,7 @@ __global__ void __launch_bounds__(32) d2_decode(const uint8_t* __restrict__ in, 
                                                 uint32_t cap, uint64_t stride, uint8_t* Lbuf, uint32_t* occbuf,
                                                 uint8_t* selbuf, uint32_t* cftab, CandInfo* infos) {
   __shared__ D2Scratch s;
-  if (threadIdx.x == 0) d2_decode_body(blockIdx.x, &s, in, n, cand, cap, stride, Lbuf, occbuf, selbuf, cftab, infos);
+  d2_decode_body(blockIdx.x, threadIdx.x, &s, in, n, cand, cap, stride, Lbuf, occbuf, selbuf, cftab, infos);
 }
 
 __global__ void __launch_bounds__(256) d3_scatter(const CandInfo* __restrict__ infos, uint64_t stride,
@@ -138,7 +138,7 @@ static void run_d2(Launcher& L, uint32_t nc, const uint8_t* in, uint64_t n, cons
   D2Scratch* s = new D2Scratch();
   for (uint32_t c = 0; c < nc; ++c) {
     memset(s, 0xA5, sizeof(*s));  // shared memory is not zeroed between CTAs either
-    d2_decode_body(c, s, in, n, cand, cap, stride, Lbuf, occ, sel, cftab, infos);
+    d2_decode_body(c, 0, s, in, n, cand, cap, stride, Lbuf, occ, sel, cftab, infos);
   }
   delete s;
 }
