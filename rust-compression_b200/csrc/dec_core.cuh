@@ -246,18 +246,13 @@ BZB_DEV int d2_symbol(const D2Scratch* s, uint32_t t, Reader& r) {
   return -1;
 }
 
-// ---- warp-resident decoder state: the MTF list and the per-byte occurrence counters live in registers, entry
-// 32*q + lane in register q of `lane`; every lane runs the (uniform) symbol loop, so v and uc below are the same in
-// all lanes.  The host emulation keeps the same state in plain arrays (one "lane").
+// ---- warp-resident MTF list: entry 32*q + lane lives in register q of `lane`; every lane runs the (uniform)
+// symbol loop, so v below is the same in all lanes.  The host emulation keeps the list in a plain array (one "lane").
 #ifdef BZB_EMU
 struct LaneState {
   uint8_t list[256];
-  uint32_t cnt[256];
   void init(const uint8_t* mtf0, uint32_t) {
-    for (int i = 0; i < 256; ++i) {
-      list[i] = mtf0[i];
-      cnt[i] = 0;
-    }
+    for (int i = 0; i < 256; ++i) list[i] = mtf0[i];
   }
   uint32_t front() const { return list[0]; }
   uint32_t pop(uint32_t v) {  // MtfPositionDecoder::pop (mtf.rs:52-64)
@@ -266,36 +261,29 @@ struct LaneState {
     list[0] = t;
     return t;
   }
-  uint32_t count_add(uint32_t uc, uint32_t add) {
-    const uint32_t old = cnt[uc];
-    cnt[uc] = old + add;
-    return old;
-  }
-  void counts_to(uint32_t* dst, uint32_t) const {
-    for (int i = 0; i < 256; ++i) dst[i] = cnt[i];
-  }
 };
 BZB_DEV void warp_sync() {}
 #else
 struct LaneState {
   uint32_t row[8];
-  uint32_t c[8];
   __device__ __forceinline__ void init(const uint8_t* mtf0, uint32_t lane) {
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      row[q] = mtf0[32 * q + lane];
-      c[q] = 0;
-    }
+    for (int q = 0; q < 8; ++q) row[q] = mtf0[32 * q + lane];
   }
   __device__ __forceinline__ uint32_t front() const { return __shfl_sync(0xffffffffu, row[0], 0); }
   __device__ __forceinline__ uint32_t pop(uint32_t v) {
     const uint32_t lane = threadIdx.x & 31u;
+    if (v < 32) {  // the usual case: two independent shuffles of row 0
+      const uint32_t t = __shfl_sync(0xffffffffu, row[0], v);
+      const uint32_t up = __shfl_up_sync(0xffffffffu, row[0], 1);
+      row[0] = lane == 0 ? t : (lane <= v ? up : row[0]);
+      return t;
+    }
     const uint32_t q = v >> 5, l = v & 31u;
-    uint32_t pick = row[0];
+    uint32_t pick = row[1];
 #pragma unroll
-    for (int k = 1; k < 8; ++k) pick = ((uint32_t)k == q) ? row[k] : pick;
+    for (int k = 2; k < 8; ++k) pick = ((uint32_t)k == q) ? row[k] : pick;
     const uint32_t t = __shfl_sync(0xffffffffu, pick, l);
-    if (v == 0) return t;
     uint32_t carry = t;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
@@ -309,24 +297,44 @@ struct LaneState {
     }
     return t;
   }
-  __device__ __forceinline__ uint32_t count_add(uint32_t uc, uint32_t add) {
-    const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t q = uc >> 5, l = uc & 31u;
-    uint32_t pick = c[0];
-#pragma unroll
-    for (int k = 1; k < 8; ++k) pick = ((uint32_t)k == q) ? c[k] : pick;
-    const uint32_t old = __shfl_sync(0xffffffffu, pick, l);
-#pragma unroll
-    for (int k = 0; k < 8; ++k) c[k] += ((uint32_t)k == q && lane == l) ? add : 0u;
-    return old;
-  }
-  __device__ __forceinline__ void counts_to(uint32_t* dst, uint32_t lane) const {
-#pragma unroll
-    for (int q = 0; q < 8; ++q) dst[32 * q + lane] = c[q];
-  }
 };
 BZB_DEV void warp_sync() { __syncwarp(); }
 #endif
+
+// Bit input of the symbol loop: like Reader, but the position is derived on demand and running past the end of the
+// input is only detected after the loop (every error of the symbol phase is a DataError, so the kind is the same
+// wherever it is raised; bits beyond the end read as zero and the loop is bounded by n_selectors * 50 symbols).
+struct FastBits {
+  const uint8_t* p;
+  uint64_t n;
+  uint64_t buf;
+  uint32_t bits;
+  uint64_t w;      // index of the word held in `ahead`
+  uint32_t ahead;
+  BZB_DEV void init(const uint8_t* p_, uint64_t n_, uint64_t pos_) {
+    p = p_;
+    n = n_;
+    w = pos_ >> 5;
+    const uint32_t sh = (uint32_t)(pos_ & 31);
+    buf = (((uint64_t)load_be32(p, n, w)) << 32) << sh;
+    bits = 32 - sh;
+    ++w;
+    ahead = load_be32(p, n, w);
+    drop(0);
+  }
+  BZB_DEV uint32_t peek(uint32_t k) const { return (uint32_t)(buf >> (64 - k)); }
+  BZB_DEV void drop(uint32_t l) {
+    buf <<= l;
+    bits -= l;
+    if (bits <= 32) {
+      buf |= ((uint64_t)ahead) << (32 - bits);
+      bits += 32;
+      ++w;
+      ahead = load_be32(p, n, w);
+    }
+  }
+  BZB_DEV uint64_t pos() const { return w * 32 - bits; }
+};
 
 // Header phase, one lane: stream position, block header, mapping table, selectors, coding tables.  Leaves the MTF
 // start list in s->mtf and the tables in s; s->go = 1 when the symbol phase should run.
@@ -448,67 +456,104 @@ BZB_DEV void d2_decode_body(uint32_t c, uint32_t lane, D2Scratch* s, const uint8
   }
   const uint32_t nsyms = s->nsyms, n_sel = s->n_sel;
   const uint32_t eob = nsyms + 1;
-  Reader r;
+  FastBits r;
   r.init(in, n, s->pos);
   LaneState st;
   st.init(s->mtf, lane);
-  // ---- symbols (decoder.rs:360-444)
+#ifdef BZB_EMU
+  for (uint32_t k = 0; k < 256; ++k) s->cnt[k] = 0;
+#else
+  for (uint32_t k = lane; k < 256; k += 32) s->cnt[k] = 0;
+#endif
+  warp_sync();
+  // ---- symbols (decoder.rs:360-444).  Occurrence counters: shared memory, written by lane 0 only.
   uint32_t err = 0;
-  uint32_t group_no = 0, group_pos = 0, tbl = 0;
-  uint64_t nn = 1, es = 0;
+  uint32_t group_no = 0, group_pos = 0;
+  uint32_t tbl_next = sel[0];  // selectors are fetched one group ahead
+  const uint16_t* lut = s->lut[0];
+  uint32_t tbl = 0;
+  uint32_t nn = 1, es = 0;     // nn < 2^21 is enforced below, so es < 2^23
   uint32_t size = 0, need = 0, nsym = 0;
   for (;;) {
     if (group_pos == 0) {
       group_no += 1;
       if (group_no > n_sel) { err = E_DATA; break; }
       group_pos = 50;
-      tbl = sel[group_no - 1];
+      tbl = tbl_next;
+      lut = s->lut[tbl];
+      tbl_next = group_no < n_sel ? sel[group_no] : 0u;
     }
     group_pos -= 1;
-    const int sym = d2_symbol(s, tbl, r);
-    if (sym < 0) { err = E_DATA; break; }
-    ++nsym;
-    const uint32_t next_sym = (uint32_t)sym;
-    if (es > 0 && next_sym != 0 && next_sym != 1) {  // flush the zero run: es copies of the list front
-      const uint32_t uc = st.front();
-      if ((uint64_t)size + es >= (uint64_t)cap) { err = E_DATA; break; }  // decoder.rs:399 at the largest level
-      const uint32_t base = st.count_add(uc, (uint32_t)es);
-#ifdef BZB_EMU
-      for (uint32_t k = 0; k < (uint32_t)es; ++k) {
-#else
-      for (uint32_t k = lane; k < (uint32_t)es; k += 32) {
-#endif
-        L[size + k] = (uint8_t)uc;
-        occ[size + k] = base + k;
+    uint32_t next_sym;
+    {
+      const uint32_t e = lut[r.peek(LUT_BITS)];
+      if (e) {
+        r.drop(e >> 9);
+        next_sym = e & 511u;
+      } else {  // a code longer than LUT_BITS, or no code at all
+        const uint32_t maxl = s->max_len[tbl];
+        uint32_t found = 0xFFFFFFFFu;
+        for (uint32_t l = LUT_BITS + 1; l <= maxl; ++l) {
+          if (!s->count[tbl][l]) continue;
+          const uint32_t cbits = r.peek(l);
+          const uint32_t f = s->first_code[tbl][l];
+          if (cbits >= f && cbits - f < s->count[tbl][l]) {
+            r.drop(l);
+            found = s->perm[tbl][s->offs[tbl][l] + (cbits - f)];
+            break;
+          }
+        }
+        if (found == 0xFFFFFFFFu) { err = E_DATA; break; }
+        next_sym = found;
       }
-      size += (uint32_t)es;
-      need = size + 1;
-      nn = 1;
-      es = 0;
     }
-    if (next_sym == eob) break;
-    if (nn >= 2u * 1024u * 1024u) { err = E_DATA; break; }  // decoder.rs:416
-    if (next_sym == 0) {
-      es += nn;
-      nn <<= 1;
-    } else if (next_sym == 1) {
-      nn <<= 1;
-      es += nn;
-    } else {
+    ++nsym;
+    if (next_sym > 1) {
+      if (es > 0) {  // flush the zero run: es copies of the list front
+        const uint32_t uc = st.front();
+        if ((uint64_t)size + es >= (uint64_t)cap) { err = E_DATA; break; }  // decoder.rs:399 at the largest level
+        warp_sync();
+        const uint32_t base = s->cnt[uc];
+        warp_sync();
+        if (lane == 0) s->cnt[uc] = base + es;
+#ifdef BZB_EMU
+        for (uint32_t k = 0; k < es; ++k) {
+#else
+        for (uint32_t k = lane; k < es; k += 32) {
+#endif
+          L[size + k] = (uint8_t)uc;
+          occ[size + k] = base + k;
+        }
+        size += es;
+        need = size + 1;
+        nn = 1;
+        es = 0;
+      }
+      if (next_sym == eob) break;
       if (size >= cap) { err = E_DATA; break; }              // decoder.rs:427 at the largest level
       const uint32_t v = next_sym - 1;
       if (v >= nsyms) { err = E_DATA; break; }
       const uint32_t uc = st.pop(v);
-      const uint32_t o = st.count_add(uc, 1);
       if (lane == 0) {
+        const uint32_t o = s->cnt[uc];
+        s->cnt[uc] = o + 1;
         L[size] = (uint8_t)uc;
         occ[size] = o;
       }
       size += 1;
       need = size;
+    } else {
+      if (nn >= 2u * 1024u * 1024u) { err = E_DATA; break; }  // decoder.rs:416
+      if (next_sym == 0) {
+        es += nn;
+        nn <<= 1;
+      } else {
+        nn <<= 1;
+        es += nn;
+      }
     }
   }
-  st.counts_to(s->cnt, lane);
+  if (!err && r.pos() > n * 8) err = E_DATA;  // the symbols ran past the end of the input (decoder.rs:376-379)
   warp_sync();
   if (lane != 0) return;
   CandInfo& I = s->info;
@@ -516,7 +561,7 @@ BZB_DEV void d2_decode_body(uint32_t c, uint32_t lane, D2Scratch* s, const uint8
   if (err) {
     I.err = err;
   } else {
-    I.end_bit = r.pos;
+    I.end_bit = r.pos();
     I.nblock = size;
     I.need_max = need;
     if (I.orig_pos >= size) {  // decoder.rs:446-450
