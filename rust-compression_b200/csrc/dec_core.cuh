@@ -19,14 +19,16 @@
 //                   0x177245385090 -> candidate list (the host later keeps the candidates that lie on the chain
 //                   "block i ends where block i+1 starts", which is what a sequential parse would have visited)
 //   D2 d2_decode    one warp per candidate, lane 0 decodes: header, tables, Huffman symbols, MTF, RUNA/RUNB ->
-//                   last column L[i], occurrence index occ[i] = #{j < i : L[j] == L[i]}, byte counts -> cftab
+//                   last column byte L[i] and occurrence index occ[i] = #{j < i : L[j] == L[i]} packed in one word,
+//                   byte counts -> cftab
 //   D3 d3_scatter   V[cftab[L[i]] + occ[i]] = i << 8 | L[i]   (the reference's tt after decoder.rs:479-484, with the
 //                   first-column byte in the low bits so that one load per step yields the output byte)
 //   D4 d4_walk_a    list ranking of the walk p -> V[p] >> 8: every SEG-th slot (and origPtr) is a splitter; a thread
 //                   walks from its splitter to the next one (length, successor)
 //      d4_schedule  one thread per block follows the splitters from origPtr and assigns output offsets; a periodic
 //                   block revisits its cycle (cycle length recorded)
-//      d4_walk_c    every scheduled splitter re-walks its segment and stores the bytes (the block before RLE1 undo)
+//      d4_walk_c    every scheduled splitter copies the bytes its first walk kept (walking on only when the segment is
+//                   longer than SEG_KEEP) to its output offset (the block before RLE1 undo)
 //   D5 d5_count     RLE1 undo as a 5-state machine (k equal bytes seen so far, k = 4: the next byte is a count): per
 //                   chunk and entry state -> exit state and expanded length
 //      d5_compose   one thread per block composes the chunk maps -> entry state and output offset of every chunk
@@ -47,6 +49,7 @@ namespace bzb {
 namespace dec {
 
 constexpr uint32_t SEG = 1024;          // splitter spacing of the inverse-BWT walks (slots)
+constexpr uint32_t SEG_KEEP = 4096;     // bytes of a walk kept by d4_walk_a for d4_walk_c (longer walks are resumed)
 constexpr uint32_t RLE_CHUNK = 1024;    // bytes of the pre-RLE1 block per d5 thread
 constexpr uint32_t LUT_BITS = 10;       // primary Huffman lookup width
 constexpr uint32_t MAX_SEL = 32768;     // n_selectors is a 15-bit field (decoder.rs:285)
@@ -442,10 +445,9 @@ BZB_DEV void d2_header(D2Scratch* s, const uint8_t* in, uint64_t n, uint64_t can
 // symbol loop in lock step — the bit reader and Huffman lookups are replicated, the MTF list and the occurrence
 // counters are spread over the lanes' registers, runs are stored by all lanes.
 BZB_DEV void d2_decode_body(uint32_t c, uint32_t lane, D2Scratch* s, const uint8_t* in, uint64_t n, const uint64_t* cand,
-                            uint32_t cap, uint64_t stride, uint8_t* Lbuf, uint32_t* occbuf, uint8_t* selbuf,
-                            uint32_t* cftab, CandInfo* infos) {
-  uint8_t* L = Lbuf + (uint64_t)c * stride;
-  uint32_t* occ = occbuf + (uint64_t)c * stride;
+                            uint32_t cap, uint64_t stride, uint32_t* occbuf, uint8_t* selbuf, uint32_t* cftab,
+                            CandInfo* infos) {
+  uint32_t* occ = occbuf + (uint64_t)c * stride;  // per position: byte << 24 | occurrence index (< 2^20)
   uint8_t* sel = selbuf + (uint64_t)c * MAX_SEL;
   uint32_t* cf = cftab + (uint64_t)c * 257;
   if (lane == 0) d2_header(s, in, n, cand[c], sel);
@@ -521,8 +523,7 @@ BZB_DEV void d2_decode_body(uint32_t c, uint32_t lane, D2Scratch* s, const uint8
 #else
         for (uint32_t k = lane; k < es; k += 32) {
 #endif
-          L[size + k] = (uint8_t)uc;
-          occ[size + k] = base + k;
+          occ[size + k] = (uc << 24) | (base + k);
         }
         size += es;
         need = size + 1;
@@ -534,11 +535,10 @@ BZB_DEV void d2_decode_body(uint32_t c, uint32_t lane, D2Scratch* s, const uint8
       const uint32_t v = next_sym - 1;
       if (v >= nsyms) { err = E_DATA; break; }
       const uint32_t uc = st.pop(v);
+      const uint32_t o = s->cnt[uc];  // every lane reads, lane 0's value is the one that counts
       if (lane == 0) {
-        const uint32_t o = s->cnt[uc];
         s->cnt[uc] = o + 1;
-        L[size] = (uint8_t)uc;
-        occ[size] = o;
+        occ[size] = (uc << 24) | o;
       }
       size += 1;
       need = size;
@@ -580,13 +580,14 @@ BZB_DEV void d2_decode_body(uint32_t c, uint32_t lane, D2Scratch* s, const uint8
 
 // ---------------------------------------------------------------------------------------------------------------
 // D3: x = position inside the block, y = candidate.
-BZB_DEV void d3_scatter_body(uint32_t x, uint32_t y, const CandInfo* infos, uint64_t stride, const uint8_t* Lbuf,
-                             const uint32_t* occbuf, const uint32_t* cftab, uint32_t* Vbuf) {
+BZB_DEV void d3_scatter_body(uint32_t x, uint32_t y, const CandInfo* infos, uint64_t stride, const uint32_t* occbuf,
+                             const uint32_t* cftab, uint32_t* Vbuf) {
   const CandInfo& I = infos[y];
   if (I.kind != 0 || I.err != 0 || x >= I.nblock) return;
   const uint64_t base = (uint64_t)y * stride;
-  const uint32_t b = Lbuf[base + x];
-  const uint32_t slot = cftab[(uint64_t)y * 257 + b] + occbuf[base + x];
+  const uint32_t w = occbuf[base + x];
+  const uint32_t b = w >> 24;
+  const uint32_t slot = cftab[(uint64_t)y * 257 + b] + (w & 0xFFFFFFu);
   Vbuf[base + slot] = (x << 8) | b;
 }
 
@@ -595,8 +596,11 @@ BZB_DEV void d3_scatter_body(uint32_t x, uint32_t y, const CandInfo* infos, uint
 // when origPtr is a multiple of SEG).  segs_pitch = splitters per candidate the arrays were sized for.
 BZB_HD uint32_t d4_nseg0(uint32_t nblock) { return (nblock + SEG - 1) / SEG; }
 
+// The walk also keeps the first SEG_KEEP bytes it passes (4 to a word, in the segment's own SEG_KEEP-byte slot of
+// Tbuf) and the slot it has reached by then, so that d4_walk_c copies instead of walking a second time.
 BZB_DEV void d4_walk_a_body(uint32_t x, uint32_t y, const CandInfo* infos, uint64_t stride, const uint32_t* Vbuf,
-                            uint32_t segs_pitch, uint32_t* seg_len, uint32_t* seg_next) {
+                            uint32_t segs_pitch, uint32_t* seg_len, uint32_t* seg_next, uint32_t* seg_resume,
+                            uint8_t* Tbuf) {
   const CandInfo& I = infos[y];
   if (I.kind != 0 || I.err != 0) return;
   const uint32_t n0 = d4_nseg0(I.nblock);
@@ -607,14 +611,26 @@ BZB_DEV void d4_walk_a_body(uint32_t x, uint32_t y, const CandInfo* infos, uint6
   else if (x == n0 && !orig_on_grid) pos = orig;
   else return;
   const uint32_t* V = Vbuf + (uint64_t)y * stride;
-  uint32_t len = 0;
+  const uint64_t o = (uint64_t)y * segs_pitch + x;
+  uint32_t* T = reinterpret_cast<uint32_t*>(Tbuf + o * SEG_KEEP);
+  uint32_t len = 0, acc = 0, resume = 0;
   do {
-    pos = V[pos] >> 8;
+    const uint32_t v = V[pos];
+    pos = v >> 8;
+    if (len < SEG_KEEP) {
+      acc |= (v & 255u) << (8 * (len & 3u));
+      if ((len & 3u) == 3u) {
+        T[len >> 2] = acc;
+        acc = 0;
+      }
+      if (len + 1 == SEG_KEEP) resume = pos;
+    }
     ++len;
   } while ((pos % SEG) != 0 && pos != orig);
-  const uint64_t o = (uint64_t)y * segs_pitch + x;
+  if (len < SEG_KEEP && (len & 3u)) T[len >> 2] = acc;  // the last, partial word
   seg_len[o] = len;
   seg_next[o] = (pos == orig && !orig_on_grid) ? n0 : pos / SEG;
+  seg_resume[o] = resume;
 }
 
 // one thread per candidate; seg_off must be filled with 0xFFFFFFFF beforehand
@@ -640,7 +656,8 @@ BZB_DEV void d4_schedule_body(uint32_t y, CandInfo* infos, uint32_t segs_pitch, 
 }
 
 BZB_DEV void d4_walk_c_body(uint32_t x, uint32_t y, const CandInfo* infos, uint64_t stride, const uint32_t* Vbuf,
-                            uint32_t segs_pitch, const uint32_t* seg_len, const uint32_t* seg_off, uint8_t* Wbuf) {
+                            uint32_t segs_pitch, const uint32_t* seg_len, const uint32_t* seg_off,
+                            const uint32_t* seg_resume, const uint8_t* Tbuf, uint8_t* Wbuf) {
   const CandInfo& I = infos[y];
   if (I.kind != 0 || I.err != 0) return;
   const uint32_t n0 = d4_nseg0(I.nblock);
@@ -651,30 +668,40 @@ BZB_DEV void d4_walk_c_body(uint32_t x, uint32_t y, const CandInfo* infos, uint6
   const uint32_t len = seg_len[so];
   const uint32_t n = I.nblock;
   const uint32_t* V = Vbuf + (uint64_t)y * stride;
+  const uint32_t* T = reinterpret_cast<const uint32_t*>(Tbuf + so * SEG_KEEP);
   uint8_t* W = Wbuf + (uint64_t)y * stride;
-  uint32_t pos = x < n0 ? x * SEG : I.orig_pos;
   if (I.cyc == 0) {
-    // bytes off .. off+len-1 (clipped to n): head byte-wise up to a 4-byte boundary, then whole words
-    uint32_t k = 0;
+    // bytes off .. off+end-1: the first SEG_KEEP come from the kept copy, the rest (long segments) from walking on;
+    // stores are byte-wise up to a 4-byte boundary of W, then whole words
     const uint32_t end = off + len < n ? len : n - off;
-    uint32_t acc = 0, have = 0;
-    for (; k < end; ++k) {
-      const uint32_t v = V[pos];
-      pos = v >> 8;
+    const uint32_t kept = end < SEG_KEEP ? end : SEG_KEEP;
+    uint32_t pos = seg_resume[so];
+    uint32_t acc = 0, have = 0, src = 0;
+    for (uint32_t k = 0; k < end; ++k) {
+      uint32_t byte;
+      if (k < kept) {
+        if ((k & 3u) == 0) src = T[k >> 2];
+        byte = (src >> (8 * (k & 3u))) & 255u;
+      } else {
+        const uint32_t v = V[pos];
+        pos = v >> 8;
+        byte = v & 255u;
+      }
       const uint32_t o = off + k;
       if (have == 0 && ((o & 3u) != 0 || end - k < 4)) {
-        W[o] = (uint8_t)v;
+        W[o] = (uint8_t)byte;
         continue;
       }
-      acc |= (v & 255u) << (8 * have);
+      acc |= byte << (8 * have);
       if (++have == 4) {
         *reinterpret_cast<uint32_t*>(W + (o - 3)) = acc;
         acc = 0;
         have = 0;
       }
     }
-  } else {
+  } else {  // periodic block: the cycle is replayed until the block is full
     const uint32_t cyc = I.cyc;
+    uint32_t pos = x < n0 ? x * SEG : I.orig_pos;
     for (uint32_t k = 0; k < len; ++k) {
       const uint32_t v = V[pos];
       pos = v >> 8;

@@ -31,22 +31,24 @@ __global__ void __launch_bounds__(256) d1_scan(const uint8_t* __restrict__ in, u
 }
 
 __global__ void __launch_bounds__(32) d2_decode(const uint8_t* __restrict__ in, uint64_t n, const uint64_t* cand,
-                                                uint32_t cap, uint64_t stride, uint8_t* Lbuf, uint32_t* occbuf,
-                                                uint8_t* selbuf, uint32_t* cftab, CandInfo* infos) {
+                                                uint32_t cap, uint64_t stride, uint32_t* occbuf, uint8_t* selbuf,
+                                                uint32_t* cftab, CandInfo* infos) {
   __shared__ D2Scratch s;
-  d2_decode_body(blockIdx.x, threadIdx.x, &s, in, n, cand, cap, stride, Lbuf, occbuf, selbuf, cftab, infos);
+  d2_decode_body(blockIdx.x, threadIdx.x, &s, in, n, cand, cap, stride, occbuf, selbuf, cftab, infos);
 }
 
 __global__ void __launch_bounds__(256) d3_scatter(const CandInfo* __restrict__ infos, uint64_t stride,
-                                                  const uint8_t* __restrict__ Lbuf, const uint32_t* __restrict__ occbuf,
+                                                  const uint32_t* __restrict__ occbuf,
                                                   const uint32_t* __restrict__ cftab, uint32_t* Vbuf) {
-  d3_scatter_body(blockIdx.x * 256u + threadIdx.x, blockIdx.y, infos, stride, Lbuf, occbuf, cftab, Vbuf);
+  d3_scatter_body(blockIdx.x * 256u + threadIdx.x, blockIdx.y, infos, stride, occbuf, cftab, Vbuf);
 }
 
 __global__ void __launch_bounds__(128) d4_walk_a(const CandInfo* __restrict__ infos, uint64_t stride,
                                                  const uint32_t* __restrict__ Vbuf, uint32_t segs_pitch,
-                                                 uint32_t* seg_len, uint32_t* seg_next) {
-  d4_walk_a_body(blockIdx.x * 128u + threadIdx.x, blockIdx.y, infos, stride, Vbuf, segs_pitch, seg_len, seg_next);
+                                                 uint32_t* seg_len, uint32_t* seg_next, uint32_t* seg_resume,
+                                                 uint8_t* Tbuf) {
+  d4_walk_a_body(blockIdx.x * 128u + threadIdx.x, blockIdx.y, infos, stride, Vbuf, segs_pitch, seg_len, seg_next,
+                 seg_resume, Tbuf);
 }
 
 __global__ void __launch_bounds__(64) d4_schedule(uint32_t nc, CandInfo* infos, uint32_t segs_pitch,
@@ -58,8 +60,11 @@ __global__ void __launch_bounds__(64) d4_schedule(uint32_t nc, CandInfo* infos, 
 __global__ void __launch_bounds__(128) d4_walk_c(const CandInfo* __restrict__ infos, uint64_t stride,
                                                  const uint32_t* __restrict__ Vbuf, uint32_t segs_pitch,
                                                  const uint32_t* __restrict__ seg_len,
-                                                 const uint32_t* __restrict__ seg_off, uint8_t* Wbuf) {
-  d4_walk_c_body(blockIdx.x * 128u + threadIdx.x, blockIdx.y, infos, stride, Vbuf, segs_pitch, seg_len, seg_off, Wbuf);
+                                                 const uint32_t* __restrict__ seg_off,
+                                                 const uint32_t* __restrict__ seg_resume,
+                                                 const uint8_t* __restrict__ Tbuf, uint8_t* Wbuf) {
+  d4_walk_c_body(blockIdx.x * 128u + threadIdx.x, blockIdx.y, infos, stride, Vbuf, segs_pitch, seg_len, seg_off,
+                 seg_resume, Tbuf, Wbuf);
 }
 
 __global__ void __launch_bounds__(128) d5_count(const CandInfo* __restrict__ infos, uint64_t stride,
@@ -92,24 +97,27 @@ static void run_d1(Launcher& L, const uint8_t* in, uint64_t n, uint64_t* cand, u
   L.launch("d1_scan", d1_scan, GRID1(nwords, 256), dim3(256), in, n, nwords, cand, count, cap);
 }
 static void run_d2(Launcher& L, uint32_t nc, const uint8_t* in, uint64_t n, const uint64_t* cand, uint32_t cap,
-                   uint64_t stride, uint8_t* Lbuf, uint32_t* occ, uint8_t* sel, uint32_t* cftab, CandInfo* infos) {
-  L.launch("d2_decode", d2_decode, dim3(nc), dim3(32), in, n, cand, cap, stride, Lbuf, occ, sel, cftab, infos);
+                   uint64_t stride, uint32_t* occ, uint8_t* sel, uint32_t* cftab, CandInfo* infos) {
+  L.launch("d2_decode", d2_decode, dim3(nc), dim3(32), in, n, cand, cap, stride, occ, sel, cftab, infos);
 }
-static void run_d3(Launcher& L, uint32_t nc, uint32_t nmax, const CandInfo* infos, uint64_t stride, const uint8_t* Lbuf,
+static void run_d3(Launcher& L, uint32_t nc, uint32_t nmax, const CandInfo* infos, uint64_t stride,
                    const uint32_t* occ, const uint32_t* cftab, uint32_t* V) {
-  L.launch("d3_scatter", d3_scatter, GRID2(nmax, 256, nc), dim3(256), infos, stride, Lbuf, occ, cftab, V);
+  L.launch("d3_scatter", d3_scatter, GRID2(nmax, 256, nc), dim3(256), infos, stride, occ, cftab, V);
 }
 static void run_d4a(Launcher& L, uint32_t nc, uint32_t segs, const CandInfo* infos, uint64_t stride, const uint32_t* V,
-                    uint32_t pitch, uint32_t* seg_len, uint32_t* seg_next) {
-  L.launch("d4_walk_a", d4_walk_a, GRID2(segs, 128, nc), dim3(128), infos, stride, V, pitch, seg_len, seg_next);
+                    uint32_t pitch, uint32_t* seg_len, uint32_t* seg_next, uint32_t* seg_resume, uint8_t* T) {
+  L.launch("d4_walk_a", d4_walk_a, GRID2(segs, 128, nc), dim3(128), infos, stride, V, pitch, seg_len, seg_next,
+           seg_resume, T);
 }
 static void run_d4s(Launcher& L, uint32_t nc, CandInfo* infos, uint32_t pitch, const uint32_t* seg_len,
                     const uint32_t* seg_next, uint32_t* seg_off) {
   L.launch("d4_schedule", d4_schedule, GRID1(nc, 64), dim3(64), nc, infos, pitch, seg_len, seg_next, seg_off);
 }
 static void run_d4c(Launcher& L, uint32_t nc, uint32_t segs, const CandInfo* infos, uint64_t stride, const uint32_t* V,
-                    uint32_t pitch, const uint32_t* seg_len, const uint32_t* seg_off, uint8_t* W) {
-  L.launch("d4_walk_c", d4_walk_c, GRID2(segs, 128, nc), dim3(128), infos, stride, V, pitch, seg_len, seg_off, W);
+                    uint32_t pitch, const uint32_t* seg_len, const uint32_t* seg_off, const uint32_t* seg_resume,
+                    const uint8_t* T, uint8_t* W) {
+  L.launch("d4_walk_c", d4_walk_c, GRID2(segs, 128, nc), dim3(128), infos, stride, V, pitch, seg_len, seg_off,
+           seg_resume, T, W);
 }
 static void run_d5a(Launcher& L, uint32_t nc, uint32_t chunks, const CandInfo* infos, uint64_t stride, const uint8_t* W,
                     uint32_t pitch, uint32_t* rle_map) {
@@ -133,26 +141,27 @@ static void run_d1(Launcher& L, const uint8_t* in, uint64_t n, uint64_t* cand, u
   for (uint64_t x = 0; x < (n + 3) / 4; ++x) d1_scan_body(x, in, n, cand, count, cap);
 }
 static void run_d2(Launcher& L, uint32_t nc, const uint8_t* in, uint64_t n, const uint64_t* cand, uint32_t cap,
-                   uint64_t stride, uint8_t* Lbuf, uint32_t* occ, uint8_t* sel, uint32_t* cftab, CandInfo* infos) {
+                   uint64_t stride, uint32_t* occ, uint8_t* sel, uint32_t* cftab, CandInfo* infos) {
   ++L.launches;
   D2Scratch* s = new D2Scratch();
   for (uint32_t c = 0; c < nc; ++c) {
     memset(s, 0xA5, sizeof(*s));  // shared memory is not zeroed between CTAs either
-    d2_decode_body(c, 0, s, in, n, cand, cap, stride, Lbuf, occ, sel, cftab, infos);
+    d2_decode_body(c, 0, s, in, n, cand, cap, stride, occ, sel, cftab, infos);
   }
   delete s;
 }
-static void run_d3(Launcher& L, uint32_t nc, uint32_t nmax, const CandInfo* infos, uint64_t stride, const uint8_t* Lbuf,
+static void run_d3(Launcher& L, uint32_t nc, uint32_t nmax, const CandInfo* infos, uint64_t stride,
                    const uint32_t* occ, const uint32_t* cftab, uint32_t* V) {
   ++L.launches;
   for (uint32_t y = 0; y < nc; ++y)
-    for (uint32_t x = 0; x < (nmax + 255) / 256 * 256; ++x) d3_scatter_body(x, y, infos, stride, Lbuf, occ, cftab, V);
+    for (uint32_t x = 0; x < (nmax + 255) / 256 * 256; ++x) d3_scatter_body(x, y, infos, stride, occ, cftab, V);
 }
 static void run_d4a(Launcher& L, uint32_t nc, uint32_t segs, const CandInfo* infos, uint64_t stride, const uint32_t* V,
-                    uint32_t pitch, uint32_t* seg_len, uint32_t* seg_next) {
+                    uint32_t pitch, uint32_t* seg_len, uint32_t* seg_next, uint32_t* seg_resume, uint8_t* T) {
   ++L.launches;
   for (uint32_t y = 0; y < nc; ++y)
-    for (uint32_t x = 0; x < (segs + 127) / 128 * 128; ++x) d4_walk_a_body(x, y, infos, stride, V, pitch, seg_len, seg_next);
+    for (uint32_t x = 0; x < (segs + 127) / 128 * 128; ++x)
+      d4_walk_a_body(x, y, infos, stride, V, pitch, seg_len, seg_next, seg_resume, T);
 }
 static void run_d4s(Launcher& L, uint32_t nc, CandInfo* infos, uint32_t pitch, const uint32_t* seg_len,
                     const uint32_t* seg_next, uint32_t* seg_off) {
@@ -160,10 +169,12 @@ static void run_d4s(Launcher& L, uint32_t nc, CandInfo* infos, uint32_t pitch, c
   for (uint32_t y = 0; y < nc; ++y) d4_schedule_body(y, infos, pitch, seg_len, seg_next, seg_off);
 }
 static void run_d4c(Launcher& L, uint32_t nc, uint32_t segs, const CandInfo* infos, uint64_t stride, const uint32_t* V,
-                    uint32_t pitch, const uint32_t* seg_len, const uint32_t* seg_off, uint8_t* W) {
+                    uint32_t pitch, const uint32_t* seg_len, const uint32_t* seg_off, const uint32_t* seg_resume,
+                    const uint8_t* T, uint8_t* W) {
   ++L.launches;
   for (uint32_t y = 0; y < nc; ++y)
-    for (uint32_t x = 0; x < (segs + 127) / 128 * 128; ++x) d4_walk_c_body(x, y, infos, stride, V, pitch, seg_len, seg_off, W);
+    for (uint32_t x = 0; x < (segs + 127) / 128 * 128; ++x)
+      d4_walk_c_body(x, y, infos, stride, V, pitch, seg_len, seg_off, seg_resume, T, W);
 }
 static void run_d5a(Launcher& L, uint32_t nc, uint32_t chunks, const CandInfo* infos, uint64_t stride, const uint8_t* W,
                     uint32_t pitch, uint32_t* rle_map) {
@@ -379,7 +390,7 @@ int dec_run(Launcher& L, DecMem& M, const uint8_t* d_in, uint64_t n, uint8_t* d_
   const uint64_t stride = ((uint64_t)cap + 63) & ~63ull;
   const uint32_t segs_pitch = d4_nseg0(cap) + 1;
   const uint32_t chunks_pitch = d5_nchunks(cap);
-  const uint64_t per_cand = stride * 10 + MAX_SEL + 257 * 4 + (uint64_t)segs_pitch * 12 + (uint64_t)chunks_pitch * 32 +
+  const uint64_t per_cand = stride * 9 + MAX_SEL + 257 * 4 + (uint64_t)segs_pitch * (16 + SEG_KEEP) + (uint64_t)chunks_pitch * 32 +
                             sizeof(CandInfo) + 64;
   size_t batch = (size_t)std::max<uint64_t>(1, batch_bytes / per_cand);
   batch = std::min<size_t>(batch, 32768);
@@ -389,7 +400,6 @@ int dec_run(Launcher& L, DecMem& M, const uint8_t* d_in, uint64_t n, uint8_t* d_
   if (!d_cand) return -2;
   DTRY(M.to_dev(d_cand, cand.data(), cand.size() * 8));
   CandInfo* d_info = slot<CandInfo>(M, DS_INFO, batch);
-  uint8_t* d_L = slot<uint8_t>(M, DS_L, batch * stride);
   uint32_t* d_occ = slot<uint32_t>(M, DS_OCC, batch * stride);
   uint32_t* d_V = slot<uint32_t>(M, DS_V, batch * stride);
   uint8_t* d_W = slot<uint8_t>(M, DS_W, batch * stride);
@@ -398,13 +408,15 @@ int dec_run(Launcher& L, DecMem& M, const uint8_t* d_in, uint64_t n, uint8_t* d_
   uint32_t* d_seglen = slot<uint32_t>(M, DS_SEGLEN, batch * segs_pitch);
   uint32_t* d_segnext = slot<uint32_t>(M, DS_SEGNEXT, batch * segs_pitch);
   uint32_t* d_segoff = slot<uint32_t>(M, DS_SEGOFF, batch * segs_pitch);
+  uint32_t* d_segres = slot<uint32_t>(M, DS_SEGRES, batch * segs_pitch);
+  uint8_t* d_T = slot<uint8_t>(M, DS_T, batch * (size_t)segs_pitch * SEG_KEEP);
   uint32_t* d_rlemap = slot<uint32_t>(M, DS_RLEMAP, batch * (size_t)chunks_pitch * 5);
   uint32_t* d_chentry = slot<uint32_t>(M, DS_CHENTRY, batch * (size_t)chunks_pitch);
   uint64_t* d_choff = slot<uint64_t>(M, DS_CHOFF, batch * (size_t)chunks_pitch);
   uint64_t* d_outoff = slot<uint64_t>(M, DS_OUTOFF, batch);
   uint64_t* d_crcoff = slot<uint64_t>(M, DS_CRCOFF, batch + 1);
   uint32_t* d_crc = slot<uint32_t>(M, DS_CRC, batch);
-  if (!d_info || !d_L || !d_occ || !d_V || !d_W || !d_sel || !d_cftab || !d_seglen || !d_segnext || !d_segoff ||
+  if (!d_info || !d_occ || !d_V || !d_W || !d_sel || !d_cftab || !d_seglen || !d_segnext || !d_segoff || !d_segres || !d_T ||
       !d_rlemap || !d_chentry || !d_choff || !d_outoff || !d_crcoff || !d_crc)
     return -2;
 
@@ -420,7 +432,7 @@ int dec_run(Launcher& L, DecMem& M, const uint8_t* d_in, uint64_t n, uint8_t* d_
     const uint32_t nc = (uint32_t)(c1 - c0);
     ++res->batches;
     // ---- D2: header, tables, symbols, MTF, runs
-    run_d2(L, nc, d_in, n, d_cand + c0, cap, stride, d_L, d_occ, d_sel, d_cftab, d_info);
+    run_d2(L, nc, d_in, n, d_cand + c0, cap, stride, d_occ, d_sel, d_cftab, d_info);
     DTRY(M.check());
     DTRY(M.to_host(infos.data(), d_info, (size_t)nc * sizeof(CandInfo)));
     uint32_t nmax = 0;
@@ -429,11 +441,11 @@ int dec_run(Launcher& L, DecMem& M, const uint8_t* d_in, uint64_t n, uint8_t* d_
     if (nmax) {
       const uint32_t segs = d4_nseg0(nmax) + 1, chunks = d5_nchunks(nmax);
       // ---- D3/D4: inverse BWT
-      run_d3(L, nc, nmax, d_info, stride, d_L, d_occ, d_cftab, d_V);
+      run_d3(L, nc, nmax, d_info, stride, d_occ, d_cftab, d_V);
       DTRY(M.fill(d_segoff, 0xFF, (size_t)nc * segs_pitch * 4));
-      run_d4a(L, nc, segs, d_info, stride, d_V, segs_pitch, d_seglen, d_segnext);
+      run_d4a(L, nc, segs, d_info, stride, d_V, segs_pitch, d_seglen, d_segnext, d_segres, d_T);
       run_d4s(L, nc, d_info, segs_pitch, d_seglen, d_segnext, d_segoff);
-      run_d4c(L, nc, segs, d_info, stride, d_V, segs_pitch, d_seglen, d_segoff, d_W);
+      run_d4c(L, nc, segs, d_info, stride, d_V, segs_pitch, d_seglen, d_segoff, d_segres, d_T, d_W);
       // ---- D5: RLE1 undo, sizes
       run_d5a(L, nc, chunks, d_info, stride, d_W, chunks_pitch, d_rlemap);
       run_d5b(L, nc, d_info, chunks_pitch, d_rlemap, d_chentry, d_choff);
