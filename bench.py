@@ -58,7 +58,7 @@ def workload_name(n_gpus):
 
 class ClockSampler:
     """SM clock and throttle reasons sampled DURING the timed region (B200_PROFILING.md).  In-process NVML
-    (nvidia_ml_py) every 100 ms: a looping `nvidia-smi --query-gpu` was measured to stretch the timed steps by up to
+    (nvidia_ml_py) every 300 ms: a looping `nvidia-smi --query-gpu` was measured to stretch the timed steps by up to
     15 % on some boxes (each query stalls launches and synchronisations); nvidia-smi remains the fallback."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -96,12 +96,18 @@ class ClockSampler:
             get_reasons(h)                                    # the timed region
 
             def loop():
+                # every NVML query takes driver locks that launches and synchronisations also need: on some boxes a
+                # 100 ms period stretched the 460-launch step by 13 %, so the period is 300 ms (first sample at 50 ms)
+                time.sleep(0.05)
                 while not self.stop_flag:
                     try:
                         self.samples.append((nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM), mx, int(get_reasons(h))))
                     except Exception:
                         pass
-                    time.sleep(0.1)
+                    for _ in range(6):
+                        if self.stop_flag:
+                            break
+                        time.sleep(0.05)
             self.how = "nvml"
             self.t = threading.Thread(target=loop, daemon=True)
             self.t.start()
@@ -135,7 +141,7 @@ class ClockSampler:
             return {"sm_mhz": statistics.median(sm) if sm else None,
                     "sm_max_mhz": self.samples[0][1] if self.samples else None,
                     "reasons": sorted(n for b, n in self.REASONS.items() if bits & b), "samples": len(self.samples),
-                    "source": "nvml, 100 ms period, during the timed region"}
+                    "source": "nvml, 300 ms period, during the timed region"}
         if not self.p:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.p.terminate()
