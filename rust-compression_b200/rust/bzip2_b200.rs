@@ -4,9 +4,10 @@
 //!
 //! SOURCE ONLY: the build image has no rustc/cargo, so this file is shipped uncompiled (INTEGRATION.md shows
 //! where it goes in the crate).  The byte sequence produced over all `next` calls is identical to the
-//! reference encoder's; bytes are handed out once `Action::Finish` has compressed the buffered input.
+//! reference encoder's; closed blocks are compressed whenever a window of input has accumulated, the rest at
+//! `Action::Finish`.  The decode side (`BZip2Decoder`) is in bzip2_decoder_b200.rs.
 //!
-//! In the crate: replace `pub use crate::bzip2::encoder::BZip2Encoder` (src/lib.rs:96-97) by this type behind a
+//! In the crate: replace `pub use crate::bzip2::encoder::BZip2Encoder` (src/lib.rs:77) by this type behind a
 //! `b200` cargo feature and link with `-lbzb200`.
 
 use crate::action::Action;
@@ -98,48 +99,48 @@ impl Encoder for BZip2Encoder {
     type In = u8;
     type Out = u8;
 
-    // encoder.rs:120-158: one output byte per call; None = drained.
+    // encoder.rs:120-158: one output byte per call; None = drained.  Under Action::Run the library compresses the
+    // blocks that have closed whenever a window of input has accumulated (bzb200_enc_write), so bytes can become
+    // available before Finish, as in the reference (encoder.rs:91-107).
     fn next<I: Iterator<Item = u8>>(&mut self, iter: &mut I, action: Action) -> Option<Result<u8, CompressionError>> {
         loop {
-            if self.outpos < self.outbuf.len() && self.finished {
+            if self.outpos < self.outbuf.len() {
                 let b = self.outbuf[self.outpos];
                 self.outpos += 1;
                 return Some(Ok(b));
             }
-            if self.finished {
-                self.outbuf.resize(CHUNK, 0);
-                if self.refill() > 0 {
-                    continue;
-                }
-                // stream fully handed out: re-arm like encoder.rs:87-90,130-133
-                self.finished = false;
-                unsafe { bzb200_enc_reset(self.handle) };
-                self.outbuf.clear();
-                return None;
-            }
-            // Action::Run side: drain the caller's iterator (the reference pulls one byte at a time, :79-85)
-            for b in iter.by_ref() {
-                self.inbuf.push(b);
-                if self.inbuf.len() == CHUNK {
-                    if let Err(e) = self.push_input() {
-                        return Some(Err(e));
+            if !self.finished {
+                // drain the caller's iterator (the reference pulls one byte at a time, :79-85)
+                for b in iter.by_ref() {
+                    self.inbuf.push(b);
+                    if self.inbuf.len() == CHUNK {
+                        if let Err(e) = self.push_input() {
+                            return Some(Err(e));
+                        }
                     }
                 }
-            }
-            if let Err(e) = self.push_input() {
-                return Some(Err(e));
-            }
-            match action {
-                Action::Finish => {
+                if let Err(e) = self.push_input() {
+                    return Some(Err(e));
+                }
+                if let Action::Finish = action {
                     if unsafe { bzb200_enc_finish(self.handle) } != 0 {
                         return Some(Err(CompressionError::Unexpected)); // encoder.rs:623 is the only error the reference yields
                     }
                     self.finished = true;
-                    self.outbuf.clear();
                 }
-                // Run: "input drained, feed more" (:106,142-144). Flush is out of contract.
-                _ => return None,
+                // Flush is out of contract and behaves like Run.
             }
+            self.outbuf.resize(CHUNK, 0);
+            if self.refill() > 0 {
+                continue;
+            }
+            self.outbuf.clear();
+            if self.finished {
+                // stream fully handed out: re-arm like encoder.rs:87-90,130-133
+                self.finished = false;
+                unsafe { bzb200_enc_reset(self.handle) };
+            }
+            return None; // Run: "input drained, feed more" (:106,142-144)
         }
     }
 }
