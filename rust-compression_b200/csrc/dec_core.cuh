@@ -53,6 +53,7 @@ constexpr uint32_t SEG_KEEP = 4096;     // bytes of a walk kept by d4_walk_a for
 constexpr uint32_t RLE_CHUNK = 1024;    // bytes of the pre-RLE1 block per d5 thread
 constexpr uint32_t LUT_BITS = 10;       // primary Huffman lookup width
 constexpr uint32_t MAX_SEL = 32768;     // n_selectors is a 15-bit field (decoder.rs:285)
+constexpr uint32_t MTF_CHUNK = 1024;    // symbols per thread of the chunk-parallel MTF stage (split path)
 constexpr uint64_t KIND_END = 1ull << 63;
 constexpr uint64_t MAGIC_BLOCK = 0x314159265359ull;
 constexpr uint64_t MAGIC_END = 0x177245385090ull;
@@ -74,7 +75,8 @@ struct CandInfo {       // one per candidate, written by d2_decode / d4_schedule
   uint32_t cyc;         // 0, or the length of the walk's cycle when it is shorter than nblock (periodic block)
   uint32_t rle_len;     // bytes after RLE1 undo
   uint32_t rle_dangling;  // 1: the block ends with four equal bytes and no count byte
-  uint32_t nsym;        // Huffman symbols decoded (incl. EOB), instrumentation
+  uint32_t nsym;        // Huffman symbols decoded (incl. EOB)
+  uint32_t nsyms;       // bytes in use in the block (the MTF alphabet; EOB = nsyms + 1)
   uint8_t tail[4];      // end of stream: the bytes after the padding (next stream's "BZh" + level, if any)
   uint32_t tail_n;      // how many of them exist
 };
@@ -357,6 +359,7 @@ BZB_DEV void d2_header(D2Scratch* s, const uint8_t* in, uint64_t n, uint64_t can
   I.rle_len = 0;
   I.rle_dangling = 0;
   I.nsym = 0;
+  I.nsyms = 0;
   I.tail_n = 0;
   for (int k = 0; k < 4; ++k) I.tail[k] = 0;
   s->go = 0;
@@ -437,6 +440,7 @@ BZB_DEV void d2_header(D2Scratch* s, const uint8_t* in, uint64_t n, uint64_t can
   s->nsyms = nsyms;
   s->n_sel = n_sel;
   s->go = 1;
+  I.nsyms = nsyms;
 }
 
 // c: candidate index inside the batch.  cap = 100000 * (largest level of any stream in the buffer): the most a block
@@ -576,6 +580,294 @@ BZB_DEV void d2_decode_body(uint32_t c, uint32_t lane, D2Scratch* s, const uint8
     }
   }
   infos[c] = I;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// D2, split path: the serial chain of a block is cut down to the Huffman symbols alone (d2_huff); the MTF list and the
+// RUNA/RUNB expansion become parallel over chunks of MTF_CHUNK symbols by list composition — the inverse of the
+// encoder's K3:
+//   d2_huff   one lane per candidate: header, tables, symbols -> sym[] (u16), the block's start list mtf0[]
+//   d2_mtf_a  one thread per chunk: MTF on the identity list of POSITIONS -> for every symbol the index p into the
+//             list the chunk starts with (P[]), the chunk's permutation, bytes emitted per index, and the run digits
+//             that lead/trail the chunk (a run may straddle chunks; digit j of a run weighs 2^j)
+//   d2_mtf_b  one warp per candidate walks the chunks: start list, per-byte counts and output offset of every chunk;
+//             block totals, cftab, and the checks of decoder.rs:399,416,427,446
+//   d2_mtf_c  one thread per chunk: byte = start_list[P], occurrence index = count before the chunk + count inside ->
+//             the same packed words the fused d2_decode writes
+struct ChunkMeta {      // written by d2_mtf_a
+  uint32_t leadval;     // sum over the leading run digits j of digit << j  (digit: RUNA 1, RUNB 2)
+  uint32_t leadcnt;     // number of leading run digits (the whole chunk if it holds nothing else)
+  uint32_t trail;       // run digits at the end of the chunk (index the next chunk's first digit continues from)
+  uint32_t rest;        // bytes emitted by everything after the leading run
+  uint32_t err;         // 1: a run has more than 21 digits (decoder.rs:416)
+  uint32_t has_lit;     // 1: the chunk contains a literal (a chunk without one extends the run it was entered with)
+};
+
+BZB_HD uint32_t d2_nchunks(uint32_t nsym) { return (nsym + MTF_CHUNK - 1) / MTF_CHUNK; }
+
+// c: candidate.  Lane 0 only.  symstride >= cap + 2 symbols per candidate.
+BZB_DEV void d2_huff_body(uint32_t c, D2Scratch* s, const uint8_t* in, uint64_t n, const uint64_t* cand, uint32_t cap,
+                          uint64_t symstride, uint16_t* symbuf, uint8_t* selbuf, uint8_t* mtf0buf, CandInfo* infos) {
+  uint8_t* sel = selbuf + (uint64_t)c * MAX_SEL;
+  uint16_t* sym = symbuf + (uint64_t)c * symstride;
+  d2_header(s, in, n, cand[c], sel);
+  if (!s->go) {
+    infos[c] = s->info;
+    return;
+  }
+  const uint32_t nsyms = s->nsyms, n_sel = s->n_sel;
+  const uint32_t eob = nsyms + 1;
+  for (uint32_t k = 0; k < 256; ++k) mtf0buf[(uint64_t)c * 256 + k] = k < nsyms ? s->mtf[k] : 0;
+  FastBits r;
+  r.init(in, n, s->pos);
+  uint32_t err = 0, group_no = 0, group_pos = 0, tbl = 0, nsym = 0;
+  uint32_t tbl_next = sel[0];
+  const uint16_t* lut = s->lut[0];
+  for (;;) {
+    if (group_pos == 0) {
+      group_no += 1;
+      if (group_no > n_sel) { err = E_DATA; break; }
+      group_pos = 50;
+      tbl = tbl_next;
+      lut = s->lut[tbl];
+      tbl_next = group_no < n_sel ? sel[group_no] : 0u;
+    }
+    group_pos -= 1;
+    uint32_t next_sym;
+    const uint32_t e = lut[r.peek(LUT_BITS)];
+    if (e) {
+      r.drop(e >> 9);
+      next_sym = e & 511u;
+    } else {
+      const uint32_t maxl = s->max_len[tbl];
+      uint32_t found = 0xFFFFFFFFu;
+      for (uint32_t l = LUT_BITS + 1; l <= maxl; ++l) {
+        if (!s->count[tbl][l]) continue;
+        const uint32_t cbits = r.peek(l);
+        const uint32_t f = s->first_code[tbl][l];
+        if (cbits >= f && cbits - f < s->count[tbl][l]) {
+          r.drop(l);
+          found = s->perm[tbl][s->offs[tbl][l] + (cbits - f)];
+          break;
+        }
+      }
+      if (found == 0xFFFFFFFFu) { err = E_DATA; break; }
+      next_sym = found;
+    }
+    // every symbol but EOB yields at least one byte, so more than cap + 1 symbols cannot pass decoder.rs:399,427
+    if (nsym > cap) { err = E_DATA; break; }
+    sym[nsym++] = (uint16_t)next_sym;
+    if (next_sym == eob) break;
+  }
+  if (!err && r.pos() > n * 8) err = E_DATA;  // the symbols ran past the end of the input (decoder.rs:376-379)
+  CandInfo& I = s->info;
+  I.nsym = nsym;
+  if (err) I.err = err;
+  else I.end_bit = r.pos();
+  infos[c] = I;
+}
+
+// x: chunk, y: candidate
+BZB_DEV void d2_mtf_a_body(uint32_t x, uint32_t y, const CandInfo* infos, uint64_t symstride, const uint16_t* symbuf,
+                           uint32_t chunks_pitch, uint8_t* Pbuf, uint8_t* permbuf, uint32_t* cntpbuf, ChunkMeta* metabuf) {
+  const CandInfo& I = infos[y];
+  if (I.kind != 0 || I.err != 0) return;
+  const uint32_t nsym = I.nsym;
+  if (x >= d2_nchunks(nsym)) return;
+  const uint32_t lo = x * MTF_CHUNK, hi = lo + MTF_CHUNK < nsym ? lo + MTF_CHUNK : nsym;
+  const uint32_t eob = I.nsyms + 1;
+  const uint16_t* sym = symbuf + (uint64_t)y * symstride;
+  uint8_t* P = Pbuf + (uint64_t)y * symstride;
+  uint8_t pl[256];
+  uint32_t cnt[256];
+  for (uint32_t k = 0; k < 256; ++k) {
+    pl[k] = (uint8_t)k;
+    cnt[k] = 0;
+  }
+  ChunkMeta m;
+  m.leadval = 0;
+  m.leadcnt = 0;
+  m.trail = 0;
+  m.rest = 0;
+  m.err = 0;
+  m.has_lit = 0;
+  uint32_t j = 0;  // index of the next digit inside the current (non-leading) run
+  for (uint32_t i = lo; i < hi; ++i) {
+    const uint32_t sy = sym[i];
+    if (sy <= 1) {
+      const uint32_t d = sy + 1;
+      if (!m.has_lit) {
+        if (m.leadcnt > 20) m.err = 1; else m.leadval += d << m.leadcnt;
+        m.leadcnt += 1;
+        P[i] = 0;
+      } else {
+        if (j > 20) {
+          m.err = 1;
+        } else {
+          const uint32_t v = d << j;
+          m.rest += v;
+          cnt[pl[0]] += v;
+        }
+        j += 1;
+        P[i] = pl[0];
+      }
+      m.trail += 1;
+    } else if (sy == eob) {
+      m.trail = 0;  // EOB flushes whatever run precedes it; nothing continues into a next chunk
+      break;
+    } else {
+      m.has_lit = 1;
+      j = 0;
+      m.trail = 0;
+      const uint32_t v = sy - 1;  // < nsyms: the alphabet has nsyms + 2 symbols
+      const uint8_t p = pl[v];
+      for (uint32_t q = v; q > 0; --q) pl[q] = pl[q - 1];
+      pl[0] = p;
+      P[i] = p;
+      cnt[p] += 1;
+      m.rest += 1;
+    }
+  }
+  const uint64_t co = (uint64_t)y * chunks_pitch + x;
+  for (uint32_t k = 0; k < 256; ++k) {
+    permbuf[co * 256 + k] = pl[k];
+    cntpbuf[co * 256 + k] = cnt[k];
+  }
+  metabuf[co] = m;
+}
+
+// One warp per candidate (the emulation runs it as one lane that covers every index).
+#ifdef BZB_EMU
+#define BZB_LANE_LOOP(i, n) for (uint32_t i = 0; i < (n); ++i)
+#else
+#define BZB_LANE_LOOP(i, n) for (uint32_t i = lane; i < (n); i += 32)
+#endif
+struct MtfBScratch {
+  uint8_t cur[256], nxt[256];
+  uint32_t cntb[256];
+  uint64_t off;
+  uint32_t d0, err, add0;
+};
+
+BZB_DEV void d2_mtf_b_body(uint32_t y, uint32_t lane, MtfBScratch* s, CandInfo* infos, uint32_t cap, uint64_t symstride,
+                           const uint16_t* symbuf, const uint8_t* mtf0buf, uint32_t chunks_pitch, const uint8_t* permbuf,
+                           const uint32_t* cntpbuf, const ChunkMeta* metabuf, uint8_t* initlbuf, uint32_t* basebuf,
+                           uint32_t* coffbuf, uint32_t* cd0buf, uint32_t* cftab) {
+  (void)lane;
+  CandInfo& I = infos[y];
+  if (I.kind != 0 || I.err != 0) return;
+  const uint32_t nsym = I.nsym, nsyms = I.nsyms;
+  const uint32_t nch = d2_nchunks(nsym);
+  BZB_LANE_LOOP(i, 256) {
+    s->cur[i] = mtf0buf[(uint64_t)y * 256 + i];
+    s->cntb[i] = 0;
+  }
+  if (lane == 0) {
+    s->off = 0;
+    s->d0 = 0;
+    s->err = 0;
+  }
+  warp_sync();
+  for (uint32_t k = 0; k < nch; ++k) {
+    const uint64_t co = (uint64_t)y * chunks_pitch + k;
+    BZB_LANE_LOOP(i, 256) {
+      initlbuf[co * 256 + i] = s->cur[i];
+      basebuf[co * 256 + i] = s->cntb[i];
+    }
+    if (lane == 0) {
+      const ChunkMeta m = metabuf[co];
+      uint32_t e = m.err;
+      const uint32_t d0 = s->d0;
+      if (m.leadcnt && d0 + m.leadcnt > 21) e = 1;  // decoder.rs:416: a run of more than 21 digits
+      uint64_t lead = e ? 0 : ((uint64_t)m.leadval << d0);
+      if (lead > cap) {  // decoder.rs:399
+        e = 1;
+        lead = 0;
+      }
+      coffbuf[co] = (uint32_t)(s->off > cap ? cap : s->off);
+      cd0buf[co] = d0;
+      s->off += lead + m.rest;
+      s->add0 = (uint32_t)lead;
+      s->d0 = m.has_lit ? m.trail : d0 + m.leadcnt;
+      if (e) s->err = 1;
+    }
+    warp_sync();
+    BZB_LANE_LOOP(p, 256) {  // cur is a permutation: every p adds to a different byte's counter
+      const uint32_t add = cntpbuf[co * 256 + p] + (p == 0 ? s->add0 : 0u);
+      if (add) s->cntb[s->cur[p]] += add;
+    }
+    BZB_LANE_LOOP(i, 256) s->nxt[i] = s->cur[permbuf[co * 256 + i]];
+    warp_sync();
+    BZB_LANE_LOOP(i, 256) s->cur[i] = s->nxt[i];
+    // read before the barrier: lane 0 changes off/err again only after it (next iteration), so every lane sees the
+    // same values and the loop exit is uniform
+    const bool stop = s->err || s->off > cap;
+    warp_sync();
+    if (stop) break;
+  }
+  if (lane != 0) return;
+  // was the last byte pushed by a run? (decides whether decoder.rs:399 or :427 was the last size check)
+  bool last_is_run = false;
+  if (nsym >= 2) last_is_run = symbuf[(uint64_t)y * symstride + nsym - 2] <= 1;
+  const uint64_t size = s->off;
+  if (s->err || size + (last_is_run ? 1 : 0) > cap) {
+    I.err = E_DATA;
+    return;
+  }
+  I.nblock = (uint32_t)size;
+  I.need_max = (uint32_t)size + (last_is_run ? 1u : 0u);
+  if (I.orig_pos >= size) {  // decoder.rs:446-450
+    I.err = E_DATA;
+    return;
+  }
+  (void)nsyms;
+  uint32_t acc = 0;
+  uint32_t* cf = cftab + (uint64_t)y * 257;
+  for (uint32_t k = 0; k < 256; ++k) {
+    cf[k] = acc;
+    acc += s->cntb[k];
+  }
+  cf[256] = acc;
+}
+
+BZB_DEV void d2_mtf_c_body(uint32_t x, uint32_t y, const CandInfo* infos, uint64_t symstride, const uint16_t* symbuf,
+                           const uint8_t* Pbuf, uint32_t chunks_pitch, const uint8_t* initlbuf, const uint32_t* basebuf,
+                           const uint32_t* coffbuf, const uint32_t* cd0buf, uint64_t stride, uint32_t* occbuf) {
+  const CandInfo& I = infos[y];
+  if (I.kind != 0 || I.err != 0) return;
+  const uint32_t nsym = I.nsym;
+  if (x >= d2_nchunks(nsym)) return;
+  const uint32_t lo = x * MTF_CHUNK, hi = lo + MTF_CHUNK < nsym ? lo + MTF_CHUNK : nsym;
+  const uint32_t eob = I.nsyms + 1;
+  const uint16_t* sym = symbuf + (uint64_t)y * symstride;
+  const uint8_t* P = Pbuf + (uint64_t)y * symstride;
+  const uint64_t co = (uint64_t)y * chunks_pitch + x;
+  const uint8_t* il = initlbuf + co * 256;
+  const uint32_t* bs = basebuf + co * 256;
+  uint32_t* occ = occbuf + (uint64_t)y * stride + coffbuf[co];
+  const uint32_t d0 = cd0buf[co];
+  uint32_t loc[256];
+  for (uint32_t k = 0; k < 256; ++k) loc[k] = 0;
+  bool has_lit = false;
+  uint32_t j = 0, jl = 0;
+  for (uint32_t i = lo; i < hi; ++i) {
+    const uint32_t sy = sym[i];
+    if (sy == eob) break;
+    const uint32_t b = il[P[i]];
+    uint32_t v = 1;
+    if (sy <= 1) {
+      if (!has_lit) v = (sy + 1) << (d0 + jl++);
+      else v = (sy + 1) << j++;
+    } else {
+      has_lit = true;
+      j = 0;
+    }
+    const uint32_t o = bs[b] + loc[b];
+    loc[b] += v;
+    const uint32_t w = (b << 24) | o;
+    for (uint32_t t = 0; t < v; ++t) occ[t] = w + t;
+    occ += v;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------------

@@ -37,6 +37,40 @@ __global__ void __launch_bounds__(32) d2_decode(const uint8_t* __restrict__ in, 
   d2_decode_body(blockIdx.x, threadIdx.x, &s, in, n, cand, cap, stride, occbuf, selbuf, cftab, infos);
 }
 
+__global__ void __launch_bounds__(32) d2_huff(const uint8_t* __restrict__ in, uint64_t n, const uint64_t* cand,
+                                              uint32_t cap, uint64_t symstride, uint16_t* symbuf, uint8_t* selbuf,
+                                              uint8_t* mtf0buf, CandInfo* infos) {
+  __shared__ D2Scratch s;
+  if (threadIdx.x == 0) d2_huff_body(blockIdx.x, &s, in, n, cand, cap, symstride, symbuf, selbuf, mtf0buf, infos);
+}
+
+__global__ void __launch_bounds__(64) d2_mtf_a(const CandInfo* __restrict__ infos, uint64_t symstride,
+                                               const uint16_t* __restrict__ symbuf, uint32_t chunks_pitch, uint8_t* Pbuf,
+                                               uint8_t* permbuf, uint32_t* cntpbuf, ChunkMeta* metabuf) {
+  d2_mtf_a_body(blockIdx.x * 64u + threadIdx.x, blockIdx.y, infos, symstride, symbuf, chunks_pitch, Pbuf, permbuf,
+                cntpbuf, metabuf);
+}
+
+__global__ void __launch_bounds__(32) d2_mtf_b(CandInfo* infos, uint32_t cap, uint64_t symstride,
+                                               const uint16_t* __restrict__ symbuf, const uint8_t* __restrict__ mtf0buf,
+                                               uint32_t chunks_pitch, const uint8_t* __restrict__ permbuf,
+                                               const uint32_t* __restrict__ cntpbuf,
+                                               const ChunkMeta* __restrict__ metabuf, uint8_t* initlbuf,
+                                               uint32_t* basebuf, uint32_t* coffbuf, uint32_t* cd0buf, uint32_t* cftab) {
+  __shared__ MtfBScratch s;
+  d2_mtf_b_body(blockIdx.x, threadIdx.x, &s, infos, cap, symstride, symbuf, mtf0buf, chunks_pitch, permbuf, cntpbuf,
+                metabuf, initlbuf, basebuf, coffbuf, cd0buf, cftab);
+}
+
+__global__ void __launch_bounds__(64) d2_mtf_c(const CandInfo* __restrict__ infos, uint64_t symstride,
+                                               const uint16_t* __restrict__ symbuf, const uint8_t* __restrict__ Pbuf,
+                                               uint32_t chunks_pitch, const uint8_t* __restrict__ initlbuf,
+                                               const uint32_t* __restrict__ basebuf, const uint32_t* __restrict__ coffbuf,
+                                               const uint32_t* __restrict__ cd0buf, uint64_t stride, uint32_t* occbuf) {
+  d2_mtf_c_body(blockIdx.x * 64u + threadIdx.x, blockIdx.y, infos, symstride, symbuf, Pbuf, chunks_pitch, initlbuf,
+                basebuf, coffbuf, cd0buf, stride, occbuf);
+}
+
 __global__ void __launch_bounds__(256) d3_scatter(const CandInfo* __restrict__ infos, uint64_t stride,
                                                   const uint32_t* __restrict__ occbuf,
                                                   const uint32_t* __restrict__ cftab, uint32_t* Vbuf) {
@@ -100,6 +134,30 @@ static void run_d2(Launcher& L, uint32_t nc, const uint8_t* in, uint64_t n, cons
                    uint64_t stride, uint32_t* occ, uint8_t* sel, uint32_t* cftab, CandInfo* infos) {
   L.launch("d2_decode", d2_decode, dim3(nc), dim3(32), in, n, cand, cap, stride, occ, sel, cftab, infos);
 }
+struct SplitBufs {
+  uint64_t symstride;
+  uint32_t chunks_pitch;
+  uint16_t* sym;
+  uint8_t* P;
+  uint8_t* mtf0;
+  uint8_t* perm;
+  uint32_t* cntp;
+  ChunkMeta* meta;
+  uint8_t* initl;
+  uint32_t* base;
+  uint32_t* coff;
+  uint32_t* cd0;
+};
+static void run_d2_split(Launcher& L, uint32_t nc, const uint8_t* in, uint64_t n, const uint64_t* cand, uint32_t cap,
+                         uint64_t stride, uint32_t* occ, uint8_t* sel, uint32_t* cftab, CandInfo* infos, SplitBufs& B) {
+  L.launch("d2_huff", d2_huff, dim3(nc), dim3(32), in, n, cand, cap, B.symstride, B.sym, sel, B.mtf0, infos);
+  L.launch("d2_mtf_a", d2_mtf_a, GRID2(B.chunks_pitch, 64, nc), dim3(64), infos, B.symstride, B.sym, B.chunks_pitch, B.P,
+           B.perm, B.cntp, B.meta);
+  L.launch("d2_mtf_b", d2_mtf_b, dim3(nc), dim3(32), infos, cap, B.symstride, B.sym, B.mtf0, B.chunks_pitch, B.perm,
+           B.cntp, B.meta, B.initl, B.base, B.coff, B.cd0, cftab);
+  L.launch("d2_mtf_c", d2_mtf_c, GRID2(B.chunks_pitch, 64, nc), dim3(64), infos, B.symstride, B.sym, B.P, B.chunks_pitch,
+           B.initl, B.base, B.coff, B.cd0, stride, occ);
+}
 static void run_d3(Launcher& L, uint32_t nc, uint32_t nmax, const CandInfo* infos, uint64_t stride,
                    const uint32_t* occ, const uint32_t* cftab, uint32_t* V) {
   L.launch("d3_scatter", d3_scatter, GRID2(nmax, 256, nc), dim3(256), infos, stride, occ, cftab, V);
@@ -149,6 +207,44 @@ static void run_d2(Launcher& L, uint32_t nc, const uint8_t* in, uint64_t n, cons
     d2_decode_body(c, 0, s, in, n, cand, cap, stride, occ, sel, cftab, infos);
   }
   delete s;
+}
+struct SplitBufs {
+  uint64_t symstride;
+  uint32_t chunks_pitch;
+  uint16_t* sym;
+  uint8_t* P;
+  uint8_t* mtf0;
+  uint8_t* perm;
+  uint32_t* cntp;
+  ChunkMeta* meta;
+  uint8_t* initl;
+  uint32_t* base;
+  uint32_t* coff;
+  uint32_t* cd0;
+};
+static void run_d2_split(Launcher& L, uint32_t nc, const uint8_t* in, uint64_t n, const uint64_t* cand, uint32_t cap,
+                         uint64_t stride, uint32_t* occ, uint8_t* sel, uint32_t* cftab, CandInfo* infos, SplitBufs& B) {
+  L.launches += 4;
+  D2Scratch* s = new D2Scratch();
+  for (uint32_t c = 0; c < nc; ++c) {
+    memset(s, 0xA5, sizeof(*s));
+    d2_huff_body(c, s, in, n, cand, cap, B.symstride, B.sym, sel, B.mtf0, infos);
+  }
+  delete s;
+  const uint32_t gx = (B.chunks_pitch + 63) / 64 * 64;
+  for (uint32_t y = 0; y < nc; ++y)
+    for (uint32_t x = 0; x < gx; ++x)
+      d2_mtf_a_body(x, y, infos, B.symstride, B.sym, B.chunks_pitch, B.P, B.perm, B.cntp, B.meta);
+  MtfBScratch* sb = new MtfBScratch();
+  for (uint32_t y = 0; y < nc; ++y) {
+    memset(sb, 0xA5, sizeof(*sb));
+    d2_mtf_b_body(y, 0, sb, infos, cap, B.symstride, B.sym, B.mtf0, B.chunks_pitch, B.perm, B.cntp, B.meta, B.initl,
+                  B.base, B.coff, B.cd0, cftab);
+  }
+  delete sb;
+  for (uint32_t y = 0; y < nc; ++y)
+    for (uint32_t x = 0; x < gx; ++x)
+      d2_mtf_c_body(x, y, infos, B.symstride, B.sym, B.P, B.chunks_pitch, B.initl, B.base, B.coff, B.cd0, stride, occ);
 }
 static void run_d3(Launcher& L, uint32_t nc, uint32_t nmax, const CandInfo* infos, uint64_t stride,
                    const uint32_t* occ, const uint32_t* cftab, uint32_t* V) {
@@ -325,7 +421,7 @@ T* slot(DecMem& M, int s, size_t count) {
   } while (0)
 
 int dec_run(Launcher& L, DecMem& M, const uint8_t* d_in, uint64_t n, uint8_t* d_out, uint64_t cap_out,
-            uint64_t batch_bytes, DecResult* res) {
+            uint64_t batch_bytes, uint32_t flags, DecResult* res) {
   *res = DecResult();
   if (n == 0) {  // the very first read fails (decoder.rs:176-181)
     res->bz_error = E_MAGIC_FIRST;
@@ -390,8 +486,13 @@ int dec_run(Launcher& L, DecMem& M, const uint8_t* d_in, uint64_t n, uint8_t* d_
   const uint64_t stride = ((uint64_t)cap + 63) & ~63ull;
   const uint32_t segs_pitch = d4_nseg0(cap) + 1;
   const uint32_t chunks_pitch = d5_nchunks(cap);
-  const uint64_t per_cand = stride * 9 + MAX_SEL + 257 * 4 + (uint64_t)segs_pitch * (16 + SEG_KEEP) + (uint64_t)chunks_pitch * 32 +
-                            sizeof(CandInfo) + 64;
+  const bool split = (flags & DEC_SPLIT_D2) != 0;
+  SplitBufs SB;
+  SB.symstride = ((uint64_t)cap + 2 + 63) & ~63ull;
+  SB.chunks_pitch = d2_nchunks(cap + 2);
+  const uint64_t per_cand = stride * 9 + MAX_SEL + 257 * 4 + (uint64_t)segs_pitch * (16 + SEG_KEEP) +
+                            (uint64_t)chunks_pitch * 32 + sizeof(CandInfo) + 64 +
+                            (split ? SB.symstride * 3 + 256 + (uint64_t)SB.chunks_pitch * (256 * 10 + 32 + 8) : 0);
   size_t batch = (size_t)std::max<uint64_t>(1, batch_bytes / per_cand);
   batch = std::min<size_t>(batch, 32768);
   batch = std::min<size_t>(batch, cand.size());
@@ -416,6 +517,21 @@ int dec_run(Launcher& L, DecMem& M, const uint8_t* d_in, uint64_t n, uint8_t* d_
   uint64_t* d_outoff = slot<uint64_t>(M, DS_OUTOFF, batch);
   uint64_t* d_crcoff = slot<uint64_t>(M, DS_CRCOFF, batch + 1);
   uint32_t* d_crc = slot<uint32_t>(M, DS_CRC, batch);
+  if (split) {
+    const size_t ch = batch * (size_t)SB.chunks_pitch;
+    SB.sym = slot<uint16_t>(M, DS_SYM, batch * SB.symstride);
+    SB.P = slot<uint8_t>(M, DS_P, batch * SB.symstride);
+    SB.mtf0 = slot<uint8_t>(M, DS_MTF0, batch * 256);
+    SB.perm = slot<uint8_t>(M, DS_PERM, ch * 256);
+    SB.cntp = slot<uint32_t>(M, DS_CNTP, ch * 256);
+    SB.meta = slot<ChunkMeta>(M, DS_CMETA, ch);
+    SB.initl = slot<uint8_t>(M, DS_INITL, ch * 256);
+    SB.base = slot<uint32_t>(M, DS_BASE, ch * 256);
+    SB.coff = slot<uint32_t>(M, DS_COFF, ch);
+    SB.cd0 = slot<uint32_t>(M, DS_CD0, ch);
+    if (!SB.sym || !SB.P || !SB.mtf0 || !SB.perm || !SB.cntp || !SB.meta || !SB.initl || !SB.base || !SB.coff || !SB.cd0)
+      return -2;
+  }
   if (!d_info || !d_occ || !d_V || !d_W || !d_sel || !d_cftab || !d_seglen || !d_segnext || !d_segoff || !d_segres || !d_T ||
       !d_rlemap || !d_chentry || !d_choff || !d_outoff || !d_crcoff || !d_crc)
     return -2;
@@ -432,7 +548,8 @@ int dec_run(Launcher& L, DecMem& M, const uint8_t* d_in, uint64_t n, uint8_t* d_
     const uint32_t nc = (uint32_t)(c1 - c0);
     ++res->batches;
     // ---- D2: header, tables, symbols, MTF, runs
-    run_d2(L, nc, d_in, n, d_cand + c0, cap, stride, d_occ, d_sel, d_cftab, d_info);
+    if (split) run_d2_split(L, nc, d_in, n, d_cand + c0, cap, stride, d_occ, d_sel, d_cftab, d_info, SB);
+    else run_d2(L, nc, d_in, n, d_cand + c0, cap, stride, d_occ, d_sel, d_cftab, d_info);
     DTRY(M.check());
     DTRY(M.to_host(infos.data(), d_info, (size_t)nc * sizeof(CandInfo)));
     uint32_t nmax = 0;

@@ -32,7 +32,8 @@ struct DecMem {
 
 enum DecSlot {
   DS_CAND = 0, DS_COUNT, DS_INFO, DS_L, DS_OCC, DS_V, DS_W, DS_SEL, DS_CFTAB, DS_SEGLEN, DS_SEGNEXT, DS_SEGOFF,
-  DS_SEGRES, DS_T, DS_RLEMAP, DS_CHENTRY, DS_CHOFF, DS_OUTOFF, DS_CRCOFF, DS_CRC, DS_NSLOTS
+  DS_SEGRES, DS_T, DS_RLEMAP, DS_CHENTRY, DS_CHOFF, DS_OUTOFF, DS_CRCOFF, DS_CRC, DS_SYM, DS_P, DS_MTF0, DS_PERM, DS_CNTP,
+  DS_CMETA, DS_INITL, DS_BASE, DS_COFF, DS_CD0, DS_NSLOTS
 };
 
 struct DecResult {
@@ -50,7 +51,9 @@ struct DecResult {
 // Decodes the (possibly multi-stream) .bz2 buffer d_in[0..n) into d_out[0..cap).  Returns 0 when the pipeline ran
 // (data errors of the stream are reported through res->bz_error exactly like the reference reports them), or a
 // negative BZB200_E_* code for CUDA / argument failures.  batch_bytes bounds the scratch memory per batch of blocks.
+// flags: DEC_SPLIT_D2 selects the split D2 (d2_huff + chunk-parallel d2_mtf_a/b/c) instead of the fused d2_decode.
+enum : uint32_t { DEC_SPLIT_D2 = 1u };
 int dec_run(Launcher& L, DecMem& M, const uint8_t* d_in, uint64_t n, uint8_t* d_out, uint64_t cap, uint64_t batch_bytes,
-            DecResult* res);
+            uint32_t flags, DecResult* res);
 
 }  // namespace bzb

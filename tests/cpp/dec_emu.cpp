@@ -61,8 +61,8 @@ extern "C" {
 
 // Returns dec_run's code; *bz_error = BZip2Error ordinal + 1 or 0; *out is malloc'ed (free with emu_free).
 // info[0..7] = streams, blocks, candidates, batches, launches, retried(0/1), 0, 0.
-int emu_decode(const uint8_t* in, size_t n, size_t first_cap, size_t batch_bytes, uint8_t** out, size_t* out_n,
-               uint32_t* bz_error, uint64_t* info) {
+int emu_decode(const uint8_t* in, size_t n, size_t first_cap, size_t batch_bytes, uint32_t flags, uint8_t** out,
+               size_t* out_n, uint32_t* bz_error, uint64_t* info) {
   EmuMem M;
   bzb::Launcher L;
   bzb::DecResult R;
@@ -70,13 +70,13 @@ int emu_decode(const uint8_t* in, size_t n, size_t first_cap, size_t batch_bytes
   uint8_t* o = (uint8_t*)malloc(cap + 64);
   uint8_t* padded = (uint8_t*)malloc(n + 4);  // exact-size copy: reads beyond n would be caught by ASan builds
   if (n) memcpy(padded, in, n);
-  int rc = bzb::dec_run(L, M, padded, n, o, cap, batch_bytes, &R);
+  int rc = bzb::dec_run(L, M, padded, n, o, cap, batch_bytes, flags, &R);
   int retried = 0;
   if (rc == 0 && R.too_small) {
     free(o);
     cap = R.needed;
     o = (uint8_t*)malloc(cap + 64);
-    rc = bzb::dec_run(L, M, padded, n, o, cap, batch_bytes, &R);
+    rc = bzb::dec_run(L, M, padded, n, o, cap, batch_bytes, flags, &R);
     retried = 1;
   }
   free(padded);

@@ -24,13 +24,14 @@ def emu():
         subprocess.check_call(["g++", "-std=c++17", "-O2", "-shared", "-fPIC", SRC, "-o", LIB])
     lib = C.CDLL(LIB)
     lib.emu_decode.restype = C.c_int
-    lib.emu_decode.argtypes = [C.c_char_p, C.c_size_t, C.c_size_t, C.c_size_t, C.POINTER(C.c_void_p),
+    lib.emu_decode.argtypes = [C.c_char_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_uint32, C.POINTER(C.c_void_p),
                                C.POINTER(C.c_size_t), C.POINTER(C.c_uint32), C.c_void_p]
     lib.emu_free.argtypes = [C.c_void_p]
 
-    def run(data, first_cap=1 << 20, batch_bytes=1 << 34):
+    def run(data, first_cap=1 << 20, batch_bytes=1 << 34, split=0):
         out, n, e, info = C.c_void_p(), C.c_size_t(0), C.c_uint32(0), (C.c_uint64 * 8)()
-        rc = lib.emu_decode(bytes(data), len(data), first_cap, batch_bytes, C.byref(out), C.byref(n), C.byref(e), info)
+        rc = lib.emu_decode(bytes(data), len(data), first_cap, batch_bytes, split, C.byref(out), C.byref(n), C.byref(e),
+                            info)
         res = C.string_at(out, n.value) if n.value else b""
         lib.emu_free(out)
         assert rc == 0
@@ -40,18 +41,20 @@ def emu():
     return run
 
 
-def test_valid_streams(emu):
+@pytest.mark.parametrize("split", [0, 1])   # 0: fused d2_decode, 1: d2_huff + chunk-parallel d2_mtf_a/b/c
+def test_valid_streams(emu, split):
     for name, buf in dec_cases.valid_cases():
         want = dec_cases.expected(buf)
         assert want[0] == 0, name
-        err, out, info = emu(buf)
+        err, out, info = emu(buf, split=split)
         assert (err, out) == want, name
 
 
-def test_malformed_streams_report_what_the_reference_reports(emu):
+@pytest.mark.parametrize("split", [0, 1])
+def test_malformed_streams_report_what_the_reference_reports(emu, split):
     for name, buf in dec_cases.malformed_cases():
         want = dec_cases.expected(buf)
-        err, out, info = emu(buf)
+        err, out, info = emu(buf, split=split)
         assert err == want[0], f"{name}: kind {err} != {want[0]}"
         assert out == want[1], f"{name}: {len(out)} bytes before the error, reference {len(want[1])}"
 

@@ -68,7 +68,9 @@ def test_decoder_object_reuse_and_error_after_bytes(rc):
 
 # ---- parity with the restated reference decoder ----
 
-def test_valid_streams(rc):
+@pytest.mark.parametrize("split", ["0", "1"])   # 0: fused d2_decode, 1: d2_huff + chunk-parallel d2_mtf_a/b/c
+def test_valid_streams(rc, monkeypatch, split):
+    monkeypatch.setenv("BZB200_DEC_SPLIT", split)
     for name, buf in dec_cases.valid_cases(big=True):
         want = dec_cases.expected(buf)
         assert want[0] == 0, name
@@ -77,7 +79,9 @@ def test_valid_streams(rc):
         assert got[1] == want[1], f"{name}: bytes differ (gpu {len(got[1])}, reference {len(want[1])})"
 
 
-def test_malformed_streams_report_what_the_reference_reports(rc):
+@pytest.mark.parametrize("split", ["0", "1"])
+def test_malformed_streams_report_what_the_reference_reports(rc, monkeypatch, split):
+    monkeypatch.setenv("BZB200_DEC_SPLIT", split)
     for name, buf in dec_cases.malformed_cases():
         want = dec_cases.expected(buf)
         got = gpu_decode(rc, buf)
@@ -115,7 +119,13 @@ def test_device_api_batches_and_small_output(rc, monkeypatch):
     ctx.close()
 
 
-def test_gpu_encoder_streams_decode_on_gpu(rc):
+@pytest.mark.parametrize("split", ["0", "1"])
+def test_gpu_encoder_streams_decode_on_gpu(rc, monkeypatch, split):
+    monkeypatch.setenv("BZB200_DEC_SPLIT", split)
+    _round_trips(rc)
+
+
+def _round_trips(rc):
     """Encoder -> decoder round trips at sizes the oracle does not need to see: levels 1 and 9, multi-block, plus the
     adversarial periodic inputs (cycle walks of the inverse BWT)."""
     cases = [(gen.text(21, 5_000_000), 9), (gen.mixed(4, 3_000_000), 1), (b"ab" * 1_000_000, 9),
