@@ -52,6 +52,7 @@ constexpr uint32_t SEG = 1024;          // splitter spacing of the inverse-BWT w
 constexpr uint32_t SEG_KEEP = 4096;     // bytes of a walk kept by d4_walk_a for d4_walk_c (longer walks are resumed)
 constexpr uint32_t RLE_CHUNK = 1024;    // bytes of the pre-RLE1 block per d5 thread
 constexpr uint32_t LUT_BITS = 10;       // primary Huffman lookup width
+constexpr uint32_t LUT2_BITS = 9;       // window of the two-symbol lookup of the split path (same 2 KB per table)
 constexpr uint32_t MAX_SEL = 32768;     // n_selectors is a 15-bit field (decoder.rs:285)
 constexpr uint32_t MTF_CHUNK = 1024;    // symbols per thread of the chunk-parallel MTF stage (split path)
 constexpr uint64_t KIND_END = 1ull << 63;
@@ -182,7 +183,7 @@ struct D2Scratch {
 };
 
 // Canonical codes of one table into scratch; false: over-subscribed (rejected as DataError, as the oracle does).
-BZB_DEV bool d2_build_table(D2Scratch* s, uint32_t t, uint32_t alpha) {
+BZB_DEV bool d2_build_table(D2Scratch* s, uint32_t t, uint32_t alpha, bool pair_lut) {
   for (uint32_t l = 0; l < 32; ++l) {
     s->count[t][l] = 0;
     s->first_code[t][l] = 0;
@@ -215,6 +216,37 @@ BZB_DEV bool d2_build_table(D2Scratch* s, uint32_t t, uint32_t alpha) {
       const uint32_t l = s->len[i];
       if (l) s->perm[t][next[l]++] = (uint16_t)i;
     }
+  }
+  if (pair_lut) {
+    // split path: the table's 2 KB hold 512 words instead — for a 9-bit window the first symbol and, when a second
+    // code fits into the same window, the second one too:
+    //   bits 0-8 sym1, 9-17 sym2, 18-21 len1, 22-25 len1 + len2, bit 26: two symbols;  0 = first code longer than 9 bits
+    uint32_t* l2 = reinterpret_cast<uint32_t*>(s->lut[t]);
+    for (uint32_t w = 0; w < (1u << LUT2_BITS); ++w) {
+      uint32_t sym[2] = {0, 0}, len[2] = {0, 0}, have = 0, used = 0;
+      for (uint32_t k = 0; k < 2; ++k) {
+        uint32_t found = 0;
+        for (uint32_t l = 1; l <= maxl && used + l <= LUT2_BITS; ++l) {
+          if (!s->count[t][l]) continue;
+          const uint32_t cbits = (w >> (LUT2_BITS - used - l)) & ((1u << l) - 1u);
+          const uint32_t f = s->first_code[t][l];
+          if (cbits >= f && cbits - f < s->count[t][l]) {
+            sym[k] = s->perm[t][s->offs[t][l] + (cbits - f)];
+            len[k] = l;
+            found = 1;
+            break;
+          }
+        }
+        if (!found) break;
+        used += len[k];
+        have = k + 1;
+      }
+      uint32_t e = 0;
+      if (have >= 1) e = sym[0] | (len[0] << 18) | (len[0] << 22);
+      if (have == 2) e = sym[0] | (sym[1] << 9) | (len[0] << 18) | ((len[0] + len[1]) << 22) | (1u << 26);
+      l2[w] = e;
+    }
+    return true;
   }
   for (uint32_t e = 0; e < (1u << LUT_BITS); ++e) s->lut[t][e] = 0;
   for (uint32_t l = 1; l <= maxl && l <= LUT_BITS; ++l) {
@@ -343,7 +375,7 @@ struct FastBits {
 
 // Header phase, one lane: stream position, block header, mapping table, selectors, coding tables.  Leaves the MTF
 // start list in s->mtf and the tables in s; s->go = 1 when the symbol phase should run.
-BZB_DEV void d2_header(D2Scratch* s, const uint8_t* in, uint64_t n, uint64_t cand, uint8_t* sel) {
+BZB_DEV void d2_header(D2Scratch* s, const uint8_t* in, uint64_t n, uint64_t cand, uint8_t* sel, bool pair_lut) {
   CandInfo& I = s->info;
   I.start_bit = cand & ~KIND_END;
   I.end_bit = 0;
@@ -434,7 +466,7 @@ BZB_DEV void d2_header(D2Scratch* s, const uint8_t* in, uint64_t n, uint64_t can
       }
       s->len[i] = (uint8_t)curr;
     }
-    if (!d2_build_table(s, t, alpha)) { I.err = E_DATA; return; }
+    if (!d2_build_table(s, t, alpha, pair_lut)) { I.err = E_DATA; return; }
   }
   s->pos = r.pos;
   s->nsyms = nsyms;
@@ -454,7 +486,7 @@ BZB_DEV void d2_decode_body(uint32_t c, uint32_t lane, D2Scratch* s, const uint8
   uint32_t* occ = occbuf + (uint64_t)c * stride;  // per position: byte << 24 | occurrence index (< 2^20)
   uint8_t* sel = selbuf + (uint64_t)c * MAX_SEL;
   uint32_t* cf = cftab + (uint64_t)c * 257;
-  if (lane == 0) d2_header(s, in, n, cand[c], sel);
+  if (lane == 0) d2_header(s, in, n, cand[c], sel, false);
   warp_sync();
   if (!s->go) {
     if (lane == 0) infos[c] = s->info;
@@ -605,12 +637,12 @@ struct ChunkMeta {      // written by d2_mtf_a
 
 BZB_HD uint32_t d2_nchunks(uint32_t nsym) { return (nsym + MTF_CHUNK - 1) / MTF_CHUNK; }
 
-// c: candidate.  Lane 0 only.  symstride >= cap + 2 symbols per candidate.
+// c: candidate.  Lane 0 only.  symstride >= cap + 4 symbols per candidate.
 BZB_DEV void d2_huff_body(uint32_t c, D2Scratch* s, const uint8_t* in, uint64_t n, const uint64_t* cand, uint32_t cap,
                           uint64_t symstride, uint16_t* symbuf, uint8_t* selbuf, uint8_t* mtf0buf, CandInfo* infos) {
   uint8_t* sel = selbuf + (uint64_t)c * MAX_SEL;
   uint16_t* sym = symbuf + (uint64_t)c * symstride;
-  d2_header(s, in, n, cand[c], sel);
+  d2_header(s, in, n, cand[c], sel, true);
   if (!s->go) {
     infos[c] = s->info;
     return;
@@ -622,26 +654,39 @@ BZB_DEV void d2_huff_body(uint32_t c, D2Scratch* s, const uint8_t* in, uint64_t 
   r.init(in, n, s->pos);
   uint32_t err = 0, group_no = 0, group_pos = 0, tbl = 0, nsym = 0;
   uint32_t tbl_next = sel[0];
-  const uint16_t* lut = s->lut[0];
+  const uint32_t* lut2 = reinterpret_cast<const uint32_t*>(s->lut[0]);
   for (;;) {
     if (group_pos == 0) {
       group_no += 1;
       if (group_no > n_sel) { err = E_DATA; break; }
       group_pos = 50;
       tbl = tbl_next;
-      lut = s->lut[tbl];
+      lut2 = reinterpret_cast<const uint32_t*>(s->lut[tbl]);
       tbl_next = group_no < n_sel ? sel[group_no] : 0u;
     }
-    group_pos -= 1;
-    uint32_t next_sym;
-    const uint32_t e = lut[r.peek(LUT_BITS)];
+    // every symbol but EOB yields at least one byte, so more than cap + 1 symbols cannot pass decoder.rs:399,427
+    if (nsym > cap) { err = E_DATA; break; }   // (a step stores at most two symbols: nsym <= cap + 2 <= symstride - 2)
+    const uint32_t e = lut2[r.peek(LUT2_BITS)];
     if (e) {
-      r.drop(e >> 9);
-      next_sym = e & 511u;
-    } else {
+      const uint32_t s1 = e & 511u;
+      if ((e >> 26) && group_pos >= 2 && s1 != eob) {  // two symbols of the same group in one step
+        const uint32_t s2 = (e >> 9) & 511u;
+        r.drop((e >> 22) & 15u);
+        sym[nsym] = (uint16_t)s1;
+        sym[nsym + 1] = (uint16_t)s2;
+        nsym += 2;
+        group_pos -= 2;
+        if (s2 == eob) break;
+      } else {
+        r.drop((e >> 18) & 15u);
+        sym[nsym++] = (uint16_t)s1;
+        group_pos -= 1;
+        if (s1 == eob) break;
+      }
+    } else {  // a code longer than the window, or no code at all
       const uint32_t maxl = s->max_len[tbl];
       uint32_t found = 0xFFFFFFFFu;
-      for (uint32_t l = LUT_BITS + 1; l <= maxl; ++l) {
+      for (uint32_t l = LUT2_BITS + 1; l <= maxl; ++l) {
         if (!s->count[tbl][l]) continue;
         const uint32_t cbits = r.peek(l);
         const uint32_t f = s->first_code[tbl][l];
@@ -652,12 +697,10 @@ BZB_DEV void d2_huff_body(uint32_t c, D2Scratch* s, const uint8_t* in, uint64_t 
         }
       }
       if (found == 0xFFFFFFFFu) { err = E_DATA; break; }
-      next_sym = found;
+      sym[nsym++] = (uint16_t)found;
+      group_pos -= 1;
+      if (found == eob) break;
     }
-    // every symbol but EOB yields at least one byte, so more than cap + 1 symbols cannot pass decoder.rs:399,427
-    if (nsym > cap) { err = E_DATA; break; }
-    sym[nsym++] = (uint16_t)next_sym;
-    if (next_sym == eob) break;
   }
   if (!err && r.pos() > n * 8) err = E_DATA;  // the symbols ran past the end of the input (decoder.rs:376-379)
   CandInfo& I = s->info;
@@ -667,9 +710,11 @@ BZB_DEV void d2_huff_body(uint32_t c, D2Scratch* s, const uint8_t* in, uint64_t 
   infos[c] = I;
 }
 
-// x: chunk, y: candidate
+// x: chunk, y: candidate.  pl / cnt: 256 entries each of per-thread scratch, entry k at [k * st] (shared memory with
+// st = threads per CTA on the GPU — a per-thread local array would thrash L1 at full occupancy).
 BZB_DEV void d2_mtf_a_body(uint32_t x, uint32_t y, const CandInfo* infos, uint64_t symstride, const uint16_t* symbuf,
-                           uint32_t chunks_pitch, uint8_t* Pbuf, uint8_t* permbuf, uint32_t* cntpbuf, ChunkMeta* metabuf) {
+                           uint32_t chunks_pitch, uint8_t* Pbuf, uint8_t* permbuf, uint32_t* cntpbuf, ChunkMeta* metabuf,
+                           uint8_t* pl, uint32_t* cnt, uint32_t st) {
   const CandInfo& I = infos[y];
   if (I.kind != 0 || I.err != 0) return;
   const uint32_t nsym = I.nsym;
@@ -678,11 +723,9 @@ BZB_DEV void d2_mtf_a_body(uint32_t x, uint32_t y, const CandInfo* infos, uint64
   const uint32_t eob = I.nsyms + 1;
   const uint16_t* sym = symbuf + (uint64_t)y * symstride;
   uint8_t* P = Pbuf + (uint64_t)y * symstride;
-  uint8_t pl[256];
-  uint32_t cnt[256];
   for (uint32_t k = 0; k < 256; ++k) {
-    pl[k] = (uint8_t)k;
-    cnt[k] = 0;
+    pl[k * st] = (uint8_t)k;
+    cnt[k * st] = 0;
   }
   ChunkMeta m;
   m.leadval = 0;
@@ -701,15 +744,16 @@ BZB_DEV void d2_mtf_a_body(uint32_t x, uint32_t y, const CandInfo* infos, uint64
         m.leadcnt += 1;
         P[i] = 0;
       } else {
+        const uint32_t front = pl[0];
         if (j > 20) {
           m.err = 1;
         } else {
           const uint32_t v = d << j;
           m.rest += v;
-          cnt[pl[0]] += v;
+          cnt[front * st] += v;
         }
         j += 1;
-        P[i] = pl[0];
+        P[i] = (uint8_t)front;
       }
       m.trail += 1;
     } else if (sy == eob) {
@@ -720,18 +764,18 @@ BZB_DEV void d2_mtf_a_body(uint32_t x, uint32_t y, const CandInfo* infos, uint64
       j = 0;
       m.trail = 0;
       const uint32_t v = sy - 1;  // < nsyms: the alphabet has nsyms + 2 symbols
-      const uint8_t p = pl[v];
-      for (uint32_t q = v; q > 0; --q) pl[q] = pl[q - 1];
-      pl[0] = p;
-      P[i] = p;
-      cnt[p] += 1;
+      const uint32_t p = pl[v * st];
+      for (uint32_t q = v; q > 0; --q) pl[q * st] = pl[(q - 1) * st];
+      pl[0] = (uint8_t)p;
+      P[i] = (uint8_t)p;
+      cnt[p * st] += 1;
       m.rest += 1;
     }
   }
   const uint64_t co = (uint64_t)y * chunks_pitch + x;
   for (uint32_t k = 0; k < 256; ++k) {
-    permbuf[co * 256 + k] = pl[k];
-    cntpbuf[co * 256 + k] = cnt[k];
+    permbuf[co * 256 + k] = pl[k * st];
+    cntpbuf[co * 256 + k] = cnt[k * st];
   }
   metabuf[co] = m;
 }
@@ -830,9 +874,12 @@ BZB_DEV void d2_mtf_b_body(uint32_t y, uint32_t lane, MtfBScratch* s, CandInfo* 
   cf[256] = acc;
 }
 
+// il / loc: per-thread scratch like in d2_mtf_a (start list of the chunk; running occurrence index per byte, which
+// starts at the count before the chunk)
 BZB_DEV void d2_mtf_c_body(uint32_t x, uint32_t y, const CandInfo* infos, uint64_t symstride, const uint16_t* symbuf,
                            const uint8_t* Pbuf, uint32_t chunks_pitch, const uint8_t* initlbuf, const uint32_t* basebuf,
-                           const uint32_t* coffbuf, const uint32_t* cd0buf, uint64_t stride, uint32_t* occbuf) {
+                           const uint32_t* coffbuf, const uint32_t* cd0buf, uint64_t stride, uint32_t* occbuf,
+                           uint8_t* il, uint32_t* loc, uint32_t st) {
   const CandInfo& I = infos[y];
   if (I.kind != 0 || I.err != 0) return;
   const uint32_t nsym = I.nsym;
@@ -842,18 +889,18 @@ BZB_DEV void d2_mtf_c_body(uint32_t x, uint32_t y, const CandInfo* infos, uint64
   const uint16_t* sym = symbuf + (uint64_t)y * symstride;
   const uint8_t* P = Pbuf + (uint64_t)y * symstride;
   const uint64_t co = (uint64_t)y * chunks_pitch + x;
-  const uint8_t* il = initlbuf + co * 256;
-  const uint32_t* bs = basebuf + co * 256;
   uint32_t* occ = occbuf + (uint64_t)y * stride + coffbuf[co];
   const uint32_t d0 = cd0buf[co];
-  uint32_t loc[256];
-  for (uint32_t k = 0; k < 256; ++k) loc[k] = 0;
+  for (uint32_t k = 0; k < 256; ++k) {
+    il[k * st] = initlbuf[co * 256 + k];
+    loc[k * st] = basebuf[co * 256 + k];
+  }
   bool has_lit = false;
   uint32_t j = 0, jl = 0;
   for (uint32_t i = lo; i < hi; ++i) {
     const uint32_t sy = sym[i];
     if (sy == eob) break;
-    const uint32_t b = il[P[i]];
+    const uint32_t b = il[(uint32_t)P[i] * st];
     uint32_t v = 1;
     if (sy <= 1) {
       if (!has_lit) v = (sy + 1) << (d0 + jl++);
@@ -862,8 +909,8 @@ BZB_DEV void d2_mtf_c_body(uint32_t x, uint32_t y, const CandInfo* infos, uint64
       has_lit = true;
       j = 0;
     }
-    const uint32_t o = bs[b] + loc[b];
-    loc[b] += v;
+    const uint32_t o = loc[b * st];
+    loc[b * st] = o + v;
     const uint32_t w = (b << 24) | o;
     for (uint32_t t = 0; t < v; ++t) occ[t] = w + t;
     occ += v;

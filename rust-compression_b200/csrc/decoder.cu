@@ -44,11 +44,13 @@ __global__ void __launch_bounds__(32) d2_huff(const uint8_t* __restrict__ in, ui
   if (threadIdx.x == 0) d2_huff_body(blockIdx.x, &s, in, n, cand, cap, symstride, symbuf, selbuf, mtf0buf, infos);
 }
 
-__global__ void __launch_bounds__(64) d2_mtf_a(const CandInfo* __restrict__ infos, uint64_t symstride,
+__global__ void __launch_bounds__(32) d2_mtf_a(const CandInfo* __restrict__ infos, uint64_t symstride,
                                                const uint16_t* __restrict__ symbuf, uint32_t chunks_pitch, uint8_t* Pbuf,
                                                uint8_t* permbuf, uint32_t* cntpbuf, ChunkMeta* metabuf) {
-  d2_mtf_a_body(blockIdx.x * 64u + threadIdx.x, blockIdx.y, infos, symstride, symbuf, chunks_pitch, Pbuf, permbuf,
-                cntpbuf, metabuf);
+  __shared__ uint32_t cnt[256 * 32];  // entry k of thread t at [k * 32 + t]: conflict-free
+  __shared__ uint8_t pl[256 * 32];
+  d2_mtf_a_body(blockIdx.x * 32u + threadIdx.x, blockIdx.y, infos, symstride, symbuf, chunks_pitch, Pbuf, permbuf,
+                cntpbuf, metabuf, pl + threadIdx.x, cnt + threadIdx.x, 32);
 }
 
 __global__ void __launch_bounds__(32) d2_mtf_b(CandInfo* infos, uint32_t cap, uint64_t symstride,
@@ -62,13 +64,15 @@ __global__ void __launch_bounds__(32) d2_mtf_b(CandInfo* infos, uint32_t cap, ui
                 metabuf, initlbuf, basebuf, coffbuf, cd0buf, cftab);
 }
 
-__global__ void __launch_bounds__(64) d2_mtf_c(const CandInfo* __restrict__ infos, uint64_t symstride,
+__global__ void __launch_bounds__(32) d2_mtf_c(const CandInfo* __restrict__ infos, uint64_t symstride,
                                                const uint16_t* __restrict__ symbuf, const uint8_t* __restrict__ Pbuf,
                                                uint32_t chunks_pitch, const uint8_t* __restrict__ initlbuf,
                                                const uint32_t* __restrict__ basebuf, const uint32_t* __restrict__ coffbuf,
                                                const uint32_t* __restrict__ cd0buf, uint64_t stride, uint32_t* occbuf) {
-  d2_mtf_c_body(blockIdx.x * 64u + threadIdx.x, blockIdx.y, infos, symstride, symbuf, Pbuf, chunks_pitch, initlbuf,
-                basebuf, coffbuf, cd0buf, stride, occbuf);
+  __shared__ uint32_t loc[256 * 32];
+  __shared__ uint8_t il[256 * 32];
+  d2_mtf_c_body(blockIdx.x * 32u + threadIdx.x, blockIdx.y, infos, symstride, symbuf, Pbuf, chunks_pitch, initlbuf,
+                basebuf, coffbuf, cd0buf, stride, occbuf, il + threadIdx.x, loc + threadIdx.x, 32);
 }
 
 __global__ void __launch_bounds__(256) d3_scatter(const CandInfo* __restrict__ infos, uint64_t stride,
@@ -151,11 +155,11 @@ struct SplitBufs {
 static void run_d2_split(Launcher& L, uint32_t nc, const uint8_t* in, uint64_t n, const uint64_t* cand, uint32_t cap,
                          uint64_t stride, uint32_t* occ, uint8_t* sel, uint32_t* cftab, CandInfo* infos, SplitBufs& B) {
   L.launch("d2_huff", d2_huff, dim3(nc), dim3(32), in, n, cand, cap, B.symstride, B.sym, sel, B.mtf0, infos);
-  L.launch("d2_mtf_a", d2_mtf_a, GRID2(B.chunks_pitch, 64, nc), dim3(64), infos, B.symstride, B.sym, B.chunks_pitch, B.P,
+  L.launch("d2_mtf_a", d2_mtf_a, GRID2(B.chunks_pitch, 32, nc), dim3(32), infos, B.symstride, B.sym, B.chunks_pitch, B.P,
            B.perm, B.cntp, B.meta);
   L.launch("d2_mtf_b", d2_mtf_b, dim3(nc), dim3(32), infos, cap, B.symstride, B.sym, B.mtf0, B.chunks_pitch, B.perm,
            B.cntp, B.meta, B.initl, B.base, B.coff, B.cd0, cftab);
-  L.launch("d2_mtf_c", d2_mtf_c, GRID2(B.chunks_pitch, 64, nc), dim3(64), infos, B.symstride, B.sym, B.P, B.chunks_pitch,
+  L.launch("d2_mtf_c", d2_mtf_c, GRID2(B.chunks_pitch, 32, nc), dim3(32), infos, B.symstride, B.sym, B.P, B.chunks_pitch,
            B.initl, B.base, B.coff, B.cd0, stride, occ);
 }
 static void run_d3(Launcher& L, uint32_t nc, uint32_t nmax, const CandInfo* infos, uint64_t stride,
@@ -232,9 +236,14 @@ static void run_d2_split(Launcher& L, uint32_t nc, const uint8_t* in, uint64_t n
   }
   delete s;
   const uint32_t gx = (B.chunks_pitch + 63) / 64 * 64;
+  uint8_t sc8[256];
+  uint32_t sc32[256];
   for (uint32_t y = 0; y < nc; ++y)
-    for (uint32_t x = 0; x < gx; ++x)
-      d2_mtf_a_body(x, y, infos, B.symstride, B.sym, B.chunks_pitch, B.P, B.perm, B.cntp, B.meta);
+    for (uint32_t x = 0; x < gx; ++x) {
+      memset(sc8, 0xA5, sizeof(sc8));
+      memset(sc32, 0xA5, sizeof(sc32));
+      d2_mtf_a_body(x, y, infos, B.symstride, B.sym, B.chunks_pitch, B.P, B.perm, B.cntp, B.meta, sc8, sc32, 1);
+    }
   MtfBScratch* sb = new MtfBScratch();
   for (uint32_t y = 0; y < nc; ++y) {
     memset(sb, 0xA5, sizeof(*sb));
@@ -243,8 +252,12 @@ static void run_d2_split(Launcher& L, uint32_t nc, const uint8_t* in, uint64_t n
   }
   delete sb;
   for (uint32_t y = 0; y < nc; ++y)
-    for (uint32_t x = 0; x < gx; ++x)
-      d2_mtf_c_body(x, y, infos, B.symstride, B.sym, B.P, B.chunks_pitch, B.initl, B.base, B.coff, B.cd0, stride, occ);
+    for (uint32_t x = 0; x < gx; ++x) {
+      memset(sc8, 0xA5, sizeof(sc8));
+      memset(sc32, 0xA5, sizeof(sc32));
+      d2_mtf_c_body(x, y, infos, B.symstride, B.sym, B.P, B.chunks_pitch, B.initl, B.base, B.coff, B.cd0, stride, occ,
+                    sc8, sc32, 1);
+    }
 }
 static void run_d3(Launcher& L, uint32_t nc, uint32_t nmax, const CandInfo* infos, uint64_t stride,
                    const uint32_t* occ, const uint32_t* cftab, uint32_t* V) {
@@ -488,7 +501,7 @@ int dec_run(Launcher& L, DecMem& M, const uint8_t* d_in, uint64_t n, uint8_t* d_
   const uint32_t chunks_pitch = d5_nchunks(cap);
   const bool split = (flags & DEC_SPLIT_D2) != 0;
   SplitBufs SB;
-  SB.symstride = ((uint64_t)cap + 2 + 63) & ~63ull;
+  SB.symstride = ((uint64_t)cap + 4 + 63) & ~63ull;
   SB.chunks_pitch = d2_nchunks(cap + 2);
   const uint64_t per_cand = stride * 9 + MAX_SEL + 257 * 4 + (uint64_t)segs_pitch * (16 + SEG_KEEP) +
                             (uint64_t)chunks_pitch * 32 + sizeof(CandInfo) + 64 +
