@@ -255,7 +255,10 @@ def check_prefix(stream, corpus_prefix):
 DEC_METRIC = "bzip2 decompress MB/s (uncompressed)"
 # Algorithmic HBM bytes of the decoder's kernels (DESIGN.md "Decoder"): st = bzb200_dec_stats + compressed size
 DEC_ALG_BYTES = {
-    "d2_decode": lambda st: st["comp_bytes"] + 5.0 * st["pre_rle_bytes"],   # bits in; L (1 B) + occ (4 B) out
+    "d2_decode": lambda st: st["comp_bytes"] + 4.0 * st["pre_rle_bytes"],   # fused path: bits in; byte ‖ occ word out
+    "d2_huff": lambda st: st["comp_bytes"] + 2.0 * st["symbols"],           # bits in; one u16 symbol out
+    "d2_mtf_a": lambda st: 4.25 * st["symbols"],   # u16 symbol in, index byte out, 1.25 KB of chunk tables per 1 024
+    "d2_mtf_c": lambda st: 4.25 * st["symbols"] + 4.0 * st["pre_rle_bytes"],  # symbol + index + tables in; word out
     "d3_scatter": lambda st: 9.0 * st["pre_rle_bytes"],                     # L + occ in, V (4 B) scattered
     "d4_walk_a": lambda st: 4.0 * st["pre_rle_bytes"],                      # one V entry per step
     "d4_walk_c": lambda st: 5.0 * st["pre_rle_bytes"],                      # one V entry per step + the byte out
