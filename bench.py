@@ -178,7 +178,10 @@ def run_reference(args, rank):
     except Exception:
         cores = os.cpu_count() or 1
     per = int(os.environ.get("BZB200_REF_BYTES_PER_CORE", str(16 << 20)))
-    with mp.Pool(cores) as pool:
+    decode = os.environ.get("BZB200_BENCH_MODE") == "decode"
+    global _REF_DECODE
+    _REF_DECODE = decode
+    with mp.Pool(cores, initializer=_ref_init, initargs=(decode,)) as pool:
         # every worker keeps its slice of the synthetic corpus between steps: the timed region is compression only
         pool.map(_ref_worker, [(i, per, True) for i in range(cores)])
 
@@ -196,33 +199,44 @@ def run_reference(args, rank):
     ms = tot / args.steps * 1e3
     val = nbytes / (ms / 1e3) / 1e6
     line = {
-        "impl": "reference", "metric": METRIC, "value": val, "unit": "MB/s", "n_gpus": args.gpus, "steps": args.steps,
+        "impl": "reference", "metric": DEC_METRIC if decode else METRIC, "value": val, "unit": "MB/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u8", "data": "synthetic",
         "config": {"workload": workload_name(args.gpus), "level": LEVEL},
         "cpu_baseline": {"value": val, "unit": "MB/s", "cores": cores, "kind": "port",
                          "sample": f"{cores} workers x {per >> 20} MiB of the same synthetic text per step (generated outside "
                                    f"the timed region), each worker one independent level-{LEVEL} stream (C++ oracle port "
-                                   "of the reference; rustc unavailable)"},
+                                   "of the reference " + ("decoder, streams compressed outside the timed region"
+                                                          if decode else "encoder") + "; rustc unavailable)"},
         "e2e": {"value": val, "unit": "MB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
 
 
 _REF_DATA = {}
+_REF_DECODE = False
+
+
+def _ref_init(decode):
+    global _REF_DECODE
+    _REF_DECODE = decode
 
 
 def _ref_worker(a):
-    """Pool worker of the reference arm: slice `idx` of the synthetic corpus, generated once per process."""
+    """Pool worker of the reference arm: slice `idx` of the synthetic corpus, generated once per process (and, for
+    the decode side case, compressed once per process: the timed region is the decoder alone)."""
     idx, n, prepare = a
     import gen
     from oracle import orc
     key = (os.getpid(), n)
     if key not in _REF_DATA:
-        _REF_DATA[key] = gen.text(1000 + idx, n) if GEN == "text" else gen.mixed(1000 + idx, n)
+        raw = gen.text(1000 + idx, n) if GEN == "text" else gen.mixed(1000 + idx, n)
+        _REF_DATA[key] = orc.compress(raw, LEVEL) if _REF_DECODE else raw
     if prepare:
         orc.lib()
         return 0
+    if _REF_DECODE:
+        return len(orc.decode(_REF_DATA[key]))
     return len(orc.compress(_REF_DATA[key], LEVEL))
 
 
