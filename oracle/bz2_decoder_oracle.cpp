@@ -303,6 +303,10 @@ struct Decoder {
 
   int run() {  // BitDecodeService::next (:545-581), looped
     for (;;) {
+      // A block that ends in four equal bytes with no count byte makes the reference read one step past the block
+      // (:566-569); n_block_used then never equals tt.len() again and the reference yields bytes forever.  The
+      // restatement stops here with its own code so that tests can run malformed inputs safely.
+      if (n_block_used > tt.size()) return 6;
       if (result_count == result_wrote) {
         if (n_block_used == tt.size()) {
           const int r = init_block();
@@ -340,7 +344,8 @@ struct Decoder {
 extern "C" {
 
 // Decodes a (possibly multi-stream) .bz2 buffer. Returns 0 or the BZip2Error ordinal + 1 (1 DataError,
-// 2 DataErrorMagicFirst, 3 DataErrorMagic, 4 UnexpectedEof, 5 Unexpected). *out is malloc'ed even on error (bytes
+// 2 DataErrorMagicFirst, 3 DataErrorMagic, 4 UnexpectedEof, 5 Unexpected; 6 = the reference would not terminate, see
+// run()). *out is malloc'ed even on error (bytes
 // decoded so far); free with orc_decode_free.
 int orc_decode(const uint8_t* in, size_t n, uint8_t** out, size_t* out_n) {
   Decoder d;

@@ -183,7 +183,8 @@ def mtf_positions(syms, k):
 
 class DecodeError(Exception):
     """BZip2Error of the restated reference decoder (bzip2/error.rs:13-19)."""
-    KINDS = {1: "DataError", 2: "DataErrorMagicFirst", 3: "DataErrorMagic", 4: "UnexpectedEof", 5: "Unexpected"}
+    KINDS = {1: "DataError", 2: "DataErrorMagicFirst", 3: "DataErrorMagic", 4: "UnexpectedEof", 5: "Unexpected",
+             6: "NonTerminating"}  # 6: not a BZip2Error — the reference never stops on this input (see the .cpp)
 
     def __init__(self, code, partial):
         super().__init__(self.KINDS.get(code, str(code)))

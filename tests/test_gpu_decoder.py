@@ -89,6 +89,15 @@ def test_malformed_streams_report_what_the_reference_reports(rc, monkeypatch, sp
         assert got[1] == want[1], f"{name}: {len(got[1])} bytes before the error, reference {len(want[1])}"
 
 
+def test_fuzzed_streams(rc):
+    """Random mutations of valid streams (the generator of the CPU emulation test): bytes and error kind as the
+    restated reference decoder reports them."""
+    for name, buf in dec_cases.fuzz_cases(120, 7):
+        want = dec_cases.expected(buf)
+        got = gpu_decode(rc, buf)
+        assert dec_cases.same_result(got, want), f"{name}: got {got[0]}/{len(got[1])} bytes, reference {want[0]}/{len(want[1])}"
+
+
 def test_device_api_batches_and_small_output(rc, monkeypatch):
     import torch
     from rust_compression_b200 import device as dv
