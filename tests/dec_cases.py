@@ -70,7 +70,34 @@ def malformed_cases():
         cases.append((f"bit flip in byte {pos}", bytes(b)))
     for tail in (b"xyz", b"B", b"BZh", b"BZh9", b"BZh0"):
         cases.append((f"trailing {tail!r}", s + tail))
+    # header fields patched in otherwise valid streams: the stream's level against the block sizes it holds
+    # (decoder.rs:399,427), origPtr against its bounds (:238, :446) and — inside the bounds — a walk that starts at
+    # the wrong rotation (CRC error after the block's bytes; a periodic block decodes to a rotation of a periodic text)
+    t = gen.text(3, 250000)
+    s9 = orc.compress(t, 9)
+    for lv in b"12348":
+        cases.append((f"level byte patched to {chr(lv)}", s9[:3] + bytes([lv]) + s9[4:]))
+    s1 = orc.compress(t[:60000], 1)
+    for v in (0, 1, 59999, 60000, 100010, 100011, 0xFFFFFF):
+        cases.append((f"origPtr patched to {v}", _set_orig(s1, v)))
+    per = orc.compress(b"abcabc" * 9000, 1)
+    for v in (0, 3, 100, 53999):
+        cases.append((f"periodic block, origPtr patched to {v}", _set_orig(per, v)))
+    alla = orc.compress(b"a" * 200000, 1)
+    for v in (0, 1, 4, 100):  # 0: the block then ends in four equal bytes without a count (see same_result)
+        cases.append((f"all-a block, origPtr patched to {v}", _set_orig(alla, v)))
     return cases
+
+
+def _set_orig(stream, v):
+    """Overwrites the 24-bit origPtr of the first block (stream header 32 bits, magic 48, CRC 32, randomised 1)."""
+    b = bytearray(stream)
+    pos = 32 + 48 + 32 + 1
+    for i in range(24):
+        p = pos + i
+        m = 0x80 >> (p & 7)
+        b[p >> 3] = (b[p >> 3] & ~m) | (m if (v >> (23 - i)) & 1 else 0)
+    return bytes(b)
 
 
 def fuzz_cases(n, seed):

@@ -55,8 +55,8 @@ def test_malformed_streams_report_what_the_reference_reports(emu, split):
     for name, buf in dec_cases.malformed_cases():
         want = dec_cases.expected(buf)
         err, out, info = emu(buf, split=split)
-        assert err == want[0], f"{name}: kind {err} != {want[0]}"
-        assert out == want[1], f"{name}: {len(out)} bytes before the error, reference {len(want[1])}"
+        assert dec_cases.same_result((err, out), want), \
+            f"{name}: kind {err}, {len(out)} bytes before the error; reference kind {want[0]}, {len(want[1])} bytes"
 
 
 def test_batches_and_output_retry(emu):
