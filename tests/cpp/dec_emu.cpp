@@ -18,9 +18,9 @@ struct EmuMem : bzb::DecMem {
     if (bytes == 0) bytes = 16;
     if (cap[s] < bytes) {
       free(p[s]);
-      p[s] = malloc(bytes + 64);
+      p[s] = malloc(bytes);
       cap[s] = bytes;
-      memset(p[s], 0xCD, bytes + 64);  // device memory is not zeroed either
+      memset(p[s], 0xCD, bytes);  // device memory is not zeroed either
     }
     return p[s];
   }
