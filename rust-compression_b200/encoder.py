@@ -73,7 +73,8 @@ class BZip2Encoder:
             raise self._err("bzb200_enc_write", rc)
 
     def finish(self):
-        """Bulk form of Action.Finish; returns the whole .bz2 stream."""
+        """Bulk form of Action.Finish; returns the bytes of the .bz2 stream that have not been read yet (the whole
+        stream unless read_available()/next() already handed out the blocks of earlier windows)."""
         L = _lib.lib()
         rc = L.bzb200_enc_finish(self._h)
         if rc != _lib.OK:
