@@ -1,5 +1,5 @@
 // decoder.h — internal interface of the block-parallel bzip2 decoder (decoder.cu) towards its host
-// (pipeline.cu for the GPU build, tests/cpp/dec_emu.cpp for the host emulation of the same kernel bodies).
+// (dec_abi.cu for the GPU build, tests/cpp/dec_emu.cpp for the host emulation of the same kernel bodies).
 #pragma once
 #include <stddef.h>
 #include <stdint.h>

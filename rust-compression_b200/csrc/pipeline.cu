@@ -1,5 +1,6 @@
-// pipeline.cu — host side of libbzb200: context, device memory, stage orchestration and the C ABI of
-// include/bzb200.h.  No CPU implementation of any stage lives here: if CUDA is unavailable every compute entry
+// pipeline.cu — host side of libbzb200: context, device memory, stage orchestration of the encode path and its part
+// of the C ABI (include/bzb200.h sections 2 and 4; the streaming encoder object is in enc_stream.cu, the decoder entry
+// points in dec_abi.cu).  No CPU implementation of any stage lives here: if CUDA is unavailable every compute entry
 // point returns BZB200_E_CUDA.
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -85,135 +86,15 @@ Launcher::~Launcher() {
   for (auto e : pool) cudaEventDestroy(e);
 }
 
-// ============================================================== context
-namespace {
-
-struct DevBuf {
-  void* p = nullptr;
-  size_t cap = 0;
-};
-
-constexpr uint32_t MAX_BATCH_BLOCKS = 32768;
-
-}  // namespace
-
-struct bzb200_ctx {
-  int device = 0;
-  cudaStream_t stream = nullptr;
-  bool own_stream = false;
-  Launcher L;
-  std::string err;
-
-  // ---- plan ----
-  int level = 0;
-  uint32_t T = 0;
-  const uint8_t* d_in = nullptr;
-  uint64_t n_in = 0;
-  uint32_t nblocks = 0;
-  uint32_t max_block_len = 0;
-  bool planned = false;
-  bool plan_open = false;  // between plan_begin and plan_finish
-  DevBuf tile_head, tile_carry, tile_cnt, tile_E, in_off, rle_off, txt, crc, inuse, scal, cut_state, cut_F;
-  uint32_t prep_lo = 0, prep_hi = 0;  // blocks whose RLE1 bytes, CRC and in-use map are on the device
-  bool crc_all = false;
-  std::vector<uint64_t> h_in_off, h_rle_off;
-  std::vector<uint32_t> h_crc;
-
-  // ---- batch scratch ----
-  DevBuf desc, A, B, rank, sa, tile_meta, cnt, hist, oshist, ticket, tsum, state, shift, sparse, stats, rounds, global, last, origptr;
-  DevBuf chunk_state, chunk_zle, chunk_base, sym, freq, mtf_count;
-  DevBuf lens, rfreq, sel, selmtf, codes, gbits, meta, lm_scratch, lm_list, lm_count, blockbit, bitcursor, combined;
-  DevBuf stage_in, stage_out;  // bzb200_compress_host staging
-  DevBuf dec_bufs[DS_NSLOTS];  // decoder scratch (decoder.cu), one buffer per role
-  DevBuf dec_in, dec_out;      // bzb200_decompress_host / bzb200_dec staging
-  DecResult dec_last;
-  cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
-  std::vector<cudaEvent_t> seg_events;
-  uint64_t batch_elems_cap = (uint64_t)1400 * 1000 * 1000;
-
-  // ---- last batch (debug) ----
-  uint32_t batch_b0 = 0, batch_nb = 0;
-  std::vector<BlockDesc> h_desc;
-  std::vector<uint64_t> h_blockbit;
-  std::vector<uint32_t> h_mtf_count;
-  uint8_t* last_out = nullptr;
-  BwtStats bstats;
-  uint64_t stat_rle = 0, stat_mtf = 0;
-
-  std::vector<DevBuf*> all;
-};
-
-namespace {
-
-#define CK(ctx, call)                                                                                  \
-  do {                                                                                                 \
-    cudaError_t e__ = (call);                                                                          \
-    if (e__ != cudaSuccess) {                                                                          \
-      (ctx)->err = std::string(#call) + ": " + cudaGetErrorString(e__);                                \
-      return BZB200_E_CUDA;                                                                            \
-    }                                                                                                  \
-  } while (0)
-
-int ensure(bzb200_ctx* c, DevBuf& b, size_t bytes) {
-  if (bytes == 0) bytes = 16;
-  if (b.cap >= bytes) return BZB200_OK;
-  if (b.p) {
-    CK(c, cudaStreamSynchronize(c->stream));
-    CK(c, cudaFree(b.p));
-    b.p = nullptr;
-    b.cap = 0;
-  }
-  size_t want = bytes + bytes / 16 + 256;
-  cudaError_t e = cudaMalloc(&b.p, want);
-  if (e != cudaSuccess) {
-    cudaGetLastError();
-    want = bytes;
-    e = cudaMalloc(&b.p, want);
-  }
-  if (e != cudaSuccess) {
-    c->err = std::string("cudaMalloc(") + std::to_string(want) + "): " + cudaGetErrorString(e);
-    b.p = nullptr;
-    return BZB200_E_CUDA;
-  }
-  b.cap = want;
-  return BZB200_OK;
-}
-
-int check_launch(bzb200_ctx* c) {
-  if (c->L.err != cudaSuccess) {
-    c->err = std::string("kernel launch ") + (c->L.err_kernel ? c->L.err_kernel : "?") + ": " +
-             cudaGetErrorString(c->L.err);
-    c->L.err = cudaSuccess;
-    return BZB200_E_CUDA;
-  }
-  return BZB200_OK;
-}
-
-template <class T>
-T* ptr(DevBuf& b) {
-  return reinterpret_cast<T*>(b.p);
-}
-
-#define TRY(x)                \
-  do {                        \
-    int r__ = (x);            \
-    if (r__ != BZB200_OK) return r__; \
-  } while (0)
-
-int level_of(const bzb200_ctx* c) { return c->level; }
-
-int set_device(bzb200_ctx* c) {
-  CK(c, cudaSetDevice(c->device));
-  return BZB200_OK;
-}
-
-}  // namespace
+#include "host_ctx.h"
 
 extern "C" {
 
 const char* bzb200_version(void) { return "bzb200 0.1 (sm_100a)"; }
 
-static int ctx_create_impl(int device, void* stream, bool own_stream, bzb200_ctx** out) {
+}  // extern "C"
+
+int bzb200_ctx_create_impl(int device, void* stream, bool own_stream, bzb200_ctx** out) {
   if (!out) return BZB200_E_ARG;
   *out = nullptr;
   bzb200_ctx* c = new bzb200_ctx();
@@ -261,7 +142,9 @@ static int ctx_create_impl(int device, void* stream, bool own_stream, bzb200_ctx
   return BZB200_OK;
 }
 
-int bzb200_ctx_create(int device, void* stream, bzb200_ctx** out) { return ctx_create_impl(device, stream, false, out); }
+extern "C" {
+
+int bzb200_ctx_create(int device, void* stream, bzb200_ctx** out) { return bzb200_ctx_create_impl(device, stream, false, out); }
 
 void bzb200_ctx_destroy(bzb200_ctx* c) {
   if (!c) return;
@@ -913,491 +796,6 @@ int bzb200_path_stats(const bzb200_ctx* c, uint64_t* out, size_t cap) {
                          c->bstats.local_elems, c->stat_rle, c->stat_mtf, 0};
   for (size_t i = 0; i < cap && i < 8; ++i) out[i] = v[i];
   return BZB200_OK;
-}
-
-// ------------------------------------------------------------------ streaming encoder (BZip2Encoder)
-// Action::Run pipelining: input accumulates in a window; when the window is full, the bytes from
-// the last block cut onwards are planned as a stream of their own, every block that is already closed is encoded and
-// its bytes become readable at once (the reference also yields a block as soon as it closes, encoder.rs:91-107), and
-// the still-open last block stays buffered.  A block cut is a piece boundary, so RLE1 restarts there exactly as in
-// the one-pass plan; the partial last byte of the bit stream is carried into the next window.
-struct bzb200_enc {
-  int level = 9;
-  int device = -1;
-  bzb200_ctx* ctx = nullptr;
-  std::vector<uint8_t> in;   // input from the last block cut onwards
-  std::vector<uint8_t> out;  // finished output bytes
-  size_t rd = 0;
-  bool finished = false;
-  bool started = false;      // the stream header has been written
-  uint32_t carry_bits = 0;   // valid bits (0..7) of the partial last byte
-  uint8_t carry = 0;
-  uint32_t combined = 0;     // combined CRC of the blocks encoded so far (encoder.rs:237-238)
-  uint64_t blocks = 0, windows = 0;
-  size_t window = (size_t)256 << 20;
-  std::string err;
-};
-
-int bzb200_enc_create(int level, int device, bzb200_enc** out) {
-  if (!out) return BZB200_E_ARG;
-  *out = nullptr;
-  if (level < 1 || level > 9) return BZB200_E_LEVEL;  // BZip2Encoder::new panics "invalid level"
-  bzb200_enc* e = new bzb200_enc();
-  e->level = level;
-  e->device = device;
-  if (const char* w = getenv("BZB200_ENC_WINDOW")) {
-    unsigned long long v = strtoull(w, nullptr, 10);
-    if (v >= 1) e->window = (size_t)v;
-  }
-  *out = e;
-  return BZB200_OK;
-}
-
-// Compresses the closed blocks of the buffered input (all blocks and the trailer when `final`).
-static int enc_pump(bzb200_enc* e, bool final) {
-  if (!e->ctx) {
-    int r = ctx_create_impl(e->device, nullptr, true, &e->ctx);
-    if (r != BZB200_OK) {
-      e->err = e->ctx ? e->ctx->err : "context creation failed";
-      if (e->ctx) { bzb200_ctx_destroy(e->ctx); e->ctx = nullptr; }
-      return r;
-    }
-  }
-  bzb200_ctx* c = e->ctx;
-  int r = BZB200_OK;
-  auto fail = [&](int code) {
-    if (code == BZB200_E_CUDA && c->err.empty()) c->err = std::string("cuda: ") + cudaGetErrorString(cudaGetLastError());
-    e->err = c->err;
-    return code;
-  };
-  if ((r = set_device(c)) != BZB200_OK) return fail(r);
-  const size_t n = e->in.size();
-  const size_t cap = bzb200_max_output_bytes(e->level, n) + 16;
-  if ((r = ensure(c, c->stage_in, n + 16)) != BZB200_OK) return fail(r);
-  if ((r = ensure(c, c->stage_out, cap)) != BZB200_OK) return fail(r);
-  uint8_t* d_in = ptr<uint8_t>(c->stage_in);
-  uint8_t* d_out = ptr<uint8_t>(c->stage_out);
-  if (n && cudaMemcpyAsync(d_in, e->in.data(), n, cudaMemcpyHostToDevice, c->stream) != cudaSuccess) return fail(BZB200_E_CUDA);
-  if (cudaMemsetAsync(d_out, 0, cap, c->stream) != cudaSuccess) return fail(BZB200_E_CUDA);
-  uint64_t bit = 0;
-  if (!e->started) {
-    if ((r = bzb200_write_stream_header(c, e->level, d_out, cap)) != BZB200_OK) return fail(r);
-    bit = 32;
-    e->started = true;
-  } else if (e->carry_bits) {
-    if (cudaMemcpyAsync(d_out, &e->carry, 1, cudaMemcpyHostToDevice, c->stream) != cudaSuccess) return fail(BZB200_E_CUDA);
-    bit = e->carry_bits;
-  }
-  uint32_t nb = 0;
-  if ((r = bzb200_plan(c, e->level, d_in, n, &nb)) != BZB200_OK) return fail(r);
-  const uint32_t nenc = final ? nb : (nb ? nb - 1 : 0);  // the last block of a window is still open
-  size_t consumed = 0;
-  if (nenc) {
-    if ((r = bzb200_encode_blocks(c, 0, nenc, d_out, cap, bit, &bit)) != BZB200_OK) return fail(r);
-    e->combined = bzb200_combine_crc(e->combined, c->h_crc.data(), nenc);
-    consumed = (size_t)c->h_in_off[nenc];
-    e->blocks += nenc;
-  }
-  size_t take = (size_t)(bit / 8);  // whole bytes that are final
-  if (final) {
-    if ((r = bzb200_write_stream_trailer(c, d_out, cap, bit, e->combined, &take)) != BZB200_OK) return fail(r);
-    e->carry_bits = 0;
-  } else {
-    e->carry_bits = (uint32_t)(bit & 7);
-  }
-  const size_t fetch = take + ((!final && e->carry_bits) ? 1 : 0);
-  const size_t at = e->out.size();
-  e->out.resize(at + fetch);
-  if (fetch && cudaMemcpyAsync(e->out.data() + at, d_out, fetch, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess)
-    return fail(BZB200_E_CUDA);
-  if (cudaStreamSynchronize(c->stream) != cudaSuccess) return fail(BZB200_E_CUDA);
-  if (fetch > take) {
-    e->carry = e->out.back();
-    e->out.pop_back();
-  }
-  e->in.erase(e->in.begin(), e->in.begin() + consumed);
-  ++e->windows;
-  return BZB200_OK;
-}
-
-int bzb200_enc_write(bzb200_enc* e, const uint8_t* p, size_t n) {
-  if (!e || (!p && n)) return BZB200_E_ARG;
-  if (e->finished) {
-    e->err = "write after finish";
-    return BZB200_E_STATE;
-  }
-  while (n) {
-    const size_t room = e->in.size() < e->window ? e->window - e->in.size() : 0;
-    const size_t take = std::min(n, std::max<size_t>(room, 1));
-    e->in.insert(e->in.end(), p, p + take);
-    p += take;
-    n -= take;
-    if (e->in.size() >= e->window) {
-      const size_t before = e->in.size();
-      int r = enc_pump(e, false);
-      if (r != BZB200_OK) return r;
-      if (e->in.size() == before) {
-        // not even one closed block in a full window (window smaller than a block): let the window grow
-        e->in.insert(e->in.end(), p, p + n);
-        e->window = std::max(e->window * 2, e->in.size() + 1);
-        n = 0;
-      }
-    }
-  }
-  return BZB200_OK;
-}
-
-int bzb200_enc_finish(bzb200_enc* e) {
-  if (!e) return BZB200_E_ARG;
-  if (e->finished) return BZB200_OK;
-  int r = enc_pump(e, true);
-  if (r != BZB200_OK) return r;
-  e->in.clear();
-  e->in.shrink_to_fit();
-  e->finished = true;
-  return BZB200_OK;
-}
-
-size_t bzb200_enc_read(bzb200_enc* e, uint8_t* dst, size_t cap) {
-  if (!e || !dst) return 0;
-  size_t n = std::min(cap, e->out.size() - e->rd);
-  if (n) memcpy(dst, e->out.data() + e->rd, n);
-  e->rd += n;
-  if (e->rd == e->out.size() && !e->finished) {  // drained mid-stream: drop the bytes already handed out
-    e->out.clear();
-    e->rd = 0;
-  }
-  return n;
-}
-
-size_t bzb200_enc_output_size(const bzb200_enc* e) { return e ? e->out.size() - e->rd : 0; }
-
-int bzb200_enc_reset(bzb200_enc* e) {
-  if (!e) return BZB200_E_ARG;
-  e->in.clear();
-  e->out.clear();
-  e->rd = 0;
-  e->finished = false;
-  e->started = false;
-  e->carry_bits = 0;
-  e->carry = 0;
-  e->combined = 0;
-  e->blocks = 0;
-  e->windows = 0;
-  e->err.clear();
-  return BZB200_OK;
-}
-
-void bzb200_enc_destroy(bzb200_enc* e) {
-  if (!e) return;
-  if (e->ctx) bzb200_ctx_destroy(e->ctx);
-  delete e;
-}
-
-const char* bzb200_enc_last_error(const bzb200_enc* e) { return e ? e->err.c_str() : "null encoder"; }
-
-int bzb200_enc_stats(const bzb200_enc* e, uint64_t* out, size_t cap) {
-  if (!e || !out) return BZB200_E_ARG;
-  const uint64_t v[4] = {e->blocks, e->windows, (uint64_t)e->in.size(), (uint64_t)(e->out.size() - e->rd)};
-  for (size_t i = 0; i < cap && i < 4; ++i) out[i] = v[i];
-  return BZB200_OK;
-}
-
-static int compress_host_with_ctx(bzb200_ctx* c, int level, const uint8_t* in, size_t n, std::vector<uint8_t>& out) {
-  DevBuf din, dout;
-  const size_t cap = bzb200_max_output_bytes(level, n);
-  int r = BZB200_OK;
-  do {
-    if ((r = ensure(c, din, n + 16)) != BZB200_OK) break;
-    if ((r = ensure(c, dout, cap)) != BZB200_OK) break;
-    if (n && cudaMemcpyAsync(din.p, in, n, cudaMemcpyHostToDevice, c->stream) != cudaSuccess) { r = BZB200_E_CUDA; break; }
-    if (cudaMemsetAsync(dout.p, 0, cap, c->stream) != cudaSuccess) { r = BZB200_E_CUDA; break; }
-    size_t out_n = 0;
-    if ((r = bzb200_compress_device(c, level, (const uint8_t*)din.p, n, (uint8_t*)dout.p, cap, &out_n)) != BZB200_OK) break;
-    out.resize(out_n);
-    if (cudaMemcpyAsync(out.data(), dout.p, out_n, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) { r = BZB200_E_CUDA; break; }
-    if (cudaStreamSynchronize(c->stream) != cudaSuccess) { r = BZB200_E_CUDA; break; }
-  } while (0);
-  if (r == BZB200_E_CUDA && c->err.empty()) c->err = std::string("cuda: ") + cudaGetErrorString(cudaGetLastError());
-  if (din.p) cudaFree(din.p);
-  if (dout.p) cudaFree(dout.p);
-  return r;
-}
-
-int bzb200_compress(int level, int device, const uint8_t* in, size_t n, uint8_t** out, size_t* out_n) {
-  if (!out || !out_n || (!in && n)) return BZB200_E_ARG;
-  *out = nullptr;
-  *out_n = 0;
-  if (level < 1 || level > 9) return BZB200_E_LEVEL;
-  bzb200_ctx* c = nullptr;
-  int r = ctx_create_impl(device, nullptr, true, &c);
-  if (r != BZB200_OK) {
-    if (c) bzb200_ctx_destroy(c);
-    return r;
-  }
-  std::vector<uint8_t> o;
-  r = compress_host_with_ctx(c, level, in, n, o);
-  if (r == BZB200_OK) {
-    *out = (uint8_t*)malloc(o.size() ? o.size() : 1);
-    if (!*out) r = BZB200_E_ARG;
-    else {
-      memcpy(*out, o.data(), o.size());
-      *out_n = o.size();
-    }
-  }
-  bzb200_ctx_destroy(c);
-  return r;
-}
-
-void bzb200_free(void* p) { free(p); }
-
-// ------------------------------------------------------------------ decoder (decoder.cu)
-}  // extern "C"
-
-namespace {
-
-struct CtxDecMem : DecMem {
-  bzb200_ctx* c;
-  explicit CtxDecMem(bzb200_ctx* c_) : c(c_) {}
-  void* buf(int slot, size_t bytes) override {
-    if (slot < 0 || slot >= DS_NSLOTS) return nullptr;
-    if (ensure(c, c->dec_bufs[slot], bytes) != BZB200_OK) return nullptr;
-    return c->dec_bufs[slot].p;
-  }
-  int cu(cudaError_t e, const char* what) {
-    if (e == cudaSuccess) return 0;
-    c->err = std::string(what) + ": " + cudaGetErrorString(e);
-    return 1;
-  }
-  int fill(void* p, int byte, size_t bytes) override {
-    return cu(cudaMemsetAsync(p, byte, bytes, c->stream), "decoder cudaMemsetAsync");
-  }
-  int to_host(void* dst, const void* src, size_t bytes) override {
-    if (cu(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream), "decoder D2H")) return 1;
-    return cu(cudaStreamSynchronize(c->stream), "decoder sync");
-  }
-  int to_dev(void* dst, const void* src, size_t bytes) override {
-    // pageable source: the runtime stages it before returning, so the caller may reuse src
-    return cu(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->stream), "decoder H2D");
-  }
-  int crc_blocks(const uint8_t* d_data, const uint64_t* d_off, uint32_t nb, uint32_t* d_crc) override {
-    launch_k5_crc(c->L, d_data, d_off, nb, d_crc);
-    return check();
-  }
-  int check() override { return check_launch(c) == BZB200_OK ? 0 : 1; }
-  std::string err() override { return c->err; }
-};
-
-uint64_t dec_batch_bytes() {
-  uint64_t v = (uint64_t)24 << 30;  // scratch per batch of blocks (about 9 MB per 900 kB block)
-  if (const char* e = getenv("BZB200_DEC_BATCH_BYTES")) {
-    unsigned long long x = strtoull(e, nullptr, 10);
-    if (x >= 1) v = x;
-  }
-  return v;
-}
-
-// decode on the device; maps the result onto the ABI's return convention
-int decode_device(bzb200_ctx* c, const uint8_t* d_in, size_t n, uint8_t* d_out, size_t cap, size_t* out_n, int* bz_error) {
-  CtxDecMem M(c);
-  DecResult R;
-  // default: split D2 (d2_huff + chunk-parallel d2_mtf_a/b/c, 100 ms per GiB of text); BZB200_DEC_SPLIT=0 selects the
-  // fused d2_decode (139 ms), kept as the second implementation the parity tests run as well
-  uint32_t flags = DEC_SPLIT_D2;
-  if (const char* e = getenv("BZB200_DEC_SPLIT")) flags = (atoi(e) != 0) ? DEC_SPLIT_D2 : 0u;
-  const int rc = dec_run(c->L, M, d_in, n, d_out, cap, dec_batch_bytes(), flags, &R);
-  c->dec_last = R;
-  if (rc != 0) {
-    if (c->err.empty()) c->err = "decoder: device memory or launch failure";
-    return rc;
-  }
-  CK(c, cudaStreamSynchronize(c->stream));
-  if (R.too_small) {
-    *out_n = (size_t)R.needed;
-    *bz_error = 0;
-    c->err = "decompress: output buffer too small: need " + std::to_string(R.needed) + " bytes";
-    return BZB200_E_ARG;
-  }
-  *out_n = (size_t)R.out_n;
-  *bz_error = (int)R.bz_error;
-  if (R.bz_error) {
-    static const char* kinds[] = {"", "DataError", "DataErrorMagicFirst", "DataErrorMagic", "UnexpectedEof", "Unexpected"};
-    c->err = std::string("bzip2 stream error: ") + kinds[R.bz_error <= 5 ? R.bz_error : 5];
-    return BZB200_E_DATA;
-  }
-  return BZB200_OK;
-}
-
-}  // namespace
-
-extern "C" {
-
-int bzb200_decompress_device(bzb200_ctx* c, const uint8_t* d_in, size_t n, uint8_t* d_out, size_t cap_bytes,
-                             size_t* out_n, int* bz_error) {
-  if (!c || !out_n || !bz_error || (!d_in && n) || (!d_out && cap_bytes)) return BZB200_E_ARG;
-  *out_n = 0;
-  *bz_error = 0;
-  TRY(set_device(c));
-  return decode_device(c, d_in, n, d_out, cap_bytes, out_n, bz_error);
-}
-
-int bzb200_decompress_host(bzb200_ctx* c, const uint8_t* h_in, size_t n, uint8_t* h_out, size_t cap_bytes,
-                           size_t* out_n, int* bz_error) {
-  if (!c || !out_n || !bz_error || (!h_in && n) || (!h_out && cap_bytes)) return BZB200_E_ARG;
-  *out_n = 0;
-  *bz_error = 0;
-  TRY(set_device(c));
-  TRY(ensure(c, c->dec_in, n + 16));
-  TRY(ensure(c, c->dec_out, cap_bytes + 16));
-  if (n) CK(c, cudaMemcpyAsync(c->dec_in.p, h_in, n, cudaMemcpyHostToDevice, c->stream));
-  const int rc = decode_device(c, ptr<uint8_t>(c->dec_in), n, ptr<uint8_t>(c->dec_out), cap_bytes, out_n, bz_error);
-  if (rc == BZB200_OK || rc == BZB200_E_DATA) {
-    if (*out_n) CK(c, cudaMemcpyAsync(h_out, c->dec_out.p, *out_n, cudaMemcpyDeviceToHost, c->stream));
-    CK(c, cudaStreamSynchronize(c->stream));
-  }
-  return rc;
-}
-
-int bzb200_dec_stats(const bzb200_ctx* c, uint64_t* out, size_t cap) {
-  if (!c || !out) return BZB200_E_ARG;
-  const DecResult& R = c->dec_last;
-  const uint64_t v[8] = {R.streams, R.blocks, R.candidates, R.batches, R.syms, R.pre_rle, R.out_n, 0};
-  for (size_t i = 0; i < cap && i < 8; ++i) out[i] = v[i];
-  return BZB200_OK;
-}
-
-// ---- streaming decoder object (BZip2Decoder)
-struct bzb200_dec {
-  int device = -1;
-  bzb200_ctx* ctx = nullptr;
-  std::vector<uint8_t> in;
-  std::vector<uint8_t> out;
-  size_t rd = 0;
-  bool finished = false;
-  int kind = 0;
-  std::string err;
-};
-
-int bzb200_dec_create(int device, bzb200_dec** out) {
-  if (!out) return BZB200_E_ARG;
-  bzb200_dec* d = new bzb200_dec();
-  d->device = device;
-  *out = d;
-  return BZB200_OK;
-}
-
-int bzb200_dec_write(bzb200_dec* d, const uint8_t* p, size_t n) {
-  if (!d || (!p && n)) return BZB200_E_ARG;
-  if (d->finished) {
-    d->err = "write after finish";
-    return BZB200_E_STATE;
-  }
-  d->in.insert(d->in.end(), p, p + n);
-  return BZB200_OK;
-}
-
-// host -> host with an output buffer that grows to the size the stream needs
-static int decompress_host_with_ctx(bzb200_ctx* c, const uint8_t* in, size_t n, std::vector<uint8_t>& out, int* kind) {
-  size_t free_b = 0, total_b = 0;
-  if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) free_b = (size_t)1 << 30;
-  size_t cap = std::max<size_t>((size_t)1 << 20, n * 6);
-  cap = std::min(cap, std::max<size_t>((size_t)1 << 20, free_b / 4));
-  TRY(ensure(c, c->dec_in, n + 16));
-  if (n) CK(c, cudaMemcpyAsync(c->dec_in.p, in, n, cudaMemcpyHostToDevice, c->stream));
-  size_t out_n = 0;
-  int rc = BZB200_OK;
-  for (int attempt = 0; attempt < 2; ++attempt) {
-    TRY(ensure(c, c->dec_out, cap + 16));
-    rc = decode_device(c, ptr<uint8_t>(c->dec_in), n, ptr<uint8_t>(c->dec_out), cap, &out_n, kind);
-    if (rc != BZB200_E_ARG) break;
-    cap = out_n;  // exact size reported by the dry pass
-  }
-  if (rc != BZB200_OK && rc != BZB200_E_DATA) return rc;
-  out.resize(out_n);
-  if (out_n) CK(c, cudaMemcpyAsync(out.data(), c->dec_out.p, out_n, cudaMemcpyDeviceToHost, c->stream));
-  CK(c, cudaStreamSynchronize(c->stream));
-  return rc;
-}
-
-int bzb200_dec_finish(bzb200_dec* d) {
-  if (!d) return BZB200_E_ARG;
-  if (d->finished) return d->kind ? BZB200_E_DATA : BZB200_OK;
-  if (!d->ctx) {
-    int r = ctx_create_impl(d->device, nullptr, true, &d->ctx);
-    if (r != BZB200_OK) {
-      d->err = d->ctx ? d->ctx->err : "context creation failed";
-      if (d->ctx) { bzb200_ctx_destroy(d->ctx); d->ctx = nullptr; }
-      return r;
-    }
-  }
-  int r = set_device(d->ctx);
-  if (r == BZB200_OK) r = decompress_host_with_ctx(d->ctx, d->in.data(), d->in.size(), d->out, &d->kind);
-  if (r != BZB200_OK && r != BZB200_E_DATA) {
-    d->err = d->ctx->err;
-    return r;
-  }
-  if (r == BZB200_E_DATA) d->err = d->ctx->err;
-  d->in.clear();
-  d->in.shrink_to_fit();
-  d->rd = 0;
-  d->finished = true;
-  return r;
-}
-
-int bzb200_dec_error_kind(const bzb200_dec* d) { return (d && d->finished) ? d->kind : 0; }
-
-size_t bzb200_dec_read(bzb200_dec* d, uint8_t* dst, size_t cap) {
-  if (!d || !d->finished || !dst) return 0;
-  size_t n = std::min(cap, d->out.size() - d->rd);
-  if (n) memcpy(dst, d->out.data() + d->rd, n);
-  d->rd += n;
-  return n;
-}
-
-size_t bzb200_dec_output_size(const bzb200_dec* d) { return (d && d->finished) ? d->out.size() : 0; }
-
-int bzb200_dec_reset(bzb200_dec* d) {
-  if (!d) return BZB200_E_ARG;
-  d->in.clear();
-  d->out.clear();
-  d->rd = 0;
-  d->finished = false;
-  d->kind = 0;
-  d->err.clear();
-  return BZB200_OK;
-}
-
-void bzb200_dec_destroy(bzb200_dec* d) {
-  if (!d) return;
-  if (d->ctx) bzb200_ctx_destroy(d->ctx);
-  delete d;
-}
-
-const char* bzb200_dec_last_error(const bzb200_dec* d) { return d ? d->err.c_str() : "null decoder"; }
-
-int bzb200_decompress(int device, const uint8_t* in, size_t n, uint8_t** out, size_t* out_n, int* bz_error) {
-  if (!out || !out_n || !bz_error || (!in && n)) return BZB200_E_ARG;
-  *out = nullptr;
-  *out_n = 0;
-  *bz_error = 0;
-  bzb200_ctx* c = nullptr;
-  int r = ctx_create_impl(device, nullptr, true, &c);
-  if (r != BZB200_OK) {
-    if (c) bzb200_ctx_destroy(c);
-    return r;
-  }
-  std::vector<uint8_t> o;
-  r = decompress_host_with_ctx(c, in, n, o, bz_error);
-  if (r == BZB200_OK || r == BZB200_E_DATA) {
-    *out = (uint8_t*)malloc(o.size() ? o.size() : 1);
-    if (!*out) r = BZB200_E_ARG;
-    else {
-      memcpy(*out, o.data(), o.size());
-      *out_n = o.size();
-    }
-  }
-  bzb200_ctx_destroy(c);
-  return r;
 }
 
 }  // extern "C"
