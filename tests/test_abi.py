@@ -66,6 +66,28 @@ def test_no_cpu_fallback_without_gpu():
     enc = rc.BZip2Encoder(9)
     with pytest.raises(rc.CompressionError):
         list(rc.encode(b"hello", enc, rc.Action.Finish))
+    # the decoder as well: a CUDA failure surfaces as BZip2Error::Unexpected, not as decoded bytes
+    stream = bytes.fromhex("425a683917724538509000000000")
+    with pytest.raises(rc.BZip2Error) as ei:
+        rc.decompress(stream)
+    assert ei.value.kind == "Unexpected"
+    with pytest.raises(rc.BZip2Error) as ei:
+        list(rc.decode(stream, rc.BZip2Decoder()))
+    assert ei.value.kind == "Unexpected"
+
+
+def test_decoder_emulation_is_test_infrastructure_only():
+    """tests/cpp/dec_emu.cpp compiles the decoder's kernel bodies for the host (-DBZB_EMU) to check the algorithm without
+    a GPU.  None of that may be in the product: the library is built without BZB_EMU and exports no emulation entry."""
+    import rust_compression_b200 as rc
+    build_py = open(os.path.join(ROOT, "rust-compression_b200", "build.py")).read()
+    assert "BZB_EMU" not in build_py
+    out = subprocess.run(["nm", "-D", "--defined-only", rc.lib_path()], capture_output=True, text=True).stdout
+    assert "emu_" not in out
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "rust-compression_b200")):
+        for f in files:
+            if f.endswith(".py"):
+                assert "libdecemu" not in open(os.path.join(dirpath, f)).read(), f
 
 
 def test_product_never_imports_oracle():
