@@ -45,6 +45,11 @@ def valid_cases(big=False):
     cases.append(("three streams, levels 1/3/5, one empty",
                   orc.compress(txt[:50000], 1) + orc.compress(b"", 3) + bz2.compress(txt[50000:120000], 5)))
     cases.append(("mixed level 1, 14 blocks", orc.compress(gen.mixed(1, 1_500_000), 1)))
+    # symbol counts of 16 384, 16 385 and 16 386: EOB as the last symbol of a full 1 024-symbol chunk of the split D2,
+    # alone in the last chunk, and second in it
+    for extra in (615, 616, 618):
+        cases.append((f"symbol count at a chunk boundary (+{extra})",
+                      orc.compress(gen.text(12, 20000) + gen.text(99, extra), 9)))
     if big:
         t2 = gen.text(7, 2_000_000)
         cases.append(("text 2 MB level 9", orc.compress(t2, 9)))
