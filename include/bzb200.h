@@ -183,7 +183,8 @@ BZB200_API int bzb200_compress_host(bzb200_ctx* c, int level, const uint8_t* h_i
  * BZB200_E_ARG when cap_bytes is too small (*out_n = bytes required; nothing useful was written). */
 BZB200_API int bzb200_decompress_device(bzb200_ctx* c, const uint8_t* d_in, size_t n, uint8_t* d_out, size_t cap_bytes,
                              size_t* out_n, int* bz_error);
-/* HOST in -> HOST out: H2D copy, decode, D2H copy of *out_n bytes; same return convention. */
+/* HOST in -> HOST out: H2D copy, decode, D2H copy of *out_n bytes; same return convention.  A device staging buffer
+ * of cap_bytes is kept in the context, so pass the expected size (BZB200_E_ARG reports the exact one), not a huge bound. */
 BZB200_API int bzb200_decompress_host(bzb200_ctx* c, const uint8_t* h_in, size_t n, uint8_t* h_out, size_t cap_bytes,
                            size_t* out_n, int* bz_error);
 /* Counters of the last decode, out[0..7]: 0 streams, 1 blocks on the chain, 2 magic candidates found, 3 batches,
