@@ -170,13 +170,16 @@ BZB200_API int bzb200_compress_host(bzb200_ctx* c, int level, const uint8_t* h_i
  *              BZip2DecoderBase::init_block       src/bzip2/decoder.rs:163-525
  *              get_next_lfm, BitDecodeService     src/bzip2/decoder.rs:527-581
  *              DecodeExt::decode                  src/traits/decoder.rs:14-43
- *    Accepts what the reference accepts (multi-stream buffers, any level, its limits decoder.rs:238,285,292,399,416,427)
+ *    Accepts what the reference accepts (multi-stream buffers, any level, its limits decoder.rs:238,285,292,399,416,427;
+ *    blocks with the `randomised` bit of bzip2 <= 0.9.0, decoder.rs:94-116,537-539; magics of which only the first byte
+ *    is right — the reference reads the other bytes without comparing them, decoder.rs:155-161,177-182,211-224,495-508)
  *    and reports what it reports: the bytes the reference would have yielded before an error, then the BZip2Error kind.
- *    Deviations, malformed input only: randomised blocks and over-subscribed coding tables are DataError (as in the
- *    restated reference decoder under oracle/); a block that ends in four equal bytes with no count byte is DataError
- *    (the reference reads past the block there and does not terminate).
- *    Environment: BZB200_DEC_BATCH_BYTES (scratch memory per batch of blocks, default 24 GB), BZB200_DEC_SPLIT=0 (fused
- *    Huffman+MTF kernel instead of the default split pipeline; same results).
+ *    Deviations, malformed input only: over-subscribed coding tables are DataError (as in the restated reference
+ *    decoder under oracle/); a block that ends in four equal bytes with no count byte is DataError (the reference reads
+ *    past the block there and does not terminate).
+ *    Environment: BZB200_DEC_BATCH_BYTES (scratch memory per batch of blocks, default 24 GB and at most 60 % of the free
+ *    device memory), BZB200_DEC_MAX_OUTPUT (largest output the host->host entry points allocate for; default half of
+ *    the free device memory), BZB200_DEC_SPLIT=0 (fused Huffman+MTF kernel instead of the default split pipeline).
  * ------------------------------------------------------------------------ */
 /* Device in -> device out on the context's stream; synchronises.  Returns BZB200_OK (*bz_error = 0, *out_n bytes
  * written), BZB200_E_DATA (*bz_error = kind, the first *out_n bytes are what the reference yields before the error), or

@@ -14,14 +14,21 @@
 // direction Left (MSB-first bit reads), src/huffman/decoder.rs + huffman/mod.rs:22-67 (canonical codes by
 // (length, symbol); a code that is not in the table is a DataError, decoder.rs:376-379).
 //
-// Deviations, malformed input only: block_randomised streams (decoder.rs:70-120 table) are rejected as DataError
-// (the encoder never sets the bit, encoder.rs:273); an over-subscribed coding table is rejected as DataError where
-// the reference's tree builder may accept or overwrite (huffman/decoder.rs:43-88).
+// Magic bytes: check_u8 (decoder.rs:155-161) returns Result<bool> and every call site discards the bool
+// (`let _ = Self::check_u8(..).map_err(..)?`, :177-182, :211-224, :495-508): the reference compares NOTHING there — only
+// a failed read matters.  So 'B','Z','h' may be any three bytes, and of the two 48-bit magics only the first byte
+// (0x31 / 0x17) selects the branch; the other five are skipped.  Restated that way here.
+// Randomised blocks (bzip2 <= 0.9.0): BlockRandomise (decoder.rs:94-116) and its use in get_next_lfm (:537-539) are
+// restated literally; the table is the format's BZ2_rNums (oracle/bz_rand_table.h, see tools/make_rand_table.py).
+// Deviation, malformed input only: an over-subscribed coding table is rejected as DataError where the reference's
+// tree builder may accept or overwrite (huffman/decoder.rs:43-88).
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
 
 #include <vector>
+
+#include "bz_rand_table.h"
 
 namespace {
 
@@ -117,6 +124,18 @@ struct Decoder {
   size_t n_block_used = 0;
   uint8_t result_char = 0;
   size_t result_count = 0, result_wrote = 0;
+  bool block_randomised = false;
+  size_t rnd_n2go = 0, rnd_t_pos = 0;  // BlockRandomise (decoder.rs:94-116)
+
+  bool rnd_next() {  // decoder.rs:104-115
+    if (rnd_n2go == 0) {
+      rnd_n2go = BZ_RAND_NUMS[rnd_t_pos];
+      rnd_t_pos += 1;
+      if (rnd_t_pos == 512) rnd_t_pos = 0;
+    }
+    rnd_n2go -= 1;
+    return rnd_n2go == 1;
+  }
 
   bool read_u8(uint32_t& v) { return rd.read(8, v); }
 
@@ -126,9 +145,8 @@ struct Decoder {
       if (block_no == 0) {
         const int magic_err = stream_no == 1 ? DataErrorMagicFirst : DataErrorMagic;
         uint32_t b;
-        const uint8_t want[3] = {'B', 'Z', 'h'};
         for (int i = 0; i < 3; ++i) {
-          if (!read_u8(b) || b != want[i]) return -magic_err;  // check_u8(..).map_err(|_| magic_err)
+          if (!read_u8(b)) return -magic_err;  // `let _ = check_u8(..).map_err(|_| magic_err)?`: the value is not compared
         }
         if (!read_u8(b)) return -UnexpectedEof;
         if (b < 1 + '0' || b > 9 + '0') return -magic_err;
@@ -142,17 +160,16 @@ struct Decoder {
       uint32_t head;
       if (!read_u8(head)) return -UnexpectedEof;
       if (head == 0x31) {
-        const uint8_t rest[5] = {0x41, 0x59, 0x26, 0x53, 0x59};
         uint32_t b;
         for (int i = 0; i < 5; ++i)
-          if (!read_u8(b) || b != rest[i]) return -DataError;
+          if (!read_u8(b)) return -DataError;  // :211-224, values not compared
         block_no += 1;
         if (!rd.read(32, block_crc)) return -UnexpectedEof;
         uint32_t randomised, orig_pos;
         if (!rd.read(1, randomised)) return -UnexpectedEof;
         if (!rd.read(24, orig_pos)) return -UnexpectedEof;
         if (orig_pos > 10 + 100000 * block_size_100k) return -DataError;  // :238
-        if (randomised) return -DataError;                                 // see header (deviation)
+        block_randomised = randomised == 1;                                // :230-234
         // mapping table (:243-275)
         uint32_t in_use16;
         if (!rd.read(16, in_use16)) return -UnexpectedEof;
@@ -265,14 +282,14 @@ struct Decoder {
         }
         t_pos = tt[orig_pos] >> 8;
         n_block_used = 0;
+        if (block_randomised) { rnd_n2go = 0; rnd_t_pos = 0; }  // :478-480
         result_count = 0;
         result_wrote = 0;
         return 1;
       } else if (head == 0x17) {
-        const uint8_t rest[5] = {0x72, 0x45, 0x38, 0x50, 0x90};
         uint32_t b;
         for (int i = 0; i < 5; ++i)
-          if (!read_u8(b) || b != rest[i]) return -DataError;
+          if (!read_u8(b)) return -DataError;  // :495-508, values not compared
         uint32_t stored;
         if (!rd.read(32, stored)) return -UnexpectedEof;
         if (stored != combined_crc) return -DataError;
@@ -298,6 +315,7 @@ struct Decoder {
     k0 = (uint8_t)position;
     t_pos = position >> 8;
     n_block_used += 1;
+    if (block_randomised) k0 ^= rnd_next() ? 1 : 0;  // :537-539
     return 0;
   }
 

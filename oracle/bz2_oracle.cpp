@@ -22,6 +22,8 @@
 #include <memory>
 #include <vector>
 
+#include "bz_rand_table.h"
+
 namespace {
 
 using usize = size_t;
@@ -641,6 +643,11 @@ struct EncoderInner {
   bool keep_sa;
   uint64_t in_pos = 0;             // number of input bytes consumed by write_rle so far
   uint64_t blk_in_start = 0;
+  // FIXTURE GENERATOR ONLY (not reference behaviour: the reference encoder always writes a 0 bit, encoder.rs:273):
+  // emit blocks the way bzip2 <= 0.9.0 did when its sorter gave up — block bytes XOR-ed with the BZ2_rNums mask
+  // before the BWT, in-use map taken from the masked bytes, randomised bit = 1 — so that the decoders' un-randomise
+  // path (decoder.rs:27-115,478-480,537-539) has valid streams to decode.  libbz2 decodes these streams too.
+  bool fixture_randomise = false;
 
   EncoderInner(usize level, BitSink* s, std::vector<BlockDump>* d, bool ksa)
       : block_size_100k(level), block_max_len(level * 100000 - 19), sink(s), dumps(d), keep_sa(ksa) {
@@ -714,7 +721,22 @@ struct EncoderInner {
       blk_in_start = in_pos;
       write_u8(0x31); write_u8(0x41); write_u8(0x59); write_u8(0x26); write_u8(0x53); write_u8(0x59);
       write(bcrc, 32);
-      write(0, 1);
+      if (fixture_randomise) {
+        usize n2go = 0, tpos = 0;
+        std::fill(in_use, in_use + 256, false);
+        for (usize i = 0; i < block_buf.size(); ++i) {
+          if (n2go == 0) { n2go = BZ_RAND_NUMS[tpos]; tpos = (tpos + 1) % 512; }
+          n2go -= 1;
+          if (n2go == 1) block_buf[i] ^= 1;
+          in_use[block_buf[i]] = true;
+        }
+        if (d) {
+          d->rle = block_buf;
+          std::fill(d->in_use, d->in_use + 8, 0u);
+          for (int s2 = 0; s2 < 256; ++s2) if (in_use[s2]) d->in_use[s2 >> 5] |= 1u << (s2 & 31);
+        }
+      }
+      write(fixture_randomise ? 1 : 0, 1);
       write_blockdata(d);
       if (d) d->bit_end = sink->nbits;
       prepare_new_block();
@@ -938,8 +960,9 @@ struct Run {
 // BZip2Encoder::new + encode(.., Action::Finish) (encoder.rs:58-158): feed every
 // byte, finish, zero-pad to a byte (bitio/writer.rs:226-242).
 static void run_encoder(int level, const uint8_t* in, size_t n, BitSink& sink, std::vector<BlockDump>* dumps,
-                        bool keep_sa) {
+                        bool keep_sa, bool fixture_randomise = false) {
   EncoderInner enc((usize)level, &sink, dumps, keep_sa);
+  enc.fixture_randomise = fixture_randomise;
   for (size_t i = 0; i < n; ++i) enc.next(in[i]);
   enc.finish();
   sink.flush();
@@ -957,6 +980,17 @@ long long orc_compress(int level, const uint8_t* in, size_t n, uint8_t* out, siz
   if (level < 1 || level > 9) return -1;  // encoder.rs:59-61 panics "invalid level"
   BitSink sink;
   run_encoder(level, in, n, sink, nullptr, false);
+  if (sink.bytes.size() > cap) return -(long long)sink.bytes.size();
+  memcpy(out, sink.bytes.data(), sink.bytes.size());
+  return (long long)sink.bytes.size();
+}
+
+// Fixture generator (see EncoderInner::fixture_randomise): the stream bzip2 <= 0.9.0 would have written with every
+// block randomised.  NOT something the reference encoder can produce.
+long long orc_compress_randomised(int level, const uint8_t* in, size_t n, uint8_t* out, size_t cap) {
+  if (level < 1 || level > 9) return -1;
+  BitSink sink;
+  run_encoder(level, in, n, sink, nullptr, false, true);
   if (sink.bytes.size() > cap) return -(long long)sink.bytes.size();
   memcpy(out, sink.bytes.data(), sink.bytes.size());
   return (long long)sink.bytes.size();
@@ -1002,6 +1036,55 @@ size_t orc_block_field(void* h, size_t b, int field, void* dst, size_t cap_elems
     case 9: case 10: case 11: case 12: case 13: return cp(d.lens[field - 9].data(), d.lens[field - 9].size(), 1);
   }
   return 0;
+}
+
+// Full-stream verifier (bench.py / tests hand every block of the GPU's block table to this, in parallel over the
+// host cores).  in[0..n) is the input range the GPU assigned to one block; it is encoded as a stream of its own — a
+// block cut is a piece boundary, so RLE1 restarts there exactly as in the one-pass encoder — and must come out as
+// exactly ONE block.  Its bit section (block magic .. last code) starts at bit 32 of that stream, i.e. at byte 4; the
+// bytes from there on are copied to out.
+// info[4]: 0 blocks the range produced, 1 block CRC, 2 bytes after RLE1, 3 bits of the block section.
+// Returns the bytes written, or -(needed) when cap is too small.
+long long orc_encode_block(int level, const uint8_t* in, size_t n, uint8_t* out, size_t cap, uint64_t* info) {
+  for (int i = 0; i < 4; ++i) info[i] = 0;
+  if (level < 1 || level > 9) return -1;
+  Run r;
+  run_encoder(level, in, n, r.sink, &r.dumps, false);
+  info[0] = r.dumps.size();
+  if (r.dumps.empty()) return 0;
+  const BlockDump& d = r.dumps[0];
+  info[1] = d.crc;
+  info[2] = d.rle.size();
+  info[3] = d.bit_end - d.bit_start;
+  if (d.bit_start != 32) return -1;
+  const size_t nbytes = (size_t)((info[3] + 7) / 8);
+  if (nbytes > cap) return -(long long)nbytes;
+  memcpy(out, r.sink.bytes.data() + 4, nbytes);
+  return (long long)nbytes;
+}
+
+// First bit (0-based) at which bits [0, nbits) of `sect` differ from bits [at_bit, at_bit+nbits) of `stream`
+// (MSB first), nbits when they are equal, or ~0 when the stream is too short to hold them.
+uint64_t orc_bits_diff(const uint8_t* stream, size_t stream_len, uint64_t at_bit, const uint8_t* sect, uint64_t nbits) {
+  if (at_bit + nbits > (uint64_t)stream_len * 8) return ~0ull;
+  auto get = [](const uint8_t* p, uint64_t bit) -> uint64_t {  // 48 bits starting at `bit` (reads 8 bytes)
+    uint64_t v = 0;
+    const uint64_t by = bit >> 3;
+    for (unsigned k = 0; k < 8; ++k) v = (v << 8) | p[by + k];
+    return (v << (bit & 7)) >> 16;
+  };
+  const uint64_t sect_len = (nbits + 7) / 8;
+  uint64_t done = 0;
+  while (done + 48 <= nbits && (done >> 3) + 8 <= sect_len && ((at_bit + done) >> 3) + 8 <= stream_len) {
+    if (get(sect, done) != get(stream, at_bit + done)) break;
+    done += 48;
+  }
+  for (; done < nbits; ++done) {
+    const uint64_t pb = at_bit + done;
+    const int ba = (sect[done >> 3] >> (7 - (done & 7))) & 1, bb = (stream[pb >> 3] >> (7 - (pb & 7))) & 1;
+    if (ba != bb) return done;
+  }
+  return nbits;
 }
 
 // suffix_array::sais::bwt (sais.rs:266-272). mode 0: literal pre-pass only (unbounded), 1: fast pre-pass only,

@@ -29,6 +29,8 @@ def lib():
         u8p, u32p, u64p = C.POINTER(C.c_uint8), C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)
         L.orc_compress.restype = C.c_longlong
         L.orc_compress.argtypes = [C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]
+        L.orc_compress_randomised.restype = C.c_longlong
+        L.orc_compress_randomised.argtypes = [C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]
         L.orc_run.restype = C.c_void_p
         L.orc_run.argtypes = [C.c_int, C.c_void_p, C.c_size_t, C.c_int]
         L.orc_free.argtypes = [C.c_void_p]
@@ -77,6 +79,21 @@ def compress(data, level=9):
         cap = -r
         out = np.empty(cap, dtype=np.uint8)
         r = lib().orc_compress(level, a.ctypes.data, a.size, out.ctypes.data, cap)
+    assert r >= 0
+    return out[:r].tobytes()
+
+
+def compress_randomised(data, level=9):
+    """FIXTURE GENERATOR, not reference behaviour: the stream bzip2 <= 0.9.0 wrote when it randomised a block (block
+    bytes XOR-ed with the BZ2_rNums mask before the BWT, randomised bit set).  Valid .bz2 that the reference decoder —
+    and libbz2 — un-randomise (decoder.rs:94-116,537-539); the reference ENcoder never produces it."""
+    a = _buf(data)
+    cap = int(a.size * 1.3) + 4096
+    out = np.empty(cap, dtype=np.uint8)
+    r = lib().orc_compress_randomised(level, a.ctypes.data, a.size, out.ctypes.data, cap)
+    if r < -1:
+        out = np.empty(-r, dtype=np.uint8)
+        r = lib().orc_compress_randomised(level, a.ctypes.data, a.size, out.ctypes.data, out.size)
     assert r >= 0
     return out[:r].tobytes()
 

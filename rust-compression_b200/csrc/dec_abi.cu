@@ -37,13 +37,31 @@ struct CtxDecMem : DecMem {
   std::string err() override { return c->err; }
 };
 
+// Scratch per batch of blocks (about 13 MB per 900 kB block on the split path): BZB200_DEC_BATCH_BYTES, else 24 GB but
+// never more than 60 % of the memory that is free on the device right now — the block count of a buffer is untrusted
+// input, the batch size must not be.
 uint64_t dec_batch_bytes() {
-  uint64_t v = (uint64_t)24 << 30;  // scratch per batch of blocks (about 9 MB per 900 kB block)
   if (const char* e = getenv("BZB200_DEC_BATCH_BYTES")) {
     unsigned long long x = strtoull(e, nullptr, 10);
-    if (x >= 1) v = x;
+    if (x >= 1) return x;
   }
-  return v;
+  uint64_t v = (uint64_t)24 << 30;
+  size_t free_b = 0, total_b = 0;
+  if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) v = std::min<uint64_t>(v, (uint64_t)free_b / 10 * 6);
+  return std::max<uint64_t>(v, (uint64_t)64 << 20);
+}
+
+// Largest output the host->host entry points will allocate for (BZB200_DEC_MAX_OUTPUT; default: half of the free device
+// memory).  A few kilobytes of highly compressible blocks can ask for terabytes; that is an argument error, not a
+// reason to bring the process down.
+uint64_t dec_max_output() {
+  if (const char* e = getenv("BZB200_DEC_MAX_OUTPUT")) {
+    unsigned long long x = strtoull(e, nullptr, 10);
+    if (x >= 1) return x;
+  }
+  size_t free_b = 0, total_b = 0;
+  if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) return (uint64_t)1 << 32;
+  return std::max<uint64_t>((uint64_t)free_b / 2, (uint64_t)1 << 20);
 }
 
 // decode on the device; maps the result onto the ABI's return convention
@@ -141,7 +159,12 @@ int bzb200_dec_write(bzb200_dec* d, const uint8_t* p, size_t n) {
     d->err = "write after finish";
     return BZB200_E_STATE;
   }
-  d->in.insert(d->in.end(), p, p + n);
+  try {
+    d->in.insert(d->in.end(), p, p + n);
+  } catch (const std::exception&) {  // std::bad_alloc must not cross the C boundary
+    d->err = "out of host memory";
+    return BZB200_E_INTERNAL;
+  }
   return BZB200_OK;
 }
 
@@ -160,6 +183,10 @@ static int decompress_host_with_ctx(bzb200_ctx* c, const uint8_t* in, size_t n, 
     rc = decode_device(c, ptr<uint8_t>(c->dec_in), n, ptr<uint8_t>(c->dec_out), cap, &out_n, kind);
     if (rc != BZB200_E_ARG) break;
     cap = out_n;  // exact size reported by the dry pass
+    if (cap > dec_max_output()) {
+      c->err = "decompress: the stream expands to " + std::to_string(cap) + " bytes, above the limit (BZB200_DEC_MAX_OUTPUT)";
+      return BZB200_E_ARG;
+    }
   }
   if (rc != BZB200_OK && rc != BZB200_E_DATA) return rc;
   out.resize(out_n);
@@ -180,7 +207,12 @@ int bzb200_dec_finish(bzb200_dec* d) {
     }
   }
   int r = set_device(d->ctx);
-  if (r == BZB200_OK) r = decompress_host_with_ctx(d->ctx, d->in.data(), d->in.size(), d->out, &d->kind);
+  try {
+    if (r == BZB200_OK) r = decompress_host_with_ctx(d->ctx, d->in.data(), d->in.size(), d->out, &d->kind);
+  } catch (const std::exception&) {
+    d->ctx->err = "out of host memory";
+    r = BZB200_E_INTERNAL;
+  }
   if (r != BZB200_OK && r != BZB200_E_DATA) {
     d->err = d->ctx->err;
     return r;
@@ -236,7 +268,11 @@ int bzb200_decompress(int device, const uint8_t* in, size_t n, uint8_t** out, si
     return r;
   }
   std::vector<uint8_t> o;
-  r = decompress_host_with_ctx(c, in, n, o, bz_error);
+  try {
+    r = decompress_host_with_ctx(c, in, n, o, bz_error);
+  } catch (const std::exception&) {
+    r = BZB200_E_INTERNAL;
+  }
   if (r == BZB200_OK || r == BZB200_E_DATA) {
     *out = (uint8_t*)malloc(o.size() ? o.size() : 1);
     if (!*out) r = BZB200_E_ARG;

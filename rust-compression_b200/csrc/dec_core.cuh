@@ -415,7 +415,8 @@ BZB_DEV void d2_header(D2Scratch* s, const uint8_t* in, uint64_t n, uint64_t can
   if (!r.read(24, I.orig_pos)) { I.err = E_EOF; return; }
   I.err_early = 0;
   // (origPtr > 10 + 100000*level is checked by the host, which knows the stream's level)
-  if (I.randomised) { I.err = E_DATA; return; }  // deviation shared with the oracle: never produced by the encoder
+  // (a randomised block — bzip2 <= 0.9.0 — is decoded like any other; its bytes are un-randomised after the inverse BWT,
+  //  d4_derand_body, as BlockRandomise does in get_next_lfm, decoder.rs:94-116,537-539)
   // ---- mapping table (decoder.rs:243-281)
   uint32_t in_use16;
   if (!r.read(16, in_use16)) { I.err = E_EOF; return; }
@@ -1058,6 +1059,19 @@ struct RleStep {
 };
 
 BZB_HD uint32_t d5_nchunks(uint32_t nblock) { return (nblock + RLE_CHUNK - 1) / RLE_CHUNK; }
+
+// Un-randomise (blocks written by bzip2 <= 0.9.0 with the `randomised` bit set; BlockRandomise, decoder.rs:94-116, applied
+// in get_next_lfm, :537-539): byte p of the block in inverse-BWT order — count bytes included — is XOR-ed with 1 on the
+// calls that leave n2go == 1, i.e. p = k * BZ_RAND_PERIOD + cum[m + 1] - 2 (cum = prefix sums of BZ2_rNums,
+// bz_rand_table.h).  Thread x handles toggle number x = 512 k + m of candidate y; the launch is skipped when no block of
+// the batch is randomised.
+BZB_DEV void d4_derand_body(uint32_t x, uint32_t y, const CandInfo* infos, uint64_t stride, const uint32_t* cum,
+                            uint32_t period, uint8_t* Wbuf) {
+  const CandInfo& I = infos[y];
+  if (I.kind != 0 || I.err || !I.randomised) return;
+  const uint64_t p = (uint64_t)(x >> 9) * period + cum[(x & 511u) + 1] - 2u;
+  if (p < I.nblock) Wbuf[(uint64_t)y * stride + p] ^= 1u;
+}
 
 // map entry: exit state in bits 29..31, expanded length in bits 0..28.  All five entry states are advanced in one
 // pass over the chunk (states that cannot occur at this chunk boundary are computed too and never used).

@@ -15,6 +15,7 @@
 #ifndef BZB_EMU
 #include "kernels.h"
 #endif
+#include "bz_rand_table.h"
 #include "dec_core.cuh"
 
 namespace bzb {
@@ -105,6 +106,11 @@ __global__ void __launch_bounds__(128) d4_walk_c(const CandInfo* __restrict__ in
                  seg_resume, Tbuf, Wbuf);
 }
 
+__global__ void __launch_bounds__(256) d4_derand(const CandInfo* __restrict__ infos, uint64_t stride,
+                                                 const uint32_t* __restrict__ cum, uint32_t period, uint8_t* Wbuf) {
+  d4_derand_body(blockIdx.x * 256u + threadIdx.x, blockIdx.y, infos, stride, cum, period, Wbuf);
+}
+
 __global__ void __launch_bounds__(128) d5_count(const CandInfo* __restrict__ infos, uint64_t stride,
                                                 const uint8_t* __restrict__ Wbuf, uint32_t chunks_pitch,
                                                 uint32_t* rle_map) {
@@ -180,6 +186,10 @@ static void run_d4c(Launcher& L, uint32_t nc, uint32_t segs, const CandInfo* inf
                     const uint8_t* T, uint8_t* W) {
   L.launch("d4_walk_c", d4_walk_c, GRID2(segs, 128, nc), dim3(128), infos, stride, V, pitch, seg_len, seg_off,
            seg_resume, T, W);
+}
+static void run_d4r(Launcher& L, uint32_t nc, uint32_t toggles, const CandInfo* infos, uint64_t stride,
+                    const uint32_t* cum, uint8_t* W) {
+  L.launch("d4_derand", d4_derand, GRID2(toggles, 256, nc), dim3(256), infos, stride, cum, (uint32_t)BZ_RAND_PERIOD, W);
 }
 static void run_d5a(Launcher& L, uint32_t nc, uint32_t chunks, const CandInfo* infos, uint64_t stride, const uint8_t* W,
                     uint32_t pitch, uint32_t* rle_map) {
@@ -285,6 +295,13 @@ static void run_d4c(Launcher& L, uint32_t nc, uint32_t segs, const CandInfo* inf
     for (uint32_t x = 0; x < (segs + 127) / 128 * 128; ++x)
       d4_walk_c_body(x, y, infos, stride, V, pitch, seg_len, seg_off, seg_resume, T, W);
 }
+static void run_d4r(Launcher& L, uint32_t nc, uint32_t toggles, const CandInfo* infos, uint64_t stride,
+                    const uint32_t* cum, uint8_t* W) {
+  ++L.launches;
+  for (uint32_t y = 0; y < nc; ++y)
+    for (uint32_t x = 0; x < (toggles + 255) / 256 * 256; ++x)
+      d4_derand_body(x, y, infos, stride, cum, (uint32_t)BZ_RAND_PERIOD, W);
+}
 static void run_d5a(Launcher& L, uint32_t nc, uint32_t chunks, const CandInfo* infos, uint64_t stride, const uint8_t* W,
                     uint32_t pitch, uint32_t* rle_map) {
   ++L.launches;
@@ -332,11 +349,11 @@ struct Chain {
     head_n = hn;
   }
 
-  bool stream_header(const uint8_t* b, uint32_t have) {  // decoder.rs:171-196
+  // decoder.rs:171-196.  The reference reads 'B','Z','h' with check_u8 and DISCARDS the comparison
+  // (`let _ = Self::check_u8(..).map_err(|_| magic_err)?`): only a missing byte is an error; the level byte is checked.
+  bool stream_header(const uint8_t* b, uint32_t have) {
     const uint32_t magic_err = stream_no == 1 ? E_MAGIC_FIRST : E_MAGIC;
-    const uint8_t want[3] = {'B', 'Z', 'h'};
-    for (uint32_t i = 0; i < 3; ++i)
-      if (have <= i || b[i] != want[i]) return fail(magic_err);
+    if (have < 3) return fail(magic_err);
     if (have < 4) return fail(E_EOF);
     if (b[3] < '1' || b[3] > '9') return fail(magic_err);
     level = b[3] - '0';
@@ -359,18 +376,19 @@ struct Chain {
   }
 
   // Walks while the next candidate lies in [c0, c1) (the batch whose infos are given).  accepted: (index inside the
-  // batch, output offset) of every block taken.  Returns false when the chain needs a later batch.
-  bool advance(size_t c0, size_t c1, const CandInfo* infos, std::vector<std::pair<uint32_t, uint64_t>>& accepted) {
+  // batch, output offset) of every block taken.  Returns DONE (verdict reached), LATER (the chain needs a later
+  // batch) or MISS: no candidate starts at `pos` — the scan lists only complete 48-bit magics, while the reference
+  // looks at the FIRST byte alone (0x31 / 0x17, decoder.rs:206-210,494) and skips the other five without comparing
+  // them; the caller reads that byte and either injects a candidate there or reports the reference's error.
+  enum { DONE = 0, LATER = 1, MISS = 2 };
+  int advance(size_t c0, size_t c1, const CandInfo* infos, std::vector<std::pair<uint32_t, uint64_t>>& accepted) {
     while (!done) {
       if (block_no == 0 && level == 0) {
         if (!stream_header(head4, head_n)) break;
       }
       const size_t ci = find(pos);
-      if (ci == (size_t)-1) {  // neither magic here: head byte missing, wrong, or the magic is cut off
-        fail(nbits - pos < 8 ? E_EOF : E_DATA);
-        break;
-      }
-      if (ci >= c1) return false;
+      if (ci == (size_t)-1) return MISS;
+      if (ci >= c1) return LATER;
       if (ci < c0) {  // cannot happen: positions only grow
         fail(E_UNEXPECTED);
         break;
@@ -417,7 +435,7 @@ struct Chain {
         }
       }
     }
-    return true;
+    return DONE;
   }
 };
 
@@ -486,148 +504,211 @@ int dec_run(Launcher& L, DecMem& M, const uint8_t* d_in, uint64_t n, uint8_t* d_
       }
     }
   }
-  Chain chain(cand, n, head4, head_n);
-  std::vector<std::pair<uint32_t, uint64_t>> accepted;
-  if (maxlevel == 0 || cand.empty()) {  // bad first header or nothing to decode: the chain alone yields the error
-    chain.advance(0, 0, nullptr, accepted);
+  if (maxlevel == 0) {  // bad first header: the chain alone yields the error
+    Chain chain(cand, n, head4, head_n);
+    std::vector<std::pair<uint32_t, uint64_t>> none;
+    chain.advance(0, 0, nullptr, none);
     if (!chain.done) chain.fail(E_UNEXPECTED);
     res->bz_error = chain.err;
     res->streams = chain.streams;
     return 0;
   }
-  const uint32_t cap = 100000u * maxlevel;
-  const uint64_t stride = ((uint64_t)cap + 63) & ~63ull;
-  const uint32_t segs_pitch = d4_nseg0(cap) + 1;
-  const uint32_t chunks_pitch = d5_nchunks(cap);
-  const bool split = (flags & DEC_SPLIT_D2) != 0;
-  SplitBufs SB;
-  SB.symstride = ((uint64_t)cap + 4 + 63) & ~63ull;
-  SB.chunks_pitch = d2_nchunks(cap + 2);
-  const uint64_t per_cand = stride * 9 + MAX_SEL + 257 * 4 + (uint64_t)segs_pitch * (16 + SEG_KEEP) +
-                            (uint64_t)chunks_pitch * 32 + sizeof(CandInfo) + 64 +
-                            (split ? SB.symstride * 3 + 256 + (uint64_t)SB.chunks_pitch * (256 * 10 + 32 + 8) : 0);
-  size_t batch = (size_t)std::max<uint64_t>(1, batch_bytes / per_cand);
-  batch = std::min<size_t>(batch, 32768);
-  batch = std::min<size_t>(batch, cand.size());
+  const uint64_t nbits = n * 8;
+  // The pass below runs again from the start in one rare case: an end-of-stream magic with damaged bytes 2..6 (found
+  // only by the chain, see Chain::advance) in front of a stream of a higher level than the buffers were sized for.
+  for (int attempt = 0;; ++attempt) {
+    bool restart = false;
+    Chain chain(cand, n, head4, head_n);
+    std::vector<std::pair<uint32_t, uint64_t>> accepted;
+    const uint32_t cap = 100000u * maxlevel;
+    const uint64_t stride = ((uint64_t)cap + 63) & ~63ull;
+    const uint32_t segs_pitch = d4_nseg0(cap) + 1;
+    const uint32_t chunks_pitch = d5_nchunks(cap);
+    const bool split = (flags & DEC_SPLIT_D2) != 0;
+    SplitBufs SB;
+    SB.symstride = ((uint64_t)cap + 4 + 63) & ~63ull;
+    SB.chunks_pitch = d2_nchunks(cap + 2);
+    const uint64_t per_cand = stride * 9 + MAX_SEL + 257 * 4 + (uint64_t)segs_pitch * (16 + SEG_KEEP) +
+                              (uint64_t)chunks_pitch * 32 + sizeof(CandInfo) + 64 +
+                              (split ? SB.symstride * 3 + 256 + (uint64_t)SB.chunks_pitch * (256 * 10 + 32 + 8) : 0);
+    size_t batch = (size_t)std::max<uint64_t>(1, batch_bytes / per_cand);
+    batch = std::min<size_t>(batch, 32768);
+    batch = std::max<size_t>(1, std::min<size_t>(batch, cand.size()));
 
-  uint64_t* d_cand = slot<uint64_t>(M, DS_CAND, cand.size());
-  if (!d_cand) return -2;
-  DTRY(M.to_dev(d_cand, cand.data(), cand.size() * 8));
-  CandInfo* d_info = slot<CandInfo>(M, DS_INFO, batch);
-  uint32_t* d_occ = slot<uint32_t>(M, DS_OCC, batch * stride);
-  uint32_t* d_V = slot<uint32_t>(M, DS_V, batch * stride);
-  uint8_t* d_W = slot<uint8_t>(M, DS_W, batch * stride);
-  uint8_t* d_sel = slot<uint8_t>(M, DS_SEL, batch * (size_t)MAX_SEL);
-  uint32_t* d_cftab = slot<uint32_t>(M, DS_CFTAB, batch * 257);
-  uint32_t* d_seglen = slot<uint32_t>(M, DS_SEGLEN, batch * segs_pitch);
-  uint32_t* d_segnext = slot<uint32_t>(M, DS_SEGNEXT, batch * segs_pitch);
-  uint32_t* d_segoff = slot<uint32_t>(M, DS_SEGOFF, batch * segs_pitch);
-  uint32_t* d_segres = slot<uint32_t>(M, DS_SEGRES, batch * segs_pitch);
-  uint8_t* d_T = slot<uint8_t>(M, DS_T, batch * (size_t)segs_pitch * SEG_KEEP);
-  uint32_t* d_rlemap = slot<uint32_t>(M, DS_RLEMAP, batch * (size_t)chunks_pitch * 5);
-  uint32_t* d_chentry = slot<uint32_t>(M, DS_CHENTRY, batch * (size_t)chunks_pitch);
-  uint64_t* d_choff = slot<uint64_t>(M, DS_CHOFF, batch * (size_t)chunks_pitch);
-  uint64_t* d_outoff = slot<uint64_t>(M, DS_OUTOFF, batch);
-  uint64_t* d_crcoff = slot<uint64_t>(M, DS_CRCOFF, batch + 1);
-  uint32_t* d_crc = slot<uint32_t>(M, DS_CRC, batch);
-  if (split) {
-    const size_t ch = batch * (size_t)SB.chunks_pitch;
-    SB.sym = slot<uint16_t>(M, DS_SYM, batch * SB.symstride);
-    SB.P = slot<uint8_t>(M, DS_P, batch * SB.symstride);
-    SB.mtf0 = slot<uint8_t>(M, DS_MTF0, batch * 256);
-    SB.perm = slot<uint8_t>(M, DS_PERM, ch * 256);
-    SB.cntp = slot<uint32_t>(M, DS_CNTP, ch * 256);
-    SB.meta = slot<ChunkMeta>(M, DS_CMETA, ch);
-    SB.initl = slot<uint8_t>(M, DS_INITL, ch * 256);
-    SB.base = slot<uint32_t>(M, DS_BASE, ch * 256);
-    SB.coff = slot<uint32_t>(M, DS_COFF, ch);
-    SB.cd0 = slot<uint32_t>(M, DS_CD0, ch);
-    if (!SB.sym || !SB.P || !SB.mtf0 || !SB.perm || !SB.cntp || !SB.meta || !SB.initl || !SB.base || !SB.coff || !SB.cd0)
+    uint64_t* d_cand = slot<uint64_t>(M, DS_CAND, cand.size() + 1);
+    if (!d_cand) return -2;
+    if (!cand.empty()) DTRY(M.to_dev(d_cand, cand.data(), cand.size() * 8));
+    CandInfo* d_info = slot<CandInfo>(M, DS_INFO, batch);
+    uint32_t* d_occ = slot<uint32_t>(M, DS_OCC, batch * stride);
+    uint32_t* d_V = slot<uint32_t>(M, DS_V, batch * stride);
+    uint8_t* d_W = slot<uint8_t>(M, DS_W, batch * stride);
+    uint8_t* d_sel = slot<uint8_t>(M, DS_SEL, batch * (size_t)MAX_SEL);
+    uint32_t* d_cftab = slot<uint32_t>(M, DS_CFTAB, batch * 257);
+    uint32_t* d_seglen = slot<uint32_t>(M, DS_SEGLEN, batch * segs_pitch);
+    uint32_t* d_segnext = slot<uint32_t>(M, DS_SEGNEXT, batch * segs_pitch);
+    uint32_t* d_segoff = slot<uint32_t>(M, DS_SEGOFF, batch * segs_pitch);
+    uint32_t* d_segres = slot<uint32_t>(M, DS_SEGRES, batch * segs_pitch);
+    uint8_t* d_T = slot<uint8_t>(M, DS_T, batch * (size_t)segs_pitch * SEG_KEEP);
+    uint32_t* d_rlemap = slot<uint32_t>(M, DS_RLEMAP, batch * (size_t)chunks_pitch * 5);
+    uint32_t* d_chentry = slot<uint32_t>(M, DS_CHENTRY, batch * (size_t)chunks_pitch);
+    uint64_t* d_choff = slot<uint64_t>(M, DS_CHOFF, batch * (size_t)chunks_pitch);
+    uint64_t* d_outoff = slot<uint64_t>(M, DS_OUTOFF, batch);
+    uint64_t* d_crcoff = slot<uint64_t>(M, DS_CRCOFF, batch + 1);
+    uint32_t* d_crc = slot<uint32_t>(M, DS_CRC, batch);
+    uint32_t* d_randcum = nullptr;  // uploaded when the first randomised block shows up
+    if (split) {
+      const size_t ch = batch * (size_t)SB.chunks_pitch;
+      SB.sym = slot<uint16_t>(M, DS_SYM, batch * SB.symstride);
+      SB.P = slot<uint8_t>(M, DS_P, batch * SB.symstride);
+      SB.mtf0 = slot<uint8_t>(M, DS_MTF0, batch * 256);
+      SB.perm = slot<uint8_t>(M, DS_PERM, ch * 256);
+      SB.cntp = slot<uint32_t>(M, DS_CNTP, ch * 256);
+      SB.meta = slot<ChunkMeta>(M, DS_CMETA, ch);
+      SB.initl = slot<uint8_t>(M, DS_INITL, ch * 256);
+      SB.base = slot<uint32_t>(M, DS_BASE, ch * 256);
+      SB.coff = slot<uint32_t>(M, DS_COFF, ch);
+      SB.cd0 = slot<uint32_t>(M, DS_CD0, ch);
+      if (!SB.sym || !SB.P || !SB.mtf0 || !SB.perm || !SB.cntp || !SB.meta || !SB.initl || !SB.base || !SB.coff || !SB.cd0)
+        return -2;
+    }
+    if (!d_info || !d_occ || !d_V || !d_W || !d_sel || !d_cftab || !d_seglen || !d_segnext || !d_segoff || !d_segres || !d_T ||
+        !d_rlemap || !d_chentry || !d_choff || !d_outoff || !d_crcoff || !d_crc)
       return -2;
-  }
-  if (!d_info || !d_occ || !d_V || !d_W || !d_sel || !d_cftab || !d_seglen || !d_segnext || !d_segoff || !d_segres || !d_T ||
-      !d_rlemap || !d_chentry || !d_choff || !d_outoff || !d_crcoff || !d_crc)
-    return -2;
 
-  std::vector<CandInfo> infos(batch);
-  std::vector<uint64_t> h_outoff(batch), h_crcoff(batch + 1);
-  std::vector<uint32_t> h_crc(batch);
-  bool dry = false;         // the output buffer is too small: finish the chain for the exact size, write nothing
-  uint32_t crc_err = 0;
-  uint64_t crc_err_out = 0;
+    std::vector<CandInfo> infos(batch);
+    std::vector<uint64_t> h_outoff(batch), h_crcoff(batch + 1);
+    std::vector<uint32_t> h_crc(batch);
+    bool dry = false;         // the output buffer is too small: finish the chain for the exact size, write nothing
+    uint32_t crc_err = 0;
+    uint64_t crc_err_out = 0;
+    res->batches = 0;
 
-  for (size_t c0 = 0; c0 < cand.size() && !chain.done && !crc_err; c0 += batch) {
-    const size_t c1 = std::min(cand.size(), c0 + batch);
-    const uint32_t nc = (uint32_t)(c1 - c0);
-    ++res->batches;
-    // ---- D2: header, tables, symbols, MTF, runs
-    if (split) run_d2_split(L, nc, d_in, n, d_cand + c0, cap, stride, d_occ, d_sel, d_cftab, d_info, SB);
-    else run_d2(L, nc, d_in, n, d_cand + c0, cap, stride, d_occ, d_sel, d_cftab, d_info);
-    DTRY(M.check());
-    DTRY(M.to_host(infos.data(), d_info, (size_t)nc * sizeof(CandInfo)));
-    uint32_t nmax = 0;
-    for (uint32_t i = 0; i < nc; ++i)
-      if (infos[i].kind == 0 && infos[i].err == 0) nmax = std::max(nmax, infos[i].nblock);
-    if (nmax) {
-      const uint32_t segs = d4_nseg0(nmax) + 1, chunks = d5_nchunks(nmax);
-      // ---- D3/D4: inverse BWT
-      run_d3(L, nc, nmax, d_info, stride, d_occ, d_cftab, d_V);
-      DTRY(M.fill(d_segoff, 0xFF, (size_t)nc * segs_pitch * 4));
-      run_d4a(L, nc, segs, d_info, stride, d_V, segs_pitch, d_seglen, d_segnext, d_segres, d_T);
-      run_d4s(L, nc, d_info, segs_pitch, d_seglen, d_segnext, d_segoff);
-      run_d4c(L, nc, segs, d_info, stride, d_V, segs_pitch, d_seglen, d_segoff, d_segres, d_T, d_W);
-      // ---- D5: RLE1 undo, sizes
-      run_d5a(L, nc, chunks, d_info, stride, d_W, chunks_pitch, d_rlemap);
-      run_d5b(L, nc, d_info, chunks_pitch, d_rlemap, d_chentry, d_choff);
-      DTRY(M.check());
-      DTRY(M.to_host(infos.data(), d_info, (size_t)nc * sizeof(CandInfo)));
-    }
-    // ---- chain: which candidates a sequential parse visits, and where their bytes go
-    accepted.clear();
-    chain.advance(c0, c1, infos.data(), accepted);
-    if (accepted.empty()) continue;
-    if (chain.out_total > cap_out) dry = true;
-    if (dry) continue;
-    for (uint32_t i = 0; i < nc; ++i) h_outoff[i] = ~0ull;
-    for (size_t k = 0; k < accepted.size(); ++k) {
-      h_outoff[accepted[k].first] = accepted[k].second;
-      h_crcoff[k] = accepted[k].second;
-    }
-    h_crcoff[accepted.size()] = chain.out_total;
-    DTRY(M.to_dev(d_outoff, h_outoff.data(), (size_t)nc * 8));
-    DTRY(M.to_dev(d_crcoff, h_crcoff.data(), (accepted.size() + 1) * 8));
-    run_d5c(L, nc, d5_nchunks(nmax), d_info, stride, d_W, chunks_pitch, d_chentry, d_choff, d_outoff, d_out);
-    DTRY(M.crc_blocks(d_out, d_crcoff, (uint32_t)accepted.size(), d_crc));
-    DTRY(M.check());
-    DTRY(M.to_host(h_crc.data(), d_crc, accepted.size() * 4));
-    for (size_t k = 0; k < accepted.size(); ++k) {
-      if (h_crc[k] != infos[accepted[k].first].stored_crc) {  // found when the next header is read (decoder.rs:198-204)
-        crc_err = E_DATA;
-        crc_err_out = h_crcoff[k + 1];
+    size_t c0 = 0;
+    while (!chain.done && !crc_err) {
+      const size_t c1 = std::min(cand.size(), c0 + batch);
+      const uint32_t nc = (uint32_t)(c1 - c0);
+      uint32_t nmax = 0;
+      if (nc) {
+        ++res->batches;
+        // ---- D2: header, tables, symbols, MTF, runs
+        if (split) run_d2_split(L, nc, d_in, n, d_cand + c0, cap, stride, d_occ, d_sel, d_cftab, d_info, SB);
+        else run_d2(L, nc, d_in, n, d_cand + c0, cap, stride, d_occ, d_sel, d_cftab, d_info);
+        DTRY(M.check());
+        DTRY(M.to_host(infos.data(), d_info, (size_t)nc * sizeof(CandInfo)));
+        bool any_rand = false;
+        for (uint32_t i = 0; i < nc; ++i)
+          if (infos[i].kind == 0 && infos[i].err == 0) {
+            nmax = std::max(nmax, infos[i].nblock);
+            any_rand |= infos[i].randomised != 0;
+          }
+        if (nmax) {
+          const uint32_t segs = d4_nseg0(nmax) + 1, chunks = d5_nchunks(nmax);
+          // ---- D3/D4: inverse BWT
+          run_d3(L, nc, nmax, d_info, stride, d_occ, d_cftab, d_V);
+          DTRY(M.fill(d_segoff, 0xFF, (size_t)nc * segs_pitch * 4));
+          run_d4a(L, nc, segs, d_info, stride, d_V, segs_pitch, d_seglen, d_segnext, d_segres, d_T);
+          run_d4s(L, nc, d_info, segs_pitch, d_seglen, d_segnext, d_segoff);
+          run_d4c(L, nc, segs, d_info, stride, d_V, segs_pitch, d_seglen, d_segoff, d_segres, d_T, d_W);
+          if (any_rand) {  // blocks written by bzip2 <= 0.9.0 (decoder.rs:94-116,537-539)
+            if (!d_randcum) {
+              d_randcum = slot<uint32_t>(M, DS_RAND, 513);
+              if (!d_randcum) return -2;
+              DTRY(M.to_dev(d_randcum, BZ_RAND_CUM, sizeof(BZ_RAND_CUM)));
+            }
+            const uint32_t toggles = (nmax / BZ_RAND_PERIOD + 1) * 512u;
+            run_d4r(L, nc, toggles, d_info, stride, d_randcum, d_W);
+          }
+          // ---- D5: RLE1 undo, sizes
+          run_d5a(L, nc, chunks, d_info, stride, d_W, chunks_pitch, d_rlemap);
+          run_d5b(L, nc, d_info, chunks_pitch, d_rlemap, d_chentry, d_choff);
+          DTRY(M.check());
+          DTRY(M.to_host(infos.data(), d_info, (size_t)nc * sizeof(CandInfo)));
+        }
+      }
+      // ---- chain: which candidates a sequential parse visits, and where their bytes go
+      accepted.clear();
+      const int verdict = chain.advance(c0, c1, infos.data(), accepted);
+      if (!accepted.empty()) {
+        if (chain.out_total > cap_out) dry = true;
+        if (!dry) {
+          for (uint32_t i = 0; i < nc; ++i) h_outoff[i] = ~0ull;
+          for (size_t k = 0; k < accepted.size(); ++k) {
+            h_outoff[accepted[k].first] = accepted[k].second;
+            h_crcoff[k] = accepted[k].second;
+          }
+          h_crcoff[accepted.size()] = chain.out_total;
+          DTRY(M.to_dev(d_outoff, h_outoff.data(), (size_t)nc * 8));
+          DTRY(M.to_dev(d_crcoff, h_crcoff.data(), (accepted.size() + 1) * 8));
+          run_d5c(L, nc, d5_nchunks(nmax), d_info, stride, d_W, chunks_pitch, d_chentry, d_choff, d_outoff, d_out);
+          DTRY(M.crc_blocks(d_out, d_crcoff, (uint32_t)accepted.size(), d_crc));
+          DTRY(M.check());
+          DTRY(M.to_host(h_crc.data(), d_crc, accepted.size() * 4));
+          for (size_t k = 0; k < accepted.size(); ++k) {
+            if (h_crc[k] != infos[accepted[k].first].stored_crc) {  // found when the next header is read (decoder.rs:198-204)
+              crc_err = E_DATA;
+              crc_err_out = h_crcoff[k + 1];
+              break;
+            }
+          }
+        }
+      }
+      if (crc_err || chain.done) break;
+      if (verdict == Chain::LATER) {
+        c0 = c1;
+        continue;
+      }
+      // verdict == MISS: no complete magic starts at chain.pos.  What the reference does there (decoder.rs:206-224,
+      // 494-508, 521-523): the head byte must exist (else UnexpectedEof) and be 0x31 or 0x17 (else DataError); the
+      // five bytes after it are read and NOT compared (a missing one is DataError).  So a block or an end-of-stream
+      // marker with damaged magic bytes 2..6 is decoded all the same: inject it as a candidate and go on from there.
+      const uint64_t pos = chain.pos;
+      if (nbits - pos < 8) {
+        chain.fail(E_EOF);
         break;
       }
+      uint8_t two[2] = {0, 0};
+      DTRY(M.to_host(two, d_in + (pos >> 3), (pos >> 3) + 2 <= n ? 2 : 1));
+      const uint32_t head = (((uint32_t)two[0] << 8 | two[1]) >> (8 - (pos & 7))) & 0xFFu;
+      if ((head != 0x31 && head != 0x17) || nbits - pos < 48) {
+        chain.fail(E_DATA);
+        break;
+      }
+      const uint64_t entry = pos | (head == 0x17 ? KIND_END : 0ull);
+      size_t at = 0;
+      while (at < cand.size() && (cand[at] & ~KIND_END) < pos) ++at;
+      cand.insert(cand.begin() + at, entry);
+      if (head == 0x17 && maxlevel < 9) {  // a stream of unknown level may follow: size for the largest and start over
+        maxlevel = 9;
+        restart = true;
+        break;
+      }
+      d_cand = slot<uint64_t>(M, DS_CAND, cand.size() + 1);
+      if (!d_cand) return -2;
+      DTRY(M.to_dev(d_cand, cand.data(), cand.size() * 8));
+      c0 = at;
     }
-  }
-  if (!chain.done && !crc_err) chain.fail(E_UNEXPECTED);  // candidates exhausted without a verdict (cannot happen)
-  res->streams = chain.streams;
-  res->blocks = chain.blocks;
-  res->syms = chain.syms;
-  res->pre_rle = chain.pre_rle;
-  if (dry) {
-    res->too_small = 1;
-    res->needed = chain.out_total;
-    res->out_n = 0;
+    if (restart && attempt < 64) continue;
+    if (!chain.done && !crc_err) chain.fail(E_UNEXPECTED);  // cannot happen
+    res->streams = chain.streams;
+    res->blocks = chain.blocks;
+    res->syms = chain.syms;
+    res->pre_rle = chain.pre_rle;
+    if (dry) {
+      res->too_small = 1;
+      res->needed = chain.out_total;
+      res->out_n = 0;
+      res->bz_error = chain.err;
+      return 0;
+    }
+    if (crc_err) {
+      res->bz_error = crc_err;
+      res->out_n = res->needed = crc_err_out;
+      return 0;
+    }
     res->bz_error = chain.err;
+    res->out_n = res->needed = chain.out_total;
     return 0;
   }
-  if (crc_err) {
-    res->bz_error = crc_err;
-    res->out_n = res->needed = crc_err_out;
-    return 0;
-  }
-  res->bz_error = chain.err;
-  res->out_n = res->needed = chain.out_total;
-  return 0;
 }
 
 }  // namespace bzb

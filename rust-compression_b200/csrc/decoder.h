@@ -33,7 +33,7 @@ struct DecMem {
 enum DecSlot {
   DS_CAND = 0, DS_COUNT, DS_INFO, DS_OCC, DS_V, DS_W, DS_SEL, DS_CFTAB, DS_SEGLEN, DS_SEGNEXT, DS_SEGOFF,
   DS_SEGRES, DS_T, DS_RLEMAP, DS_CHENTRY, DS_CHOFF, DS_OUTOFF, DS_CRCOFF, DS_CRC, DS_SYM, DS_P, DS_MTF0, DS_PERM, DS_CNTP,
-  DS_CMETA, DS_INITL, DS_BASE, DS_COFF, DS_CD0, DS_NSLOTS
+  DS_CMETA, DS_INITL, DS_BASE, DS_COFF, DS_CD0, DS_RAND, DS_NSLOTS
 };
 
 struct DecResult {

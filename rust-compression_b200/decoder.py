@@ -104,13 +104,21 @@ class BZip2Decoder:
             return None
         L = _lib.lib()
         pending = bytearray()
+
+        def push():
+            rc = L.bzb200_dec_write(self._h, bytes(pending), len(pending))
+            if rc != _lib.OK:  # e.g. E_STATE after a failed finish: input must not be dropped silently
+                msg = L.bzb200_dec_last_error(self._h)
+                L.bzb200_dec_reset(self._h)
+                raise BZip2Error("Unexpected", detail=f"bzb200_dec_write rc={rc}: {msg.decode() if msg else ''}")
+            pending.clear()
+
         for x in it:
             pending.append(x)
             if len(pending) >= (1 << 20):
-                L.bzb200_dec_write(self._h, bytes(pending), len(pending))
-                pending.clear()
+                push()
         if pending:
-            L.bzb200_dec_write(self._h, bytes(pending), len(pending))
+            push()
         out, kind = self._run()
         self._chunk, self._pos = out, 0
         self._decoded = True

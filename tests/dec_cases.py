@@ -45,6 +45,8 @@ def valid_cases(big=False):
     cases.append(("three streams, levels 1/3/5, one empty",
                   orc.compress(txt[:50000], 1) + orc.compress(b"", 3) + bz2.compress(txt[50000:120000], 5)))
     cases.append(("mixed level 1, 14 blocks", orc.compress(gen.mixed(1, 1_500_000), 1)))
+    cases += randomised_cases()
+    cases += damaged_magic_cases(valid=True)
     # symbol counts of 16 384, 16 385 and 16 386: EOB as the last symbol of a full 1 024-symbol chunk of the split D2,
     # alone in the last chunk, and second in it
     for extra in (615, 616, 618):
@@ -57,6 +59,69 @@ def valid_cases(big=False):
         cases.append(("period 2, full block", orc.compress(b"ab" * 500_000, 9)))
         cases.append(("period 4 + tail, full block", orc.compress(b"aabb" * 230_000 + b"q", 9)))
     return cases
+
+
+def randomised_cases():
+    """Streams with the `randomised` bit set, as bzip2 <= 0.9.0 wrote them (decoder.rs:94-116,230-234,478-480,537-539).
+    No such encoder exists any more, so the fixtures come from oracle.orc.compress_randomised (the format's rule: block
+    bytes XOR the BZ2_rNums mask before the BWT) and are pinned on libbz2, which still decodes them."""
+    txt = gen.text(3, 250000)
+    out = []
+    for name, data, lvl in (("text level 1, 3 blocks", txt, 1), ("text level 9", gen.text(5, 1_200_000), 9),
+                            ("all a", b"a" * 300000, 1), ("period 2", b"ab" * 70000, 2),
+                            ("mixed level 1", gen.mixed(2, 350000), 1)):
+        s = orc.compress_randomised(data, lvl)
+        assert bz2.decompress(s) == data, name
+        out.append((f"randomised blocks: {name}", s))
+    # a randomised stream between two ordinary ones (multi-stream), and a randomised block next to an ordinary one
+    out.append(("randomised stream between ordinary streams",
+                orc.compress(txt[:40000], 2) + orc.compress_randomised(txt[40000:90000], 1) + bz2.compress(txt[90000:], 3)))
+    return out
+
+
+def _xor_bits(stream, bitpos, nbytes, mask=0xFF):
+    """XORs `nbytes` bytes starting at bit offset bitpos (unaligned) with mask."""
+    b = bytearray(stream)
+    for k in range(nbytes):
+        for i in range(8):
+            if (mask >> (7 - i)) & 1:
+                p = bitpos + 8 * k + i
+                b[p >> 3] ^= 0x80 >> (p & 7)
+    return bytes(b)
+
+
+def damaged_magic_cases(valid):
+    """The reference reads every magic byte except the first of each 48-bit magic with check_u8 and discards the
+    comparison (decoder.rs:155-161,177-182,211-224,495-508): 'B','Z','h' and bytes 2..6 of both magics may hold
+    anything (valid=True: these decode normally); the level byte and the first magic byte are checked
+    (valid=False: DataErrorMagicFirst / DataErrorMagic / DataError)."""
+    txt = gen.text(3, 250000)
+    s = orc.compress(txt, 1)                       # three blocks
+    r = orc.Run(txt, 1)
+    starts = [r.info(b)["bit_start"] for b in range(r.nblocks)]
+    end = r.info(r.nblocks - 1)["bit_end"]
+    r.close()
+    two = orc.compress(txt[:30000], 1)
+    if valid:
+        out = [("stream magic 'XZh'", b"X" + s[1:]), ("stream magic all zero", b"\0\0\0" + s[3:]),
+               ("block magic bytes 2..6 damaged, first block", _xor_bits(s, starts[0] + 8, 5)),
+               ("block magic byte 4 damaged, second block (unaligned)", _xor_bits(s, starts[1] + 24, 1, 0x10)),
+               ("block magic bytes 2 and 6 damaged, last block", _xor_bits(_xor_bits(s, starts[2] + 8, 1), starts[2] + 40, 1)),
+               ("every block magic damaged", _xor_bits(_xor_bits(_xor_bits(s, starts[0] + 16, 2), starts[1] + 8, 5),
+                                                       starts[2] + 32, 1, 0x01)),
+               ("end magic bytes 2..6 damaged", _xor_bits(s, end + 8, 5)),
+               ("end magic damaged, a level-9 stream follows", _xor_bits(two, len(two) * 8 - 80 + 16, 1)[:len(two)] +
+                orc.compress(gen.text(8, 300000), 9)),
+               ("second stream magic 'QQQ'", two + b"QQQ" + orc.compress(txt[:20000], 3)[3:])]
+        return out
+    return [("first block magic, first byte damaged", _xor_bits(s, starts[0], 1, 0x01)),
+            ("second block magic, first byte damaged", _xor_bits(s, starts[1], 1, 0x80)),
+            ("end magic, first byte damaged", _xor_bits(s, end, 1, 0x02)),
+            ("block head byte 0x17 instead of 0x31", _xor_bits(s, starts[1], 1, 0x31 ^ 0x17)),
+            ("end head byte 0x31 instead of 0x17", _xor_bits(s, end, 1, 0x31 ^ 0x17)),
+            ("level byte '0' with magic 'XZh'", b"XZh0" + s[4:]),
+            ("second stream level byte ':'", two + b"BZh:" + orc.compress(txt[:20000], 3)[4:]),
+            ("damaged block magic cut off after 3 bytes", _xor_bits(s, starts[2] + 8, 2)[:(starts[2] + 24 + 7) // 8])]
 
 
 def malformed_cases():
@@ -91,6 +156,16 @@ def malformed_cases():
     alla = orc.compress(b"a" * 200000, 1)
     for v in (0, 1, 4, 100):  # 0: the block then ends in four equal bytes without a count (see same_result)
         cases.append((f"all-a block, origPtr patched to {v}", _set_orig(alla, v)))
+    cases += damaged_magic_cases(valid=False)
+    # a randomised stream that is damaged: truncated inside the block, and with the randomised bit cleared (CRC error)
+    rs = orc.compress_randomised(t[:90000], 1)
+    cases.append(("randomised stream truncated", rs[:len(rs) // 2]))
+    b = bytearray(rs)
+    b[(32 + 48 + 32) >> 3] ^= 0x80 >> ((32 + 48 + 32) & 7)
+    cases.append(("randomised bit cleared", bytes(b)))
+    b = bytearray(orc.compress(t[:90000], 1))
+    b[(32 + 48 + 32) >> 3] ^= 0x80 >> ((32 + 48 + 32) & 7)
+    cases.append(("randomised bit set on an ordinary block", bytes(b)))
     return cases
 
 

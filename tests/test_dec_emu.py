@@ -19,7 +19,7 @@ LIB = os.path.join(ROOT, "tests", "cpp", "libdecemu.so")
 @pytest.fixture(scope="module")
 def emu():
     deps = [SRC] + [os.path.join(ROOT, "rust-compression_b200", "csrc", f) for f in
-                    ("decoder.cu", "decoder.h", "dec_core.cuh")]
+                    ("decoder.cu", "decoder.h", "dec_core.cuh", "bz_rand_table.h")]
     if not os.path.exists(LIB) or any(os.path.getmtime(d) > os.path.getmtime(LIB) for d in deps):
         subprocess.check_call(["g++", "-std=c++17", "-O2", "-shared", "-fPIC", SRC, "-o", LIB])
     lib = C.CDLL(LIB)
@@ -69,6 +69,19 @@ def test_batches_and_output_retry(emu):
     name, buf = [c for c in dec_cases.valid_cases() if c[0].startswith("three streams")][0]
     err, out, info = emu(buf, batch_bytes=1)               # one candidate per batch, chain crosses streams
     assert (err, out) == dec_cases.expected(buf) and info["streams"] == 3
+
+
+@pytest.mark.parametrize("split", [0, 1])
+def test_damaged_magics_and_randomised_blocks_across_batches(emu, split):
+    """Candidates the magic scan cannot see (magic bytes 2..6 damaged: the reference does not compare them) are
+    injected by the chain; randomised blocks are un-randomised after the inverse BWT.  One candidate per batch, so
+    every injection lands on a batch boundary, and a too-small first output buffer, so the dry pass sees them too."""
+    for name, buf in dec_cases.damaged_magic_cases(True) + dec_cases.damaged_magic_cases(False) + \
+            dec_cases.randomised_cases():
+        want = dec_cases.expected(buf)
+        for kw in (dict(batch_bytes=1), dict(first_cap=1000), dict()):
+            err, out, info = emu(buf, split=split, **kw)
+            assert dec_cases.same_result((err, out), want), f"{name} {kw}: got {err}/{len(out)}, reference {want[0]}/{len(want[1])}"
 
 
 @pytest.mark.parametrize("split", [0, 1])

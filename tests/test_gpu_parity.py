@@ -154,7 +154,15 @@ def test_generators_multiblock():
     parity.assert_parity(gen.g1(1, 250000), 1)      # 3 blocks, App. B
     parity.assert_parity(gen.g2(2, 4000000), 1)     # 255-splits, count bytes, T..T+4 slack
     parity.assert_parity(gen.mixed(1, 1500000), 1)  # mixed binary/text, many small blocks
-    parity.assert_parity(gen.text(1, 899000), 9)    # BASELINE config 2: one 900 kB text block
+
+
+def test_config2_single_text_block():
+    """BASELINE config 2 as SURVEY.md section 8(d) writes it: TEXT(seed=1, n=899 900) at level 9 is exactly one block."""
+    data = gen.text(1, 899_900)
+    r = orc.Run(data, 9)
+    assert r.nblocks == 1
+    r.close()
+    parity.assert_parity(data, 9)
 
 
 @pytest.mark.parametrize("level", [1, 9])
@@ -305,11 +313,11 @@ def test_large_corpus_properties():
     # (2) block sizes: every block but the last holds between T and T+4 bytes (encoder.rs:692)
     sizes = np.diff(rle_off.astype(np.int64))
     assert ((sizes[:-1] >= 899981) & (sizes[:-1] <= 899985)).all() and 0 < sizes[-1] <= 899985
-    # (3) leading blocks bit-exact vs the oracle, and a libbz2 round trip of the first 32 MiB
-    pre = orc.Run(data[:4 << 20], 9)
-    bits = pre.info(pre.nblocks - 2)["bit_end"]
-    assert stream[:bits // 8] == pre.out[:bits // 8]
-    pre.close()
+    # (3) EVERY block section and the trailer bit-exact vs the oracle (block-parallel on the host cores), and a libbz2
+    # round trip of the first 32 MiB
+    from oracle import verify
+    ok, msg, st = verify.verify_stream(data, 9, stream, in_off)
+    assert ok and st["blocks_checked"] == len(crc), msg
     dec = bz2.BZ2Decompressor()
     got = bytearray()
     pos = 0
@@ -318,4 +326,69 @@ def test_large_corpus_properties():
         pos += 1 << 20
     m = min(len(got), 32 << 20)
     assert bytes(got[:m]) == data[:m]
+    ctx.close()
+
+
+# ---- K7: the bit-granular join of shard bit strings (BitWriter<Left> across shard boundaries, bitio/writer.rs:186-224) ----
+
+def test_bit_append_against_numpy():
+    """bzb200_bit_append alone: random source bits OR-ed at random destination bit offsets (all 32 word phases, lengths
+    that end inside a word, zero length) must equal the same concatenation done with numpy on the host."""
+    import torch
+    from rust_compression_b200 import device as dv
+    rng = np.random.default_rng(3)
+    ctx = dv.Context()
+    for trial in range(40):
+        nbits = int(rng.integers(0, 200_000)) if trial else 0
+        dst_bit = int(rng.integers(0, 4096)) if trial % 2 else trial
+        src = rng.integers(0, 256, size=(nbits + 7) // 8 + 8, dtype=np.uint8)
+        head = rng.integers(0, 256, size=(dst_bit + 7) // 8, dtype=np.uint8)
+        hb = np.unpackbits(head)[:dst_bit]
+        want = np.concatenate([hb, np.unpackbits(src)[:nbits]])
+        cap = ((dst_bit + nbits + 31) // 32) * 4 + 8
+        dst = np.zeros(cap, dtype=np.uint8)
+        dst[:(dst_bit + 7) // 8] = np.packbits(hb)  # bits below dst_bit set, everything above zero
+        d_dst = torch.from_numpy(dst).cuda()
+        d_src = torch.from_numpy(np.concatenate([src, np.zeros((-src.size) % 4, dtype=np.uint8)])).cuda()
+        ctx.bit_append(d_dst, dst_bit, d_src, nbits)
+        ctx.sync()
+        got = np.unpackbits(d_dst.cpu().numpy())
+        assert (got[:want.size] == want).all(), (trial, dst_bit, nbits)
+        assert not got[want.size:].any(), (trial, "bits written past the end")
+    ctx.close()
+
+
+@pytest.mark.parametrize("level,make", [(1, lambda: gen.mixed(7, 1_300_000) + gen.g2(3, 500_000)),
+                                        (9, lambda: gen.text(3, 4_000_000))])
+def test_shard_streams_joined_by_bit_append(level, make):
+    """What a sharded run does at a rank boundary: blocks [0,k) and [k,nb) are encoded into separate buffers (the
+    second one from bit 0, as a rank other than 0 does), joined with bzb200_bit_append at the — unaligned — bit where
+    the first part ends, the trailer is appended, and the result must be the oracle's stream bit for bit; every
+    split point k is tried, and a three-way split."""
+    import torch
+    from rust_compression_b200 import device as dv
+    data = make()
+    want = orc.compress(data, level)
+    d_in = torch.frombuffer(bytearray(data), dtype=torch.uint8).cuda()
+    ctx = dv.Context()
+    nb = ctx.plan(level, d_in)
+    assert nb >= 4
+    cap = (dv.max_output_bytes(level, len(data)) + 64 + 3) & ~3
+    splits = [(k,) for k in range(1, nb)] + [(1, nb - 1), (nb // 3, 2 * nb // 3)]
+    for cuts in splits:
+        edges = [0] + list(cuts) + [nb]
+        d_out = torch.zeros(cap, dtype=torch.uint8, device="cuda")
+        ctx.write_stream_header(level, d_out)
+        cur = ctx.encode_blocks(edges[0], edges[1], d_out, 32)
+        crcs = [ctx.block_table(with_crc=False)[2][edges[0]:edges[1]].copy()]
+        for lo, hi in zip(edges[1:-1], edges[2:]):
+            part = torch.zeros(cap, dtype=torch.uint8, device="cuda")
+            nbits = ctx.encode_blocks(lo, hi, part, 0)
+            crcs.append(ctx.block_table(with_crc=False)[2][lo:hi].copy())
+            ctx.bit_append(d_out, cur, part, nbits)
+            cur += nbits
+        total = ctx.write_stream_trailer(d_out, cur, ctx.combine_crc(np.concatenate(crcs)))
+        ctx.sync()
+        got = d_out[:total].cpu().numpy().tobytes()
+        assert got == want, f"split {cuts}: joined stream differs from the oracle"
     ctx.close()
