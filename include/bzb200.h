@@ -60,10 +60,18 @@ typedef struct bzb200_enc bzb200_enc;
 
 /* level 1..9 (else BZB200_E_LEVEL); device = CUDA ordinal, -1 = current device. */
 BZB200_API int bzb200_enc_create(int level, int device, bzb200_enc** out);
-/* Action::Run: append n input bytes.  Input accumulates in a window (256 MiB, env BZB200_ENC_WINDOW); whenever the
- * window is full, every block that is already closed is compressed on the GPU and its bytes become readable, while
- * the still-open last block stays buffered (the reference also yields a block as soon as it
- * closes, encoder.rs:91-107).  Only the concatenation of all bytes read is defined, not which call yields which. */
+/* The same object over several GPUs of the box: every window of input is sharded block-wise over `ngpus` devices
+ * (devices[ngpus], NULL = 0..ngpus-1) by the in-library engine of section 2c — one host thread per GPU inside the
+ * library, slices copied over all PCIe links in parallel, bit strings joined at bit granularity on the host.  This is
+ * what `BZip2Encoder::new(level)` binds on a multi-GPU box (SURVEY.md section 8(b),(e)); the stream is bit-identical
+ * to the single-GPU one. */
+BZB200_API int bzb200_enc_create_multi(int level, int ngpus, const int* devices, bzb200_enc** out);
+/* Action::Run: append n input bytes (copied into one of two pinned window buffers; 256 MiB per GPU, env
+ * BZB200_ENC_WINDOW).  A full window is handed to the object's worker thread, which compresses every block that has
+ * already closed while the caller keeps writing into the other buffer; their bytes become readable as soon as the
+ * window is done, and the still-open last block is carried in front of the next window (the
+ * reference also yields a block as soon as it closes, encoder.rs:91-107).  The call returns after the copy unless both
+ * buffers are busy.  Only the concatenation of all bytes read is defined, not which call yields which. */
 BZB200_API int bzb200_enc_write(bzb200_enc* e, const uint8_t* p, size_t n);
 /* Action::Finish: compress the remaining blocks and append the stream trailer. */
 BZB200_API int bzb200_enc_finish(bzb200_enc* e);
@@ -104,19 +112,6 @@ BZB200_API int bzb200_sync(bzb200_ctx* c);
  * over the whole input.  replaces EncoderInner::next/write_rle (encoder.rs:671-716), the cut test
  * (:692-696) and crc32::Digest (crc32.rs:82-84,129-131).  Synchronises once (block count -> host). */
 BZB200_API int bzb200_plan(bzb200_ctx* c, int level, const uint8_t* d_in, size_t n, uint32_t* nblocks);
-/* The same plan in four steps, for a sharded caller: K1's per-tile summaries (last run head, emitted bytes) are
- * computed by the rank that owns the tile range [t0,t1) into CALLER-owned device arrays of `ntiles` entries, the
- * caller exchanges the ranges between ranks (rust-compression_b200/sharded.py: NCCL all-gather), and every rank
- * finishes with the cheap global part (prefix sum + cut chain).  A tile is bzb200_plan_tile_bytes() input bytes.
- *   begin  : binds level/input, sizes the buffers, returns ntiles
- *   heads  : d_tile_head[t0..t1) = index of the last run head inside the tile (-1: none)
- *   counts : needs d_tile_head complete; d_tile_cnt[t0..t1) = RLE1 bytes the tile emits
- *   finish : needs d_tile_cnt complete; block cuts -> host; afterwards identical to bzb200_plan */
-BZB200_API size_t bzb200_plan_tile_bytes(void);
-BZB200_API int bzb200_plan_begin(bzb200_ctx* c, int level, const uint8_t* d_in, size_t n, uint64_t* ntiles);
-BZB200_API int bzb200_plan_heads(bzb200_ctx* c, uint64_t t0, uint64_t t1, int64_t* d_tile_head);
-BZB200_API int bzb200_plan_counts(bzb200_ctx* c, const int64_t* d_tile_head, uint64_t t0, uint64_t t1, uint32_t* d_tile_cnt);
-BZB200_API int bzb200_plan_finish(bzb200_ctx* c, const uint32_t* d_tile_cnt, uint32_t* nblocks);
 /* Number of blocks of the current plan (0 before any plan). */
 BZB200_API uint32_t bzb200_num_blocks(const bzb200_ctx* c);
 /* Block table of the current plan: in_off[nblocks+1] (input byte offsets), rle_off[nblocks+1] (offsets into the
@@ -163,6 +158,77 @@ BZB200_API int bzb200_compress_device(bzb200_ctx* c, int level, const uint8_t* d
  * across calls.  Pinned (page-locked) host buffers make both copies asynchronous DMA; pageable buffers work too. */
 BZB200_API int bzb200_compress_host(bzb200_ctx* c, int level, const uint8_t* h_in, size_t n, uint8_t* h_out, size_t cap_bytes,
                          size_t* out_n);
+
+/* ------------------------------------------------------------------------
+ * 2b. Sliced plan — the K1 plan when a context holds only ONE SLICE of the stream (a rank of a sharded run, one GPU of
+ *     the engine of 2c).  The reference cuts blocks in one sequential pass (encoder.rs:671-716, cut test :692-696);
+ *     here every slice works on its own bytes and three tiny exchanges between the slices — done by the caller, NCCL
+ *     all-gathers in rust-compression_b200/sharded.py, host memory in the engine — reproduce the same cuts:
+ *       begin   -> exchange the last run head of every slice (1 word)   -> counts
+ *       counts  -> exchange the bytes every slice emits (1 word)        -> prefix
+ *       windows -> exchange the cut-window rows (2 KB per block)        -> bzb200_cut_walk on the host (repeat from
+ *                  `windows` with the new start while the walk is not done: only when the drift of the cut positions
+ *                  leaves a window) -> set_blocks
+ *     A slice then encodes (bzb200_encode_blocks) the blocks that START inside it; the last of them ends in the next
+ *     slice's bytes: bzb200_slice_blocks says how far the input must be resident, the caller copies that tail behind
+ *     the slice and calls bzb200_slice_extend.  No O(input) array is exchanged.
+ * ------------------------------------------------------------------------ */
+/* Bytes behind the slice end that must be resident at bzb200_slice_begin (a cut window reaches that far at most). */
+BZB200_API size_t bzb200_slice_halo_bytes(void);
+/* Slice granularity: lo must be a multiple, hi too unless hi == N. */
+BZB200_API size_t bzb200_plan_tile_bytes(void);
+/* Binds the slice [lo, hi) of an N-byte stream.  d_lo = device address of input byte lo, 16-byte aligned; the bytes
+ * [lo - 16 (if lo > 0), avail_hi) must be in device memory around it, avail_hi >= min(N, hi + halo); reserve_hi = how
+ * far the resident part may grow later (bzb200_slice_extend; at most one block's input span past hi + halo).
+ * *last_head = input index of the last run head inside [lo, hi) (-1: none).  Synchronises. */
+BZB200_API int bzb200_slice_begin(bzb200_ctx* c, int level, uint64_t N, uint64_t lo, uint64_t hi, const uint8_t* d_lo,
+                                  uint64_t avail_hi, uint64_t reserve_hi, int64_t* last_head);
+/* carry_in = max of the last_head values of all slices in front of this one (-1: none).  *emitted = RLE1 bytes the
+ * slice emits.  Synchronises. */
+BZB200_API int bzb200_slice_counts(bzb200_ctx* c, int64_t carry_in, uint64_t* emitted);
+/* E_lo = bytes emitted by all slices in front, E_tot = by the whole stream. */
+BZB200_API int bzb200_slice_prefix(bzb200_ctx* c, uint64_t E_lo, uint64_t E_tot);
+/* Cut windows of the phase that starts at emitted offset x0 whose centre x0 + (j+1) T falls into the slice: rows
+ * j0 .. j0 + nj - 1, bzb200_cut_window() 64-bit entries each, in device memory owned by the context (*d_F, valid until
+ * the next call; stream ordered). */
+BZB200_API int bzb200_slice_windows(bzb200_ctx* c, uint64_t x0, uint64_t* j0, uint32_t* nj, const uint64_t** d_F);
+BZB200_API uint32_t bzb200_cut_window(void);
+/* HOST: follows the greedy cut chain (encoder.rs:692-696) through the rows F[0 .. K) of one phase.  state[4] = {blocks
+ * cut so far, emitted offset where the open block starts, done, longest block} — all zero before the first phase; the
+ * phase's x0 is state[1] on entry.  in_off / rle_off need max_blocks + 1 entries (max_blocks = (N + N/4 + 64)/T + 2).
+ * When state[2] becomes 1 the table is complete: *nblocks, *max_block_len, in_off[nblocks] = N, rle_off[nblocks] = Etot. */
+BZB200_API int bzb200_cut_walk(const uint64_t* F, uint64_t K, uint32_t T, uint64_t Etot, uint64_t N, uint32_t max_blocks,
+                               uint64_t* state, uint64_t* in_off, uint64_t* rle_off, uint32_t* nblocks,
+                               uint32_t* max_block_len);
+/* Gives the context the block table every slice agreed on; afterwards bzb200_block_table / bzb200_encode_blocks /
+ * bzb200_debug_stage work as after bzb200_plan, for blocks whose input is resident. */
+BZB200_API int bzb200_slice_set_blocks(bzb200_ctx* c, uint32_t nblocks, const uint64_t* in_off, const uint64_t* rle_off,
+                                       uint32_t max_block_len);
+/* [*b0, *b1) = the blocks that start inside the slice; *need_hi = how far the input must be resident to encode them. */
+BZB200_API int bzb200_slice_blocks(const bzb200_ctx* c, uint32_t* b0, uint32_t* b1, uint64_t* need_hi);
+/* More input bytes have been copied behind the slice: the resident part now ends at avail_hi (<= reserve_hi). */
+BZB200_API int bzb200_slice_extend(bzb200_ctx* c, uint64_t avail_hi);
+
+/* ------------------------------------------------------------------------
+ * 2c. Multi-GPU engine, one process: a pool of contexts (one worker thread per GPU inside the library) that compresses
+ *     HOST buffers block-wise over several GPUs with the sliced plan of 2b.  Every GPU copies its own slice in and its
+ *     own bit string out (all PCIe links in parallel); the bit strings are shifted to their bit phase on their GPU
+ *     (K7), the bytes two neighbours share are OR-ed and the trailer written on the host — the bit-granular
+ *     concatenation of BitWriter<Left> (bitio/writer.rs:186-242).  Bit-identical to bzb200_compress_host.
+ *     Environment: BZB200_MG_CTX_PER_GPU (contexts and worker threads per GPU, default 1).
+ * ------------------------------------------------------------------------ */
+typedef struct bzb200_pool bzb200_pool;
+/* devices[ngpus] = CUDA ordinals, NULL = 0 .. ngpus-1. */
+BZB200_API int bzb200_pool_create(int ngpus, const int* devices, bzb200_pool** out);
+BZB200_API void bzb200_pool_destroy(bzb200_pool* p);
+/* Workers (contexts) of the pool. */
+BZB200_API int bzb200_pool_size(const bzb200_pool* p);
+BZB200_API const char* bzb200_pool_last_error(const bzb200_pool* p);
+/* Whole stream, HOST in -> HOST out (pinned buffers make every copy asynchronous DMA); synchronised on return. */
+BZB200_API int bzb200_pool_compress_host(bzb200_pool* p, int level, const uint8_t* h_in, size_t n, uint8_t* h_out,
+                                         size_t cap_bytes, size_t* out_n);
+/* out[0..3]: spans compressed, blocks encoded, cut-chain phases run, kernels launched by all workers. */
+BZB200_API int bzb200_pool_stats(const bzb200_pool* p, uint64_t* out, size_t cap);
 
 /* ------------------------------------------------------------------------
  * 3. Decoder — block-parallel bzip2 decompression of whole buffers.

@@ -45,10 +45,25 @@ SIGNATURES = {
     "bzb200_path_stats": (C.c_int, [_P, C.POINTER(C.c_uint64), C.c_size_t]),
     "bzb200_block_crcs": (C.c_int, [_P, C.c_void_p, C.c_size_t]),
     "bzb200_plan_tile_bytes": (C.c_size_t, []),
-    "bzb200_plan_begin": (C.c_int, [_P, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_uint64)]),
-    "bzb200_plan_heads": (C.c_int, [_P, C.c_uint64, C.c_uint64, C.c_void_p]),
-    "bzb200_plan_counts": (C.c_int, [_P, C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]),
-    "bzb200_plan_finish": (C.c_int, [_P, C.c_void_p, C.POINTER(C.c_uint32)]),
+    "bzb200_enc_create_multi": (C.c_int, [C.c_int, C.c_int, _P, C.POINTER(_P)]),
+    "bzb200_slice_halo_bytes": (C.c_size_t, []),
+    "bzb200_slice_begin": (C.c_int, [_P, C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, _P, C.c_uint64, C.c_uint64,
+                                     C.POINTER(C.c_int64)]),
+    "bzb200_slice_counts": (C.c_int, [_P, C.c_int64, C.POINTER(C.c_uint64)]),
+    "bzb200_slice_prefix": (C.c_int, [_P, C.c_uint64, C.c_uint64]),
+    "bzb200_slice_windows": (C.c_int, [_P, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint32), C.POINTER(_P)]),
+    "bzb200_cut_window": (C.c_uint32, []),
+    "bzb200_cut_walk": (C.c_int, [_P, C.c_uint64, C.c_uint32, C.c_uint64, C.c_uint64, C.c_uint32, _P, _P, _P,
+                                  C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
+    "bzb200_slice_set_blocks": (C.c_int, [_P, C.c_uint32, _P, _P, C.c_uint32]),
+    "bzb200_slice_blocks": (C.c_int, [_P, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)]),
+    "bzb200_slice_extend": (C.c_int, [_P, C.c_uint64]),
+    "bzb200_pool_create": (C.c_int, [C.c_int, _P, C.POINTER(_P)]),
+    "bzb200_pool_destroy": (None, [_P]),
+    "bzb200_pool_size": (C.c_int, [_P]),
+    "bzb200_pool_last_error": (C.c_char_p, [_P]),
+    "bzb200_pool_compress_host": (C.c_int, [_P, C.c_int, _P, C.c_size_t, _P, C.c_size_t, C.POINTER(C.c_size_t)]),
+    "bzb200_pool_stats": (C.c_int, [_P, _P, C.c_size_t]),
     "bzb200_version": (C.c_char_p, []),
     "bzb200_decompress_device": (C.c_int, [_P, _P, C.c_size_t, _P, C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(C.c_int)]),
     "bzb200_decompress_host": (C.c_int, [_P, _P, C.c_size_t, _P, C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(C.c_int)]),

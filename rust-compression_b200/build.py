@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libbzb200.so")
-SOURCES = ["k1_rle.cu", "k2_bwt.cu", "k3_mtf.cu", "k4_huff.cu", "k6_pack.cu", "decoder.cu", "pipeline.cu", "enc_stream.cu", "dec_abi.cu"]
+SOURCES = ["k1_rle.cu", "k2_bwt.cu", "k3_mtf.cu", "k4_huff.cu", "k6_pack.cu", "decoder.cu", "pipeline.cu", "slice_plan.cu", "mgpu.cu", "enc_stream.cu", "dec_abi.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
          "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr"]

@@ -3,38 +3,305 @@
 // host side; every stage runs through the context API of pipeline.cu.
 #include "host_ctx.h"
 
+#include <condition_variable>
+#include <deque>
+#include <mutex>
+#include <thread>
+
+#include "mgpu.h"
+
 extern "C" {
+int bzb200_pool_create(int ngpus, const int* devices, bzb200_pool** out);
+void bzb200_pool_destroy(bzb200_pool* p);
+}
 
 // ------------------------------------------------------------------ streaming encoder (BZip2Encoder)
-// Action::Run pipelining: input accumulates in a window; when the window is full, the bytes from
-// the last block cut onwards are planned as a stream of their own, every block that is already closed is encoded and
-// its bytes become readable at once (the reference also yields a block as soon as it closes, encoder.rs:91-107), and
-// the still-open last block stays buffered.  A block cut is a piece boundary, so RLE1 restarts there exactly as in
-// the one-pass plan; the partial last byte of the bit stream is carried into the next window.
+// Action::Run pipelining (the reference hands a block out as soon as it closes, encoder.rs:91-107).
+// The caller's bytes are copied into one of two pinned window buffers; a full window is handed to the object's worker
+// thread, which runs it through the GPU engine (mgpu.cu: all GPUs of the object) while the caller keeps filling the
+// other buffer.  A window is planned as a stream of its own from the last block cut onwards — a cut is a piece
+// boundary, so RLE1 restarts there exactly as in the one-pass plan — every block but the still-open last one is
+// encoded, their bytes become readable at once, and the open block's input is carried in front of the next window
+// together with the partial last byte of the bit stream.
+namespace {
+
+struct HostBuf {  // pinned when possible (async DMA), pageable otherwise
+  uint8_t* p = nullptr;
+  size_t cap = 0;
+  bool pinned = false;
+  void release() {
+    if (p) {
+      if (pinned) cudaFreeHost(p);
+      else free(p);
+    }
+    p = nullptr;
+    cap = 0;
+  }
+  bool reserve(size_t bytes, size_t keep_lo = 0, size_t keep_hi = 0, size_t shift = 0) {  // keeps [keep_lo,keep_hi), moved up by shift
+    if (cap >= bytes && shift == 0) return true;
+    uint8_t* q = nullptr;
+    bool pin = cudaHostAlloc((void**)&q, bytes, cudaHostAllocPortable) == cudaSuccess;
+    if (!pin) {
+      cudaGetLastError();
+      q = (uint8_t*)malloc(bytes);
+      if (!q) return false;
+    }
+    if (p && keep_hi > keep_lo) memcpy(q + keep_lo + shift, p + keep_lo, keep_hi - keep_lo);
+    release();
+    p = q;
+    cap = bytes;
+    pinned = pin;
+    return true;
+  }
+};
+
+struct OutChunk {
+  HostBuf buf;
+  size_t len = 0, rd = 0;
+};
+
+}  // namespace
+
 struct bzb200_enc {
   int level = 9;
-  int device = -1;
-  bzb200_ctx* ctx = nullptr;
-  std::vector<uint8_t> in;   // input from the last block cut onwards
-  std::vector<uint8_t> out;  // finished output bytes
-  size_t rd = 0;
-  bool finished = false;
-  bool started = false;      // the stream header has been written
-  uint32_t carry_bits = 0;   // valid bits (0..7) of the partial last byte
-  uint8_t carry = 0;
-  uint32_t combined = 0;     // combined CRC of the blocks encoded so far (encoder.rs:237-238)
-  uint64_t blocks = 0, windows = 0;
+  std::vector<int> devs;     // one entry per GPU; {-1} = the current device
+  bzb200_pool* pool = nullptr;
   size_t window = (size_t)256 << 20;
+  // the window being filled: data in win[cur].p[lo, hi); room in front of lo for the carried open block
+  HostBuf win[2];
+  int cur = 0;
+  size_t lo = 0, hi = 0;
+  // worker
+  std::thread th;
+  std::mutex mu;
+  std::condition_variable cv;
+  bool has_task = false, busy = false, quit = false, th_started = false;
+  int t_buf = 0;
+  size_t t_lo = 0, t_hi = 0;
+  bool t_final = false;
+  size_t tail_lo = 0, tail_hi = 0;  // result of the last task: the open block's input inside its buffer
+  int tail_buf = -1;
+  bool last_closed_none = false;
+  // stream state (touched by the worker while busy, by the caller otherwise)
+  bool started = false, finished = false;
+  uint8_t carry = 0;
+  uint32_t carry_bits = 0, combined = 0;
+  uint64_t blocks = 0, windows = 0, total_in = 0;
+  std::deque<OutChunk*> outq;
+  std::vector<OutChunk*> spare;
+  int rc = BZB200_OK;
   std::string err;
 };
 
-int bzb200_enc_create(int level, int device, bzb200_enc** out) {
+namespace {
+
+OutChunk* get_chunk(bzb200_enc* e, size_t bytes) {
+  OutChunk* c = nullptr;
+  {
+    std::lock_guard<std::mutex> g(e->mu);
+    for (size_t i = 0; i < e->spare.size(); ++i)
+      if (e->spare[i]->buf.cap >= bytes) {
+        c = e->spare[i];
+        e->spare.erase(e->spare.begin() + i);
+        break;
+      }
+    if (!c && !e->spare.empty()) {
+      c = e->spare.back();
+      e->spare.pop_back();
+    }
+  }
+  if (!c) c = new OutChunk();
+  if (c->buf.cap < bytes && !c->buf.reserve(bytes + bytes / 8)) {
+    delete c;
+    return nullptr;
+  }
+  c->len = c->rd = 0;
+  return c;
+}
+
+void put_bits_msb(uint8_t* out, uint64_t pos, uint64_t value, int len) {
+  for (int i = len - 1; i >= 0; --i, ++pos)
+    if ((value >> i) & 1) out[pos >> 3] |= (uint8_t)(0x80u >> (pos & 7));
+}
+
+// Worker side: one window through the engine.
+int run_window(bzb200_enc* e, int buf, size_t lo, size_t hi, bool final) {
+  if (!e->pool) {
+    std::vector<int> devs = e->devs;
+    if (devs.size() == 1 && devs[0] < 0) {
+      int d = 0;
+      if (cudaGetDevice(&d) != cudaSuccess) {
+        e->err = std::string("cudaGetDevice: ") + cudaGetErrorString(cudaGetLastError());
+        return BZB200_E_CUDA;
+      }
+      devs[0] = d;
+    }
+    const int r = bzb200_pool_create((int)devs.size(), devs.data(), &e->pool);
+    if (r != BZB200_OK) {
+      e->err = r == BZB200_E_CUDA ? std::string("no usable CUDA device: ") + cudaGetErrorString(cudaGetLastError())
+                                  : "pool creation failed";
+      e->pool = nullptr;
+      return r;
+    }
+  }
+  const size_t n = hi - lo;
+  if (n == 0) {  // only possible for an empty stream: header + trailer (encoder.rs:224-291 with nblock == 0)
+    OutChunk* c = get_chunk(e, 64);
+    if (!c) return BZB200_E_INTERNAL;
+    memset(c->buf.p, 0, 16);
+    uint64_t bit = 0;
+    if (!e->started) {
+      c->buf.p[0] = 'B'; c->buf.p[1] = 'Z'; c->buf.p[2] = 'h'; c->buf.p[3] = (uint8_t)('0' + e->level);
+      bit = 32;
+      e->started = true;
+    } else if (e->carry_bits) {
+      c->buf.p[0] = e->carry;
+      bit = e->carry_bits;
+    }
+    put_bits_msb(c->buf.p, bit, 0x177245385090ull, 48);
+    put_bits_msb(c->buf.p, bit + 48, e->combined, 32);
+    c->len = (size_t)((bit + 80 + 7) / 8);
+    e->carry_bits = 0;
+    std::lock_guard<std::mutex> g(e->mu);
+    e->outq.push_back(c);
+    return BZB200_OK;
+  }
+  const size_t cap = bzb200_max_output_bytes(e->level, n) + 64;
+  OutChunk* c = get_chunk(e, cap);
+  if (!c) {
+    e->err = "out of host memory";
+    return BZB200_E_INTERNAL;
+  }
+  SpanJob J;
+  J.level = e->level;
+  J.h_in = e->win[buf].p + lo;
+  J.n = n;
+  J.first = !e->started;
+  J.final = final;
+  J.carry = e->carry;
+  J.carry_bits = e->started ? e->carry_bits : 0;
+  J.combined = e->combined;
+  J.h_out = c->buf.p;
+  J.cap = c->buf.cap;
+  J.end_bits = J.consumed = J.blocks = 0;
+  const int r = pool_run_span(e->pool, &J);
+  if (r != BZB200_OK) {
+    e->err = pool_error(e->pool);
+    std::lock_guard<std::mutex> g(e->mu);
+    e->spare.push_back(c);
+    return r;
+  }
+  e->started = true;
+  e->combined = J.combined;
+  e->blocks += J.blocks;
+  e->windows += 1;
+  if (final) {
+    c->len = (size_t)((J.end_bits + 7) / 8);
+    e->carry_bits = 0;
+    e->tail_buf = -1;
+  } else {
+    c->len = (size_t)(J.end_bits / 8);
+    e->carry_bits = (uint32_t)(J.end_bits & 7);
+    e->carry = e->carry_bits ? c->buf.p[c->len] : 0;
+    e->tail_buf = buf;
+    e->tail_lo = lo + (size_t)J.consumed;
+    e->tail_hi = hi;
+    e->last_closed_none = J.blocks == 0;
+  }
+  std::lock_guard<std::mutex> g(e->mu);
+  if (c->len) e->outq.push_back(c);
+  else e->spare.push_back(c);
+  return BZB200_OK;
+}
+
+void enc_worker(bzb200_enc* e) {
+  for (;;) {
+    int buf;
+    size_t lo, hi;
+    bool final;
+    {
+      std::unique_lock<std::mutex> lk(e->mu);
+      e->cv.wait(lk, [&] { return e->quit || e->has_task; });
+      if (e->quit) return;
+      buf = e->t_buf; lo = e->t_lo; hi = e->t_hi; final = e->t_final;
+      e->has_task = false;
+    }
+    int r;
+    try {
+      r = run_window(e, buf, lo, hi, final);
+    } catch (const std::exception&) {
+      r = BZB200_E_INTERNAL;
+      e->err = "out of host memory";
+    }
+    {
+      std::lock_guard<std::mutex> lk(e->mu);
+      if (r != BZB200_OK && e->rc == BZB200_OK) e->rc = r;
+      e->busy = false;
+    }
+    e->cv.notify_all();
+  }
+}
+
+void wait_idle(bzb200_enc* e) {
+  std::unique_lock<std::mutex> lk(e->mu);
+  e->cv.wait(lk, [&] { return !e->busy; });
+}
+
+// Caller side: hands win[cur][lo,hi) to the worker (after the previous window is done and its open block has been
+// put in front of this one) and switches to the other buffer.
+int submit(bzb200_enc* e, bool final) {
+  wait_idle(e);
+  if (e->rc != BZB200_OK) return e->rc;
+  if (e->tail_buf >= 0 && e->tail_hi > e->tail_lo) {  // carried open block: goes in front of the current data
+    const size_t tail = e->tail_hi - e->tail_lo;
+    HostBuf& B = e->win[e->cur];
+    if (e->lo < tail) {  // not enough room in front: move the data up (rare: a window smaller than a block)
+      const size_t shift = tail - e->lo + (tail >> 1);
+      if (!B.reserve(B.cap + shift + 64, e->lo, e->hi, shift)) return BZB200_E_INTERNAL;
+      e->lo += shift;
+      e->hi += shift;
+    }
+    memcpy(B.p + e->lo - tail, e->win[e->tail_buf].p + e->tail_lo, tail);
+    e->lo -= tail;
+    if (e->last_closed_none) e->window = std::max(e->window * 2, (e->hi - e->lo) + 1);  // let the window grow
+  }
+  e->tail_buf = -1;
+  if (!e->th_started) {
+    e->th = std::thread(enc_worker, e);
+    e->th_started = true;
+  }
+  {
+    std::lock_guard<std::mutex> lk(e->mu);
+    e->t_buf = e->cur;
+    e->t_lo = e->lo;
+    e->t_hi = e->hi;
+    e->t_final = final;
+    e->has_task = true;
+    e->busy = true;
+  }
+  e->cv.notify_all();
+  e->cur ^= 1;
+  e->lo = e->hi = 0;  // set up by the next write
+  return BZB200_OK;
+}
+
+// Room for the carried open block in front of a window: a level-9 block of text spans ~0.9 MB of input; longer spans
+// (runs) are handled by moving the data (submit).
+size_t front_room(const bzb200_enc* e) { return std::min<size_t>(e->window, (size_t)e->level * 200000) + 4096; }
+
+}  // namespace
+
+extern "C" {
+
+static int enc_create(int level, const int* devices, int ngpus, bzb200_enc** out) {
   if (!out) return BZB200_E_ARG;
   *out = nullptr;
   if (level < 1 || level > 9) return BZB200_E_LEVEL;  // BZip2Encoder::new panics "invalid level"
+  if (ngpus < 1 || ngpus > 64) return BZB200_E_ARG;
   bzb200_enc* e = new bzb200_enc();
   e->level = level;
-  e->device = device;
+  for (int g = 0; g < ngpus; ++g) e->devs.push_back(devices ? devices[g] : g);
+  e->window = ((size_t)256 << 20) * (size_t)ngpus;
   if (const char* w = getenv("BZB200_ENC_WINDOW")) {
     unsigned long long v = strtoull(w, nullptr, 10);
     if (v >= 1) e->window = (size_t)v;
@@ -43,71 +310,10 @@ int bzb200_enc_create(int level, int device, bzb200_enc** out) {
   return BZB200_OK;
 }
 
-// Compresses the closed blocks of the buffered input (all blocks and the trailer when `final`).
-static int enc_pump(bzb200_enc* e, bool final) {
-  if (!e->ctx) {
-    int r = bzb200_ctx_create_impl(e->device, nullptr, true, &e->ctx);
-    if (r != BZB200_OK) {
-      e->err = e->ctx ? e->ctx->err : "context creation failed";
-      if (e->ctx) { bzb200_ctx_destroy(e->ctx); e->ctx = nullptr; }
-      return r;
-    }
-  }
-  bzb200_ctx* c = e->ctx;
-  int r = BZB200_OK;
-  auto fail = [&](int code) {
-    if (code == BZB200_E_CUDA && c->err.empty()) c->err = std::string("cuda: ") + cudaGetErrorString(cudaGetLastError());
-    e->err = c->err;
-    return code;
-  };
-  if ((r = set_device(c)) != BZB200_OK) return fail(r);
-  const size_t n = e->in.size();
-  const size_t cap = bzb200_max_output_bytes(e->level, n) + 16;
-  if ((r = ensure(c, c->stage_in, n + 16)) != BZB200_OK) return fail(r);
-  if ((r = ensure(c, c->stage_out, cap)) != BZB200_OK) return fail(r);
-  uint8_t* d_in = ptr<uint8_t>(c->stage_in);
-  uint8_t* d_out = ptr<uint8_t>(c->stage_out);
-  if (n && cudaMemcpyAsync(d_in, e->in.data(), n, cudaMemcpyHostToDevice, c->stream) != cudaSuccess) return fail(BZB200_E_CUDA);
-  if (cudaMemsetAsync(d_out, 0, cap, c->stream) != cudaSuccess) return fail(BZB200_E_CUDA);
-  uint64_t bit = 0;
-  if (!e->started) {
-    if ((r = bzb200_write_stream_header(c, e->level, d_out, cap)) != BZB200_OK) return fail(r);
-    bit = 32;
-    e->started = true;
-  } else if (e->carry_bits) {
-    if (cudaMemcpyAsync(d_out, &e->carry, 1, cudaMemcpyHostToDevice, c->stream) != cudaSuccess) return fail(BZB200_E_CUDA);
-    bit = e->carry_bits;
-  }
-  uint32_t nb = 0;
-  if ((r = bzb200_plan(c, e->level, d_in, n, &nb)) != BZB200_OK) return fail(r);
-  const uint32_t nenc = final ? nb : (nb ? nb - 1 : 0);  // the last block of a window is still open
-  size_t consumed = 0;
-  if (nenc) {
-    if ((r = bzb200_encode_blocks(c, 0, nenc, d_out, cap, bit, &bit)) != BZB200_OK) return fail(r);
-    e->combined = bzb200_combine_crc(e->combined, c->h_crc.data(), nenc);
-    consumed = (size_t)c->h_in_off[nenc];
-    e->blocks += nenc;
-  }
-  size_t take = (size_t)(bit / 8);  // whole bytes that are final
-  if (final) {
-    if ((r = bzb200_write_stream_trailer(c, d_out, cap, bit, e->combined, &take)) != BZB200_OK) return fail(r);
-    e->carry_bits = 0;
-  } else {
-    e->carry_bits = (uint32_t)(bit & 7);
-  }
-  const size_t fetch = take + ((!final && e->carry_bits) ? 1 : 0);
-  const size_t at = e->out.size();
-  e->out.resize(at + fetch);
-  if (fetch && cudaMemcpyAsync(e->out.data() + at, d_out, fetch, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess)
-    return fail(BZB200_E_CUDA);
-  if (cudaStreamSynchronize(c->stream) != cudaSuccess) return fail(BZB200_E_CUDA);
-  if (fetch > take) {
-    e->carry = e->out.back();
-    e->out.pop_back();
-  }
-  e->in.erase(e->in.begin(), e->in.begin() + consumed);
-  ++e->windows;
-  return BZB200_OK;
+int bzb200_enc_create(int level, int device, bzb200_enc** out) { return enc_create(level, &device, 1, out); }
+
+int bzb200_enc_create_multi(int level, int ngpus, const int* devices, bzb200_enc** out) {
+  return enc_create(level, devices, ngpus, out);
 }
 
 int bzb200_enc_write(bzb200_enc* e, const uint8_t* p, size_t n) {
@@ -116,23 +322,36 @@ int bzb200_enc_write(bzb200_enc* e, const uint8_t* p, size_t n) {
     e->err = "write after finish";
     return BZB200_E_STATE;
   }
-  while (n) {
-    const size_t room = e->in.size() < e->window ? e->window - e->in.size() : 0;
-    const size_t take = std::min(n, std::max<size_t>(room, 1));
-    e->in.insert(e->in.end(), p, p + take);
-    p += take;
-    n -= take;
-    if (e->in.size() >= e->window) {
-      const size_t before = e->in.size();
-      int r = enc_pump(e, false);
-      if (r != BZB200_OK) return r;
-      if (e->in.size() == before) {
-        // not even one closed block in a full window (window smaller than a block): let the window grow
-        e->in.insert(e->in.end(), p, p + n);
-        e->window = std::max(e->window * 2, e->in.size() + 1);
-        n = 0;
+  if (e->rc != BZB200_OK) return e->rc;
+  try {
+    while (n) {
+      HostBuf& B = e->win[e->cur];
+      if (e->hi == e->lo && e->lo == 0) e->lo = e->hi = front_room(e);  // a fresh window
+      const size_t want = e->lo + e->window;
+      if (B.cap < want + 64) {
+        // first use (or a grown window): the buffer is sized once for the window, not per write
+        if (!B.reserve(want + 64, e->lo, e->hi)) {
+          e->err = "out of host memory";
+          return BZB200_E_INTERNAL;
+        }
+      }
+      const size_t room = want > e->hi ? want - e->hi : 0;
+      const size_t take = std::min(n, room);
+      if (take) {
+        memcpy(B.p + e->hi, p, take);
+        e->hi += take;
+        e->total_in += take;
+        p += take;
+        n -= take;
+      }
+      if (e->hi >= want) {
+        const int r = submit(e, false);
+        if (r != BZB200_OK) return r;
       }
     }
+  } catch (const std::exception&) {
+    e->err = "out of host memory";
+    return BZB200_E_INTERNAL;
   }
   return BZB200_OK;
 }
@@ -140,33 +359,64 @@ int bzb200_enc_write(bzb200_enc* e, const uint8_t* p, size_t n) {
 int bzb200_enc_finish(bzb200_enc* e) {
   if (!e) return BZB200_E_ARG;
   if (e->finished) return BZB200_OK;
-  int r = enc_pump(e, true);
-  if (r != BZB200_OK) return r;
-  e->in.clear();
-  e->in.shrink_to_fit();
+  if (e->rc != BZB200_OK) return e->rc;
+  try {
+    if (e->hi == e->lo && e->lo == 0) {  // nothing in the current buffer: it still has to carry the open block
+      if (!e->win[e->cur].reserve(front_room(e) + 64)) return BZB200_E_INTERNAL;
+      e->lo = e->hi = front_room(e);
+    }
+    const int r = submit(e, true);
+    if (r != BZB200_OK) return r;
+  } catch (const std::exception&) {
+    e->err = "out of host memory";
+    return BZB200_E_INTERNAL;
+  }
+  wait_idle(e);
+  if (e->rc != BZB200_OK) return e->rc;
   e->finished = true;
   return BZB200_OK;
 }
 
 size_t bzb200_enc_read(bzb200_enc* e, uint8_t* dst, size_t cap) {
   if (!e || !dst) return 0;
-  size_t n = std::min(cap, e->out.size() - e->rd);
-  if (n) memcpy(dst, e->out.data() + e->rd, n);
-  e->rd += n;
-  if (e->rd == e->out.size() && !e->finished) {  // drained mid-stream: drop the bytes already handed out
-    e->out.clear();
-    e->rd = 0;
+  size_t got = 0;
+  std::lock_guard<std::mutex> g(e->mu);
+  while (got < cap && !e->outq.empty()) {
+    OutChunk* c = e->outq.front();
+    const size_t n = std::min(cap - got, c->len - c->rd);
+    memcpy(dst + got, c->buf.p + c->rd, n);
+    c->rd += n;
+    got += n;
+    if (c->rd == c->len) {
+      e->outq.pop_front();
+      e->spare.push_back(c);
+    }
   }
+  return got;
+}
+
+size_t bzb200_enc_output_size(const bzb200_enc* e) {
+  if (!e) return 0;
+  bzb200_enc* m = const_cast<bzb200_enc*>(e);
+  std::lock_guard<std::mutex> g(m->mu);
+  size_t n = 0;
+  for (const OutChunk* c : e->outq) n += c->len - c->rd;
   return n;
 }
 
-size_t bzb200_enc_output_size(const bzb200_enc* e) { return e ? e->out.size() - e->rd : 0; }
-
 int bzb200_enc_reset(bzb200_enc* e) {
   if (!e) return BZB200_E_ARG;
-  e->in.clear();
-  e->out.clear();
-  e->rd = 0;
+  wait_idle(e);
+  {
+    std::lock_guard<std::mutex> g(e->mu);
+    for (OutChunk* c : e->outq) e->spare.push_back(c);
+    e->outq.clear();
+  }
+  e->lo = e->hi = 0;
+  e->cur = 0;
+  e->tail_buf = -1;
+  e->tail_lo = e->tail_hi = 0;
+  e->last_closed_none = false;
   e->finished = false;
   e->started = false;
   e->carry_bits = 0;
@@ -174,13 +424,28 @@ int bzb200_enc_reset(bzb200_enc* e) {
   e->combined = 0;
   e->blocks = 0;
   e->windows = 0;
+  e->total_in = 0;
+  e->rc = BZB200_OK;
   e->err.clear();
   return BZB200_OK;
 }
 
 void bzb200_enc_destroy(bzb200_enc* e) {
   if (!e) return;
-  if (e->ctx) bzb200_ctx_destroy(e->ctx);
+  if (e->th_started) {
+    wait_idle(e);
+    {
+      std::lock_guard<std::mutex> lk(e->mu);
+      e->quit = true;
+    }
+    e->cv.notify_all();
+    e->th.join();
+  }
+  if (e->pool) bzb200_pool_destroy(e->pool);
+  for (OutChunk* c : e->outq) { c->buf.release(); delete c; }
+  for (OutChunk* c : e->spare) { c->buf.release(); delete c; }
+  e->win[0].release();
+  e->win[1].release();
   delete e;
 }
 
@@ -188,7 +453,8 @@ const char* bzb200_enc_last_error(const bzb200_enc* e) { return e ? e->err.c_str
 
 int bzb200_enc_stats(const bzb200_enc* e, uint64_t* out, size_t cap) {
   if (!e || !out) return BZB200_E_ARG;
-  const uint64_t v[4] = {e->blocks, e->windows, (uint64_t)e->in.size(), (uint64_t)(e->out.size() - e->rd)};
+  const uint64_t v[4] = {e->blocks, e->windows, (uint64_t)(e->hi - e->lo) + (e->tail_buf >= 0 ? e->tail_hi - e->tail_lo : 0),
+                         (uint64_t)bzb200_enc_output_size(e)};
   for (size_t i = 0; i < cap && i < 4; ++i) out[i] = v[i];
   return BZB200_OK;
 }

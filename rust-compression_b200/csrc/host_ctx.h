@@ -44,6 +44,18 @@ struct bzb200_ctx {
   DevBuf tile_head, tile_carry, tile_cnt, tile_E, in_off, rle_off, txt, crc, inuse, scal, cut_state, cut_F;
   uint32_t prep_lo = 0, prep_hi = 0;  // blocks whose RLE1 bytes, CRC and in-use map are on the device
   bool crc_all = false;
+  // ---- sliced plan (include/bzb200.h section 2b): this context holds input bytes [sl_lo, sl_avail) of an n_in-byte
+  // stream; d_in / tile arrays / txt are then addressed through the v_*() accessors below, which shift the pointers so
+  // that GLOBAL byte, tile and emitted-offset indices work unchanged in every kernel
+  bool sliced = false;
+  const uint8_t* sl_d_lo = nullptr;            // device address of input byte sl_lo
+  uint64_t sl_lo = 0, sl_hi = 0, sl_avail = 0;  // own bytes [sl_lo, sl_hi); resident up to sl_avail (halo / block tail)
+  uint64_t sl_t0 = 0, sl_t1 = 0, sl_tn = 0;    // own tiles [t0, t1); tiles [t0, tn) have summaries (resident + 1 byte)
+  long long sl_carry_in = -1;                  // last run head before the slice
+  uint64_t sl_E_lo = 0, sl_E_hi = 0, sl_E_tot = 0;  // emitted offsets at sl_lo / sl_hi / end of the stream
+  uint64_t txt_origin = 0;                     // emitted offset of txt.p[0]
+  int sl_stage = 0;                            // 1 begun, 2 counted, 3 prefixed
+  DevBuf sl_F, sl_sum;
   std::vector<uint64_t> h_in_off, h_rle_off;
   std::vector<uint32_t> h_crc;
 
@@ -128,6 +140,14 @@ T* ptr(DevBuf& b) {
 
 inline int level_of(const bzb200_ctx* c) { return c->level; }
 
+// Pointers addressed by global indices (identity unless the plan is sliced).
+inline const uint8_t* v_in(const bzb200_ctx* c) { return c->sliced ? c->sl_d_lo - c->sl_lo : c->d_in; }
+inline long long* v_carry(bzb200_ctx* c) { return ptr<long long>(c->tile_carry) - (c->sliced ? c->sl_t0 : 0); }
+inline long long* v_head(bzb200_ctx* c) { return ptr<long long>(c->tile_head) - (c->sliced ? c->sl_t0 : 0); }
+inline uint32_t* v_cnt(bzb200_ctx* c) { return ptr<uint32_t>(c->tile_cnt) - (c->sliced ? c->sl_t0 : 0); }
+inline uint64_t* v_E(bzb200_ctx* c) { return ptr<uint64_t>(c->tile_E) - (c->sliced ? c->sl_t0 : 0); }
+inline uint8_t* v_txt(bzb200_ctx* c) { return ptr<uint8_t>(c->txt) - c->txt_origin; }
+
 inline int set_device(bzb200_ctx* c) {
   CK(c, cudaSetDevice(c->device));
   return BZB200_OK;
@@ -136,3 +156,6 @@ inline int set_device(bzb200_ctx* c) {
 // Creates a context; own_stream: the context creates (and later destroys) a non-blocking stream of its own.
 // Defined in pipeline.cu; hidden visibility (only BZB200_API symbols are exported).
 int bzb200_ctx_create_impl(int device, void* stream, bool own_stream, bzb200_ctx** out);
+
+// slice_plan.cu: sizes the RLE1 buffer of a sliced context for blocks [b0, b1) and sets its origin.
+int slice_reserve_txt(bzb200_ctx* c, uint32_t b0, uint32_t b1);

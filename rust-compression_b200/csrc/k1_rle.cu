@@ -136,14 +136,15 @@ __global__ void __launch_bounds__(K1_NT) k1_tile_heads(const uint8_t* __restrict
 
 // ---- generic single-CTA scans over per-tile arrays ----
 constexpr int SC_NT = 1024;
+// `init` = value carried into element 0 (a slice of a longer array: the maximum of everything before the slice).
 __global__ void __launch_bounds__(SC_NT) k_scan_max64_excl(const long long* __restrict__ in, long long* __restrict__ out,
-                                                           uint64_t n) {
+                                                           uint64_t n, long long init) {
   __shared__ long long ws[SC_NT / 32];
   uint64_t per = (n + SC_NT - 1) / SC_NT;
   uint64_t lo = min(n, per * threadIdx.x), hi = min(n, lo + per);
   long long m = -1;
   for (uint64_t i = lo; i < hi; ++i) m = max(m, in[i]);
-  long long carry = cta_excl_scan_max64<SC_NT>(m, ws);
+  long long carry = max(cta_excl_scan_max64<SC_NT>(m, ws), init);
   for (uint64_t i = lo; i < hi; ++i) {
     long long v = in[i];
     out[i] = carry;
@@ -151,9 +152,9 @@ __global__ void __launch_bounds__(SC_NT) k_scan_max64_excl(const long long* __re
   }
 }
 
-// out has n+1 entries: exclusive prefix, out[n] = total.
+// out has n+1 entries: exclusive prefix, out[n] = total; `init` is added to all of them (a slice of a longer array).
 __global__ void __launch_bounds__(SC_NT) k_scan_add64_excl(const uint32_t* __restrict__ in, uint64_t* __restrict__ out,
-                                                           uint64_t n) {
+                                                           uint64_t n, unsigned long long init) {
   __shared__ unsigned long long ws[SC_NT / 32 + 1];
   uint64_t per = (n + SC_NT - 1) / SC_NT;
   uint64_t lo = min(n, per * threadIdx.x), hi = min(n, lo + per);
@@ -181,13 +182,38 @@ __global__ void __launch_bounds__(SC_NT) k_scan_add64_excl(const uint32_t* __res
     if (lane_id() == 31) ws[32] = xi;
   }
   __syncthreads();
-  unsigned long long carry = inc - s + ws[w];
+  unsigned long long carry = inc - s + ws[w] + init;
   for (uint64_t i = lo; i < hi; ++i) {
     uint32_t v = in[i];
     out[i] = carry;
     carry += v;
   }
-  if (threadIdx.x == 0) out[n] = ws[32];
+  if (threadIdx.x == 0) out[n] = ws[32] + init;
+}
+
+// Slice summaries for a sharded plan: out[0] = max of head[0..n) (-1: none), out[1] = sum of cnt[0..n).  One CTA.
+__global__ void __launch_bounds__(SC_NT) k1_slice_summary(const long long* __restrict__ head, const uint32_t* __restrict__ cnt,
+                                                          uint64_t n, unsigned long long* __restrict__ out) {
+  __shared__ long long wm[SC_NT / 32];
+  __shared__ unsigned long long wsum[SC_NT / 32];
+  long long m = -1;
+  unsigned long long s = 0;
+  for (uint64_t i = threadIdx.x; i < n; i += SC_NT) {
+    if (head) m = max(m, head[i]);
+    if (cnt) s += cnt[i];
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    m = max(m, __shfl_xor_sync(0xffffffffu, m, d));
+    s += __shfl_xor_sync(0xffffffffu, s, d);
+  }
+  if (lane_id() == 0) { wm[threadIdx.x >> 5] = m; wsum[threadIdx.x >> 5] = s; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < SC_NT / 32; ++w) { m = max(m, wm[w]); s += wsum[w]; }
+    if (head) out[0] = (unsigned long long)m;
+    if (cnt) out[1] = s;
+  }
 }
 
 // Evaluate one tile with the whole CTA: per-thread ThreadEval + exclusive emitted offset inside the tile.
@@ -248,21 +274,19 @@ __global__ void __launch_bounds__(K1_NT) k1_scatter(const uint8_t* __restrict__ 
 constexpr int CW_W = 256;
 constexpr uint64_t CW_LAST = 1ull << 63;  // the piece is the last piece of the input: no cut (encoder.rs:729-739)
 
-__global__ void __launch_bounds__(K1_NT) k1_cut_windows(const uint8_t* __restrict__ in, uint64_t N,
-                                                        const long long* __restrict__ tile_carry,
-                                                        const uint64_t* __restrict__ tile_E, uint64_t ntiles, uint32_t T,
-                                                        const uint64_t* __restrict__ state, uint64_t* __restrict__ F) {
+// One window: CTA-wide.  The first tile t with tile_E[t+1] >= center is searched in [t_lo, t_hi] (the whole input, or —
+// sharded plan — the tiles of the slice the center lies in); tiles are evaluated up to t_limit (exclusive), which must
+// reach the tile where the emitted offset passes center + CW_W + 4 (the slice's halo guarantees it).
+__device__ __forceinline__ void cut_window_body(const uint8_t* __restrict__ in, uint64_t N,
+                                                const long long* __restrict__ tile_carry,
+                                                const uint64_t* __restrict__ tile_E, uint64_t t_lo, uint64_t t_hi,
+                                                uint64_t t_limit, uint64_t center, uint64_t* __restrict__ Fj) {
   __shared__ long long ws64[K1_NT / 32];
   __shared__ uint32_t ws32[K1_NT / 32 + 1];
   __shared__ uint64_t s_lo, s_hi;
   __shared__ uint32_t s_first;
-  if (state[2]) return;  // chain already finished
-  const uint64_t x0 = state[1];
-  const uint64_t Etot = tile_E[ntiles];
-  const uint64_t center = x0 + (uint64_t)(blockIdx.x + 1) * T;
-  if (center > Etot) return;
   // first tile t with tile_E[t+1] >= center (256-ary search)
-  if (threadIdx.x == 0) { s_lo = 0; s_hi = ntiles - 1; }
+  if (threadIdx.x == 0) { s_lo = t_lo; s_hi = t_hi; }
   __syncthreads();
   while (true) {
     const uint64_t lo = s_lo, hi = s_hi;
@@ -283,8 +307,7 @@ __global__ void __launch_bounds__(K1_NT) k1_cut_windows(const uint8_t* __restric
     }
     __syncthreads();
   }
-  uint64_t* Fj = F + (uint64_t)blockIdx.x * CW_W;
-  for (uint64_t t = s_lo; t < ntiles; ++t) {
+  for (uint64_t t = s_lo; t < t_limit; ++t) {
     ThreadBytes tb;
     ThreadEval ev;
     uint32_t q[K1_BPT];
@@ -312,6 +335,31 @@ __global__ void __launch_bounds__(K1_NT) k1_cut_windows(const uint8_t* __restric
     if (tile_E[t + 1] >= center + CW_W + 4) break;  // every piece that covers an offset of the window ends by here
     __syncthreads();
   }
+}
+
+__global__ void __launch_bounds__(K1_NT) k1_cut_windows(const uint8_t* __restrict__ in, uint64_t N,
+                                                        const long long* __restrict__ tile_carry,
+                                                        const uint64_t* __restrict__ tile_E, uint64_t ntiles, uint32_t T,
+                                                        const uint64_t* __restrict__ state, uint64_t* __restrict__ F) {
+  if (state[2]) return;  // chain already finished
+  const uint64_t x0 = state[1];
+  const uint64_t Etot = tile_E[ntiles];
+  const uint64_t center = x0 + (uint64_t)(blockIdx.x + 1) * T;
+  if (center > Etot) return;
+  cut_window_body(in, N, tile_carry, tile_E, 0, ntiles - 1, ntiles, center, F + (uint64_t)blockIdx.x * CW_W);
+}
+
+// Sharded plan: windows j0 .. j0 + gridDim.x - 1 of a phase that starts at emitted offset x0, tabulated by the rank whose
+// slice [t_lo, t_hi] holds the tile the center falls into; in / tile_carry / tile_E are addressed by GLOBAL byte and
+// tile indices (the caller passes pointers shifted by the slice origin), valid for tiles [t_lo, t_limit).
+__global__ void __launch_bounds__(K1_NT) k1_cut_windows_slice(const uint8_t* __restrict__ in, uint64_t N,
+                                                              const long long* __restrict__ tile_carry,
+                                                              const uint64_t* __restrict__ tile_E, uint64_t t_lo,
+                                                              uint64_t t_hi, uint64_t t_limit, uint64_t Etot, uint32_t T,
+                                                              uint64_t x0, uint64_t j0, uint64_t* __restrict__ F) {
+  const uint64_t center = x0 + (j0 + blockIdx.x + 1) * (uint64_t)T;
+  if (center > Etot) return;
+  cut_window_body(in, N, tile_carry, tile_E, t_lo, t_hi, t_limit, center, F + (uint64_t)blockIdx.x * CW_W);
 }
 
 // state[0] = blocks cut so far (k), [1] = emitted offset where the current block starts (S), [2] = done,
@@ -495,17 +543,49 @@ void launch_k1_heads(Launcher& L, const uint8_t* d_in, uint64_t N, uint64_t t0, 
 void launch_k1_counts(Launcher& L, const uint8_t* d_in, uint64_t N, uint64_t t0, uint64_t t1,
                       const long long* d_tile_head, long long* d_tile_carry, uint32_t* d_tile_cnt) {
   uint64_t nt = k1_num_tiles(N);
-  L.launch("k_scan_max64_excl", k_scan_max64_excl, dim3(1), dim3(SC_NT), d_tile_head, d_tile_carry, nt);
+  L.launch("k_scan_max64_excl", k_scan_max64_excl, dim3(1), dim3(SC_NT), d_tile_head, d_tile_carry, nt, -1ll);
   if (t1 > t0)
     L.launch("k1_tile_counts", k1_tile_counts, dim3((unsigned)(t1 - t0)), dim3(K1_NT), d_in, N, t0,
              (const long long*)d_tile_carry, d_tile_cnt);
 }
 void launch_k1_prefix(Launcher& L, uint64_t N, const uint32_t* d_tile_cnt, uint64_t* d_tile_E) {
   uint64_t nt = k1_num_tiles(N);
-  L.launch("k_scan_add64_excl", k_scan_add64_excl, dim3(1), dim3(SC_NT), d_tile_cnt, d_tile_E, nt);
+  L.launch("k_scan_add64_excl", k_scan_add64_excl, dim3(1), dim3(SC_NT), d_tile_cnt, d_tile_E, nt, 0ull);
 }
 
 uint32_t k1_cut_window() { return CW_W; }
+
+// ---- sharded plan (one slice of the input per context; see pipeline.cu "sliced plan") ----
+// All pointers are shifted so that GLOBAL byte / tile indices address them; only tiles [t_a, t_b) are touched.
+void launch_k1_slice_heads(Launcher& L, const uint8_t* v_in, uint64_t N, uint64_t t_a, uint64_t t_b, long long* v_tile_head) {
+  if (t_b > t_a)
+    L.launch("k1_tile_heads", k1_tile_heads, dim3((unsigned)(t_b - t_a)), dim3(K1_NT), v_in, N, t_a, v_tile_head);
+}
+void launch_k1_slice_summary(Launcher& L, const long long* head, const uint32_t* cnt, uint64_t n, uint64_t* d_out2) {
+  L.launch("k1_slice_summary", k1_slice_summary, dim3(1), dim3(SC_NT), head, cnt, n,
+           reinterpret_cast<unsigned long long*>(d_out2));
+}
+void launch_k1_slice_counts(Launcher& L, const uint8_t* v_in, uint64_t N, uint64_t t_a, uint64_t t_b, long long carry_in,
+                            const long long* v_tile_head, long long* v_tile_carry, uint32_t* v_tile_cnt) {
+  if (t_b <= t_a) return;
+  L.launch("k_scan_max64_excl", k_scan_max64_excl, dim3(1), dim3(SC_NT), v_tile_head + t_a, v_tile_carry + t_a, t_b - t_a,
+           carry_in);
+  L.launch("k1_tile_counts", k1_tile_counts, dim3((unsigned)(t_b - t_a)), dim3(K1_NT), v_in, N, t_a,
+           (const long long*)v_tile_carry, v_tile_cnt);
+}
+void launch_k1_slice_prefix(Launcher& L, uint64_t t_a, uint64_t t_b, uint64_t E_in, const uint32_t* v_tile_cnt,
+                            uint64_t* v_tile_E) {
+  if (t_b <= t_a) return;
+  L.launch("k_scan_add64_excl", k_scan_add64_excl, dim3(1), dim3(SC_NT), v_tile_cnt + t_a, v_tile_E + t_a, t_b - t_a,
+           (unsigned long long)E_in);
+}
+void launch_k1_slice_windows(Launcher& L, const uint8_t* v_in, uint64_t N, uint32_t T, const long long* v_tile_carry,
+                             const uint64_t* v_tile_E, uint64_t t_lo, uint64_t t_hi, uint64_t t_limit, uint64_t Etot,
+                             uint64_t x0, uint64_t j0, uint32_t nj, uint64_t* d_F) {
+  if (nj)
+    L.launch("k1_cut_windows", k1_cut_windows_slice, dim3(nj), dim3(K1_NT), v_in, N, v_tile_carry, v_tile_E, t_lo, t_hi,
+             t_limit, Etot, T, x0, j0, d_F);
+}
 
 // One phase of the cut chain: K windows from the chain state in d_state, then the walk.
 void launch_k1_cut_phase(Launcher& L, const uint8_t* d_in, uint64_t N, uint32_t T, const long long* d_tile_carry,

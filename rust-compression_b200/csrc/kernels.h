@@ -74,6 +74,16 @@ void launch_k1_prefix(Launcher& L, uint64_t N, const uint32_t* d_tile_cnt, uint6
 void launch_k1_cut_phase(Launcher& L, const uint8_t* d_in, uint64_t N, uint32_t T, const long long* d_tile_carry,
                          const uint64_t* d_tile_E, uint32_t K, uint64_t* d_F, uint64_t* d_state, uint64_t* d_in_off,
                          uint64_t* d_rle_off, uint32_t max_blocks, uint32_t* d_nblocks, uint32_t* d_maxlen);
+// sharded plan: pointers shifted to global indices (v_*), tiles [t_a, t_b) only
+void launch_k1_slice_heads(Launcher& L, const uint8_t* v_in, uint64_t N, uint64_t t_a, uint64_t t_b, long long* v_tile_head);
+void launch_k1_slice_summary(Launcher& L, const long long* head, const uint32_t* cnt, uint64_t n, uint64_t* d_out2);
+void launch_k1_slice_counts(Launcher& L, const uint8_t* v_in, uint64_t N, uint64_t t_a, uint64_t t_b, long long carry_in,
+                            const long long* v_tile_head, long long* v_tile_carry, uint32_t* v_tile_cnt);
+void launch_k1_slice_prefix(Launcher& L, uint64_t t_a, uint64_t t_b, uint64_t E_in, const uint32_t* v_tile_cnt,
+                            uint64_t* v_tile_E);
+void launch_k1_slice_windows(Launcher& L, const uint8_t* v_in, uint64_t N, uint32_t T, const long long* v_tile_carry,
+                             const uint64_t* v_tile_E, uint64_t t_lo, uint64_t t_hi, uint64_t t_limit, uint64_t Etot,
+                             uint64_t x0, uint64_t j0, uint32_t nj, uint64_t* d_F);
 void launch_k1_scatter(Launcher& L, const uint8_t* d_in, uint64_t N, uint64_t in_lo, uint64_t in_hi,
                        const long long* d_tile_carry, const uint64_t* d_tile_E, uint8_t* d_txt);
 void launch_k5_crc(Launcher& L, const uint8_t* d_in, const uint64_t* d_in_off, uint32_t nblocks, uint32_t* d_crc);

@@ -136,7 +136,7 @@ int bzb200_ctx_create_impl(int device, void* stream, bool own_stream, bzb200_ctx
             &c->stats, &c->rounds, &c->global, &c->last, &c->origptr, &c->chunk_state, &c->chunk_zle, &c->chunk_base,
             &c->sym, &c->freq, &c->mtf_count, &c->lens, &c->rfreq, &c->sel, &c->selmtf, &c->codes, &c->gbits, &c->meta,
             &c->lm_scratch, &c->lm_list, &c->lm_count, &c->blockbit, &c->bitcursor, &c->combined, &c->stage_in,
-            &c->stage_out, &c->dec_in, &c->dec_out};
+            &c->stage_out, &c->dec_in, &c->dec_out, &c->sl_F, &c->sl_sum};
   for (DevBuf& b : c->dec_bufs) c->all.push_back(&b);
   *out = c;
   return BZB200_OK;
@@ -187,6 +187,9 @@ int bzb200_plan_begin(bzb200_ctx* c, int level, const uint8_t* d_in, size_t n, u
   TRY(set_device(c));
   c->planned = false;
   c->plan_open = false;
+  c->sliced = false;
+  c->sl_stage = 0;
+  c->txt_origin = 0;
   c->level = level;
   c->T = (uint32_t)level * 100000u - 19u;  // encoder.rs:186
   c->d_in = d_in;
@@ -313,6 +316,10 @@ int bzb200_block_table(bzb200_ctx* c, uint64_t* in_off, uint64_t* rle_off, uint3
   if (rle_off) memcpy(rle_off, c->h_rle_off.data(), c->h_rle_off.size() * 8);
   if (crc && c->nblocks) {
     if (!c->crc_all && !(c->prep_lo == 0 && c->prep_hi == c->nblocks)) {  // CRCs of blocks this context did not encode
+      if (c->sliced) {
+        c->err = "block_table: a sliced context holds the CRCs of its own blocks only (bzb200_block_crcs)";
+        return BZB200_E_STATE;
+      }
       TRY(set_device(c));
       launch_k5_crc(c->L, c->d_in, ptr<uint64_t>(c->in_off), c->nblocks, ptr<uint32_t>(c->crc));
       TRY(check_launch(c));
@@ -334,10 +341,17 @@ int bzb200_block_crcs(const bzb200_ctx* c, uint32_t* crc, size_t cap) {
 // RLE1 bytes, CRCs and in-use maps of blocks [b0, b1) (K1 scatter, K5, in-use) — only what this context encodes.
 static int prepare_blocks(bzb200_ctx* c, uint32_t b0, uint32_t b1) {
   if (b0 >= b1 || (b0 >= c->prep_lo && b1 <= c->prep_hi)) return BZB200_OK;
-  launch_k1_scatter(c->L, c->d_in, c->n_in, c->h_in_off[b0], c->h_in_off[b1], ptr<long long>(c->tile_carry),
-                    ptr<uint64_t>(c->tile_E), ptr<uint8_t>(c->txt));
-  launch_k5_crc(c->L, c->d_in, ptr<uint64_t>(c->in_off) + b0, b1 - b0, ptr<uint32_t>(c->crc) + b0);
-  launch_k1_inuse(c->L, ptr<uint8_t>(c->txt), ptr<uint64_t>(c->rle_off) + b0, b1 - b0,
+  if (c->sliced) {
+    const uint64_t need = std::min<uint64_t>(c->n_in, (c->h_in_off[b1] + k1_tile_bytes() - 1) / k1_tile_bytes() * k1_tile_bytes());
+    const uint64_t tn_need = (need + k1_tile_bytes() - 1) / k1_tile_bytes();
+    if (c->h_in_off[b0] < c->sl_lo || tn_need > c->sl_tn) {
+      c->err = "encode_blocks: blocks reach outside the resident part of the slice (bzb200_slice_extend)";
+      return BZB200_E_STATE;
+    }
+  }
+  launch_k1_scatter(c->L, v_in(c), c->n_in, c->h_in_off[b0], c->h_in_off[b1], v_carry(c), v_E(c), v_txt(c));
+  launch_k5_crc(c->L, v_in(c), ptr<uint64_t>(c->in_off) + b0, b1 - b0, ptr<uint32_t>(c->crc) + b0);
+  launch_k1_inuse(c->L, v_txt(c), ptr<uint64_t>(c->rle_off) + b0, b1 - b0,
                   ptr<uint32_t>(c->inuse) + (size_t)b0 * 8);
   TRY(check_launch(c));
   CK(c, cudaMemcpyAsync(c->h_crc.data() + b0, ptr<uint32_t>(c->crc) + b0, (size_t)(b1 - b0) * 4, cudaMemcpyDeviceToHost,
@@ -413,7 +427,7 @@ static int encode_batch(bzb200_ctx* c, uint32_t b0, uint32_t nb, uint8_t* d_out,
   TRY(ensure(c, c->blockbit, ((size_t)nb + 1) * 8));
 
   CK(c, cudaMemcpyAsync(c->desc.p, c->h_desc.data(), (size_t)nb * sizeof(BlockDesc), cudaMemcpyHostToDevice, c->stream));
-  const uint8_t* d_txt = ptr<uint8_t>(c->txt) + base;
+  const uint8_t* d_txt = v_txt(c) + base;
   const BlockDesc* d_desc = ptr<BlockDesc>(c->desc);
   const uint32_t* d_inuse = ptr<uint32_t>(c->inuse) + (size_t)b0 * 8;
   const uint32_t* d_crc = ptr<uint32_t>(c->crc) + b0;
@@ -506,6 +520,7 @@ int bzb200_encode_blocks(bzb200_ctx* c, uint32_t b0, uint32_t b1, uint8_t* d_out
     return BZB200_E_ARG;
   }
   TRY(set_device(c));
+  if (c->sliced && !(b0 >= c->prep_lo && b1 <= c->prep_hi)) TRY(slice_reserve_txt(c, b0, b1));
   TRY(prepare_blocks(c, b0, b1));
   TRY(ensure(c, c->bitcursor, 16));
   CK(c, cudaMemcpyAsync(c->bitcursor.p, &start_bit, 8, cudaMemcpyHostToDevice, c->stream));
@@ -708,7 +723,7 @@ int bzb200_debug_stage(bzb200_ctx* c, uint32_t block, int field, void* host_dst,
   const void* src = nullptr;
   size_t n = 0, esz = 1;
   switch (field) {
-    case BZB200_F_RLE: src = ptr<uint8_t>(c->txt) + c->h_rle_off[block]; n = d.n; esz = 1; break;
+    case BZB200_F_RLE: src = v_txt(c) + c->h_rle_off[block]; n = d.n; esz = 1; break;
     case BZB200_F_RANK: src = ptr<uint32_t>(c->rank) + d.off; n = d.n; esz = 4; break;
     case BZB200_F_LAST: src = ptr<uint8_t>(c->last) + d.off; n = d.n; esz = 1; break;
     case BZB200_F_MTF: src = ptr<uint16_t>(c->sym) + d.symoff; n = mc; esz = 2; break;

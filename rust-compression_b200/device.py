@@ -82,31 +82,55 @@ class Context:
         self.nblocks = nb.value
         return nb.value
 
-    # ---- the plan in four steps (sharded.py: per-tile summaries are computed per rank and all-gathered)
-    def plan_begin(self, level, d_in):
-        self._u8(d_in)
-        nt = C.c_uint64(0)
-        self._check(_lib.lib().bzb200_plan_begin(self._h, level, C.c_void_p(d_in.data_ptr()), d_in.numel(), C.byref(nt)),
-                    "bzb200_plan_begin")
-        self._keep_in = d_in
+    # ---- sliced plan (include/bzb200.h section 2b): this context holds one slice of the stream
+    def slice_begin(self, level, n_total, lo, hi, d_buf, buf_lo_offset, avail_hi, reserve_hi):
+        """d_buf: device uint8 tensor that holds input byte `lo` at index buf_lo_offset (16-byte aligned address), the 16
+        bytes in front of it when lo > 0, and the bytes up to avail_hi behind it.  Returns the slice's last run head."""
+        self._u8(d_buf)
+        lh = C.c_int64(-1)
+        self._check(_lib.lib().bzb200_slice_begin(self._h, level, n_total, lo, hi,
+                                                  C.c_void_p(d_buf.data_ptr() + buf_lo_offset), avail_hi, reserve_hi,
+                                                  C.byref(lh)), "bzb200_slice_begin")
+        self._keep_in = d_buf
         self.level = level
-        return int(nt.value)
+        return lh.value
 
-    def plan_heads(self, t0, t1, t_head):
-        assert t_head.is_cuda and t_head.dtype == torch.int64 and t_head.is_contiguous()
-        self._check(_lib.lib().bzb200_plan_heads(self._h, t0, t1, C.c_void_p(t_head.data_ptr())), "bzb200_plan_heads")
+    def slice_counts(self, carry_in):
+        em = C.c_uint64(0)
+        self._check(_lib.lib().bzb200_slice_counts(self._h, carry_in, C.byref(em)), "bzb200_slice_counts")
+        return em.value
 
-    def plan_counts(self, t_head, t0, t1, t_cnt):
-        assert t_cnt.is_cuda and t_cnt.dtype == torch.int32 and t_cnt.is_contiguous()
-        self._check(_lib.lib().bzb200_plan_counts(self._h, C.c_void_p(t_head.data_ptr()), t0, t1,
-                                                  C.c_void_p(t_cnt.data_ptr())), "bzb200_plan_counts")
+    def slice_prefix(self, e_lo, e_tot):
+        self._check(_lib.lib().bzb200_slice_prefix(self._h, e_lo, e_tot), "bzb200_slice_prefix")
 
-    def plan_finish(self, t_cnt):
-        nb = C.c_uint32(0)
-        self._check(_lib.lib().bzb200_plan_finish(self._h, C.c_void_p(t_cnt.data_ptr()), C.byref(nb)),
-                    "bzb200_plan_finish")
-        self.nblocks = nb.value
-        return nb.value
+    def slice_windows(self, x0, out_rows):
+        """Tabulates the slice's cut windows of the phase starting at x0 into the leading rows of out_rows (device int64
+        tensor [rows, bzb200_cut_window()], stream ordered).  Returns (j0, nj)."""
+        L = _lib.lib()
+        j0, nj, d_f = C.c_uint64(0), C.c_uint32(0), C.c_void_p()
+        self._check(L.bzb200_slice_windows(self._h, x0, C.byref(j0), C.byref(nj), C.byref(d_f)), "bzb200_slice_windows")
+        if nj.value:
+            assert out_rows.is_cuda and out_rows.dtype == torch.int64 and out_rows.is_contiguous()
+            assert out_rows.shape[0] >= nj.value and out_rows.shape[1] == cut_window()
+            with torch.cuda.stream(self.stream):
+                src = _as_tensor(d_f.value, nj.value * cut_window(), self.device)
+                out_rows.view(-1)[:nj.value * cut_window()].copy_(src, non_blocking=True)
+        return int(j0.value), int(nj.value)
+
+    def slice_set_blocks(self, in_off, rle_off, max_block_len):
+        a = np.ascontiguousarray(in_off, dtype=np.uint64)
+        b = np.ascontiguousarray(rle_off, dtype=np.uint64)
+        self._check(_lib.lib().bzb200_slice_set_blocks(self._h, a.size - 1, a.ctypes.data, b.ctypes.data, max_block_len),
+                    "bzb200_slice_set_blocks")
+        self.nblocks = a.size - 1
+
+    def slice_blocks(self):
+        b0, b1, need = C.c_uint32(0), C.c_uint32(0), C.c_uint64(0)
+        self._check(_lib.lib().bzb200_slice_blocks(self._h, C.byref(b0), C.byref(b1), C.byref(need)), "bzb200_slice_blocks")
+        return b0.value, b1.value, need.value
+
+    def slice_extend(self, avail_hi):
+        self._check(_lib.lib().bzb200_slice_extend(self._h, avail_hi), "bzb200_slice_extend")
 
     def block_table(self, with_crc=True):
         """(in_off, rle_off, crc) of the planned blocks.  CRCs are computed for the blocks this context encodes;
@@ -243,6 +267,86 @@ class Context:
         return {"rounds": r.value, "radix_passes": p.value, "elems_sorted": e.value,
                 "elems_sorted_radix": int(v[3]), "elems_local": int(v[4]), "n_rle": int(v[5]),
                 "mtf_symbols": int(v[6])}
+
+
+def cut_window():
+    return int(_lib.lib().bzb200_cut_window())
+
+
+def slice_halo_bytes():
+    return int(_lib.lib().bzb200_slice_halo_bytes())
+
+
+def plan_tile_bytes():
+    return int(_lib.lib().bzb200_plan_tile_bytes())
+
+
+def cut_walk(F, T, e_tot, n, state, in_off, rle_off):
+    """bzb200_cut_walk (host): one phase of the cut chain through the window rows F (numpy uint64 [K, cut_window()]).
+    state / in_off / rle_off are numpy uint64 arrays updated in place.  Returns (nblocks, max_block_len) once
+    state[2] == 1."""
+    nb, ml = C.c_uint32(0), C.c_uint32(0)
+    F = np.ascontiguousarray(F, dtype=np.uint64)
+    rc = _lib.lib().bzb200_cut_walk(F.ctypes.data if F.size else None, F.shape[0] if F.ndim == 2 else 0, T, e_tot, n,
+                                    in_off.size - 1, state.ctypes.data, in_off.ctypes.data, rle_off.ctypes.data,
+                                    C.byref(nb), C.byref(ml))
+    if rc != _lib.OK:
+        raise CompressionError("Unexpected", f"bzb200_cut_walk rc={rc}")
+    return nb.value, ml.value
+
+
+def _as_tensor(ptr, n_int64, device):
+    """A torch view (int64) of device memory owned by the library (no copy)."""
+    class _Ext:
+        pass
+    e = _Ext()
+    e.__cuda_array_interface__ = {"shape": (n_int64,), "typestr": "<i8", "data": (ptr, False), "version": 2}
+    return torch.as_tensor(e, device=device)
+
+
+class Pool:
+    """The in-library multi-GPU engine (include/bzb200.h section 2c): host buffers in, host buffers out, one process."""
+
+    def __init__(self, devices):
+        L = _lib.lib()
+        devs = (C.c_int * len(devices))(*devices)
+        self._h = C.c_void_p()
+        rc = L.bzb200_pool_create(len(devices), devs, C.byref(self._h))
+        if rc != _lib.OK:
+            self._h = None
+            raise CompressionError("Unexpected", f"bzb200_pool_create rc={rc}")
+        self.devices = list(devices)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _lib.lib().bzb200_pool_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def size(self):
+        return int(_lib.lib().bzb200_pool_size(self._h))
+
+    def compress_host(self, level, h_in, h_out):
+        assert (not h_in.is_cuda) and (not h_out.is_cuda) and h_in.dtype == torch.uint8 and h_out.dtype == torch.uint8
+        n = C.c_size_t(0)
+        rc = _lib.lib().bzb200_pool_compress_host(self._h, level, C.c_void_p(h_in.data_ptr()), h_in.numel(),
+                                                  C.c_void_p(h_out.data_ptr()), h_out.numel(), C.byref(n))
+        if rc == _lib.E_LEVEL:
+            raise ValueError("invalid level")
+        if rc != _lib.OK:
+            msg = _lib.lib().bzb200_pool_last_error(self._h)
+            raise CompressionError("Unexpected", f"bzb200_pool_compress_host rc={rc}: {msg.decode() if msg else ''}")
+        return n.value
+
+    def stats(self):
+        v = (C.c_uint64 * 4)()
+        _lib.lib().bzb200_pool_stats(self._h, v, 4)
+        return {"spans": int(v[0]), "blocks": int(v[1]), "phases": int(v[2]), "launches": int(v[3])}
 
 
 def compress_tensor(ctx, level, d_in):

@@ -39,13 +39,19 @@ class CompressionError(Exception):
 
 
 class BZip2Encoder:
-    def __init__(self, level=9, device=-1):
+    def __init__(self, level=9, device=-1, devices=None):
+        """devices: list of CUDA ordinals — the same object sharding every window of input block-wise over several GPUs
+        of the box (bzb200_enc_create_multi); default: one GPU (`device`, -1 = the current one)."""
         if level < 1 or level > 9:
             raise ValueError("invalid level")  # the reference panics (encoder.rs:59-61)
         self.level = level
         self._h = C.c_void_p()
         L = _lib.lib()
-        rc = L.bzb200_enc_create(level, device, C.byref(self._h))
+        if devices:
+            arr = (C.c_int * len(devices))(*devices)
+            rc = L.bzb200_enc_create_multi(level, len(devices), arr, C.byref(self._h))
+        else:
+            rc = L.bzb200_enc_create(level, device, C.byref(self._h))
         if rc != _lib.OK:
             raise CompressionError("Unexpected", f"bzb200_enc_create rc={rc}")
         self._finished = False   # encoder.rs:45 `finished`

@@ -157,11 +157,18 @@ def test_generators_multiblock():
 
 
 def test_config2_single_text_block():
-    """BASELINE config 2 as SURVEY.md section 8(d) writes it: TEXT(seed=1, n=899 900) at level 9 is exactly one block."""
+    """BASELINE config 2: a single 900 kB block of synthetic text at level 9.  SURVEY.md section 8(d) writes it as
+    TEXT(seed=1, n=899 900) expecting RLE1 to add fewer than 81 bytes; with this generator RLE1 adds 105 (the block
+    closes after 899 876 input bytes), so the single-block input is the first 899 876 bytes — the whole first block of
+    TEXT(1, 899 900) — and the 899 900-byte input itself is the two-block case (a full block plus a 24-byte one)."""
     data = gen.text(1, 899_900)
     r = orc.Run(data, 9)
+    assert r.nblocks == 2 and r.info(0)["in_end"] == 899_876 and r.info(0)["nblock"] == 899_981
+    r.close()
+    r = orc.Run(data[:899_876], 9)
     assert r.nblocks == 1
     r.close()
+    parity.assert_parity(data[:899_876], 9)
     parity.assert_parity(data, 9)
 
 
@@ -221,36 +228,72 @@ def test_doubling_rounds_group_sizes():
     parity.assert_parity(d3, 9)
 
 
-def test_plan_in_steps_equals_plan():
-    """bzb200_plan_begin/heads/counts/finish over two tile ranges (what sharded.py does per rank) == bzb200_plan."""
+def test_sliced_plan_equals_plan():
+    """include/bzb200.h section 2b driven by hand for three slices held by three contexts on this GPU (what
+    sharded.py does per rank and the engine of 2c per GPU): same block table as bzb200_plan, and the blocks encode
+    identically from a slice."""
     import torch
     from rust_compression_b200 import device as dv
+    from rust_compression_b200 import sharded
     data = gen.g2(5, 3_000_000) + gen.text(8, 700_000)
+    n, level = len(data), 1
     d_in = torch.frombuffer(bytearray(data), dtype=torch.uint8).cuda()
     a = dv.Context()
-    nb = a.plan(1, d_in)
+    nb = a.plan(level, d_in)
     want = a.block_table(with_crc=False)
-    b = dv.Context()
-    nt = b.plan_begin(1, d_in)
-    half = nt // 3
-    t_head = torch.full((nt,), -1, dtype=torch.int64, device="cuda")
-    t_cnt = torch.zeros(nt, dtype=torch.int32, device="cuda")
-    b.plan_heads(half, nt, t_head)
-    b.plan_heads(0, half, t_head)
-    b.plan_counts(t_head, 0, half, t_cnt)
-    b.plan_counts(t_head, half, nt, t_cnt)
-    assert b.plan_finish(t_cnt) == nb
-    got = b.block_table(with_crc=False)
-    assert (got[0] == want[0]).all() and (got[1] == want[1]).all()
-    # and the blocks encode identically from either plan
-    cap = dv.max_output_bytes(1, len(data))
+    halo, W, T = dv.slice_halo_bytes(), dv.cut_window(), level * 100000 - 19
+    bounds = sharded.slice_bounds(n, 3)
+    ctxs, bufs = [], []
+    heads = []
+    for lo, hi in bounds:
+        c = dv.Context()
+        reserve = min(n, hi + sharded.tail_reserve(level))
+        buf = torch.zeros(sharded.LEFT + reserve - lo + 64, dtype=torch.uint8, device="cuda")
+        left = 16 if lo else 0
+        avail = min(n, hi + halo)
+        buf[sharded.LEFT - left:sharded.LEFT + avail - lo] = d_in[lo - left:avail]
+        heads.append(c.slice_begin(level, n, lo, hi, buf, sharded.LEFT, avail, reserve))
+        ctxs.append(c)
+        bufs.append(buf)
+    emitted = [c.slice_counts(max([-1] + heads[:r])) for r, c in enumerate(ctxs)]
+    for r, c in enumerate(ctxs):
+        c.slice_prefix(sum(emitted[:r]), sum(emitted))
+    e_tot = sum(emitted)
+    max_blocks = (n + n // 4 + 64) // T + 2
+    state = np.zeros(4, dtype=np.uint64)
+    in_off = np.zeros(max_blocks + 1, dtype=np.uint64)
+    rle_off = np.zeros(max_blocks + 1, dtype=np.uint64)
+    while not state[2]:
+        x0 = int(state[1])
+        K = (e_tot - x0) // T if e_tot >= x0 + T else 0
+        F = np.zeros((K, W), dtype=np.uint64)
+        rows = torch.zeros((max(K, 1), W), dtype=torch.int64, device="cuda")
+        for c in ctxs:
+            j0, nj = c.slice_windows(x0, rows)
+            c.sync()
+            if nj:
+                F[j0:j0 + nj] = rows[:nj].cpu().numpy().view(np.uint64)
+        got_nb, ml = dv.cut_walk(F, T, e_tot, n, state, in_off, rle_off)
+    assert got_nb == nb
+    assert (in_off[:nb + 1] == want[0]).all() and (rle_off[:nb + 1] == want[1]).all()
+    # the middle slice encodes its blocks from its resident bytes (+ the tail of its last block)
+    c, (lo, hi), buf = ctxs[1], bounds[1], bufs[1]
+    c.slice_set_blocks(in_off[:nb + 1], rle_off[:nb + 1], ml)
+    b0, b1, need = c.slice_blocks()
+    assert b1 > b0 and int(in_off[b0]) >= lo and int(in_off[b1 - 1]) < hi
+    avail = min(n, hi + halo)
+    if need > avail:
+        buf[sharded.LEFT + avail - lo:sharded.LEFT + need - lo] = d_in[avail:need]
+        c.slice_extend(need)
+    cap = dv.max_output_bytes(level, n)
     o1 = torch.zeros(cap, dtype=torch.uint8, device="cuda")
     o2 = torch.zeros(cap, dtype=torch.uint8, device="cuda")
-    e1 = a.encode_blocks(0, nb, o1, 0)
-    e2 = b.encode_blocks(0, nb, o2, 0)
+    e1 = a.encode_blocks(b0, b1, o1, 5)
+    e2 = c.encode_blocks(b0, b1, o2, 5)
     assert e1 == e2 and torch.equal(o1, o2)
-    a.close()
-    b.close()
+    assert (a.block_table(with_crc=False)[2][b0:b1] == c.block_table(with_crc=False)[2][b0:b1]).all()
+    for x in ctxs + [a]:
+        x.close()
 
 
 def test_host_path_segmented_pipeline(monkeypatch):
