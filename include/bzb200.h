@@ -83,7 +83,8 @@ BZB200_API size_t bzb200_enc_output_size(const bzb200_enc* e);
 /* Re-arm for a new stream at the same level (the reference resets its latches when it returns None,
  * encoder.rs:87-90,130-133). */
 BZB200_API int bzb200_enc_reset(bzb200_enc* e);
-/* out[0..3]: blocks encoded so far, windows compressed, input bytes still buffered, output bytes ready. */
+/* out[0..3]: blocks encoded so far, windows compressed, input bytes still buffered, output bytes ready.  Waits for the
+ * window that is in flight, if any. */
 BZB200_API int bzb200_enc_stats(const bzb200_enc* e, uint64_t* out, size_t cap);
 BZB200_API void bzb200_enc_destroy(bzb200_enc* e);
 BZB200_API const char* bzb200_enc_last_error(const bzb200_enc* e);

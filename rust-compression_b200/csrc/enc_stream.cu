@@ -453,6 +453,7 @@ const char* bzb200_enc_last_error(const bzb200_enc* e) { return e ? e->err.c_str
 
 int bzb200_enc_stats(const bzb200_enc* e, uint64_t* out, size_t cap) {
   if (!e || !out) return BZB200_E_ARG;
+  wait_idle(const_cast<bzb200_enc*>(e));  // the counters belong to the worker while a window is in flight
   const uint64_t v[4] = {e->blocks, e->windows, (uint64_t)(e->hi - e->lo) + (e->tail_buf >= 0 ? e->tail_hi - e->tail_lo : 0),
                          (uint64_t)bzb200_enc_output_size(e)};
   for (size_t i = 0; i < cap && i < 4; ++i) out[i] = v[i];

@@ -410,7 +410,7 @@ int bzb200_pool_create(int ngpus, const int* devices, bzb200_pool** out) {
   if (!out || ngpus < 1 || ngpus > 64) return BZB200_E_ARG;
   *out = nullptr;
   int per = 1;
-  if (const char* e = getenv("BZB200_MG_CTX_PER_GPU")) per = std::max(1, std::min(4, atoi(e)));
+  if (const char* e = getenv("BZB200_MG_CTX_PER_GPU")) per = std::max(1, std::min(8, atoi(e)));
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) return BZB200_E_CUDA;
   bzb200_pool* p = new bzb200_pool();

@@ -285,8 +285,10 @@ int slice_reserve_txt(bzb200_ctx* c, uint32_t b0, uint32_t b1) {
   const uint64_t span = c->h_rle_off[b1] - c->h_rle_off[b0];
   const uint64_t slack = 2 * (uint64_t)k1_tile_bytes() * 5 / 4 + 256;
   CK(c, cudaStreamSynchronize(c->stream));
-  TRY(ensure(c, c->txt, span + 2 * slack));
-  c->txt_origin = c->h_rle_off[b0] >= slack ? c->h_rle_off[b0] - slack : 0;
+  TRY(ensure(c, c->txt, span + 2 * slack + 256));
+  // a multiple of 256: kernels that read txt with 128-bit loads align on the INDEX (k1_inuse), so the shifted base must
+  // keep the alignment of the allocation
+  c->txt_origin = (c->h_rle_off[b0] >= slack ? c->h_rle_off[b0] - slack : 0) & ~(uint64_t)255;
   c->prep_lo = c->prep_hi = 0;
   return BZB200_OK;
 }
