@@ -1038,6 +1038,36 @@ size_t orc_block_field(void* h, size_t b, int field, void* dst, size_t cap_elems
   return 0;
 }
 
+// The reference's block cuts alone (EncoderInner::next / write_rle, encoder.rs:671-716; cut test :692-696; finish
+// :729-739): the same run counter and block_buf length bookkeeping as EncoderInner above with everything but the
+// lengths left out.  in_off[k] = input offset where block k starts; returns the number of blocks (in_off has nb + 1
+// entries, the last one n), or -(needed) when cap is too small.  Used by bench.py --impl reference to hand the blocks
+// of one stream to all host cores.
+long long orc_cut_table(int level, const uint8_t* in, size_t n, uint64_t* in_off, size_t cap) {
+  if (level < 1 || level > 9) return -1;
+  const size_t T = (size_t)level * 100000 - 19;
+  std::vector<uint64_t> cuts{0};
+  size_t blk = 0;          // block_buf.len()
+  size_t rle_count = 0;
+  uint8_t rle_buffer = 0;
+  uint64_t consumed = 0;   // input bytes whose runs have been flushed
+  for (size_t i = 0; i < n; ++i) {
+    const uint8_t b = in[i];
+    if (rle_count == 0) { rle_buffer = b; rle_count = 1; continue; }
+    if (rle_buffer == b && rle_count < 255) { rle_count += 1; continue; }
+    blk += rle_count < 4 ? rle_count : 5;  // write_rle: up to 4 literals + a count byte
+    consumed += rle_count;
+    rle_count = 1;
+    rle_buffer = b;
+    if (blk >= T) { cuts.push_back(consumed); blk = 0; }
+  }
+  if (n) cuts.push_back(n);  // finish(): the pending run goes into the last block
+  const size_t nb = cuts.size() - 1;
+  if (cuts.size() > cap) return -(long long)cuts.size();
+  for (size_t k = 0; k < cuts.size(); ++k) in_off[k] = cuts[k];
+  return (long long)nb;
+}
+
 // Full-stream verifier (bench.py / tests hand every block of the GPU's block table to this, in parallel over the
 // host cores).  in[0..n) is the input range the GPU assigned to one block; it is encoded as a stream of its own — a
 // block cut is a piece boundary, so RLE1 restarts there exactly as in the one-pass encoder — and must come out as

@@ -39,6 +39,8 @@ def _lib():
     if not getattr(L, "_verify_ready", False):
         L.orc_encode_block.restype = C.c_longlong
         L.orc_encode_block.argtypes = [C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p]
+        L.orc_cut_table.restype = C.c_longlong
+        L.orc_cut_table.argtypes = [C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]
         L.orc_bits_diff.restype = C.c_uint64
         L.orc_bits_diff.argtypes = [C.c_void_p, C.c_size_t, C.c_uint64, C.c_void_p, C.c_uint64]
         L._verify_ready = True
@@ -51,6 +53,39 @@ def _get_bits(a, bit, n):
     for k in range(bit, bit + n):
         v = (v << 1) | ((int(a[k >> 3]) >> (7 - (k & 7))) & 1)
     return v
+
+
+def cut_table(data, level):
+    """in_off[nb + 1] of the reference's block cuts (sequential pass, oracle/bz2_oracle.cpp orc_cut_table)."""
+    L = _lib()
+    a = np.frombuffer(data, dtype=np.uint8) if not isinstance(data, np.ndarray) else np.ascontiguousarray(data)
+    cap = a.size // (level * 100000 - 19) * 2 + 8
+    out = np.zeros(cap, dtype=np.uint64)
+    r = L.orc_cut_table(level, a.ctypes.data, a.size, out.ctypes.data, cap)
+    if r < -1:
+        out = np.zeros(-r, dtype=np.uint64)
+        r = L.orc_cut_table(level, a.ctypes.data, a.size, out.ctypes.data, out.size)
+    assert r >= 0
+    return out[:r + 1].astype(np.int64)
+
+
+def encode_blocks_parallel(data, level, in_off, threads=None):
+    """Every block of the table encoded by the oracle, block-parallel on `threads` host threads (ctypes releases the
+    GIL).  Returns (total compressed bits, list of block CRCs)."""
+    L = _lib()
+    a = np.frombuffer(data, dtype=np.uint8) if not isinstance(data, np.ndarray) else np.ascontiguousarray(data)
+    cap = level * 100000 + level * 100000 // 4 + 8192
+
+    def enc(b):
+        lo, hi = int(in_off[b]), int(in_off[b + 1])
+        out = np.empty(cap, dtype=np.uint8)
+        info = np.zeros(4, dtype=np.uint64)
+        L.orc_encode_block(level, a.ctypes.data + lo, hi - lo, out.ctypes.data, cap, info.ctypes.data)
+        return int(info[3]), int(info[1])
+
+    with ThreadPoolExecutor(max_workers=threads or _threads()) as ex:
+        res = list(ex.map(enc, range(len(in_off) - 1)))
+    return sum(r[0] for r in res), [r[1] for r in res]
 
 
 def verify_stream(data, level, stream, in_off, threads=None, blocks=None):

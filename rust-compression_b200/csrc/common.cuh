@@ -4,7 +4,27 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <mutex>
+
 namespace bzb {
+
+// Kernel attributes (cudaFuncSetAttribute) are per DEVICE: run(f) executes f once per device (the calling thread's
+// current one) and makes concurrent callers on the same device wait until it is done, so that a process that drives
+// several GPUs and several contexts per GPU — the multi-GPU engine, mgpu.cu — configures its kernels on each of them.
+struct PerDeviceOnce {
+  std::mutex mu;
+  unsigned long long done[2] = {0, 0};
+  template <class F>
+  void run(F f) {
+    int d = 0;
+    if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d > 127) d = 0;
+    std::lock_guard<std::mutex> g(mu);
+    const unsigned long long bit = 1ull << (d & 63);
+    if (done[d >> 6] & bit) return;
+    f();
+    done[d >> 6] |= bit;
+  }
+};
 
 // ---- constants of the format (bzip2/mod.rs:20, encoder.rs:186,294-298) ----
 constexpr int G_SIZE = 50;          // BZ_G_SIZE

@@ -996,10 +996,12 @@ struct OsState {
 static void radix_sort40(Launcher& L, uint64_t*& src, uint64_t*& dst, const uint8_t* d_txt, const BlockDesc* d_desc,
                          uint32_t nb, uint32_t maxcnt, BwtScratch& S, OsState& os) {
   // tile geometry of the pass kernel (BZB200_OS_VARIANT picks another one for experiments)
-  static int variant = -1;
-  if (variant < 0) {
+  static const int variant = [] {
     const char* v = getenv("BZB200_OS_VARIANT");
-    variant = v ? atoi(v) : 5;  // measured on B200: 256 threads x 8 elements (2 048-element tiles, 4 CTAs/SM) is fastest
+    return v ? atoi(v) : 5;  // measured on B200: 256 threads x 8 elements (2 048-element tiles, 4 CTAs/SM) is fastest
+  }();
+  static PerDeviceOnce once_os;
+  once_os.run([] {
     cudaFuncSetAttribute((const void*)k2_os_scatter<512, 8, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          (int)sizeof(OsSmemT<512, 8>));
     cudaFuncSetAttribute((const void*)k2_os_scatter<256, 16, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1014,7 +1016,7 @@ static void radix_sort40(Launcher& L, uint64_t*& src, uint64_t*& dst, const uint
                          (int)sizeof(OsSmemT<256, 8>));
     cudaFuncSetAttribute((const void*)k2_os_scatter<256, 8, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          (int)sizeof(OsSmemT<256, 8>));
-  }
+  });
   const uint32_t tile_elems = variant == 2 || variant == 3 ? 8192u : variant == 4 ? 4608u : (variant == 0 || variant == 1) ? 4096u : 2048u;
   const uint32_t tiles = (maxcnt + tile_elems - 1) / tile_elems;
   if (tiles == 0) return;
@@ -1086,18 +1088,19 @@ int run_bwt(Launcher& L, const uint8_t* d_txt, const BlockDesc* d_desc, uint32_t
   cudaMemsetAsync(S.sparse, 0, nb * sizeof(uint32_t), st);
   cudaMemsetAsync(S.global, 0, 4 * sizeof(uint32_t), st);
 
-  static bool attr_set = false;
-  static int ls_enum = ENUM_MAX_DEFAULT;
-  if (!attr_set) {
+  static const int ls_enum = [] {
+    const char* e = getenv("BZB200_LS_ENUM");
+    return e ? atoi(e) : ENUM_MAX_DEFAULT;
+  }();
+  static PerDeviceOnce once_ls;
+  once_ls.run([] {
     cudaFuncSetAttribute((const void*)k2_local_sort<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LsSmem));
     cudaFuncSetAttribute((const void*)k2_local_sort<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LsSmem));
     cudaFuncSetAttribute((const void*)k2_local_sort<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LsSmem));
     cudaFuncSetAttribute((const void*)k2_local_sort<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LsSmem));
     cudaFuncSetAttribute((const void*)k2_local_sort<48>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LsSmem));
     cudaFuncSetAttribute((const void*)k2_local_sort<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LsSmem));
-    if (const char* e = getenv("BZB200_LS_ENUM")) ls_enum = atoi(e);
-    attr_set = true;
-  }
+  });
   uint32_t rounds = 0, passes = 0;
   uint64_t elems = 0, radix_elem_passes = 5ull * M, local_elems = 0;
   uint64_t *src = S.A, *dst = S.B;

@@ -471,11 +471,10 @@ void launch_huffman(Launcher& L, const uint16_t* d_sym, const BlockDesc* d_desc,
                     const uint32_t* d_freq, const uint32_t* d_inuse, uint32_t nb, uint32_t max_groups_per_block,
                     HuffBuffers& H) {
   uint32_t* lm_list = reinterpret_cast<uint32_t*>(H.lm_list);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce once_lm;
+  once_lm.run([] {
     cudaFuncSetAttribute((const void*)k4_lm_fallback, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LM_BYTES);
-    attr_set = true;
-  }
+  });
   L.launch("k4_init", k4_init, dim3((nb + 63) / 64), dim3(64), nb, d_mtf_count, d_freq, d_inuse, H.lens, H.meta,
            H.rfreq);
   const dim3 cgrid((max_groups_per_block + CS_NT - 1) / CS_NT, nb);

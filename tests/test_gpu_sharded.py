@@ -165,6 +165,12 @@ def test_pool_over_two_gpus():
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs")
     from rust_compression_b200 import device as dv
+    # kernel attributes are per device: the process has used GPU 0 alone before the pool drives GPU 1 as well
+    warm = dv.Context(0)
+    d = gen.text(4, 2_000_000)
+    assert dv.compress_tensor(warm, 9, torch.frombuffer(bytearray(d), dtype=torch.uint8).cuda(0)).cpu().numpy().tobytes() \
+        == orc.compress(d, 9)
+    warm.close()
     pool = dv.Pool([0, 1])
     for name, data, level in _cases():
         want = orc.compress(data, level)
