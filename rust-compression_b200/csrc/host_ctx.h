@@ -58,9 +58,10 @@ struct bzb200_ctx {
   DevBuf sl_F, sl_sum;
   std::vector<uint64_t> h_in_off, h_rle_off;
   std::vector<uint32_t> h_crc;
+  std::vector<uint32_t> h_inuse;  // [nblocks][8] in-use byte maps of the prepared blocks (alphabet sizes for K2 / K3)
 
   // ---- batch scratch ----
-  DevBuf desc, A, B, rank, sa, tile_meta, cnt, hist, oshist, ticket, tsum, state, shift, sparse, stats, rounds, global, last, origptr;
+  DevBuf desc, A, B, rank, sa, tile_meta, cnt, hist, oshist, pairhist, ticket, tsum, state, shift, sparse, stats, rounds, global, last, origptr;
   DevBuf chunk_state, chunk_zle, chunk_base, sym, freq, mtf_count;
   DevBuf lens, rfreq, sel, selmtf, codes, gbits, meta, lm_scratch, lm_list, lm_count, blockbit, bitcursor, combined;
   DevBuf stage_in, stage_out;  // bzb200_compress_host staging

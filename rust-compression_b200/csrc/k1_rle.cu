@@ -573,6 +573,18 @@ void launch_k1_slice_counts(Launcher& L, const uint8_t* v_in, uint64_t N, uint64
   L.launch("k1_tile_counts", k1_tile_counts, dim3((unsigned)(t_b - t_a)), dim3(K1_NT), v_in, N, t_a,
            (const long long*)v_tile_carry, v_tile_cnt);
 }
+void launch_k1_slice_scan_carry(Launcher& L, uint64_t t_a, uint64_t t_b, long long carry_in, const long long* v_tile_head,
+                                long long* v_tile_carry) {
+  if (t_b > t_a)
+    L.launch("k_scan_max64_excl", k_scan_max64_excl, dim3(1), dim3(SC_NT), v_tile_head + t_a, v_tile_carry + t_a, t_b - t_a,
+             carry_in);
+}
+void launch_k1_slice_tile_counts(Launcher& L, const uint8_t* v_in, uint64_t N, uint64_t t_a, uint64_t t_b,
+                                 const long long* v_tile_carry, uint32_t* v_tile_cnt) {
+  if (t_b > t_a)
+    L.launch("k1_tile_counts", k1_tile_counts, dim3((unsigned)(t_b - t_a)), dim3(K1_NT), v_in, N, t_a, v_tile_carry,
+             v_tile_cnt);
+}
 void launch_k1_slice_prefix(Launcher& L, uint64_t t_a, uint64_t t_b, uint64_t E_in, const uint32_t* v_tile_cnt,
                             uint64_t* v_tile_E) {
   if (t_b <= t_a) return;

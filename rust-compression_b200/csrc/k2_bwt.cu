@@ -40,54 +40,69 @@ constexpr uint64_t POS_MASK = 0xFFFFFull;
 
 uint32_t bwt_tile_elems() { return RS_TILE / 2; }  // sizing unit of the per-tile arrays (smallest tile of any pass variant)
 
-// ------------------------------------------------------------------ round 0 keys
-__global__ void __launch_bounds__(RS_NT) k2_init_keys(const uint8_t* __restrict__ txt, const BlockDesc* __restrict__ desc,
-                                                      uint64_t* __restrict__ A, uint32_t* __restrict__ cnt) {
-  const BlockDesc d = desc[blockIdx.y];
-  const uint32_t n = d.n;
-  const uint32_t base = blockIdx.x * RS_TILE;
-  if (base >= n) return;
-  if (blockIdx.x == 0 && threadIdx.x == 0) cnt[blockIdx.y] = n;
-  const uint8_t* t = txt + d.off;
-#pragma unroll 4
-  for (int k = 0; k < RS_IPT; ++k) {
-    uint32_t pos = base + threadIdx.x + k * RS_NT;
-    if (pos < n) {
-      uint64_t key = 0;
-      uint32_t idx = pos;
+// ------------------------------------------------------------------ one-sweep LSD radix pass (per-block segments)
+// Digit histograms of all passes are taken once (k2_os_hist* / k2_pair_hist + k2_digit_offsets), turned into bucket
+// offsets, and each pass is then ONE kernel: a CTA ranks its tile (warp match + per-warp counters), publishes the
+// tile's digit counts, obtains the counts of the preceding tiles of its block by decoupled look-back over the status
+// words of those tiles, and scatters through shared memory.  Tiles of a block are numbered by a ticket, so a tile only
+// ever waits for tiles that are already running.  The grid is (block, tile): CTAs in flight belong to different
+// blocks, which keeps the look-back chains short.
+//
+// Initial sort keys.  The key of rotation pos is the first S symbols of the rotation, BITS bits each, where a symbol is
+// the rank of the byte among the block's in-use bytes (order preserving).  The batch's largest alphabet picks the mode:
+//   > 128 bytes in use : BITS 8, S 5, 5 passes of 8-bit digits  (a digit is a byte: every pass has the byte histogram)
+//   65..128            : BITS 7, S 5, 4 passes of 9-bit digits
+//   17..64 (text)      : BITS 6, S 6, 4 passes of 9-bit digits  (one pass less AND one symbol more than bytes give)
+//   <= 16              : BITS 4, S 8, 4 passes of 8-bit digits
+// In the compact modes a digit straddles at most two neighbouring symbols of the key, and every pair of neighbouring
+// text symbols is digit p of exactly one rotation, so all digit histograms follow from ONE histogram of symbol pairs
+// (k2_pair_hist, 1 B read per element) — no pass over the keys.
+constexpr uint32_t ST_AGG = 1u << 20, ST_PREFIX = 2u << 20, ST_VAL = 0xFFFFFu;
+constexpr int OS_NT = 256, OS_IPT = 8, OS_MINB = 4;  // 2 048-element tiles, 4 CTAs per SM: the fastest geometry measured
+constexpr int OS_TILE = OS_NT * OS_IPT;
+constexpr int OS_BINS_MAX = 512;   // row pitch of the histogram / status arrays
+constexpr int OS_PASSES_MAX = 5;
+
+template <int BINS>
+struct OsSmemT {
+  static constexpr int WARPS = OS_NT / 32;
+  uint64_t stage[OS_TILE];
+  uint32_t wcnt[WARPS][BINS];
+  uint32_t dstart[BINS];
+  int goff[BINS];
+  uint32_t ws[OS_NT / 32 + 1];
+  uint32_t tile;
+  uint8_t lut[256];
+};
+
+struct KeyMode {
+  int bits;    // bits per symbol
+  int syms;    // symbols in the initial key (= step h of the first doubling round)
+  int wbits;   // digit width of a pass
+  int passes;
+};
+static KeyMode key_mode(uint32_t max_alpha) {
+  if (max_alpha == 0 || max_alpha > 128) return {8, 5, 8, 5};
+  if (max_alpha > 64) return {7, 5, 9, 4};
+  if (max_alpha > 16) return {6, 6, 9, 4};
+  return {4, 8, 8, 4};
+}
+
+// byte -> rank among the block's in-use bytes
+__device__ __forceinline__ void build_sym_lut(const uint32_t* __restrict__ inuse8, uint8_t* lut) {
+  for (int v = threadIdx.x; v < 256; v += blockDim.x) {
+    uint32_t r = 0;
 #pragma unroll
-      for (int j = 0; j < 5; ++j) {
-        key = (key << 8) | t[idx];
-        ++idx;
-        if (idx == n) idx = 0;
-      }
-      A[(uint64_t)d.off + pos] = (key << KEY_LO) | pos;
+    for (int wd = 0; wd < 8; ++wd) {
+      const uint32_t m = inuse8[wd];
+      if (wd < (v >> 5)) r += __popc(m);
+      else if (wd == (v >> 5)) r += __popc(m & ((1u << (v & 31)) - 1u));
     }
+    lut[v] = (uint8_t)r;
   }
 }
 
-// ------------------------------------------------------------------ one-sweep LSD radix pass (per-block segments)
-// Digit histograms of all five passes are taken once (k2_os_hist*), turned into bucket offsets (k2_os_offsets), and
-// each pass is then ONE kernel: a CTA ranks its tile (warp match + per-warp counters), publishes the tile's digit
-// counts, obtains the counts of the preceding tiles of its block by decoupled look-back over the status words of
-// those tiles, and scatters through shared memory.  Tiles of a block are numbered by a ticket, so a tile only ever
-// waits for tiles that are already running.  The grid is (block, tile): CTAs in flight belong to different blocks,
-// which keeps the look-back chains short.
-constexpr uint32_t ST_AGG = 1u << 20, ST_PREFIX = 2u << 20, ST_VAL = 0xFFFFFu;
-
-template <int NT, int IPT>
-struct OsSmemT {
-  static constexpr int TILE = NT * IPT;
-  static constexpr int WARPS = NT / 32;
-  uint64_t stage[TILE];
-  uint32_t wcnt[WARPS][256];
-  uint32_t dstart[256];
-  int goff[256];
-  uint32_t ws[NT / 32 + 1];
-  uint32_t tile;
-};
-
-// Byte histogram of a block's text = digit histogram of every pass of the initial sort (every byte of the block is
+// Byte histogram of a block's text = digit histogram of every pass of the byte-key sort (every byte of the block is
 // digit p of exactly one rotation).  grid (chunks, nb); hist[b][p][d] accumulated with global atomics.
 __global__ void __launch_bounds__(256) k2_os_hist_txt(const uint8_t* __restrict__ txt, const BlockDesc* __restrict__ desc,
                                                       uint32_t* __restrict__ hist, uint32_t* __restrict__ cnt,
@@ -108,9 +123,71 @@ __global__ void __launch_bounds__(256) k2_os_hist_txt(const uint8_t* __restrict_
 #pragma unroll
   for (int k = 0; k < 8; ++k) v += h[k][threadIdx.x];
   if (v) {
-    uint32_t* o = hist + (uint64_t)blockIdx.y * 5 * 256 + threadIdx.x;
+    uint32_t* o = hist + (uint64_t)blockIdx.y * OS_PASSES_MAX * OS_BINS_MAX + threadIdx.x;
 #pragma unroll
-    for (int p = 0; p < 5; ++p) atomicAdd(o + p * 256, v);
+    for (int p = 0; p < 5; ++p) atomicAdd(o + p * OS_BINS_MAX, v);
+  }
+}
+
+// Histogram of the pairs (symbol at i, symbol at i+1 cyclic) of a block, symbols = ranks among the in-use bytes.
+// grid (chunks, nb); pair[b][x << BITS | y] accumulated with global atomics (the table must be zero on entry).
+template <int BITS>
+__global__ void __launch_bounds__(256) k2_pair_hist(const uint8_t* __restrict__ txt, const BlockDesc* __restrict__ desc,
+                                                    const uint32_t* __restrict__ inuse, uint32_t* __restrict__ pair,
+                                                    uint32_t* __restrict__ cnt, uint32_t chunk) {
+  extern __shared__ __align__(16) uint32_t ph_raw[];  // [1 << 2 BITS] counters, then the 256-byte symbol table
+  constexpr int NP = 1 << (2 * BITS);
+  uint8_t* lut = reinterpret_cast<uint8_t*>(ph_raw + NP);
+  const BlockDesc d = desc[blockIdx.y];
+  const uint32_t lo = blockIdx.x * chunk;
+  if (lo >= d.n) return;
+  if (blockIdx.x == 0 && threadIdx.x == 0) cnt[blockIdx.y] = d.n;  // list length of the initial sort
+  const uint32_t hi = min(d.n, lo + chunk);
+  for (int i = threadIdx.x; i < NP; i += 256) ph_raw[i] = 0;
+  build_sym_lut(inuse + blockIdx.y * 8, lut);
+  __syncthreads();
+  const uint8_t* t = txt + d.off;
+  for (uint32_t i = lo + threadIdx.x; i < hi; i += 256) {
+    const uint32_t x = lut[t[i]], y = lut[t[i + 1 == d.n ? 0 : i + 1]];
+    atomicAdd(&ph_raw[(x << BITS) | y], 1u);
+  }
+  __syncthreads();
+  uint32_t* o = pair + (uint64_t)blockIdx.y * NP;
+  for (int i = threadIdx.x; i < NP; i += 256) {
+    const uint32_t v = ph_raw[i];
+    if (v) atomicAdd(o + i, v);
+  }
+}
+
+// Bucket offsets of every pass of the compact-key sort from the pair histogram: digit p covers key bits
+// [p W, p W + W); its lowest bit lies in key symbol k0 = p W / BITS (counted from the LAST symbol of the key) at bit
+// o = p W - k0 BITS, so digit = ((x << BITS | y) >> o) & (2^W - 1) with (x, y) = key symbols (k0 + 1, k0) — two
+// neighbouring text symbols, x first; above the first symbol of the key (k0 + 1 == S) x is 0.  One CTA per block.
+template <int BITS, int S, int W>
+__global__ void __launch_bounds__(512) k2_digit_offsets(const uint32_t* __restrict__ pair, uint32_t* __restrict__ hist) {
+  constexpr int NP = 1 << (2 * BITS), BINS = 1 << W, P = (BITS * S + W - 1) / W;
+  static_assert(BINS <= 512 && P <= OS_PASSES_MAX, "histogram row pitch");
+  __shared__ uint32_t h[BINS];
+  __shared__ uint32_t ws[512 / 32 + 1];
+  const uint32_t* pr = pair + (uint64_t)blockIdx.x * NP;
+  uint32_t* out = hist + (uint64_t)blockIdx.x * OS_PASSES_MAX * OS_BINS_MAX;
+  for (int p = 0; p < P; ++p) {
+    for (int i = threadIdx.x; i < BINS; i += 512) h[i] = 0;
+    __syncthreads();
+    const int k0 = p * W / BITS, o = p * W - k0 * BITS;
+    const bool top = k0 + 1 >= S;
+    for (int i = threadIdx.x; i < NP; i += 512) {
+      const uint32_t c = pr[i];
+      if (c) {
+        const uint32_t pv = top ? (uint32_t)(i & ((1 << BITS) - 1)) : (uint32_t)i;
+        atomicAdd(&h[(pv >> o) & (BINS - 1)], c);
+      }
+    }
+    __syncthreads();
+    const uint32_t v = threadIdx.x < BINS ? h[threadIdx.x] : 0u;
+    const uint32_t ex = cta_excl_scan_add<512>(v, ws, nullptr);
+    if (threadIdx.x < BINS) out[p * OS_BINS_MAX + threadIdx.x] = ex;
+    __syncthreads();
   }
 }
 
@@ -133,21 +210,21 @@ __global__ void __launch_bounds__(256) k2_os_hist(const uint64_t* __restrict__ s
     for (int p = 0; p < 5; ++p) atomicAdd(&hw[p][(uint32_t)(k >> (8 * p)) & 255u], 1u);
   }
   __syncthreads();
-  uint32_t* o = hist + (uint64_t)blockIdx.y * 5 * 256 + threadIdx.x;
+  uint32_t* o = hist + (uint64_t)blockIdx.y * OS_PASSES_MAX * OS_BINS_MAX + threadIdx.x;
 #pragma unroll
   for (int p = 0; p < 5; ++p) {
     const uint32_t v = h[0][p][threadIdx.x] + h[1][p][threadIdx.x] + h[2][p][threadIdx.x] + h[3][p][threadIdx.x];
-    if (v) atomicAdd(o + p * 256, v);
+    if (v) atomicAdd(o + p * OS_BINS_MAX, v);
   }
 }
 
-// counts -> exclusive bucket offsets, per block and pass.  grid (nb), 256 threads.
+// counts -> exclusive bucket offsets, per block and pass (8-bit digits, five passes).  grid (nb), 256 threads.
 __global__ void __launch_bounds__(256) k2_os_offsets(uint32_t* __restrict__ hist) {
   __shared__ uint32_t ws[256 / 32 + 1];
-  uint32_t* h = hist + (uint64_t)blockIdx.x * 5 * 256;
+  uint32_t* h = hist + (uint64_t)blockIdx.x * OS_PASSES_MAX * OS_BINS_MAX;
   for (int p = 0; p < 5; ++p) {
-    const uint32_t v = h[p * 256 + threadIdx.x];
-    h[p * 256 + threadIdx.x] = cta_excl_scan_add<256>(v, ws, nullptr);
+    const uint32_t v = h[p * OS_BINS_MAX + threadIdx.x];
+    h[p * OS_BINS_MAX + threadIdx.x] = cta_excl_scan_add<256>(v, ws, nullptr);
   }
 }
 
@@ -160,19 +237,23 @@ __device__ __forceinline__ void st_status(uint32_t* p, uint32_t v) {
   asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-// FROM_TEXT: pass 0 of the initial sort builds its elements (first 5 bytes of the rotation | pos) from the block's
-// text instead of reading a materialised key array.
-template <int OS_NT, int OS_IPT, int OS_MINB, bool FROM_TEXT>
+// KBITS: 0 = the list holds 64-bit elements; 8 / 7 / 6 / 4 = pass 0 of the initial sort builds its elements (the first
+// KSYMS symbols of the rotation, KBITS bits each | pos) from the block's text instead of reading a key array.
+// WBITS = digit width of the pass.
+template <int KBITS, int KSYMS, int WBITS>
 __global__ void __launch_bounds__(OS_NT, OS_MINB) k2_os_scatter(const uint64_t* __restrict__ src, uint64_t* __restrict__ dst,
                                                           const BlockDesc* __restrict__ desc,
                                                           const uint32_t* __restrict__ cnt,
                                                           const uint32_t* __restrict__ bucket_off,
                                                           uint32_t* __restrict__ status, uint32_t* __restrict__ ticket,
                                                           uint32_t ticket_base, uint32_t tiles_cap, uint32_t epoch,
-                                                          int pass) {
+                                                          int pass, const uint32_t* __restrict__ inuse) {
   extern __shared__ __align__(16) uint8_t os_raw[];
-  using OsSmem = OsSmemT<OS_NT, OS_IPT>;
-  constexpr int OS_TILE = OS_NT * OS_IPT, OS_WARPS = OS_NT / 32, OS_WCH = OS_TILE / OS_WARPS;
+  constexpr int BINS = 1 << WBITS;
+  constexpr int DPT = BINS / OS_NT;  // digits per thread in the per-digit phases (1 or 2)
+  static_assert(DPT >= 1 && BINS % OS_NT == 0, "digit count must be a multiple of the CTA size");
+  using OsSmem = OsSmemT<BINS>;
+  constexpr int OS_WARPS = OS_NT / 32, OS_WCH = OS_TILE / OS_WARPS;
   OsSmem& sm = *reinterpret_cast<OsSmem*>(os_raw);
   const uint32_t b = blockIdx.x;
   const uint32_t c = cnt[b];
@@ -180,7 +261,8 @@ __global__ void __launch_bounds__(OS_NT, OS_MINB) k2_os_scatter(const uint64_t* 
   const int w = threadIdx.x >> 5;
   const uint32_t lane = lane_id();
 #pragma unroll
-  for (int i = lane; i < 256; i += 32) sm.wcnt[w][i] = 0;
+  for (int i = lane; i < BINS; i += 32) sm.wcnt[w][i] = 0;
+  if (KBITS != 0 && KBITS != 8) build_sym_lut(inuse + b * 8, sm.lut);
   __syncthreads();
   const uint32_t tile = sm.tile;
   const uint32_t base = tile * OS_TILE;
@@ -188,7 +270,8 @@ __global__ void __launch_bounds__(OS_NT, OS_MINB) k2_os_scatter(const uint64_t* 
   const uint32_t tcount = min((uint32_t)OS_TILE, c - base);
   const uint32_t off = desc[b].off;
   const uint64_t* s = src + off + base;
-  const int shift = KEY_LO + 8 * pass;
+  const int shift = KEY_LO + WBITS * pass;
+  constexpr uint32_t DMASK = BINS - 1;
 
   // ---- rank inside the warp's 256-element chunk; memory order == (warp, row, lane), so the pass is stable
   uint64_t e[OS_IPT];
@@ -196,7 +279,7 @@ __global__ void __launch_bounds__(OS_NT, OS_MINB) k2_os_scatter(const uint64_t* 
 #pragma unroll
   for (int it = 0; it < OS_IPT; ++it) {
     const uint32_t li = w * OS_WCH + it * 32 + lane;
-    if (FROM_TEXT) {
+    if (KBITS != 0) {
       e[it] = ~0ull;
       if (li < tcount) {
         const uint8_t* t = reinterpret_cast<const uint8_t*>(src) + off;  // src carries the text pointer
@@ -204,8 +287,9 @@ __global__ void __launch_bounds__(OS_NT, OS_MINB) k2_os_scatter(const uint64_t* 
         uint64_t key = 0;
         uint32_t idx = pos;
 #pragma unroll
-        for (int j = 0; j < 5; ++j) {
-          key = (key << 8) | t[idx];
+        for (int j = 0; j < KSYMS; ++j) {
+          const uint32_t by = t[idx];
+          key = (key << KBITS) | (KBITS == 8 ? by : (uint32_t)sm.lut[by]);
           ++idx;
           if (idx == c) idx = 0;  // c == block length in pass 0
         }
@@ -221,13 +305,13 @@ __global__ void __launch_bounds__(OS_NT, OS_MINB) k2_os_scatter(const uint64_t* 
 #pragma unroll
   for (int it = 0; it < OS_IPT; ++it) {
     const uint32_t li = w * OS_WCH + it * 32 + lane;
-    const uint32_t dgt = li < tcount ? (uint32_t)(e[it] >> shift) & 255u : 0xFFFFu;
+    const uint32_t dgt = li < tcount ? (uint32_t)(e[it] >> shift) & DMASK : 0xFFFFu;
     peers[it] = __match_any_sync(0xffffffffu, dgt);
   }
 #pragma unroll
   for (int it = 0; it < OS_IPT; ++it) {
     const uint32_t li = w * OS_WCH + it * 32 + lane;
-    const uint32_t dgt = (uint32_t)(e[it] >> shift) & 255u;
+    const uint32_t dgt = (uint32_t)(e[it] >> shift) & DMASK;
     rk[it] = 0;
     if (li < tcount && (peers[it] & lanemask_lt()) == 0)  // lowest lane of the peer group
       rk[it] = atomicAdd(&sm.wcnt[w][dgt], (uint32_t)__popc(peers[it]));
@@ -239,45 +323,74 @@ __global__ void __launch_bounds__(OS_NT, OS_MINB) k2_os_scatter(const uint64_t* 
   }
   __syncthreads();
 
-  // ---- per digit: exclusive prefix over the warps, tile count, start inside the tile; publish + look back
-  uint32_t run = 0;
-  if (threadIdx.x < 256) {
+  // ---- per digit (thread t owns digits t*DPT .. t*DPT+DPT-1): exclusive prefix over the warps, tile count, start
+  // inside the tile; publish + look back
+  uint32_t run[DPT];
+  uint32_t tsum = 0;
+#pragma unroll
+  for (int q = 0; q < DPT; ++q) {
+    const uint32_t dgt = threadIdx.x * DPT + q;
+    uint32_t r = 0;
 #pragma unroll
     for (int ww = 0; ww < OS_WARPS; ++ww) {
-      const uint32_t t = sm.wcnt[ww][threadIdx.x];
-      sm.wcnt[ww][threadIdx.x] = run;
-      run += t;
+      const uint32_t t = sm.wcnt[ww][dgt];
+      sm.wcnt[ww][dgt] = r;
+      r += t;
     }
+    run[q] = r;
+    tsum += r;
   }
-  const uint32_t ds = cta_excl_scan_add<OS_NT>(run, sm.ws, nullptr);
-  if (threadIdx.x < 256) {
-    const uint32_t dgt = threadIdx.x;
-    uint32_t* st = status + ((uint64_t)b * tiles_cap) * 256 + dgt;
+  uint32_t ds = cta_excl_scan_add<OS_NT>(tsum, sm.ws, nullptr);
+  {
+    // the thread's DPT look-back chains advance in lock step: the status words of one earlier tile are fetched for
+    // all of them before any is waited for
+    uint32_t* st = status + ((uint64_t)b * tiles_cap) * OS_BINS_MAX + threadIdx.x * DPT;
     const uint32_t tag = epoch << 22;
-    uint32_t excl = 0;
+    uint32_t excl[DPT];
+#pragma unroll
+    for (int q = 0; q < DPT; ++q) excl[q] = 0;
     if (tile == 0) {
-      st_status(st, tag | ST_PREFIX | run);
+#pragma unroll
+      for (int q = 0; q < DPT; ++q) st_status(st + q, tag | ST_PREFIX | run[q]);
     } else {
-      st_status(st + (uint64_t)tile * 256, tag | ST_AGG | run);
-      for (int t = (int)tile - 1; t >= 0; --t) {
-        uint32_t v;
+#pragma unroll
+      for (int q = 0; q < DPT; ++q) st_status(st + (uint64_t)tile * OS_BINS_MAX + q, tag | ST_AGG | run[q]);
+      uint32_t open_mask = (1u << DPT) - 1u;
+      for (int t = (int)tile - 1; t >= 0 && open_mask; --t) {
+        uint32_t v[DPT];
+        bool ready;
         do {
-          v = ld_status(st + (uint64_t)t * 256);
-        } while ((v >> 22) != epoch);
-        excl += v & ST_VAL;
-        if (v & ST_PREFIX) break;
+          ready = true;
+#pragma unroll
+          for (int q = 0; q < DPT; ++q) v[q] = ld_status(st + (uint64_t)t * OS_BINS_MAX + q);
+#pragma unroll
+          for (int q = 0; q < DPT; ++q) ready &= (v[q] >> 22) == epoch;
+        } while (!ready);
+#pragma unroll
+        for (int q = 0; q < DPT; ++q) {
+          if (open_mask & (1u << q)) {
+            excl[q] += v[q] & ST_VAL;
+            if (v[q] & ST_PREFIX) open_mask &= ~(1u << q);
+          }
+        }
       }
-      st_status(st + (uint64_t)tile * 256, tag | ST_PREFIX | (excl + run));
+#pragma unroll
+      for (int q = 0; q < DPT; ++q) st_status(st + (uint64_t)tile * OS_BINS_MAX + q, tag | ST_PREFIX | (excl[q] + run[q]));
     }
-    sm.dstart[dgt] = ds;
-    sm.goff[dgt] = (int)(bucket_off[((uint64_t)b * 5 + pass) * 256 + dgt] + excl) - (int)ds;
+#pragma unroll
+    for (int q = 0; q < DPT; ++q) {
+      const uint32_t dgt = threadIdx.x * DPT + q;
+      sm.dstart[dgt] = ds;
+      sm.goff[dgt] = (int)(bucket_off[((uint64_t)b * OS_PASSES_MAX + pass) * OS_BINS_MAX + dgt] + excl[q]) - (int)ds;
+      ds += run[q];
+    }
   }
   __syncthreads();
 #pragma unroll
   for (int it = 0; it < OS_IPT; ++it) {
     const uint32_t li = w * OS_WCH + it * 32 + lane;
     if (li < tcount) {
-      const uint32_t dgt = (uint32_t)(e[it] >> shift) & 255u;
+      const uint32_t dgt = (uint32_t)(e[it] >> shift) & DMASK;
       sm.stage[sm.dstart[dgt] + sm.wcnt[w][dgt] + rk[it]] = e[it];
     }
   }
@@ -288,7 +401,7 @@ __global__ void __launch_bounds__(OS_NT, OS_MINB) k2_os_scatter(const uint64_t* 
     const uint32_t i = threadIdx.x + k * OS_NT;
     if (i < tcount) {
       const uint64_t v = sm.stage[i];
-      const uint32_t dgt = (uint32_t)(v >> shift) & 255u;
+      const uint32_t dgt = (uint32_t)(v >> shift) & DMASK;
       o[sm.goff[dgt] + (int)i] = v;
     }
   }
@@ -986,80 +1099,86 @@ __global__ void __launch_bounds__(G_NT) k2_finish(const uint8_t* __restrict__ tx
 }
 
 // ------------------------------------------------------------------ host driver
-// One 40-bit LSD sort of every block's list (cnt[b] elements at src + desc[b].off).  `txt` non-null: the list is
-// the initial key list and the digit histograms are the block's byte histogram.
 struct OsState {
   uint32_t epoch = 0;        // status-word tag of the most recent pass (10 bits; status is cleared at 0)
   uint32_t ticket_base = 0;  // tickets handed out per block so far
 };
 
-static void radix_sort40(Launcher& L, uint64_t*& src, uint64_t*& dst, const uint8_t* d_txt, const BlockDesc* d_desc,
-                         uint32_t nb, uint32_t maxcnt, BwtScratch& S, OsState& os) {
-  // tile geometry of the pass kernel (BZB200_OS_VARIANT picks another one for experiments)
-  static const int variant = [] {
-    const char* v = getenv("BZB200_OS_VARIANT");
-    return v ? atoi(v) : 5;  // measured on B200: 256 threads x 8 elements (2 048-element tiles, 4 CTAs/SM) is fastest
-  }();
-  static PerDeviceOnce once_os;
-  once_os.run([] {
-    cudaFuncSetAttribute((const void*)k2_os_scatter<512, 8, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         (int)sizeof(OsSmemT<512, 8>));
-    cudaFuncSetAttribute((const void*)k2_os_scatter<256, 16, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         (int)sizeof(OsSmemT<256, 16>));
-    cudaFuncSetAttribute((const void*)k2_os_scatter<1024, 8, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         (int)sizeof(OsSmemT<1024, 8>));
-    cudaFuncSetAttribute((const void*)k2_os_scatter<512, 16, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         (int)sizeof(OsSmemT<512, 16>));
-    cudaFuncSetAttribute((const void*)k2_os_scatter<384, 12, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         (int)sizeof(OsSmemT<384, 12>));
-    cudaFuncSetAttribute((const void*)k2_os_scatter<256, 8, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         (int)sizeof(OsSmemT<256, 8>));
-    cudaFuncSetAttribute((const void*)k2_os_scatter<256, 8, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         (int)sizeof(OsSmemT<256, 8>));
+template <int KBITS, int KSYMS, int WBITS>
+static void launch_pass(Launcher& L, const uint64_t* src, uint64_t* dst, const BlockDesc* d_desc, uint32_t nb,
+                        uint32_t tiles, BwtScratch& S, OsState& os, int pass, const uint32_t* d_inuse) {
+  static PerDeviceOnce once;
+  once.run([] {
+    cudaFuncSetAttribute((const void*)k2_os_scatter<KBITS, KSYMS, WBITS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)sizeof(OsSmemT<1 << WBITS>));
   });
-  const uint32_t tile_elems = variant == 2 || variant == 3 ? 8192u : variant == 4 ? 4608u : (variant == 0 || variant == 1) ? 4096u : 2048u;
-  const uint32_t tiles = (maxcnt + tile_elems - 1) / tile_elems;
-  if (tiles == 0) return;
-  const bool fuse_keys = d_txt && variant >= 5;  // default geometry: pass 0 reads the text, no key array
-  if (d_txt && !fuse_keys) {
-    const uint32_t tiles_n = (maxcnt + RS_TILE - 1) / RS_TILE;
-    L.launch("k2_init_keys", k2_init_keys, dim3(tiles_n, nb), dim3(RS_NT), d_txt, d_desc, src, S.cnt);
+  if (os.epoch == 1023) {  // tag space exhausted: start over with a clean status array
+    cudaMemsetAsync(S.hist, 0, (size_t)nb * S.tiles_cap * OS_BINS_MAX * sizeof(uint32_t), L.stream);
+    os.epoch = 0;
   }
-  cudaMemsetAsync(S.oshist, 0, (size_t)nb * 5 * 256 * sizeof(uint32_t), L.stream);
+  ++os.epoch;
+  L.launch_smem("k2_rs_scatter", k2_os_scatter<KBITS, KSYMS, WBITS>, dim3(nb, tiles), dim3(OS_NT),
+                sizeof(OsSmemT<1 << WBITS>), src, dst, d_desc, S.cnt, S.oshist, S.hist, S.ticket, os.ticket_base,
+                S.tiles_cap, os.epoch, pass, d_inuse);
+  os.ticket_base += tiles;
+}
+
+// LSD sort of every block's rotations by their initial key (built from the text in pass 0).  Returns the number of
+// passes; the sorted list ends up in `src`.
+template <int KBITS, int KSYMS, int WBITS>
+static int initial_sort_mode(Launcher& L, uint64_t*& src, uint64_t*& dst, const uint8_t* d_txt, const BlockDesc* d_desc,
+                             const uint32_t* d_inuse, uint32_t nb, uint32_t nmax, BwtScratch& S, OsState& os) {
+  constexpr int P = (KBITS * KSYMS + WBITS - 1) / WBITS;
+  const uint32_t tiles = (nmax + OS_TILE - 1) / OS_TILE;
+  const uint32_t chunk = 16 * 4096;
+  const uint32_t chunks = (nmax + chunk - 1) / chunk;
+  if (KBITS == 8) {
+    cudaMemsetAsync(S.oshist, 0, (size_t)nb * OS_PASSES_MAX * OS_BINS_MAX * sizeof(uint32_t), L.stream);
+    L.launch("k2_os_hist_txt", k2_os_hist_txt, dim3(chunks, nb), dim3(256), d_txt, d_desc, S.oshist, S.cnt, chunk);
+    L.launch("k2_os_offsets", k2_os_offsets, dim3(nb), dim3(256), S.oshist);
+  } else {
+    constexpr int BITS = KBITS == 8 ? 4 : KBITS;  // (the byte mode never gets here; keeps the table small when instantiated)
+    constexpr size_t NP = (size_t)1 << (2 * BITS);
+    static PerDeviceOnce once;
+    once.run([] {
+      cudaFuncSetAttribute((const void*)k2_pair_hist<BITS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)(NP * 4 + 256));
+    });
+    cudaMemsetAsync(S.pairhist, 0, (size_t)nb * NP * sizeof(uint32_t), L.stream);
+    L.launch_smem("k2_pair_hist", k2_pair_hist<BITS>, dim3(chunks, nb), dim3(256), NP * 4 + 256, d_txt, d_desc, d_inuse,
+                  S.pairhist, S.cnt, chunk);
+    L.launch("k2_digit_offsets", k2_digit_offsets<BITS, KSYMS, WBITS>, dim3(nb), dim3(512), (const uint32_t*)S.pairhist,
+             S.oshist);
+  }
+  for (int p = 0; p < P; ++p) {
+    if (p == 0)
+      launch_pass<KBITS, KSYMS, WBITS>(L, reinterpret_cast<const uint64_t*>(d_txt), dst, d_desc, nb, tiles, S, os, p,
+                                       d_inuse);
+    else
+      launch_pass<0, 0, WBITS>(L, src, dst, d_desc, nb, tiles, S, os, p, d_inuse);
+    uint64_t* t = src; src = dst; dst = t;
+  }
+  return P;
+}
+
+size_t bwt_pairhist_bytes(uint32_t nb, uint32_t max_alpha) {
+  const KeyMode m = key_mode(max_alpha);
+  return m.bits == 8 ? 16 : (size_t)nb * ((size_t)1 << (2 * m.bits)) * sizeof(uint32_t);
+}
+
+// One 40-bit LSD sort (five 8-bit passes) of every block's list of (group, key, pos) elements (cnt[b] elements at
+// src + desc[b].off): the BIG-group path of a doubling round.
+static void radix_sort40(Launcher& L, uint64_t*& src, uint64_t*& dst, const BlockDesc* d_desc, uint32_t nb,
+                         uint32_t maxcnt, BwtScratch& S, OsState& os) {
+  const uint32_t tiles = (maxcnt + OS_TILE - 1) / OS_TILE;
+  if (tiles == 0) return;
+  cudaMemsetAsync(S.oshist, 0, (size_t)nb * OS_PASSES_MAX * OS_BINS_MAX * sizeof(uint32_t), L.stream);
   const uint32_t chunk = 16 * 4096;
   const uint32_t chunks = (maxcnt + chunk - 1) / chunk;
-  if (d_txt)
-    L.launch("k2_os_hist_txt", k2_os_hist_txt, dim3(chunks, nb), dim3(256), d_txt, d_desc, S.oshist, S.cnt, chunk);
-  else
-    L.launch("k2_os_hist", k2_os_hist, dim3(chunks, nb), dim3(256), src, d_desc, S.cnt, S.oshist, chunk);
+  L.launch("k2_os_hist", k2_os_hist, dim3(chunks, nb), dim3(256), src, d_desc, S.cnt, S.oshist, chunk);
   L.launch("k2_os_offsets", k2_os_offsets, dim3(nb), dim3(256), S.oshist);
   for (int p = 0; p < 5; ++p) {
-    if (os.epoch == 1023) {  // tag space exhausted: start over with a clean status array
-      cudaMemsetAsync(S.hist, 0, (size_t)nb * S.tiles_cap * 256 * sizeof(uint32_t), L.stream);
-      os.epoch = 0;
-    }
-    ++os.epoch;
-#define OS_LAUNCH(NT, IPT, MB)                                                                                     \
-  L.launch_smem("k2_rs_scatter", k2_os_scatter<NT, IPT, MB, false>, dim3(nb, tiles), dim3(NT),                     \
-                sizeof(OsSmemT<NT, IPT>), src, dst, d_desc, S.cnt, S.oshist, S.hist, S.ticket, os.ticket_base,     \
-                S.tiles_cap, os.epoch, p)
-    switch (variant) {
-      case 1: OS_LAUNCH(256, 16, 2); break;
-      case 2: OS_LAUNCH(1024, 8, 1); break;
-      case 3: OS_LAUNCH(512, 16, 1); break;
-      case 4: OS_LAUNCH(384, 12, 2); break;
-      case 0: OS_LAUNCH(512, 8, 2); break;
-      default:
-        if (p == 0 && fuse_keys)  // elements built from the text on the fly
-          L.launch_smem("k2_rs_scatter", k2_os_scatter<256, 8, 4, true>, dim3(nb, tiles), dim3(256),
-                        sizeof(OsSmemT<256, 8>), reinterpret_cast<const uint64_t*>(d_txt), dst, d_desc, S.cnt, S.oshist,
-                        S.hist, S.ticket, os.ticket_base, S.tiles_cap, os.epoch, p);
-        else
-          OS_LAUNCH(256, 8, 4);
-        break;
-    }
-#undef OS_LAUNCH
-    os.ticket_base += tiles;
+    launch_pass<0, 0, 8>(L, src, dst, d_desc, nb, tiles, S, os, p, nullptr);
     uint64_t* t = src; src = dst; dst = t;
   }
 }
@@ -1077,8 +1196,8 @@ static void regroup(Launcher& L, const uint64_t* srt, const BlockDesc* d_desc, u
                   srt, d_desc, S.cnt, S.tsum, S.tiles_cap, S.rank, S.sa, S.stats);
 }
 
-int run_bwt(Launcher& L, const uint8_t* d_txt, const BlockDesc* d_desc, uint32_t nb, uint32_t nmax, uint64_t M,
-            BwtScratch& S, uint8_t* d_last, uint32_t* d_origptr, BwtStats* stats) {
+int run_bwt(Launcher& L, const uint8_t* d_txt, const BlockDesc* d_desc, const uint32_t* d_inuse, uint32_t max_alpha,
+            uint32_t nb, uint32_t nmax, uint64_t M, BwtScratch& S, uint8_t* d_last, uint32_t* d_origptr, BwtStats* stats) {
   cudaStream_t st = L.stream;
   const uint32_t ls_tiles = (nmax + LS_T - 1) / LS_T;
   cudaMemsetAsync(S.state, 0, nb * sizeof(uint32_t), st);
@@ -1102,13 +1221,25 @@ int run_bwt(Launcher& L, const uint8_t* d_txt, const BlockDesc* d_desc, uint32_t
     cudaFuncSetAttribute((const void*)k2_local_sort<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LsSmem));
   });
   uint32_t rounds = 0, passes = 0;
-  uint64_t elems = 0, radix_elem_passes = 5ull * M, local_elems = 0;
+  uint64_t elems = 0, local_elems = 0;
   uint64_t *src = S.A, *dst = S.B;
   OsState os;
-  cudaMemsetAsync(S.hist, 0, (size_t)nb * S.tiles_cap * 256 * sizeof(uint32_t), st);
+  cudaMemsetAsync(S.hist, 0, (size_t)nb * S.tiles_cap * OS_BINS_MAX * sizeof(uint32_t), st);
   cudaMemsetAsync(S.ticket, 0, nb * sizeof(uint32_t), st);
-  radix_sort40(L, src, dst, d_txt, d_desc, nb, nmax, S, os);
-  passes += 5;
+  static const int force_mode = [] {
+    const char* e = getenv("BZB200_KEY_BITS");  // experiments: 8 forces the byte-key sort
+    return e ? atoi(e) : 0;
+  }();
+  const KeyMode km = key_mode(force_mode == 8 ? 0u : max_alpha);
+  int p0;
+  switch (km.bits) {
+    case 7: p0 = initial_sort_mode<7, 5, 9>(L, src, dst, d_txt, d_desc, d_inuse, nb, nmax, S, os); break;
+    case 6: p0 = initial_sort_mode<6, 6, 9>(L, src, dst, d_txt, d_desc, d_inuse, nb, nmax, S, os); break;
+    case 4: p0 = initial_sort_mode<4, 8, 8>(L, src, dst, d_txt, d_desc, d_inuse, nb, nmax, S, os); break;
+    default: p0 = initial_sort_mode<8, 5, 8>(L, src, dst, d_txt, d_desc, d_inuse, nb, nmax, S, os); break;
+  }
+  passes += p0;
+  uint64_t radix_elem_passes = (uint64_t)p0 * M;
   elems += M;
   regroup(L, src, d_desc, nb, nmax, S, 1);
   L.launch("k2_round_finalize", k2_round_finalize, dim3((nb + 255) / 256), dim3(256), nb, 0u, d_desc, S.cnt, S.stats,
@@ -1119,7 +1250,7 @@ int run_bwt(Launcher& L, const uint8_t* d_txt, const BlockDesc* d_desc, uint32_t
   if (cudaMemcpyAsync(g, S.global, sizeof(g), cudaMemcpyDeviceToHost, st) != cudaSuccess) return -2;
   if (cudaStreamSynchronize(st) != cudaSuccess) return -2;
 
-  uint32_t h = 5;
+  uint32_t h = (uint32_t)km.syms;  // the initial key covers the first h symbols of every rotation
   while (g[0] > 0) {
     if (g[3]) return -5;
     ++rounds;
@@ -1160,7 +1291,7 @@ int run_bwt(Launcher& L, const uint8_t* d_txt, const BlockDesc* d_desc, uint32_t
     const uint32_t maxbig = g[1];
     if (maxbig > 0) {
       uint64_t *s2 = S.A, *d2 = S.B;
-      radix_sort40(L, s2, d2, nullptr, d_desc, nb, maxbig, S, os);
+      radix_sort40(L, s2, d2, d_desc, nb, maxbig, S, os);
       passes += 5;
       regroup(L, s2, d_desc, nb, maxbig, S, 0);
     }

@@ -160,7 +160,8 @@ __global__ void __launch_bounds__(256) k3_chunk_scan_b(const BlockDesc* __restri
 // chunk at its start is rebuilt by the whole warp from the chunk's `last occurrence` state (rank of every byte's
 // previous occurrence).
 constexpr int MTF_FRONT = 32;                      // list entries held in registers (8 packed words)
-constexpr int MTF_DEEP_WORDS = (256 - MTF_FRONT) / 4;  // the rest: packed words in shared memory, one column per lane
+constexpr int MTF_DEEP_WORDS = (256 - MTF_FRONT) / 4;  // the rest: packed words in shared memory, one column per lane;
+                                                       // a launch keeps only as many as the batch's largest alphabet needs
 
 struct MtfLane {
   uint32_t f[8];
@@ -174,7 +175,8 @@ __device__ __forceinline__ uint32_t mtf_word_hit(uint32_t f, uint32_t carry, uin
 
 // Moves byte c (not at the front) to the front of the lane's list, returns its previous position.  The register
 // part is branch-free (lanes of a warp sit at different depths; a branch per word would serialise them).
-__device__ __forceinline__ uint32_t mtf_lane_access(MtfLane& l, uint32_t c, uint32_t* deep /* column, stride 32 */) {
+__device__ __forceinline__ uint32_t mtf_lane_access(MtfLane& l, uint32_t c, uint32_t* deep /* column, stride 32 */,
+                                                    uint32_t deep_words) {
   const uint32_t x = c * 0x01010101u;
   // every word's new value depends only on OLD values (the byte entering word k is the top byte of old word k-1),
   // so the eight updates are independent instructions
@@ -199,7 +201,7 @@ __device__ __forceinline__ uint32_t mtf_lane_access(MtfLane& l, uint32_t c, uint
   }
   const bool done = before == 0;
   if (done) return pos;
-  for (uint32_t k = 0; k < (uint32_t)MTF_DEEP_WORDS; ++k) {  // every entry in front of c moves down by one
+  for (uint32_t k = 0; k < deep_words; ++k) {  // every entry in front of c moves down by one
     const uint32_t f = deep[k * 32];
     const uint32_t m = __vcmpeq4(f, x);
     if (m) {
@@ -258,13 +260,16 @@ __global__ void __launch_bounds__(MTF_WARPS * 32) k3_apply(const uint8_t* __rest
                                                            const uint32_t* __restrict__ inuse,
                                                            const int* __restrict__ chunk_state,
                                                            const uint2* __restrict__ chunk_base, uint32_t chunks_cap,
-                                                           uint32_t nb, uint32_t groups_cap,
+                                                           uint32_t nb, uint32_t groups_cap, uint32_t deep_words,
                                                            uint16_t* __restrict__ sym, uint32_t* __restrict__ freq) {
+  // deep_words = words of the shared-memory tail every lane keeps: ceil((largest alphabet of the batch - 32) / 4); text
+  // (~70 symbols) needs 10 of the 56 a full byte alphabet takes, which is what lets 2-3x more warps live on an SM
   __shared__ uint8_t s_front[MTF_WARPS][MTF_FRONT];
-  __shared__ uint32_t s_deep[MTF_WARPS][MTF_DEEP_WORDS][32];
   __shared__ uint32_t s_freqw[MTF_WARPS][MAX_ALPHA + 2];
+  extern __shared__ __align__(16) uint32_t s_deep_raw[];  // [MTF_WARPS][deep_words][32]
   const int w = threadIdx.x >> 5;
   const uint32_t lane = lane_id();
+  uint32_t* s_deepw = s_deep_raw + (size_t)w * deep_words * 32;
   // warp task = (block, group of 32 chunks); the warps of a CTA may belong to different blocks
   const uint32_t task = blockIdx.x * MTF_WARPS + w;
   const uint32_t blk = task / groups_cap;
@@ -288,7 +293,7 @@ __global__ void __launch_bounds__(MTF_WARPS * 32) k3_apply(const uint8_t* __rest
       for (int k = 0; k < 8; ++k) mine[k] = cs[k * 32 + lane];
       // filler behind the in-use bytes (a real 0xFF always sits in front of it)
       s_front[w][lane] = 0xFFu;
-      for (int q = lane; q < MTF_DEEP_WORDS; q += 32) s_deep[w][q][j] = 0xFFFFFFFFu;
+      for (uint32_t q = lane; q < deep_words; q += 32) s_deepw[q * 32 + j] = 0xFFFFFFFFu;
       // rank of every byte's previous occurrence among the in-use bytes = its list position; the 256 values are
       // broadcast from the registers that hold them
       uint32_t rank[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -307,7 +312,7 @@ __global__ void __launch_bounds__(MTF_WARPS * 32) k3_apply(const uint8_t* __rest
         if (mine[k] != NEG_UNUSED) {
           const uint32_t p = rank[k];
           if (p < (uint32_t)MTF_FRONT) s_front[w][p] = (uint8_t)(k * 32 + lane);
-          else reinterpret_cast<uint8_t*>(&s_deep[w][(p - MTF_FRONT) >> 2][j])[(p - MTF_FRONT) & 3u] = (uint8_t)(k * 32 + lane);
+          else reinterpret_cast<uint8_t*>(&s_deepw[((p - MTF_FRONT) >> 2) * 32 + j])[(p - MTF_FRONT) & 3u] = (uint8_t)(k * 32 + lane);
         }
       }
       __syncwarp();
@@ -336,14 +341,14 @@ __global__ void __launch_bounds__(MTF_WARPS * 32) k3_apply(const uint8_t* __rest
       mo.freq = s_freq;
       uint32_t zrun = cb.y;
       uint32_t prev = c0 > 0 ? L[-1] : smallest_inuse(inuse + blk * 8);
-      uint32_t* deep = &s_deep[w][0][lane];
+      uint32_t* deep = s_deepw + lane;
       auto step = [&](uint32_t c) {
         if (c == prev) {
           ++zrun;
         } else {
           mo.zero_run(zrun);
           zrun = 0;
-          mo.put(mtf_lane_access(ml, c, deep) + 1u);  // position p > 0 is written as p+1 (encoder.rs:340)
+          mo.put(mtf_lane_access(ml, c, deep, deep_words) + 1u);  // position p > 0 is written as p+1 (encoder.rs:340)
           prev = c;
         }
       };
@@ -379,8 +384,8 @@ __global__ void __launch_bounds__(MTF_WARPS * 32) k3_apply(const uint8_t* __rest
 }
 
 void launch_mtf(Launcher& L, const uint8_t* d_last, const BlockDesc* d_desc, const uint32_t* d_inuse, uint32_t nb,
-                uint32_t nmax, int* d_chunk_state, uint4* d_chunk_zle, uint2* d_chunk_base, uint32_t chunks_cap,
-                uint16_t* d_sym, uint32_t* d_freq, uint32_t* d_mtf_count) {
+                uint32_t nmax, uint32_t max_alpha_bytes, int* d_chunk_state, uint4* d_chunk_zle, uint2* d_chunk_base,
+                uint32_t chunks_cap, uint16_t* d_sym, uint32_t* d_freq, uint32_t* d_mtf_count) {
   const uint32_t nch = (nmax + MTF_CHUNK - 1) / MTF_CHUNK;
   const uint32_t gx = (nch + MTF_WARPS - 1) / MTF_WARPS;
   cudaMemsetAsync(d_freq, 0, (size_t)nb * MAX_ALPHA * sizeof(uint32_t), L.stream);
@@ -390,8 +395,12 @@ void launch_mtf(Launcher& L, const uint8_t* d_last, const BlockDesc* d_desc, con
            (const uint4*)d_chunk_zle, d_chunk_base, chunks_cap, d_mtf_count);
   const uint32_t groups_cap = (nch + 31) / 32;  // warp tasks per block: one lane per chunk
   const uint32_t ntask = groups_cap * nb;
-  L.launch("k3_apply", k3_apply, dim3((ntask + MTF_WARPS - 1) / MTF_WARPS), dim3(MTF_WARPS * 32), d_last, d_desc,
-           d_inuse, (const int*)d_chunk_state, (const uint2*)d_chunk_base, chunks_cap, nb, groups_cap, d_sym, d_freq);
+  // in-use bytes of the batch's largest alphabet beyond the 32 register entries, in packed words (at least one)
+  const uint32_t a = max_alpha_bytes < 1 || max_alpha_bytes > 256 ? 256u : max_alpha_bytes;
+  const uint32_t deep_words = a > (uint32_t)MTF_FRONT ? (a - MTF_FRONT + 3) / 4 : 1u;
+  L.launch_smem("k3_apply", k3_apply, dim3((ntask + MTF_WARPS - 1) / MTF_WARPS), dim3(MTF_WARPS * 32),
+                (size_t)MTF_WARPS * deep_words * 32 * sizeof(uint32_t), d_last, d_desc, d_inuse, (const int*)d_chunk_state,
+                (const uint2*)d_chunk_base, chunks_cap, nb, groups_cap, deep_words, d_sym, d_freq);
 }
 
 }  // namespace bzb

@@ -79,6 +79,10 @@ void launch_k1_slice_heads(Launcher& L, const uint8_t* v_in, uint64_t N, uint64_
 void launch_k1_slice_summary(Launcher& L, const long long* head, const uint32_t* cnt, uint64_t n, uint64_t* d_out2);
 void launch_k1_slice_counts(Launcher& L, const uint8_t* v_in, uint64_t N, uint64_t t_a, uint64_t t_b, long long carry_in,
                             const long long* v_tile_head, long long* v_tile_carry, uint32_t* v_tile_cnt);
+void launch_k1_slice_scan_carry(Launcher& L, uint64_t t_a, uint64_t t_b, long long carry_in, const long long* v_tile_head,
+                                long long* v_tile_carry);
+void launch_k1_slice_tile_counts(Launcher& L, const uint8_t* v_in, uint64_t N, uint64_t t_a, uint64_t t_b,
+                                 const long long* v_tile_carry, uint32_t* v_tile_cnt);
 void launch_k1_slice_prefix(Launcher& L, uint64_t t_a, uint64_t t_b, uint64_t E_in, const uint32_t* v_tile_cnt,
                             uint64_t* v_tile_E);
 void launch_k1_slice_windows(Launcher& L, const uint8_t* v_in, uint64_t N, uint32_t T, const long long* v_tile_carry,
@@ -98,8 +102,9 @@ struct BwtScratch {
   uint2* tile_meta;     // [nb][ls_tiles] (entries in the tile's work list, entries before its first group head)
   uint32_t ls_tiles_cap;
   uint32_t* cnt;        // [nb] active elements per block
-  uint32_t* hist;       // [nb][tiles][256] radix pass: per-tile status words (decoupled look-back)
-  uint32_t* oshist;     // [nb][5][256] digit histograms -> bucket offsets of the five passes
+  uint32_t* hist;       // [nb][tiles][512] radix pass: per-tile status words (decoupled look-back)
+  uint32_t* oshist;     // [nb][5][512] digit histograms -> bucket offsets of the passes (row pitch 512)
+  uint32_t* pairhist;   // [nb][2^(2 bits)] symbol-pair histogram of the compact-key initial sort
   uint32_t* ticket;     // [nb] tile tickets
   int4* tsum;           // [nb][tiles] regroup tile summaries
   uint32_t* state;      // [nb] 0 active, 1 fix-up pending, 2 done
@@ -121,13 +126,17 @@ struct BwtStats {
   uint64_t radix_elem_passes = 0;  // elements moved by radix passes (list length x 5, summed)
   uint64_t local_elems = 0;        // work-list entries handled by k2_local_sort
 };
-int run_bwt(Launcher& L, const uint8_t* d_txt, const BlockDesc* d_desc, uint32_t nb, uint32_t nmax, uint64_t M,
-            BwtScratch& S, uint8_t* d_last, uint32_t* d_origptr, BwtStats* stats);
+// d_inuse[nb][8] = in-use byte maps of the blocks, max_alpha = most in-use byte values of any block (0: unknown): the
+// initial sort packs its keys with the bit width that alphabet needs (k2_bwt.cu, "Initial sort keys").
+size_t bwt_pairhist_bytes(uint32_t nb, uint32_t max_alpha);
+int run_bwt(Launcher& L, const uint8_t* d_txt, const BlockDesc* d_desc, const uint32_t* d_inuse, uint32_t max_alpha,
+            uint32_t nb, uint32_t nmax, uint64_t M, BwtScratch& S, uint8_t* d_last, uint32_t* d_origptr, BwtStats* stats);
 
 // ---- k3_mtf.cu ----
 uint32_t mtf_chunk_elems();
 void launch_mtf(Launcher& L, const uint8_t* d_last, const BlockDesc* d_desc, const uint32_t* d_inuse, uint32_t nb,
-                uint32_t nmax, int* d_chunk_state /*[nb][chunks][256]*/, uint4* d_chunk_zle /*[nb][chunks]*/,
+                uint32_t nmax, uint32_t max_alpha_bytes /* most in-use byte values of any block, 0 = unknown */,
+                int* d_chunk_state /*[nb][chunks][256]*/, uint4* d_chunk_zle /*[nb][chunks]*/,
                 uint2* d_chunk_base /*[nb][chunks]*/, uint32_t chunks_cap, uint16_t* d_sym, uint32_t* d_freq /*[nb][258]*/,
                 uint32_t* d_mtf_count /*[nb]*/);
 

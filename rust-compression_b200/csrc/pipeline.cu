@@ -136,7 +136,7 @@ int bzb200_ctx_create_impl(int device, void* stream, bool own_stream, bzb200_ctx
             &c->stats, &c->rounds, &c->global, &c->last, &c->origptr, &c->chunk_state, &c->chunk_zle, &c->chunk_base,
             &c->sym, &c->freq, &c->mtf_count, &c->lens, &c->rfreq, &c->sel, &c->selmtf, &c->codes, &c->gbits, &c->meta,
             &c->lm_scratch, &c->lm_list, &c->lm_count, &c->blockbit, &c->bitcursor, &c->combined, &c->stage_in,
-            &c->stage_out, &c->dec_in, &c->dec_out, &c->sl_F, &c->sl_sum};
+            &c->stage_out, &c->dec_in, &c->dec_out, &c->sl_F, &c->sl_sum, &c->pairhist};
   for (DevBuf& b : c->dec_bufs) c->all.push_back(&b);
   *out = c;
   return BZB200_OK;
@@ -356,6 +356,9 @@ static int prepare_blocks(bzb200_ctx* c, uint32_t b0, uint32_t b1) {
   TRY(check_launch(c));
   CK(c, cudaMemcpyAsync(c->h_crc.data() + b0, ptr<uint32_t>(c->crc) + b0, (size_t)(b1 - b0) * 4, cudaMemcpyDeviceToHost,
                         c->stream));
+  if (c->h_inuse.size() < (size_t)c->nblocks * 8) c->h_inuse.resize((size_t)c->nblocks * 8);
+  CK(c, cudaMemcpyAsync(c->h_inuse.data() + (size_t)b0 * 8, ptr<uint32_t>(c->inuse) + (size_t)b0 * 8,
+                        (size_t)(b1 - b0) * 32, cudaMemcpyDeviceToHost, c->stream));
   CK(c, cudaStreamSynchronize(c->stream));
   c->prep_lo = b0;
   c->prep_hi = b1;
@@ -395,8 +398,15 @@ static int encode_batch(bzb200_ctx* c, uint32_t b0, uint32_t nb, uint8_t* d_out,
   const uint32_t ls_tiles = (nmax + ls_tile - 1) / ls_tile + 1;
   TRY(ensure(c, c->tile_meta, (size_t)nb * ls_tiles * 8));
   TRY(ensure(c, c->cnt, (size_t)nb * 4));
-  TRY(ensure(c, c->hist, (size_t)nb * tiles * 256 * 4));
-  TRY(ensure(c, c->oshist, (size_t)nb * 5 * 256 * 4));
+  TRY(ensure(c, c->hist, (size_t)nb * tiles * 512 * 4));
+  TRY(ensure(c, c->oshist, (size_t)nb * 5 * 512 * 4));
+  uint32_t max_alpha = 0;  // most in-use byte values of any block of the batch
+  for (uint32_t i = 0; i < nb; ++i) {
+    uint32_t a = 0;
+    for (int k = 0; k < 8; ++k) a += (uint32_t)__builtin_popcount(c->h_inuse[(size_t)(b0 + i) * 8 + k]);
+    max_alpha = std::max(max_alpha, a);
+  }
+  TRY(ensure(c, c->pairhist, bwt_pairhist_bytes(nb, max_alpha)));
   TRY(ensure(c, c->ticket, (size_t)nb * 4));
   TRY(ensure(c, c->tsum, (size_t)nb * tiles * sizeof(int4)));
   TRY(ensure(c, c->state, (size_t)nb * 4));
@@ -442,6 +452,7 @@ static int encode_batch(bzb200_ctx* c, uint32_t b0, uint32_t nb, uint8_t* d_out,
   S.cnt = ptr<uint32_t>(c->cnt);
   S.hist = ptr<uint32_t>(c->hist);
   S.oshist = ptr<uint32_t>(c->oshist);
+  S.pairhist = ptr<uint32_t>(c->pairhist);
   S.ticket = ptr<uint32_t>(c->ticket);
   S.tsum = ptr<int4>(c->tsum);
   S.state = ptr<uint32_t>(c->state);
@@ -451,7 +462,8 @@ static int encode_batch(bzb200_ctx* c, uint32_t b0, uint32_t nb, uint8_t* d_out,
   S.rounds = ptr<uint32_t>(c->rounds);
   S.global = ptr<uint32_t>(c->global);
   S.tiles_cap = tiles;
-  int r = run_bwt(c->L, d_txt, d_desc, nb, nmax, M, S, ptr<uint8_t>(c->last), ptr<uint32_t>(c->origptr), &c->bstats);
+  int r = run_bwt(c->L, d_txt, d_desc, d_inuse, max_alpha, nb, nmax, M, S, ptr<uint8_t>(c->last), ptr<uint32_t>(c->origptr),
+                  &c->bstats);
   c->stat_rle += M;
   if (r != 0) {
     TRY(check_launch(c));
@@ -461,7 +473,7 @@ static int encode_batch(bzb200_ctx* c, uint32_t b0, uint32_t nb, uint8_t* d_out,
     return r == -5 ? BZB200_E_INTERNAL : BZB200_E_CUDA;
   }
 
-  launch_mtf(c->L, ptr<uint8_t>(c->last), d_desc, d_inuse, nb, nmax, ptr<int>(c->chunk_state),
+  launch_mtf(c->L, ptr<uint8_t>(c->last), d_desc, d_inuse, nb, nmax, max_alpha, ptr<int>(c->chunk_state),
              ptr<uint4>(c->chunk_zle), ptr<uint2>(c->chunk_base), chunks, ptr<uint16_t>(c->sym),
              ptr<uint32_t>(c->freq), ptr<uint32_t>(c->mtf_count));
 

@@ -37,12 +37,14 @@ int ensure_tiles(bzb200_ctx* c, uint64_t ntl) {
   return BZB200_OK;
 }
 
-// heads -> carry -> counts -> prefix for tiles [ta, tb) with the slice's carried-in values (ta == sl_t0: from scratch)
-int summarise(bzb200_ctx* c, uint64_t tb) {
-  const uint64_t ta = c->sl_t0;
-  launch_k1_slice_heads(c->L, v_in(c), c->n_in, ta, tb, v_head(c));
-  launch_k1_slice_counts(c->L, v_in(c), c->n_in, ta, tb, c->sl_carry_in, v_head(c), v_carry(c), v_cnt(c));
-  launch_k1_slice_prefix(c->L, ta, tb, c->sl_E_lo, v_cnt(c), v_E(c));
+// Tile summaries of the new tiles [told, tb) behind the ones the slice already has: the per-tile kernels run on the new
+// tiles only; the two single-CTA scans run again over [t0, tb) (they rewrite the old entries with the same values).
+int summarise_more(bzb200_ctx* c, uint64_t told, uint64_t tb) {
+  const uint64_t t0 = c->sl_t0;
+  launch_k1_slice_heads(c->L, v_in(c), c->n_in, told, tb, v_head(c));
+  launch_k1_slice_scan_carry(c->L, t0, tb, c->sl_carry_in, v_head(c), v_carry(c));
+  launch_k1_slice_tile_counts(c->L, v_in(c), c->n_in, told, tb, v_carry(c), v_cnt(c));
+  launch_k1_slice_prefix(c->L, t0, tb, c->sl_E_lo, v_cnt(c), v_E(c));
   return check_launch(c);
 }
 
@@ -270,8 +272,9 @@ int bzb200_slice_extend(bzb200_ctx* c, uint64_t avail_hi) {
       return BZB200_E_ARG;
     }
   }
+  const uint64_t told = c->sl_tn;
   c->sl_tn = tn;
-  return summarise(c, tn);
+  return summarise_more(c, told, tn);
 }
 
 }  // extern "C"
