@@ -686,18 +686,27 @@ def main():
         base = h_in.data_ptr()
         piece = 1 << 20
 
+        phase_s = {"write": 0.0, "finish": 0.0, "read": 0.0}
+
         def drive(h):
+            got = 0
+            t0 = time.perf_counter()
             for lo in range(0, total_bytes, piece):
                 rc = L.bzb200_enc_write(h, C.c_void_p(base + lo), min(piece, total_bytes - lo))
                 assert rc == 0, L.bzb200_enc_last_error(h)
+                if L.bzb200_enc_output_size(h):  # blocks that have closed are taken out while the input is still coming
+                    got += L.bzb200_enc_read(h, C.c_void_p(h_out.data_ptr() + got), h_out.numel() - got)
+            t1 = time.perf_counter()
             rc = L.bzb200_enc_finish(h)
             assert rc == 0, L.bzb200_enc_last_error(h)
-            got = 0
+            t2 = time.perf_counter()
             while True:
                 k = L.bzb200_enc_read(h, C.c_void_p(h_out.data_ptr() + got), h_out.numel() - got)
                 if k == 0:
                     break
                 got += k
+            t3 = time.perf_counter()
+            phase_s["write"], phase_s["finish"], phase_s["read"] = t1 - t0, t2 - t1, t3 - t2
             L.bzb200_enc_reset(h)
             return got
         h = step_stream()
@@ -713,7 +722,9 @@ def main():
         stream_leg = {"value": total_bytes / (ms_s / 1e3) / 1e6, "unit": "MB/s", "ms_per_step": ms_s, "steps": s_steps,
                       "api": "bzb200_enc_write x %d (1 MiB pieces) + bzb200_enc_finish + bzb200_enc_read, %d GPU(s)"
                              % ((total_bytes + piece - 1) // piece, world),
-                      "window_bytes": int(os.environ.get("BZB200_ENC_WINDOW", str((256 << 20) * world)))}
+                      "window_bytes": int(os.environ.get("BZB200_ENC_WINDOW", str((256 << 20) * world))),
+                      "last_step_ms": {k: round(v * 1e3, 1) for k, v in phase_s.items()},
+                      "pattern": "write 1 MiB, take out whatever has become readable, ...; finish; read the rest"}
     if world > 1:
         dist.barrier(group=idle)
 

@@ -66,12 +66,16 @@ BZB200_API int bzb200_enc_create(int level, int device, bzb200_enc** out);
  * what `BZip2Encoder::new(level)` binds on a multi-GPU box (SURVEY.md section 8(b),(e)); the stream is bit-identical
  * to the single-GPU one. */
 BZB200_API int bzb200_enc_create_multi(int level, int ngpus, const int* devices, bzb200_enc** out);
-/* Action::Run: append n input bytes (copied into one of two pinned window buffers; 256 MiB per GPU, env
- * BZB200_ENC_WINDOW).  A full window is handed to the object's worker thread, which compresses every block that has
- * already closed while the caller keeps writing into the other buffer; their bytes become readable as soon as the
- * window is done, and the still-open last block is carried in front of the next window (the
- * reference also yields a block as soon as it closes, encoder.rs:91-107).  The call returns after the copy unless both
- * buffers are busy.  Only the concatenation of all bytes read is defined, not which call yields which. */
+/* Action::Run: append n input bytes (copied before the call returns) to the window being filled (256 MiB per GPU, the
+ * first window of a stream 64 MiB per GPU; env BZB200_ENC_WINDOW, BZB200_ENC_FIRST_WINDOW).  A full window is handed
+ * to the object's worker thread, which compresses every block that has already closed while the caller keeps writing
+ * into the second window; their bytes become readable as soon as the window is done, and the still-open last block is
+ * carried in front of the next window (the reference also yields a block as soon as it
+ * closes, encoder.rs:91-107).  Only the concatenation of all bytes read is defined, not which call yields which.
+ *   One GPU: the windows live in device memory — the call is one DMA from p into HBM when p is pinned memory (the
+ *   driver's staged copy otherwise), the finished bytes stay on the device until bzb200_enc_read copies them into dst
+ *   (BZB200_ENC_DEVICE_WINDOWS=0: host windows as below).
+ *   Several GPUs: the windows are pinned host buffers (memcpy), from which every GPU's worker copies its slice. */
 BZB200_API int bzb200_enc_write(bzb200_enc* e, const uint8_t* p, size_t n);
 /* Action::Finish: compress the remaining blocks and append the stream trailer. */
 BZB200_API int bzb200_enc_finish(bzb200_enc* e);

@@ -276,10 +276,10 @@ __global__ void __launch_bounds__(OS_NT, OS_MINB) k2_os_scatter(const uint64_t* 
   // ---- rank inside the warp's 256-element chunk; memory order == (warp, row, lane), so the pass is stable
   uint64_t e[OS_IPT];
   uint32_t rk[OS_IPT];
+  if (KBITS != 0) {
 #pragma unroll
-  for (int it = 0; it < OS_IPT; ++it) {
-    const uint32_t li = w * OS_WCH + it * 32 + lane;
-    if (KBITS != 0) {
+    for (int it = 0; it < OS_IPT; ++it) {
+      const uint32_t li = w * OS_WCH + it * 32 + lane;
       e[it] = ~0ull;
       if (li < tcount) {
         const uint8_t* t = reinterpret_cast<const uint8_t*>(src) + off;  // src carries the text pointer
@@ -295,31 +295,47 @@ __global__ void __launch_bounds__(OS_NT, OS_MINB) k2_os_scatter(const uint64_t* 
         }
         e[it] = (key << KEY_LO) | pos;
       }
-    } else {
+    }
+  } else {
+#pragma unroll
+    for (int it = 0; it < OS_IPT; ++it) {
+      const uint32_t li = w * OS_WCH + it * 32 + lane;
       e[it] = li < tcount ? s[li] : ~0ull;
     }
   }
-  // three separate sweeps so that the eight matches, the eight leader atomics and the eight broadcasts of a thread
-  // are independent instructions the scheduler can overlap
-  uint32_t peers[OS_IPT];
+  if (KBITS != 0) {
+    // pass 0 need not be stable (nothing is ordered yet; rotations with equal keys end up in one group whatever their
+    // order), so an element's rank inside (warp, digit) is simply what the counter returns.  The digits of 32
+    // neighbouring rotations are almost all different, which is the worst case for match.any and the best for atomics.
 #pragma unroll
-  for (int it = 0; it < OS_IPT; ++it) {
-    const uint32_t li = w * OS_WCH + it * 32 + lane;
-    const uint32_t dgt = li < tcount ? (uint32_t)(e[it] >> shift) & DMASK : 0xFFFFu;
-    peers[it] = __match_any_sync(0xffffffffu, dgt);
-  }
+    for (int it = 0; it < OS_IPT; ++it) {
+      const uint32_t li = w * OS_WCH + it * 32 + lane;
+      const uint32_t dgt = (uint32_t)(e[it] >> shift) & DMASK;
+      rk[it] = li < tcount ? atomicAdd(&sm.wcnt[w][dgt], 1u) : 0u;
+    }
+  } else {
+    // three separate sweeps so that the eight matches, the eight leader atomics and the eight broadcasts of a thread
+    // are independent instructions the scheduler can overlap
+    uint32_t peers[OS_IPT];
 #pragma unroll
-  for (int it = 0; it < OS_IPT; ++it) {
-    const uint32_t li = w * OS_WCH + it * 32 + lane;
-    const uint32_t dgt = (uint32_t)(e[it] >> shift) & DMASK;
-    rk[it] = 0;
-    if (li < tcount && (peers[it] & lanemask_lt()) == 0)  // lowest lane of the peer group
-      rk[it] = atomicAdd(&sm.wcnt[w][dgt], (uint32_t)__popc(peers[it]));
-  }
+    for (int it = 0; it < OS_IPT; ++it) {
+      const uint32_t li = w * OS_WCH + it * 32 + lane;
+      const uint32_t dgt = li < tcount ? (uint32_t)(e[it] >> shift) & DMASK : (uint32_t)BINS;  // invalid lanes: own class
+      peers[it] = __match_any_sync(0xffffffffu, dgt);
+    }
 #pragma unroll
-  for (int it = 0; it < OS_IPT; ++it) {
-    const int leader = __ffs(peers[it]) - 1;
-    rk[it] = __shfl_sync(0xffffffffu, rk[it], leader) + __popc(peers[it] & lanemask_lt());
+    for (int it = 0; it < OS_IPT; ++it) {
+      const uint32_t li = w * OS_WCH + it * 32 + lane;
+      const uint32_t dgt = (uint32_t)(e[it] >> shift) & DMASK;
+      rk[it] = 0;
+      if (li < tcount && (peers[it] & lanemask_lt()) == 0)  // lowest lane of the peer group
+        rk[it] = atomicAdd(&sm.wcnt[w][dgt], (uint32_t)__popc(peers[it]));
+    }
+#pragma unroll
+    for (int it = 0; it < OS_IPT; ++it) {
+      const int leader = __ffs(peers[it]) - 1;
+      rk[it] = __shfl_sync(0xffffffffu, rk[it], leader) + __popc(peers[it] & lanemask_lt());
+    }
   }
   __syncthreads();
 
@@ -1213,12 +1229,9 @@ int run_bwt(Launcher& L, const uint8_t* d_txt, const BlockDesc* d_desc, const ui
   }();
   static PerDeviceOnce once_ls;
   once_ls.run([] {
-    cudaFuncSetAttribute((const void*)k2_local_sort<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LsSmem));
     cudaFuncSetAttribute((const void*)k2_local_sort<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LsSmem));
-    cudaFuncSetAttribute((const void*)k2_local_sort<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LsSmem));
     cudaFuncSetAttribute((const void*)k2_local_sort<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LsSmem));
     cudaFuncSetAttribute((const void*)k2_local_sort<48>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LsSmem));
-    cudaFuncSetAttribute((const void*)k2_local_sort<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LsSmem));
   });
   uint32_t rounds = 0, passes = 0;
   uint64_t elems = 0, local_elems = 0;
@@ -1262,31 +1275,21 @@ int run_bwt(Launcher& L, const uint8_t* d_txt, const BlockDesc* d_desc, const ui
     // BIG-group / sparse-block elements -> S.A
     L.launch("k2_gather", k2_gather, dim3(ls_tiles, nb), dim3(G_NT), d_desc, S.rank, S.sa, S.state, S.shift, S.sparse, h,
              S.B, S.A, S.cnt, S.tile_meta, S.ls_tiles_cap);
-    switch (ls_enum) {
-      case 8:
-        L.launch_smem("k2_local_sort", k2_local_sort<8>, dim3(ls_tiles, nb), dim3(LS_NT), sizeof(LsSmem), d_desc, S.state,
-                      S.sparse, S.sa, S.B, S.rank, S.tile_meta, S.ls_tiles_cap, S.stats);
-        break;
-      case 24:
-        L.launch_smem("k2_local_sort", k2_local_sort<24>, dim3(ls_tiles, nb), dim3(LS_NT), sizeof(LsSmem), d_desc, S.state,
-                      S.sparse, S.sa, S.B, S.rank, S.tile_meta, S.ls_tiles_cap, S.stats);
-        break;
-      case 16:
-        L.launch_smem("k2_local_sort", k2_local_sort<16>, dim3(ls_tiles, nb), dim3(LS_NT), sizeof(LsSmem), d_desc, S.state,
-                      S.sparse, S.sa, S.B, S.rank, S.tile_meta, S.ls_tiles_cap, S.stats);
-        break;
-      case 64:
-        L.launch_smem("k2_local_sort", k2_local_sort<64>, dim3(ls_tiles, nb), dim3(LS_NT), sizeof(LsSmem), d_desc, S.state,
-                      S.sparse, S.sa, S.B, S.rank, S.tile_meta, S.ls_tiles_cap, S.stats);
-        break;
-      case 32:
-        L.launch_smem("k2_local_sort", k2_local_sort<32>, dim3(ls_tiles, nb), dim3(LS_NT), sizeof(LsSmem), d_desc, S.state,
-                      S.sparse, S.sa, S.B, S.rank, S.tile_meta, S.ls_tiles_cap, S.stats);
-        break;
-      default:
-        L.launch_smem("k2_local_sort", k2_local_sort<ENUM_MAX_DEFAULT>, dim3(ls_tiles, nb), dim3(LS_NT), sizeof(LsSmem),
-                      d_desc, S.state, S.sparse, S.sa, S.B, S.rank, S.tile_meta, S.ls_tiles_cap, S.stats);
-        break;
+    {
+      switch (ls_enum) {
+        case 16:
+          L.launch_smem("k2_local_sort", k2_local_sort<16>, dim3(ls_tiles, nb), dim3(LS_NT), sizeof(LsSmem), d_desc,
+                        S.state, S.sparse, S.sa, S.B, S.rank, S.tile_meta, S.ls_tiles_cap, S.stats);
+          break;
+        case 32:
+          L.launch_smem("k2_local_sort", k2_local_sort<32>, dim3(ls_tiles, nb), dim3(LS_NT), sizeof(LsSmem), d_desc,
+                        S.state, S.sparse, S.sa, S.B, S.rank, S.tile_meta, S.ls_tiles_cap, S.stats);
+          break;
+        default:
+          L.launch_smem("k2_local_sort", k2_local_sort<ENUM_MAX_DEFAULT>, dim3(ls_tiles, nb), dim3(LS_NT), sizeof(LsSmem),
+                        d_desc, S.state, S.sparse, S.sa, S.B, S.rank, S.tile_meta, S.ls_tiles_cap, S.stats);
+          break;
+      }
     }
     const uint32_t maxbig = g[1];
     if (maxbig > 0) {

@@ -123,10 +123,79 @@ void put_bits_host(uint8_t* out, uint64_t pos, uint64_t value, int len) {  // MS
     if ((value >> i) & 1) out[pos >> 3] |= (uint8_t)(0x80u >> (pos & 7));
 }
 
+// One worker: no slicing — the plain one-context path (plan, encode, framing on the device), with the input either
+// copied here or already resident (a streaming encoder copies every piece as it is written).
+int run_span_single(bzb200_pool* p) {
+  SpanJob& J = *p->job;
+  bzb200_ctx* c = p->ctx[0];
+  c->err.clear();
+  TRY(set_device(c));
+  const uint8_t* d_in = J.d_in;
+  if (!d_in) {
+    TRY(ensure(c, c->stage_in, J.n + 64));
+    CK(c, cudaMemcpyAsync(c->stage_in.p, J.h_in, J.n, cudaMemcpyHostToDevice, c->stream));
+    d_in = ptr<uint8_t>(c->stage_in);
+  }
+  uint32_t nb = 0;
+  TRY(bzb200_plan(c, J.level, d_in, J.n, &nb));
+  const uint32_t nenc = J.final ? nb : nb - 1;
+  size_t cap = bzb200_max_output_bytes(J.level, nenc ? (size_t)c->h_in_off[nenc] : 0) + 64;
+  uint8_t* d_out = J.d_out;
+  if (d_out) {
+    cap = std::min(cap, J.cap) & ~(size_t)3;
+  } else {
+    TRY(ensure(c, c->stage_out, cap));
+    d_out = ptr<uint8_t>(c->stage_out);
+  }
+  CK(c, cudaMemsetAsync(d_out, 0, cap, c->stream));
+  uint64_t bit = 0;
+  if (J.first) {
+    TRY(bzb200_write_stream_header(c, J.level, d_out, cap));
+    bit = 32;
+  } else if (J.carry_bits) {
+    CK(c, cudaMemcpyAsync(d_out, &J.carry, 1, cudaMemcpyHostToDevice, c->stream));
+    bit = J.carry_bits;
+  }
+  if (nenc) TRY(bzb200_encode_blocks(c, 0, nenc, d_out, cap, bit, &bit));
+  J.combined = bzb200_combine_crc(J.combined, c->h_crc.data(), nenc);
+  size_t bytes = (size_t)((bit + 7) / 8);
+  if (J.final) {
+    TRY(bzb200_write_stream_trailer(c, d_out, cap, bit, J.combined, &bytes));
+    bit += 80;
+  }
+  if (bytes > J.cap) {
+    c->err = "output buffer too small: need " + std::to_string(bytes) + " bytes";
+    return BZB200_E_ARG;
+  }
+  if (!J.d_out && bytes) CK(c, cudaMemcpyAsync(J.h_out, d_out, bytes, cudaMemcpyDeviceToHost, c->stream));
+  J.last_byte = 0;
+  if (bytes) CK(c, cudaMemcpyAsync(&J.last_byte, d_out + bytes - 1, 1, cudaMemcpyDeviceToHost, c->stream));
+  CK(c, cudaStreamSynchronize(c->stream));
+  J.end_bits = bit;
+  J.consumed = nenc ? c->h_in_off[nenc] : 0;
+  J.blocks = nenc;
+  p->stat_spans += 1;
+  p->stat_blocks += nenc;
+  p->stat_phases += 1;
+  return BZB200_OK;
+}
+
 void run_span(bzb200_pool* p, int w) {
   SpanJob& J = *p->job;
   bzb200_ctx* c = p->ctx[w];
   const int W = p->n;
+  if (W == 1) {
+    const int r = run_span_single(p);
+    if (r != BZB200_OK) {
+      if (r == BZB200_E_CUDA && c->err.empty()) c->err = std::string("cuda: ") + cudaGetErrorString(cudaGetLastError());
+      pool_fail(p, 0, r, c->err);
+    }
+    return;
+  }
+  if (J.d_in || J.d_out || !J.h_in || !J.h_out) {  // the sliced path copies its slices from / to host memory
+    pool_fail(p, w, BZB200_E_ARG, "device-resident spans need a pool of one worker");
+    return;
+  }
   const uint64_t N = J.n;
   const uint64_t tile = k1_tile_bytes();
   const uint64_t halo = bzb200_slice_halo_bytes();
@@ -353,6 +422,7 @@ void run_span(bzb200_pool* p, int w) {
       pos += 80;
     }
     J.end_bits = pos;
+    J.last_byte = pos ? J.h_out[(pos - 1) >> 3] : 0;
     J.consumed = nenc ? p->in_off[nenc] : 0;
     J.blocks = nenc;
     p->stat_spans += 1;
@@ -404,13 +474,18 @@ int pool_run_span(bzb200_pool* p, SpanJob* J) {
 
 const std::string& pool_error(const bzb200_pool* p) { return p->err; }
 
+int pool_contexts_per_gpu() {
+  int per = 1;
+  if (const char* e = getenv("BZB200_MG_CTX_PER_GPU")) per = std::max(1, std::min(8, atoi(e)));
+  return per;
+}
+
 extern "C" {
 
 int bzb200_pool_create(int ngpus, const int* devices, bzb200_pool** out) {
   if (!out || ngpus < 1 || ngpus > 64) return BZB200_E_ARG;
   *out = nullptr;
-  int per = 1;
-  if (const char* e = getenv("BZB200_MG_CTX_PER_GPU")) per = std::max(1, std::min(8, atoi(e)));
+  const int per = pool_contexts_per_gpu();
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) return BZB200_E_CUDA;
   bzb200_pool* p = new bzb200_pool();
@@ -472,6 +547,11 @@ void bzb200_pool_destroy(bzb200_pool* p) {
 }
 
 int bzb200_pool_size(const bzb200_pool* p) { return p ? p->n : 0; }
+}  // extern "C"
+
+int pool_device(const bzb200_pool* p, int w) { return p->dev[w]; }
+
+extern "C" {
 const char* bzb200_pool_last_error(const bzb200_pool* p) { return p ? p->err.c_str() : "null pool"; }
 
 int bzb200_pool_stats(const bzb200_pool* p, uint64_t* out, size_t cap) {

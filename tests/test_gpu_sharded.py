@@ -45,7 +45,9 @@ def test_pool_slices_on_one_gpu(monkeypatch, per_gpu):
             n = pool.compress_host(level, h_in, h_out)
             assert h_out[:n].numpy().tobytes() == want, f"{name}: {per_gpu} contexts, run {rep}"
     st = pool.stats()
-    assert st["spans"] == 2 * len(_cases()) and st["phases"] > st["spans"]  # aaaab needs more than one phase
+    assert st["spans"] == 2 * len(_cases())
+    if per_gpu > 1:
+        assert st["phases"] > st["spans"]  # aaaab needs more than one phase of the sliced cut chain
     # empty input and a too-small output buffer
     h_out = torch.empty(64, dtype=torch.uint8)
     assert pool.compress_host(9, torch.empty(0, dtype=torch.uint8), h_out) == 14
