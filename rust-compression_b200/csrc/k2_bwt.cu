@@ -22,6 +22,7 @@
 //   k2_round_finalize  per-block state machine: done / periodic fix-up pending / active / sparse
 // Fix-up   : a round that splits nothing means the block is periodic and the groups are the sets of equal
 //            rotations; one more round with key = n-1-((pos-shift) mod n) applies the reference's tie-break.
+#include <stdio.h>
 #include <stdlib.h>
 
 #include <algorithm>
@@ -240,67 +241,76 @@ __device__ __forceinline__ void st_status(uint32_t* p, uint32_t v) {
 // KBITS: 0 = the list holds 64-bit elements; 8 / 7 / 6 / 4 = pass 0 of the initial sort builds its elements (the first
 // KSYMS symbols of the rotation, KBITS bits each | pos) from the block's text instead of reading a key array.
 // WBITS = digit width of the pass.
-template <int KBITS, int KSYMS, int WBITS>
-__global__ void __launch_bounds__(OS_NT, OS_MINB) k2_os_scatter(const uint64_t* __restrict__ src, uint64_t* __restrict__ dst,
-                                                          const BlockDesc* __restrict__ desc,
-                                                          const uint32_t* __restrict__ cnt,
-                                                          const uint32_t* __restrict__ bucket_off,
-                                                          uint32_t* __restrict__ status, uint32_t* __restrict__ ticket,
-                                                          uint32_t ticket_base, uint32_t tiles_cap, uint32_t epoch,
-                                                          int pass, const uint32_t* __restrict__ inuse) {
-  extern __shared__ __align__(16) uint8_t os_raw[];
+template <int KBITS, int KSYMS, int WBITS, bool FULL>
+__device__ __forceinline__ void os_tile(OsSmemT<1 << WBITS>& sm, const uint64_t* __restrict__ src,
+                                        uint64_t* __restrict__ dst, const BlockDesc* __restrict__ desc,
+                                        uint32_t* __restrict__ status, uint32_t tiles_cap, uint32_t epoch, int pass,
+                                        uint32_t b, uint32_t c, uint32_t tile, uint32_t base, uint32_t tcount,
+                                        const uint32_t (&boff)[(1 << WBITS) / OS_NT]) {
   constexpr int BINS = 1 << WBITS;
-  constexpr int DPT = BINS / OS_NT;  // digits per thread in the per-digit phases (1 or 2)
-  static_assert(DPT >= 1 && BINS % OS_NT == 0, "digit count must be a multiple of the CTA size");
-  using OsSmem = OsSmemT<BINS>;
+  constexpr int DPT = BINS / OS_NT;
   constexpr int OS_WARPS = OS_NT / 32, OS_WCH = OS_TILE / OS_WARPS;
-  OsSmem& sm = *reinterpret_cast<OsSmem*>(os_raw);
-  const uint32_t b = blockIdx.x;
-  const uint32_t c = cnt[b];
-  if (threadIdx.x == 0) sm.tile = atomicAdd(&ticket[b], 1u) - ticket_base;
   const int w = threadIdx.x >> 5;
   const uint32_t lane = lane_id();
-#pragma unroll
-  for (int i = lane; i < BINS; i += 32) sm.wcnt[w][i] = 0;
-  if (KBITS != 0 && KBITS != 8) build_sym_lut(inuse + b * 8, sm.lut);
-  __syncthreads();
-  const uint32_t tile = sm.tile;
-  const uint32_t base = tile * OS_TILE;
-  if (base >= c) return;
-  const uint32_t tcount = min((uint32_t)OS_TILE, c - base);
   const uint32_t off = desc[b].off;
   const uint64_t* s = src + off + base;
   const int shift = KEY_LO + WBITS * pass;
   constexpr uint32_t DMASK = BINS - 1;
 
   // ---- rank inside the warp's 256-element chunk; memory order == (warp, row, lane), so the pass is stable
+  // (pass 0 of the initial sort need not be stable — nothing is ordered yet — and assigns OS_IPT CONSECUTIVE rotations
+  // to a thread: their keys are one sliding window over OS_IPT + KSYMS - 1 symbols of the text)
   uint64_t e[OS_IPT];
   uint32_t rk[OS_IPT];
   if (KBITS != 0) {
+    // the tile's symbols (text bytes through the alphabet table), staged once: symbol i of the tile at tx[i]
+    uint8_t* tx = reinterpret_cast<uint8_t*>(sm.stage);  // free until the scatter phase
+    const uint8_t* t = reinterpret_cast<const uint8_t*>(src) + off;  // src carries the text pointer; c == block length
+    const uint32_t need = tcount + KSYMS - 1;
+    constexpr int NLD = (OS_TILE + KSYMS - 1 + OS_NT - 1) / OS_NT;
+    uint32_t by[NLD];
+    if (c >= need) {  // all byte loads of the thread are issued before any of them is used
+#pragma unroll
+      for (int k = 0; k < NLD; ++k) {
+        const uint32_t i = threadIdx.x + k * OS_NT;
+        uint32_t p = base + i;
+        p = p >= c ? p - c : p;  // cyclic: only the last tile of a block wraps
+        by[k] = i < need ? t[p] : 0u;
+      }
+    } else {  // a block shorter than a key window wraps more than once
+#pragma unroll
+      for (int k = 0; k < NLD; ++k) {
+        const uint32_t i = threadIdx.x + k * OS_NT;
+        by[k] = i < need ? t[(base + i) % c] : 0u;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < NLD; ++k) {
+      const uint32_t i = threadIdx.x + k * OS_NT;
+      if (i < need) tx[i] = KBITS == 8 ? (uint8_t)by[k] : sm.lut[by[k]];
+    }
+    __syncthreads();
+    static_assert(OS_IPT == 8 && KSYMS <= 9, "a thread's window is two 8-byte words of the staged symbols");
+    const uint2* tw = reinterpret_cast<const uint2*>(tx) + threadIdx.x;  // symbols 8t .. 8t+15
+    const uint2 w0 = tw[0], w1 = tw[1];
+    const uint64_t lo = (uint64_t)w0.x | ((uint64_t)w0.y << 32), hi = (uint64_t)w1.x | ((uint64_t)w1.y << 32);
+    constexpr uint64_t KMASK = (1ull << (KBITS * KSYMS)) - 1ull;
+    uint64_t key = 0;
+#pragma unroll
+    for (int j = 0; j < KSYMS - 1; ++j) key = (key << KBITS) | ((lo >> (8 * j)) & 0xFFull);
 #pragma unroll
     for (int it = 0; it < OS_IPT; ++it) {
-      const uint32_t li = w * OS_WCH + it * 32 + lane;
-      e[it] = ~0ull;
-      if (li < tcount) {
-        const uint8_t* t = reinterpret_cast<const uint8_t*>(src) + off;  // src carries the text pointer
-        const uint32_t pos = base + li;
-        uint64_t key = 0;
-        uint32_t idx = pos;
-#pragma unroll
-        for (int j = 0; j < KSYMS; ++j) {
-          const uint32_t by = t[idx];
-          key = (key << KBITS) | (KBITS == 8 ? by : (uint32_t)sm.lut[by]);
-          ++idx;
-          if (idx == c) idx = 0;  // c == block length in pass 0
-        }
-        e[it] = (key << KEY_LO) | pos;
-      }
+      const int q = it + KSYMS - 1;  // symbol entering the window
+      const uint64_t sy = q < 8 ? (lo >> (8 * q)) & 0xFFull : (hi >> (8 * (q - 8))) & 0xFFull;
+      key = ((key << KBITS) | sy) & KMASK;
+      const uint32_t li = threadIdx.x * OS_IPT + it;
+      e[it] = (FULL || li < tcount) ? (key << KEY_LO) | (uint64_t)(base + li) : ~0ull;
     }
   } else {
 #pragma unroll
     for (int it = 0; it < OS_IPT; ++it) {
       const uint32_t li = w * OS_WCH + it * 32 + lane;
-      e[it] = li < tcount ? s[li] : ~0ull;
+      e[it] = (FULL || li < tcount) ? s[li] : ~0ull;
     }
   }
   if (KBITS != 0) {
@@ -309,9 +319,9 @@ __global__ void __launch_bounds__(OS_NT, OS_MINB) k2_os_scatter(const uint64_t* 
     // neighbouring rotations are almost all different, which is the worst case for match.any and the best for atomics.
 #pragma unroll
     for (int it = 0; it < OS_IPT; ++it) {
-      const uint32_t li = w * OS_WCH + it * 32 + lane;
+      const uint32_t li = threadIdx.x * OS_IPT + it;
       const uint32_t dgt = (uint32_t)(e[it] >> shift) & DMASK;
-      rk[it] = li < tcount ? atomicAdd(&sm.wcnt[w][dgt], 1u) : 0u;
+      rk[it] = (FULL || li < tcount) ? atomicAdd(&sm.wcnt[w][dgt], 1u) : 0u;
     }
   } else {
     // three separate sweeps so that the eight matches, the eight leader atomics and the eight broadcasts of a thread
@@ -320,7 +330,7 @@ __global__ void __launch_bounds__(OS_NT, OS_MINB) k2_os_scatter(const uint64_t* 
 #pragma unroll
     for (int it = 0; it < OS_IPT; ++it) {
       const uint32_t li = w * OS_WCH + it * 32 + lane;
-      const uint32_t dgt = li < tcount ? (uint32_t)(e[it] >> shift) & DMASK : (uint32_t)BINS;  // invalid lanes: own class
+      const uint32_t dgt = (FULL || li < tcount) ? (uint32_t)(e[it] >> shift) & DMASK : (uint32_t)BINS;  // invalid lanes: own class
       peers[it] = __match_any_sync(0xffffffffu, dgt);
     }
 #pragma unroll
@@ -328,7 +338,7 @@ __global__ void __launch_bounds__(OS_NT, OS_MINB) k2_os_scatter(const uint64_t* 
       const uint32_t li = w * OS_WCH + it * 32 + lane;
       const uint32_t dgt = (uint32_t)(e[it] >> shift) & DMASK;
       rk[it] = 0;
-      if (li < tcount && (peers[it] & lanemask_lt()) == 0)  // lowest lane of the peer group
+      if ((FULL || li < tcount) && (peers[it] & lanemask_lt()) == 0)  // lowest lane of the peer group
         rk[it] = atomicAdd(&sm.wcnt[w][dgt], (uint32_t)__popc(peers[it]));
     }
 #pragma unroll
@@ -356,12 +366,26 @@ __global__ void __launch_bounds__(OS_NT, OS_MINB) k2_os_scatter(const uint64_t* 
     run[q] = r;
     tsum += r;
   }
-  uint32_t ds = cta_excl_scan_add<OS_NT>(tsum, sm.ws, nullptr);
+  uint32_t* st = status + ((uint64_t)b * tiles_cap) * OS_BINS_MAX + threadIdx.x * DPT;
+  const uint32_t tag = epoch << 22;
+  if (tile != 0) {  // the tile's own counts are known: let the tiles behind it make progress while this one scans
+#pragma unroll
+    for (int q = 0; q < DPT; ++q) st_status(st + (uint64_t)tile * OS_BINS_MAX + q, tag | ST_AGG | run[q]);
+  }
+  // exclusive scan of the per-thread digit totals over the CTA (one barrier: every thread sums the warp totals before it)
+  uint32_t ds;
+  {
+    const uint32_t inc = warp_incl_scan_add(tsum);
+    if (lane == 31) sm.ws[w] = inc;
+    __syncthreads();
+    uint32_t wb = 0;
+#pragma unroll
+    for (int ww = 0; ww < OS_WARPS; ++ww) wb += ww < w ? sm.ws[ww] : 0u;
+    ds = wb + inc - tsum;
+  }
   {
     // the thread's DPT look-back chains advance in lock step: the status words of one earlier tile are fetched for
     // all of them before any is waited for
-    uint32_t* st = status + ((uint64_t)b * tiles_cap) * OS_BINS_MAX + threadIdx.x * DPT;
-    const uint32_t tag = epoch << 22;
     uint32_t excl[DPT];
 #pragma unroll
     for (int q = 0; q < DPT; ++q) excl[q] = 0;
@@ -369,8 +393,6 @@ __global__ void __launch_bounds__(OS_NT, OS_MINB) k2_os_scatter(const uint64_t* 
 #pragma unroll
       for (int q = 0; q < DPT; ++q) st_status(st + q, tag | ST_PREFIX | run[q]);
     } else {
-#pragma unroll
-      for (int q = 0; q < DPT; ++q) st_status(st + (uint64_t)tile * OS_BINS_MAX + q, tag | ST_AGG | run[q]);
       uint32_t open_mask = (1u << DPT) - 1u;
       for (int t = (int)tile - 1; t >= 0 && open_mask; --t) {
         uint32_t v[DPT];
@@ -397,15 +419,15 @@ __global__ void __launch_bounds__(OS_NT, OS_MINB) k2_os_scatter(const uint64_t* 
     for (int q = 0; q < DPT; ++q) {
       const uint32_t dgt = threadIdx.x * DPT + q;
       sm.dstart[dgt] = ds;
-      sm.goff[dgt] = (int)(bucket_off[((uint64_t)b * OS_PASSES_MAX + pass) * OS_BINS_MAX + dgt] + excl[q]) - (int)ds;
+      sm.goff[dgt] = (int)(boff[q] + excl[q]) - (int)ds;
       ds += run[q];
     }
   }
   __syncthreads();
 #pragma unroll
   for (int it = 0; it < OS_IPT; ++it) {
-    const uint32_t li = w * OS_WCH + it * 32 + lane;
-    if (li < tcount) {
+    const uint32_t li = KBITS != 0 ? threadIdx.x * OS_IPT + it : w * OS_WCH + it * 32 + lane;
+    if ((FULL || li < tcount)) {
       const uint32_t dgt = (uint32_t)(e[it] >> shift) & DMASK;
       sm.stage[sm.dstart[dgt] + sm.wcnt[w][dgt] + rk[it]] = e[it];
     }
@@ -415,12 +437,50 @@ __global__ void __launch_bounds__(OS_NT, OS_MINB) k2_os_scatter(const uint64_t* 
 #pragma unroll
   for (int k = 0; k < OS_IPT; ++k) {
     const uint32_t i = threadIdx.x + k * OS_NT;
-    if (i < tcount) {
+    if (FULL || i < tcount) {
       const uint64_t v = sm.stage[i];
       const uint32_t dgt = (uint32_t)(v >> shift) & DMASK;
       o[sm.goff[dgt] + (int)i] = v;
     }
   }
+}
+
+template <int KBITS, int KSYMS, int WBITS>
+__global__ void __launch_bounds__(OS_NT, OS_MINB) k2_os_scatter(const uint64_t* __restrict__ src, uint64_t* __restrict__ dst,
+                                                          const BlockDesc* __restrict__ desc,
+                                                          const uint32_t* __restrict__ cnt,
+                                                          const uint32_t* __restrict__ bucket_off,
+                                                          uint32_t* __restrict__ status, uint32_t* __restrict__ ticket,
+                                                          uint32_t ticket_base, uint32_t tiles_cap, uint32_t epoch,
+                                                          int pass, const uint32_t* __restrict__ inuse) {
+  extern __shared__ __align__(16) uint8_t os_raw[];
+  constexpr int BINS = 1 << WBITS;
+  constexpr int DPT = BINS / OS_NT;  // digits per thread in the per-digit phases (1 or 2)
+  static_assert(DPT >= 1 && BINS % OS_NT == 0, "digit count must be a multiple of the CTA size");
+  using OsSmem = OsSmemT<BINS>;
+  OsSmem& sm = *reinterpret_cast<OsSmem*>(os_raw);
+  const uint32_t b = blockIdx.x;
+  const uint32_t c = cnt[b];
+  if (threadIdx.x == 0) sm.tile = atomicAdd(&ticket[b], 1u) - ticket_base;
+  const int w = threadIdx.x >> 5;
+  const uint32_t lane = lane_id();
+  uint32_t boff[DPT];  // bucket offsets of the thread's digits: fetched now, used after the look-back
+#pragma unroll
+  for (int q = 0; q < DPT; ++q)
+    boff[q] = bucket_off[((uint64_t)b * OS_PASSES_MAX + pass) * OS_BINS_MAX + threadIdx.x * DPT + q];
+#pragma unroll
+  for (int i = lane; i < BINS; i += 32) sm.wcnt[w][i] = 0;
+  if (KBITS != 0 && KBITS != 8) build_sym_lut(inuse + b * 8, sm.lut);
+  __syncthreads();
+  const uint32_t tile = sm.tile;
+  const uint32_t base = tile * OS_TILE;
+  if (base >= c) return;
+  const uint32_t tcount = min((uint32_t)OS_TILE, c - base);
+  // full tiles (all but the last of a list) run without per-element bounds checks
+  if (tcount == (uint32_t)OS_TILE)
+    os_tile<KBITS, KSYMS, WBITS, true>(sm, src, dst, desc, status, tiles_cap, epoch, pass, b, c, tile, base, tcount, boff);
+  else
+    os_tile<KBITS, KSYMS, WBITS, false>(sm, src, dst, desc, status, tiles_cap, epoch, pass, b, c, tile, base, tcount, boff);
 }
 
 // ------------------------------------------------------------------ SA entry layout / local-sort geometry
@@ -734,7 +794,7 @@ __global__ void __launch_bounds__(256) k2_periodic_shift(const BlockDesc* __rest
 //                  tile_meta[b][t] = (entries, entries before the tile's first HEAD slot) lets the CTA that owns a
 //                  group spanning two tiles pick up its tail.
 //   BIG groups / sparse blocks : [59:40] g | [39:20] key | [19:0] pos appended to A (any order), counted in cnt[b].
-__global__ void __launch_bounds__(G_NT) k2_gather(const BlockDesc* __restrict__ desc, const uint32_t* __restrict__ rank,
+__global__ void __launch_bounds__(G_NT, 5) k2_gather(const BlockDesc* __restrict__ desc, const uint32_t* __restrict__ rank,
                                                   const uint32_t* __restrict__ sa, const uint32_t* __restrict__ state,
                                                   const uint32_t* __restrict__ shiftv,
                                                   const uint32_t* __restrict__ sparse, uint32_t h,
@@ -743,7 +803,8 @@ __global__ void __launch_bounds__(G_NT) k2_gather(const BlockDesc* __restrict__ 
                                                   uint32_t ls_tiles_cap) {
   __shared__ uint32_t ws[G_NT / 32 + 1];
   __shared__ uint32_t s_wtot[G_NT / 32];
-  __shared__ uint32_t s_base, s_fh, s_lead;
+  __shared__ int s_whead[G_NT / 32];
+  __shared__ uint32_t s_base, s_lead;
   constexpr int ROWS = LS_T / G_NT;  // 8 rows of 32 slots per warp
   const BlockDesc d = desc[blockIdx.y];
   const uint32_t n = d.n;
@@ -751,7 +812,8 @@ __global__ void __launch_bounds__(G_NT) k2_gather(const BlockDesc* __restrict__ 
   if (base >= n) return;
   const uint32_t st = state[blockIdx.y];
   if (st == 2) return;
-  if (threadIdx.x == 0) { s_fh = NONE; s_lead = 0; }
+  const uint64_t ti = (uint64_t)blockIdx.y * ls_tiles_cap + blockIdx.x;
+  if (threadIdx.x == 0) s_lead = 0;
   const uint32_t* rk = rank + d.off;
   const uint32_t* s = sa + d.off;
   const uint32_t hm = h % n;
@@ -765,15 +827,25 @@ __global__ void __launch_bounds__(G_NT) k2_gather(const BlockDesc* __restrict__ 
     const uint32_t i = base + w * (ROWS * 32) + k * 32 + lane;
     ev[k] = i < n ? s[i] : SA_SINGLE;
   }
-  uint32_t fh = NONE, nbig = 0, wrun = 0;
-  uint64_t ent[ROWS];      // 0: nothing; bit 63: BIG-path element; else small-group entry (bit 62 set as marker)
-  uint32_t lidx[ROWS];     // index of the small-group entry inside the warp's part of the list
+  // The head slot of a small group is read off the HEAD flags of the tile (ballots inside a row, carried down the
+  // warp's rows and across the warps); only entries whose group starts in the previous tile (the tile's lead entries)
+  // and the elements of the radix path fetch rank[pos] for it.
+  uint32_t nbig = 0, wrun = 0;
+  uint32_t kk[ROWS];  // [19:0] key | [21:20] 0 nothing, 1 small-group entry, 2 radix-path element | [29:22] index of the
+                      // small-group entry inside the warp's part of the list
+  int hg[ROWS];       // small entry: head slot relative to the tile base (-1: not in an earlier row of this warp);
+                      // radix path: head slot from rank[pos]
+  int carry = -1;
 #pragma unroll
   for (int k = 0; k < ROWS; ++k) {
-    const uint32_t i = base + w * (ROWS * 32) + k * 32 + lane;
+    const uint32_t rel = w * (ROWS * 32) + k * 32 + lane;
+    const uint32_t i = base + rel;
     const uint32_t e = ev[k];
-    if (i < n && (e & SA_HEAD)) fh = min(fh, i);
-    ent[k] = 0;
+    const uint32_t hb = __ballot_sync(0xffffffffu, i < n && (e & SA_HEAD));
+    const uint32_t mine = hb & (lanemask_lt() | (1u << lane));
+    hg[k] = mine ? (int)(rel - lane) + 31 - __clz(mine) : carry;
+    if (hb) carry = (int)(rel - lane) + 31 - __clz(hb);
+    kk[k] = 0;
     bool small = false;
     if (!(e & SA_SINGLE)) {
       const uint32_t pos = e & RANK_MASK;
@@ -783,36 +855,36 @@ __global__ void __launch_bounds__(G_NT) k2_gather(const BlockDesc* __restrict__ 
         if (p2 >= n) p2 -= n;
         k2 = rk[p2] & RANK_MASK;
       } else {
-        const uint32_t rel = pos >= sh ? pos - sh : pos + n - sh;  // (pos - shift) mod n
-        k2 = n - 1 - rel;
+        const uint32_t rl = pos >= sh ? pos - sh : pos + n - sh;  // (pos - shift) mod n
+        k2 = n - 1 - rl;
       }
-      const uint32_t g = rk[pos] & RANK_MASK;
       if (sp || (e & SA_BIG)) {
-        ent[k] = ((uint64_t)g << 40) | ((uint64_t)k2 << 20) | pos | (1ull << 63);
+        hg[k] = (int)(rk[pos] & RANK_MASK);
+        kk[k] = k2 | (2u << 20);
         ++nbig;
       } else {
-        ent[k] = (uint64_t)pos | ((uint64_t)k2 << 20) | ((uint64_t)(i - g) << 40) | ((uint64_t)(i - base) << 51) |
-                 (1ull << 62);
+        kk[k] = k2 | (1u << 20);
         small = true;
       }
     }
     const uint32_t bal = __ballot_sync(0xffffffffu, small);
-    lidx[k] = wrun + __popc(bal & lanemask_lt());
+    kk[k] |= (wrun + __popc(bal & lanemask_lt())) << 22;
     wrun += __popc(bal);
   }
-#pragma unroll
-  for (int dlt = 16; dlt > 0; dlt >>= 1) fh = min(fh, __shfl_xor_sync(0xffffffffu, fh, dlt));
   __syncthreads();
   if (lane == 0) {
-    if (fh != NONE) atomicMin(&s_fh, fh);
     s_wtot[w] = wrun;
+    s_whead[w] = carry;
   }
   const int anybig = __syncthreads_or((int)nbig);
-  const uint32_t cfh = s_fh;
   uint32_t wbase = 0, acnt = 0;
+  int cin = -1;  // last head slot in the warps before this one
 #pragma unroll
   for (int ww = 0; ww < G_NT / 32; ++ww) {
-    if (ww < w) wbase += s_wtot[ww];
+    if (ww < w) {
+      wbase += s_wtot[ww];
+      cin = max(cin, s_whead[ww]);
+    }
     acnt += s_wtot[ww];
   }
   // entries before the tile's first HEAD slot belong to a group owned by the previous tile
@@ -820,16 +892,26 @@ __global__ void __launch_bounds__(G_NT) k2_gather(const BlockDesc* __restrict__ 
   uint64_t* lo = lst + d.off + base;
 #pragma unroll
   for (int k = 0; k < ROWS; ++k) {
-    const uint32_t i = base + w * (ROWS * 32) + k * 32 + lane;
-    const bool small = (ent[k] >> 62) == 1;
-    if (small) lo[wbase + lidx[k]] = ent[k] & ~(1ull << 62);
-    lead += small && (i < cfh);
+    if (((kk[k] >> 20) & 3u) == 1u) {
+      const uint32_t rel = w * (ROWS * 32) + k * 32 + lane;
+      const uint32_t pos = ev[k] & RANK_MASK;
+      const int h = hg[k] < 0 ? cin : hg[k];
+      uint32_t dist;
+      if (h < 0) {  // the group's head lies in the previous tile
+        dist = base + rel - (rk[pos] & RANK_MASK);
+        ++lead;
+      } else {
+        dist = rel - (uint32_t)h;
+      }
+      lo[wbase + ((kk[k] >> 22) & 0xFFu)] =
+          (uint64_t)pos | ((uint64_t)(kk[k] & RANK_MASK) << 20) | ((uint64_t)dist << 40) | ((uint64_t)rel << 51);
+    }
   }
 #pragma unroll
   for (int dlt = 16; dlt > 0; dlt >>= 1) lead += __shfl_xor_sync(0xffffffffu, lead, dlt);
   if (lane == 0 && lead) atomicAdd(&s_lead, lead);
   __syncthreads();
-  if (threadIdx.x == 0) tile_meta[(uint64_t)blockIdx.y * ls_tiles_cap + blockIdx.x] = make_uint2(acnt, s_lead);
+  if (threadIdx.x == 0) tile_meta[ti] = make_uint2(acnt, s_lead);
   if (!anybig) return;
   uint32_t total;
   const uint32_t ex = cta_excl_scan_add<G_NT>(nbig, ws, &total);
@@ -838,7 +920,8 @@ __global__ void __launch_bounds__(G_NT) k2_gather(const BlockDesc* __restrict__ 
   uint64_t* o = A + d.off + s_base + ex;
 #pragma unroll
   for (int k = 0; k < ROWS; ++k)
-    if (ent[k] >> 63) *o++ = ent[k] & ~(1ull << 63);
+    if (((kk[k] >> 20) & 3u) == 2u)
+      *o++ = ((uint64_t)(uint32_t)hg[k] << 40) | ((uint64_t)(kk[k] & RANK_MASK) << 20) | (ev[k] & RANK_MASK);
 }
 
 // ------------------------------------------------------------------ k2_local_sort: groups up to LOCAL_MAX slots
@@ -1083,6 +1166,249 @@ __global__ void __launch_bounds__(LS_NT, 2) k2_local_sort(const BlockDesc* __res
   }
 }
 
+// ------------------------------------------------------------------ k2_local_sort_rx: the group sort as an LSD radix sort
+// Same contract as k2_local_sort (groups up to LOCAL_MAX slots, owned by the tile that holds their HEAD), different
+// method: the CTA's window is sorted as a whole, in shared memory, by the 32-bit composite (group start | key) with
+// four stable 8-bit counting passes (match.any ranking + per-warp counters, like k2_os_scatter but without leaving the
+// SM).  The work per entry no longer depends on the group sizes (the enumeration sort scans the whole group for every
+// entry, and the lanes of a warp wait for the largest group among them), and equal (group, key) runs — the new groups —
+// are read off the sorted window with ballots.
+//   * a CTA owns `tpc` consecutive tiles and packs as many of them as fit (<= LS_CAP entries) into one window, so the
+//     sparse lists of the later rounds are sorted a few thousand entries at a time instead of a few dozen;
+//   * element = (composite [31:20] group start (window index) | [19:0] key, pos); window index i of a group maps to
+//     slot ghead[group start] + i - group start, so SA and rank are written in place as before;
+//   * the window is padded with all-ones elements to a whole number of rows per warp (they sort to the end), and the
+//     passes are compiled once per row count, so the inner loops carry no bounds checks.
+constexpr int RX_NT = 512, RX_WARPS = RX_NT / 32;
+constexpr int RX_ROWS = (LS_CAP + 1 + RX_NT - 1) / RX_NT;  // rows of 32 entries per warp: at most 7
+constexpr int RX_TPC_MAX = 32;                              // tiles per CTA
+static_assert(RX_ROWS * RX_NT == LS_CAP + 1, "the padded window fills the stage exactly");
+struct RxSmem {
+  uint2 stage[LS_CAP + 1];  // .x = pos, .y = composite
+  uint32_t wcnt[RX_WARPS][256];
+  uint32_t dstart[256];
+  uint32_t ghead[LS_CAP + 1];
+  uint32_t ws[RX_WARPS];
+  int whead[RX_WARPS];
+  uint32_t tcnt[RX_TPC_MAX + 2], tlead[RX_TPC_MAX + 2];
+  uint32_t red[3][RX_WARPS];
+};
+size_t bwt_rx_smem_bytes() { return sizeof(RxSmem); }
+
+// shared-memory atomicAdd executed by the lanes with p set (a predicated ATOMS, no divergent region)
+__device__ __forceinline__ uint32_t atoms_add_if(bool p, uint32_t* addr, uint32_t v) {
+  uint32_t r = 0;
+  asm volatile(
+      "{\n .reg .pred q;\n setp.ne.u32 q, %3, 0;\n @q atom.shared.add.u32 %0, [%1], %2;\n}"
+      : "+r"(r)
+      : "r"((uint32_t)__cvta_generic_to_shared(addr)), "r"(v), "r"((uint32_t)p)
+      : "memory");
+  return r;
+}
+__device__ __forceinline__ uint32_t lanemask_gt() {
+  uint32_t m;
+  asm("mov.u32 %0, %%lanemask_gt;" : "=r"(m));
+  return m;
+}
+
+// Sorts the padded window (RPW rows per warp) and writes SA / rank.  Returns (new heads, unresolved) of this thread.
+template <int RPW>
+__device__ __forceinline__ void rx_sort_window(RxSmem& sm, uint32_t count, uint32_t* __restrict__ s,
+                                               uint32_t* __restrict__ rk, uint32_t& n_heads, uint32_t& n_unres) {
+  const int w = threadIdx.x >> 5;
+  const uint32_t lane = lane_id();
+  const uint32_t wbase = w * RPW * 32;
+  const uint32_t lt = lanemask_lt(), gt = lanemask_gt();
+  uint32_t* wc = sm.wcnt[w];
+#pragma unroll 1
+  for (uint32_t pass = 0; pass < 4; ++pass) {
+    const uint32_t sel = 0x4440u | pass;  // byte `pass` of the composite
+    uint2 ev[RPW];
+    uint32_t rkv[RPW], peers[RPW];
+#pragma unroll
+    for (int it = 0; it < RPW; ++it) ev[it] = sm.stage[wbase + it * 32 + lane];
+#pragma unroll
+    for (int it = 0; it < RPW; ++it) peers[it] = __match_any_sync(0xffffffffu, __byte_perm(ev[it].y, 0u, sel));
+#pragma unroll
+    for (int it = 0; it < RPW; ++it)  // the highest lane of a peer group counts for the group
+      rkv[it] = atoms_add_if((peers[it] & gt) == 0u, wc + __byte_perm(ev[it].y, 0u, sel), (uint32_t)__popc(peers[it]));
+#pragma unroll
+    for (int it = 0; it < RPW; ++it)
+      rkv[it] = __shfl_sync(0xffffffffu, rkv[it], 31 - __clz(peers[it])) + __popc(peers[it] & lt);
+    __syncthreads();  // every entry is in registers, every counter final
+    uint32_t run = 0, inc = 0;
+    if (threadIdx.x < 256) {
+#pragma unroll
+      for (int ww = 0; ww < RX_WARPS; ++ww) {
+        const uint32_t t = sm.wcnt[ww][threadIdx.x];
+        sm.wcnt[ww][threadIdx.x] = run;
+        run += t;
+      }
+      inc = warp_incl_scan_add(run);
+      if (lane == 31) sm.ws[w] = inc;
+    }
+    __syncthreads();
+    if (threadIdx.x < 256) {
+      uint32_t base = 0;
+#pragma unroll
+      for (int ww = 0; ww < 8; ++ww) base += ww < w ? sm.ws[ww] : 0u;
+      sm.dstart[threadIdx.x] = base + inc - run;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int it = 0; it < RPW; ++it) {
+      const uint32_t dgt = __byte_perm(ev[it].y, 0u, sel);
+      sm.stage[sm.dstart[dgt] + wc[dgt] + rkv[it]] = ev[it];
+    }
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) wc[i * 32 + lane] = 0;  // the warp's own row, for the next pass / window
+    __syncthreads();
+  }
+
+  // ---- the sorted window: runs of equal composites are the new groups.  hd = index of the run's first entry: last
+  // run start at or before li (ballots inside a row, carried down the warp's rows, then across the warps)
+  uint2 cur[RPW];
+  uint32_t flg[RPW];  // bit 0: first of its run, bit 1: last of its run
+  int hd[RPW];
+  int carry = -1;
+#pragma unroll
+  for (int it = 0; it < RPW; ++it) {
+    const uint32_t li = wbase + it * 32 + lane;
+    cur[it] = sm.stage[li];
+    const uint32_t pv = li > 0 ? sm.stage[li - 1].y : ~cur[it].y;
+    const uint32_t nx = li + 1 < count ? sm.stage[li + 1].y : ~cur[it].y;
+    const bool valid = li < count;
+    const bool first = valid && cur[it].y != pv;
+    flg[it] = (first ? 1u : 0u) | ((valid && cur[it].y != nx) ? 2u : 0u);
+    const uint32_t bal = __ballot_sync(0xffffffffu, first);
+    const uint32_t mine = bal & ~gt;
+    hd[it] = mine ? (int)(wbase + it * 32) + 31 - __clz(mine) : carry;
+    if (bal) carry = (int)(wbase + it * 32) + 31 - __clz(bal);
+  }
+  if (lane == 0) sm.whead[w] = carry;
+  __syncthreads();
+  int cin = -1;
+#pragma unroll
+  for (int ww = 0; ww < RX_WARPS; ++ww) cin = max(cin, ww < w ? sm.whead[ww] : -1);
+#pragma unroll
+  for (int it = 0; it < RPW; ++it) {
+    const uint32_t li = wbase + it * 32 + lane;
+    if (li < count) {
+      const uint32_t h0 = (uint32_t)(hd[it] < 0 ? cin : hd[it]);
+      const uint32_t gs = cur[it].y >> 20, pos = cur[it].x;
+      const uint32_t hs = sm.ghead[gs];
+      const bool single = flg[it] == 3u;
+      uint32_t fl = (flg[it] & 1u) ? SA_HEAD : 0u;
+      if (single) fl |= SA_SINGLE; else ++n_unres;
+      n_heads += flg[it] & 1u;
+      s[hs + (li - gs)] = pos | fl;
+      rk[pos] = (hs + (h0 - gs)) | (single ? RANK_RESOLVED : 0u);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(RX_NT, 2) k2_local_sort_rx(const BlockDesc* __restrict__ desc,
+                                                              const uint32_t* __restrict__ state,
+                                                              const uint32_t* __restrict__ sparse,
+                                                              uint32_t* __restrict__ sa, const uint64_t* __restrict__ lst,
+                                                              uint32_t* __restrict__ rank,
+                                                              const uint2* __restrict__ tile_meta,
+                                                              uint32_t ls_tiles_cap, uint32_t* __restrict__ stats,
+                                                              uint32_t tpc) {
+  extern __shared__ __align__(16) uint8_t rx_raw[];
+  RxSmem& sm = *reinterpret_cast<RxSmem*>(rx_raw);
+  const uint32_t b = blockIdx.y;
+  const BlockDesc d = desc[b];
+  const uint32_t n = d.n;
+  const uint32_t ntiles = (n + LS_T - 1) / LS_T;
+  const uint32_t T0 = blockIdx.x * tpc;
+  if (T0 >= ntiles) return;
+  if (state[b] == 2 || sparse[b]) return;
+  const uint32_t nt = min(tpc, ntiles - T0);  // tiles of this CTA: T0 .. T0+nt-1 (tile T0+nt only lends its lead entries)
+  if (threadIdx.x <= nt) {
+    const uint32_t t = T0 + threadIdx.x;
+    const uint2 m = t < ntiles ? tile_meta[(uint64_t)b * ls_tiles_cap + t] : make_uint2(0u, 0u);
+    sm.tcnt[threadIdx.x] = m.x;
+    sm.tlead[threadIdx.x] = m.y;
+  }
+  const int w = threadIdx.x >> 5;
+  const uint32_t lane = lane_id();
+  for (int i = lane; i < 256; i += 32) sm.wcnt[w][i] = 0;
+  __syncthreads();
+  uint32_t* s = sa + d.off;
+  uint32_t* rk = rank + d.off;
+  const uint64_t* lb = lst + d.off;
+  uint32_t n_heads = 0, n_unres = 0, heads_before = 0;
+
+  uint32_t a = 0;
+  while (a < nt) {
+    // ---- the next window: tiles a .. e-1 (+ the lead entries of tile e), as many as fit
+    uint32_t e = a + 1;
+    uint32_t count = sm.tcnt[a] - sm.tlead[a];
+    while (e < nt && count + sm.tcnt[e] + sm.tlead[e + 1] <= (uint32_t)LS_CAP) {
+      count += sm.tcnt[e];
+      ++e;
+    }
+    count += sm.tlead[e];
+    if (count == 0) {
+      a = e;
+      continue;
+    }
+    const uint32_t rpw = (((count + 31) >> 5) + RX_WARPS - 1) / RX_WARPS;  // rows per warp, <= RX_ROWS
+    // ---- load: list entry [19:0] pos | [39:20] key | [50:40] slot - head slot | [61:51] slot - tile base
+    {
+      uint32_t wb = 0;  // window index of the first entry taken from tile j
+      for (uint32_t j = a; j <= e; ++j) {
+        const uint32_t lo = j == a ? sm.tlead[a] : 0u;
+        const uint32_t hi = j == e ? sm.tlead[e] : sm.tcnt[j];
+        const uint64_t* lt = lb + (uint64_t)(T0 + j) * LS_T;
+        const uint32_t tb = (T0 + j) * LS_T;
+        for (uint32_t i = lo + threadIdx.x; i < hi; i += RX_NT) {
+          const uint64_t en = lt[i];
+          const uint32_t r = wb + (i - lo);
+          const uint32_t dist = (uint32_t)(en >> 40) & 0x7FFu;
+          const uint32_t gs = r - dist;
+          sm.stage[r] = make_uint2((uint32_t)en & RANK_MASK, (gs << 20) | ((uint32_t)(en >> 20) & RANK_MASK));
+          if (dist == 0) {
+            sm.ghead[r] = tb + ((uint32_t)(en >> 51) & 0x7FFu);
+            ++heads_before;
+          }
+        }
+        wb += hi - lo;
+      }
+      for (uint32_t r = count + threadIdx.x; r < rpw * RX_NT; r += RX_NT) sm.stage[r] = make_uint2(~0u, ~0u);
+    }
+    __syncthreads();
+    switch (rpw) {
+      case 1: rx_sort_window<1>(sm, count, s, rk, n_heads, n_unres); break;
+      case 2: rx_sort_window<2>(sm, count, s, rk, n_heads, n_unres); break;
+      case 3: rx_sort_window<3>(sm, count, s, rk, n_heads, n_unres); break;
+      case 4: rx_sort_window<4>(sm, count, s, rk, n_heads, n_unres); break;
+      case 5: rx_sort_window<5>(sm, count, s, rk, n_heads, n_unres); break;
+      case 6: rx_sort_window<6>(sm, count, s, rk, n_heads, n_unres); break;
+      default: rx_sort_window<7>(sm, count, s, rk, n_heads, n_unres); break;
+    }
+    __syncthreads();  // stage, ghead and whead are reused by the next window
+    a = e;
+  }
+#pragma unroll
+  for (int dlt = 16; dlt > 0; dlt >>= 1) {
+    n_heads += __shfl_xor_sync(0xffffffffu, n_heads, dlt);
+    n_unres += __shfl_xor_sync(0xffffffffu, n_unres, dlt);
+    heads_before += __shfl_xor_sync(0xffffffffu, heads_before, dlt);
+  }
+  if (lane == 0) { sm.red[0][w] = n_heads; sm.red[1][w] = n_unres; sm.red[2][w] = heads_before; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t hh = 0, u = 0, hb = 0;
+    for (int ww = 0; ww < RX_WARPS; ++ww) { hh += sm.red[0][ww]; u += sm.red[1][ww]; hb += sm.red[2][ww]; }
+    uint32_t* stp = stats + b * 4;
+    if (hh > hb) atomicAdd(&stp[0], hh - hb);
+    if (u) atomicAdd(&stp[2], u);
+  }
+}
+
 // ------------------------------------------------------------------ last column + origPtr (slot order)
 __global__ void __launch_bounds__(G_NT) k2_finish(const uint8_t* __restrict__ txt, const BlockDesc* __restrict__ desc,
                                                    const uint32_t* __restrict__ sa, uint8_t* __restrict__ last,
@@ -1227,8 +1553,19 @@ int run_bwt(Launcher& L, const uint8_t* d_txt, const BlockDesc* d_desc, const ui
     const char* e = getenv("BZB200_LS_ENUM");
     return e ? atoi(e) : ENUM_MAX_DEFAULT;
   }();
+  static const int ls_rx = [] {
+    // 0: the enumeration group sort (k2_local_sort) in every round, 1: the radix group sort (k2_local_sort_rx) in
+    // every round, 2 (default): enumeration while the lists are dense, radix windows once they are sparse
+    const char* e = getenv("BZB200_LS_RX");
+    return e ? atoi(e) : 2;
+  }();
+  static const int ls_tpc = [] {
+    const char* e = getenv("BZB200_LS_TPC");  // experiments: tiles per CTA of k2_local_sort_rx (0 = by list density)
+    return e ? atoi(e) : 0;
+  }();
   static PerDeviceOnce once_ls;
   once_ls.run([] {
+    cudaFuncSetAttribute((const void*)k2_local_sort_rx, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RxSmem));
     cudaFuncSetAttribute((const void*)k2_local_sort<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LsSmem));
     cudaFuncSetAttribute((const void*)k2_local_sort<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LsSmem));
     cudaFuncSetAttribute((const void*)k2_local_sort<48>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LsSmem));
@@ -1263,6 +1600,10 @@ int run_bwt(Launcher& L, const uint8_t* d_txt, const BlockDesc* d_desc, const ui
   if (cudaMemcpyAsync(g, S.global, sizeof(g), cudaMemcpyDeviceToHost, st) != cudaSuccess) return -2;
   if (cudaStreamSynchronize(st) != cudaSuccess) return -2;
 
+  static const bool trace = getenv("BZB200_TRACE_ROUNDS") != nullptr;  // per-round work, for the ncu tables
+  if (trace)
+    fprintf(stderr, "k2 initial: elems %llu passes %d key %dx%d bits -> unresolved %u max_radix %u radix %u\n",
+            (unsigned long long)M, p0, km.syms, km.bits, g[0], g[1], g[2]);
   uint32_t h = (uint32_t)km.syms;  // the initial key covers the first h symbols of every rotation
   while (g[0] > 0) {
     if (g[3]) return -5;
@@ -1275,7 +1616,17 @@ int run_bwt(Launcher& L, const uint8_t* d_txt, const BlockDesc* d_desc, const ui
     // BIG-group / sparse-block elements -> S.A
     L.launch("k2_gather", k2_gather, dim3(ls_tiles, nb), dim3(G_NT), d_desc, S.rank, S.sa, S.state, S.shift, S.sparse, h,
              S.B, S.A, S.cnt, S.tile_meta, S.ls_tiles_cap);
-    {
+    if (g[0] == g[2]) {
+      // every unresolved rotation takes the radix path: the lists are empty
+    } else if (ls_rx == 1 || (ls_rx == 2 && (g[0] - g[2]) < (uint64_t)nb * ls_tiles * (LS_T / 4))) {
+      // tiles per CTA: enough of them that a window holds a few thousand entries (g[0] - g[2] entries in all lists)
+      const uint64_t local_total = g[0] - g[2];
+      const uint64_t avg = std::max<uint64_t>(1, local_total / std::max<uint64_t>(1, (uint64_t)nb * ls_tiles));
+      uint32_t tpc = ls_tpc > 0 ? (uint32_t)ls_tpc : (uint32_t)std::min<uint64_t>(RX_TPC_MAX, (3000 + avg - 1) / avg);
+      tpc = std::max(1u, std::min(tpc, (uint32_t)RX_TPC_MAX));
+      L.launch_smem("k2_local_sort", k2_local_sort_rx, dim3((ls_tiles + tpc - 1) / tpc, nb), dim3(RX_NT), sizeof(RxSmem),
+                    d_desc, S.state, S.sparse, S.sa, S.B, S.rank, S.tile_meta, S.ls_tiles_cap, S.stats, tpc);
+    } else {
       switch (ls_enum) {
         case 16:
           L.launch_smem("k2_local_sort", k2_local_sort<16>, dim3(ls_tiles, nb), dim3(LS_NT), sizeof(LsSmem), d_desc,
@@ -1298,6 +1649,7 @@ int run_bwt(Launcher& L, const uint8_t* d_txt, const BlockDesc* d_desc, const ui
       passes += 5;
       regroup(L, s2, d_desc, nb, maxbig, S, 0);
     }
+    const uint32_t elems_round = g[0], radix_round = g[2];
     elems += g[0];
     radix_elem_passes += 5ull * g[2];
     local_elems += g[0] - g[2];
@@ -1306,6 +1658,9 @@ int run_bwt(Launcher& L, const uint8_t* d_txt, const BlockDesc* d_desc, const ui
     if (L.err != cudaSuccess) return -2;
     if (cudaMemcpyAsync(g, S.global, sizeof(g), cudaMemcpyDeviceToHost, st) != cudaSuccess) return -2;
     if (cudaStreamSynchronize(st) != cudaSuccess) return -2;
+    if (trace)
+      fprintf(stderr, "k2 round %u (h %u): local %u radix %u -> unresolved %u max_radix %u radix %u\n", rounds, h,
+              (uint32_t)(elems_round - radix_round), radix_round, g[0], g[1], g[2]);
     if (h < (1u << 21)) h *= 2;
   }
   if (g[3]) return -5;

@@ -656,6 +656,9 @@ int bzb200_compress_host(bzb200_ctx* c, int level, const uint8_t* h_in, size_t n
   }
   if (!c->h2d_stream) CK(c, cudaStreamCreateWithFlags(&c->h2d_stream, cudaStreamNonBlocking));
   if (!c->d2h_stream) CK(c, cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking));
+  // Every exit below — also the user-triggerable "output buffer too small" ones — leaves with the copy streams
+  // drained: the caller may free h_in / h_out as soon as the call returns.
+  const int rc = [&]() -> int {
   std::vector<size_t> ends;
   for (size_t e = first; e < n; e += seg) ends.push_back(e);
   if (ends.size() && n - ends.back() < seg / 4) ends.pop_back();  // no tiny tail segment
@@ -715,6 +718,13 @@ int bzb200_compress_host(bzb200_ctx* c, int level, const uint8_t* h_in, size_t n
   CK(c, cudaStreamSynchronize(c->d2h_stream));
   *out_n = got;
   return BZB200_OK;
+  }();
+  if (rc != BZB200_OK) {
+    cudaStreamSynchronize(c->h2d_stream);
+    cudaStreamSynchronize(c->d2h_stream);
+    cudaStreamSynchronize(c->stream);
+  }
+  return rc;
 }
 
 // ------------------------------------------------------------------ instrumentation

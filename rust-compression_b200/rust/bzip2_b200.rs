@@ -57,7 +57,10 @@ impl BZip2Encoder {
         let mut handle: *mut BzbEnc = std::ptr::null_mut();
         let rc = unsafe { bzb200_enc_create(level as c_int, -1, &mut handle) };
         if rc != 0 || handle.is_null() {
-            panic!("bzb200_enc_create failed: {}", rc);
+            // no CUDA device / library error: the constructor cannot fail in the reference's API (encoder.rs:58-72),
+            // so the object is built without a handle and every `next` yields Err(Unexpected), the one error the
+            // reference's encoder surfaces (encoder.rs:623)
+            handle = std::ptr::null_mut();
         }
         Self {
             handle,
@@ -90,7 +93,9 @@ impl BZip2Encoder {
 
 impl Drop for BZip2Encoder {
     fn drop(&mut self) {
-        unsafe { bzb200_enc_destroy(self.handle) }
+        if !self.handle.is_null() {
+            unsafe { bzb200_enc_destroy(self.handle) }
+        }
     }
 }
 
@@ -103,6 +108,9 @@ impl Encoder for BZip2Encoder {
     // blocks that have closed whenever a window of input has accumulated (bzb200_enc_write), so bytes can become
     // available before Finish, as in the reference (encoder.rs:91-107).
     fn next<I: Iterator<Item = u8>>(&mut self, iter: &mut I, action: Action) -> Option<Result<u8, CompressionError>> {
+        if self.handle.is_null() {
+            return Some(Err(CompressionError::Unexpected)); // bzb200_enc_create failed in `new`
+        }
         loop {
             if self.outpos < self.outbuf.len() {
                 let b = self.outbuf[self.outpos];

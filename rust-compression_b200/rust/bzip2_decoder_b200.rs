@@ -46,7 +46,9 @@ impl BZip2Decoder {
         let mut handle: *mut BzbDec = std::ptr::null_mut();
         let rc = unsafe { bzb200_dec_create(-1, &mut handle) };
         if rc != BZB200_OK || handle.is_null() {
-            panic!("bzb200_dec_create failed: {}", rc);
+            // `new` cannot fail in the reference's API (decoder.rs:584-601): without a device every `next` yields
+            // Err(Unexpected)
+            handle = std::ptr::null_mut();
         }
         Self { handle, outbuf: Vec::new(), outpos: 0, decoded: false }
     }
@@ -71,7 +73,9 @@ impl Default for BZip2Decoder {
 
 impl Drop for BZip2Decoder {
     fn drop(&mut self) {
-        unsafe { bzb200_dec_destroy(self.handle) }
+        if !self.handle.is_null() {
+            unsafe { bzb200_dec_destroy(self.handle) }
+        }
     }
 }
 
@@ -82,6 +86,9 @@ impl Decoder for BZip2Decoder {
 
     // decoder.rs:607-614
     fn next<I: Iterator<Item = u8>>(&mut self, iter: &mut I) -> Option<Result<u8, BZip2Error>> {
+        if self.handle.is_null() {
+            return Some(Err(BZip2Error::Unexpected)); // bzb200_dec_create failed in `new`
+        }
         loop {
             if self.outpos < self.outbuf.len() {
                 let b = self.outbuf[self.outpos];
