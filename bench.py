@@ -54,19 +54,20 @@ ALG_BYTES = {
 
 def ncu_traffic_ratio(kernel):
     """DRAM traffic per algorithmic byte of `kernel`, read from the committed ncu table of THIS round
-    (profiles/r2_ncu_kernels.csv: one `ncu --set full` record per kernel of the shipped library; columns kernel,
-    dram_read_bytes, dram_write_bytes, alg_bytes).  None when the table has no row for the kernel."""
+    (profiles/r2_ncu_kernels.csv, written by profiles/make_traffic_table.py from one `ncu --set full` record per kernel
+    of the shipped library: columns kernel, bench_name, dram_read_bytes, dram_write_bytes, alg_bytes of the SAME
+    launch).  Returns (ratio, kernel name in the table, path); ratio None when the table has no row."""
     path = os.path.join(ROOT, "profiles", "r2_ncu_kernels.csv")
     try:
         import csv
         for row in csv.DictReader(open(path)):
-            if row.get("kernel", "").split("<")[0].split("(")[0] in (kernel, "k2_os_scatter" if kernel == "k2_rs_scatter" else kernel):
+            if row.get("bench_name") == kernel:
                 alg = float(row.get("alg_bytes") or 0)
                 if alg > 0:
-                    return (float(row["dram_read_bytes"]) + float(row["dram_write_bytes"])) / alg, path
+                    return (float(row["dram_read_bytes"]) + float(row["dram_write_bytes"])) / alg, row["kernel"], path
     except Exception:
         pass
-    return None, path
+    return None, None, path
 
 
 def workload_name(n_gpus, level=None, gen_name=None, total=None):
@@ -751,15 +752,16 @@ def main():
         else:
             alg_bytes = total_bytes / world + out_bytes / world
         achieved = alg_bytes / (kms / 1e3) / 1e9 if kms > 0 else 0.0
-        ratio, ratio_src = ncu_traffic_ratio(name)
+        ratio, ncu_name, ratio_src = ncu_traffic_ratio(name)
         roofline = {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": peak, "unit": "GB/s",
                     "frac": achieved / peak,
                     "frac_is": "per-kernel model: algorithmic bytes of the dominant kernel's launches / their summed "
                                "CUDA-event time / measured copy peak (NOT the SURVEY 8(d) whole-path figure: that is "
                                "roofline.path)",
                     "traffic": (ratio * alg_bytes / max(1, nl)) if ratio else None,
-                    "traffic_source": (ratio_src + ": (dram_read_bytes + dram_write_bytes) / alg_bytes of the kernel's "
-                                       "ncu --set full record x algorithmic bytes per launch") if ratio else
+                    "traffic_source": (f"profiles/r2_ncu_kernels.csv row {ncu_name}: measured (dram_read_bytes + "
+                                       f"dram_write_bytes) / alg_bytes of that launch = {ratio:.3f}, x the algorithmic "
+                                       "bytes per launch of this step") if ratio else
                                       "no ncu row for this kernel in " + ratio_src,
                     "peak_source": peak_src,
                     "launches_per_step": nl, "avg_launch_ms": kms / max(1, nl),

@@ -241,8 +241,11 @@ __device__ __forceinline__ void st_status(uint32_t* p, uint32_t v) {
 // KBITS: 0 = the list holds 64-bit elements; 8 / 7 / 6 / 4 = pass 0 of the initial sort builds its elements (the first
 // KSYMS symbols of the rotation, KBITS bits each | pos) from the block's text instead of reading a key array.
 // WBITS = digit width of the pass.
-template <int KBITS, int KSYMS, int WBITS, bool FULL>
-__device__ __forceinline__ void os_tile(OsSmemT<1 << WBITS>& sm, const uint64_t* __restrict__ src,
+// SM: shared-memory block with wcnt / dstart / goff / ws (/ lut for pass 0); `stage` = the tile-sized staging buffer of the
+// scatter (pass 0 also stages the tile's symbols there); `tin` != nullptr: the tile's elements are already in shared
+// memory (k2_os_scatter_pf brings them in with a bulk copy), read from there instead of from `src`.
+template <int KBITS, int KSYMS, int WBITS, bool FULL, class SM>
+__device__ __forceinline__ void os_tile(SM& sm, uint64_t* stage, const uint64_t* tin, const uint64_t* __restrict__ src,
                                         uint64_t* __restrict__ dst, const BlockDesc* __restrict__ desc,
                                         uint32_t* __restrict__ status, uint32_t tiles_cap, uint32_t epoch, int pass,
                                         uint32_t b, uint32_t c, uint32_t tile, uint32_t base, uint32_t tcount,
@@ -264,7 +267,7 @@ __device__ __forceinline__ void os_tile(OsSmemT<1 << WBITS>& sm, const uint64_t*
   uint32_t rk[OS_IPT];
   if (KBITS != 0) {
     // the tile's symbols (text bytes through the alphabet table), staged once: symbol i of the tile at tx[i]
-    uint8_t* tx = reinterpret_cast<uint8_t*>(sm.stage);  // free until the scatter phase
+    uint8_t* tx = reinterpret_cast<uint8_t*>(stage);  // free until the scatter phase
     const uint8_t* t = reinterpret_cast<const uint8_t*>(src) + off;  // src carries the text pointer; c == block length
     const uint32_t need = tcount + KSYMS - 1;
     constexpr int NLD = (OS_TILE + KSYMS - 1 + OS_NT - 1) / OS_NT;
@@ -310,7 +313,7 @@ __device__ __forceinline__ void os_tile(OsSmemT<1 << WBITS>& sm, const uint64_t*
 #pragma unroll
     for (int it = 0; it < OS_IPT; ++it) {
       const uint32_t li = w * OS_WCH + it * 32 + lane;
-      e[it] = (FULL || li < tcount) ? s[li] : ~0ull;
+      e[it] = (FULL || li < tcount) ? (tin ? tin[li] : s[li]) : ~0ull;
     }
   }
   if (KBITS != 0) {
@@ -353,18 +356,33 @@ __device__ __forceinline__ void os_tile(OsSmemT<1 << WBITS>& sm, const uint64_t*
   // inside the tile; publish + look back
   uint32_t run[DPT];
   uint32_t tsum = 0;
-#pragma unroll
-  for (int q = 0; q < DPT; ++q) {
-    const uint32_t dgt = threadIdx.x * DPT + q;
-    uint32_t r = 0;
+  if (DPT == 2) {  // both digits of the thread with one 64-bit shared access per warp row
+    uint32_t r0 = 0, r1 = 0;
 #pragma unroll
     for (int ww = 0; ww < OS_WARPS; ++ww) {
-      const uint32_t t = sm.wcnt[ww][dgt];
-      sm.wcnt[ww][dgt] = r;
-      r += t;
+      uint2* cell = reinterpret_cast<uint2*>(&sm.wcnt[ww][threadIdx.x * 2]);
+      const uint2 t = *cell;
+      *cell = make_uint2(r0, r1);
+      r0 += t.x;
+      r1 += t.y;
     }
-    run[q] = r;
-    tsum += r;
+    run[0] = r0;
+    run[DPT - 1] = r1;
+    tsum = r0 + r1;
+  } else {
+#pragma unroll
+    for (int q = 0; q < DPT; ++q) {
+      const uint32_t dgt = threadIdx.x * DPT + q;
+      uint32_t r = 0;
+#pragma unroll
+      for (int ww = 0; ww < OS_WARPS; ++ww) {
+        const uint32_t t = sm.wcnt[ww][dgt];
+        sm.wcnt[ww][dgt] = r;
+        r += t;
+      }
+      run[q] = r;
+      tsum += r;
+    }
   }
   uint32_t* st = status + ((uint64_t)b * tiles_cap) * OS_BINS_MAX + threadIdx.x * DPT;
   const uint32_t tag = epoch << 22;
@@ -429,7 +447,7 @@ __device__ __forceinline__ void os_tile(OsSmemT<1 << WBITS>& sm, const uint64_t*
     const uint32_t li = KBITS != 0 ? threadIdx.x * OS_IPT + it : w * OS_WCH + it * 32 + lane;
     if ((FULL || li < tcount)) {
       const uint32_t dgt = (uint32_t)(e[it] >> shift) & DMASK;
-      sm.stage[sm.dstart[dgt] + sm.wcnt[w][dgt] + rk[it]] = e[it];
+      stage[sm.dstart[dgt] + sm.wcnt[w][dgt] + rk[it]] = e[it];
     }
   }
   __syncthreads();
@@ -438,7 +456,7 @@ __device__ __forceinline__ void os_tile(OsSmemT<1 << WBITS>& sm, const uint64_t*
   for (int k = 0; k < OS_IPT; ++k) {
     const uint32_t i = threadIdx.x + k * OS_NT;
     if (FULL || i < tcount) {
-      const uint64_t v = sm.stage[i];
+      const uint64_t v = stage[i];
       const uint32_t dgt = (uint32_t)(v >> shift) & DMASK;
       o[sm.goff[dgt] + (int)i] = v;
     }
@@ -469,7 +487,7 @@ __global__ void __launch_bounds__(OS_NT, OS_MINB) k2_os_scatter(const uint64_t* 
   for (int q = 0; q < DPT; ++q)
     boff[q] = bucket_off[((uint64_t)b * OS_PASSES_MAX + pass) * OS_BINS_MAX + threadIdx.x * DPT + q];
 #pragma unroll
-  for (int i = lane; i < BINS; i += 32) sm.wcnt[w][i] = 0;
+  for (int i = lane; i < BINS / 4; i += 32) reinterpret_cast<uint4*>(sm.wcnt[w])[i] = make_uint4(0u, 0u, 0u, 0u);
   if (KBITS != 0 && KBITS != 8) build_sym_lut(inuse + b * 8, sm.lut);
   __syncthreads();
   const uint32_t tile = sm.tile;
@@ -478,9 +496,157 @@ __global__ void __launch_bounds__(OS_NT, OS_MINB) k2_os_scatter(const uint64_t* 
   const uint32_t tcount = min((uint32_t)OS_TILE, c - base);
   // full tiles (all but the last of a list) run without per-element bounds checks
   if (tcount == (uint32_t)OS_TILE)
-    os_tile<KBITS, KSYMS, WBITS, true>(sm, src, dst, desc, status, tiles_cap, epoch, pass, b, c, tile, base, tcount, boff);
+    os_tile<KBITS, KSYMS, WBITS, true>(sm, sm.stage, nullptr, src, dst, desc, status, tiles_cap, epoch, pass, b, c, tile,
+                                       base, tcount, boff);
   else
-    os_tile<KBITS, KSYMS, WBITS, false>(sm, src, dst, desc, status, tiles_cap, epoch, pass, b, c, tile, base, tcount, boff);
+    os_tile<KBITS, KSYMS, WBITS, false>(sm, sm.stage, nullptr, src, dst, desc, status, tiles_cap, epoch, pass, b, c, tile,
+                                        base, tcount, boff);
+}
+
+// ------------------------------------------------------------------ the same pass, persistent, tiles brought in by TMA
+// k2_os_scatter_pf: passes over 64-bit elements (KBITS == 0).  The grid is one wave of CTAs; a CTA takes tiles from a
+// global ticket counter (ticket g -> block g % nb, tile g / nb: a tile's ticket is always larger than the tickets of
+// the tiles in front of it in its block, which is all the look-back needs) and keeps TWO tiles in shared memory: while
+// it ranks and scatters tile i, the bulk-copy engine (cp.async.bulk, 1-D TMA, completion on an mbarrier) brings in
+// tile i+1, and thread 0 already holds the ticket of tile i+2 — so neither the ticket's atomic round trip nor the
+// tile's load latency is on a CTA's critical path.  The buffer a tile arrived in doubles as the staging buffer of its
+// scatter.  A bulk copy needs 16-byte alignment and a tile starts at an arbitrary 8-byte element, so the copy starts at
+// the even element at or below it (`a` = 0 or 1 elements of skew).
+template <int BINS>
+struct OsPfSmem {
+  static constexpr int WARPS = OS_NT / 32;
+  uint64_t buf[2][OS_TILE + 2];
+  uint32_t wcnt[WARPS][BINS];
+  uint32_t dstart[BINS];
+  int goff[BINS];
+  uint32_t ws[OS_NT / 32 + 1];
+  uint32_t g[4];            // ticket ring
+  uint64_t mbar[2];
+  uint8_t lut[4];           // (unused: os_tile's pass-0 branch is not instantiated here)
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n .reg .pred p;\n WAIT_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @p bra DONE_%=;\n"
+      " bra WAIT_%=;\n DONE_%=:\n}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+template <int WBITS>
+__global__ void __launch_bounds__(OS_NT, OS_MINB) k2_os_scatter_pf(const uint64_t* __restrict__ src, uint64_t* __restrict__ dst,
+                                                             const BlockDesc* __restrict__ desc,
+                                                             const uint32_t* __restrict__ cnt,
+                                                             const uint32_t* __restrict__ bucket_off,
+                                                             uint32_t* __restrict__ status, uint32_t* __restrict__ gticket,
+                                                             uint32_t nb, uint32_t tiles, uint32_t tiles_cap,
+                                                             uint32_t epoch, int pass) {
+  extern __shared__ __align__(128) uint8_t os_pf_raw[];
+  constexpr int BINS = 1 << WBITS;
+  constexpr int DPT = BINS / OS_NT;
+  using Sm = OsPfSmem<BINS>;
+  Sm& sm = *reinterpret_cast<Sm*>(os_pf_raw);
+  const int w = threadIdx.x >> 5;
+  const uint32_t lane = lane_id();
+  const uint32_t total = nb * tiles;
+
+  // tile of a ticket: list length c, first element, elements, skew of the bulk copy
+  struct Tile { uint32_t b, tile, c, base, tcount, a; const uint64_t* gsrc; uint32_t bytes; };
+  auto decode = [&](uint32_t g) {
+    Tile t;
+    t.b = g % nb;
+    t.tile = g / nb;
+    t.c = cnt[t.b];
+    t.base = t.tile * OS_TILE;
+    t.tcount = t.base < t.c ? min((uint32_t)OS_TILE, t.c - t.base) : 0u;
+    const uint64_t first = (uint64_t)desc[t.b].off + t.base;
+    t.a = (uint32_t)(first & 1u);
+    t.gsrc = src + (first - t.a);
+    t.bytes = ((t.a + t.tcount + 1u) & ~1u) * 8u;
+    return t;
+  };
+  if (threadIdx.x == 0) {
+    mbar_init(&sm.mbar[0], 1);
+    mbar_init(&sm.mbar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    const uint32_t g0 = atomicAdd(gticket, 1u), g1 = atomicAdd(gticket, 1u);
+    sm.g[0] = g0;
+    sm.g[1] = g1;
+  }
+#pragma unroll
+  for (int i = lane; i < BINS / 4; i += 32) reinterpret_cast<uint4*>(sm.wcnt[w])[i] = make_uint4(0u, 0u, 0u, 0u);
+  __syncthreads();
+  if (threadIdx.x == 0 && sm.g[0] < total) {  // tile 0 on its way
+    const Tile t = decode(sm.g[0]);
+    if (t.tcount) {
+      mbar_expect_tx(&sm.mbar[0], t.bytes);
+      bulk_g2s(sm.buf[0], t.gsrc, t.bytes, &sm.mbar[0]);
+    }
+  }
+  uint32_t phases = 0;  // bit k: parity of the next completion of mbar[k]
+  uint32_t boff[DPT], boff_next[DPT];
+  {
+    const uint32_t g0 = sm.g[0];
+#pragma unroll
+    for (int q = 0; q < DPT; ++q)
+      boff[q] = g0 < total ? bucket_off[((uint64_t)(g0 % nb) * OS_PASSES_MAX + pass) * OS_BINS_MAX + threadIdx.x * DPT + q] : 0u;
+  }
+  for (uint32_t it = 0;; ++it) {
+    const uint32_t cur = it & 1u;
+    const uint32_t g = sm.g[it % 3u];
+    if (g >= total) break;  // tickets only grow: nothing follows either
+    const uint32_t gn = sm.g[(it + 1u) % 3u];
+    uint32_t g2 = total;
+    if (threadIdx.x == 0) {
+      // the ticket of tile it+2: asked for now, stored at the end of the iteration (its slot of the ring was read by
+      // everybody before the last barrier of tile it-1), so the atomic's round trip hides behind tile it
+      if (gn < total) g2 = atomicAdd(gticket, 1u);
+      if (gn < total) {  // tile it+1 into the buffer tile it-1 has left
+        const Tile t = decode(gn);
+        if (t.tcount) {
+          mbar_expect_tx(&sm.mbar[cur ^ 1u], t.bytes);
+          bulk_g2s(sm.buf[cur ^ 1u], t.gsrc, t.bytes, &sm.mbar[cur ^ 1u]);
+        }
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < DPT; ++q)
+      boff_next[q] = gn < total ? bucket_off[((uint64_t)(gn % nb) * OS_PASSES_MAX + pass) * OS_BINS_MAX + threadIdx.x * DPT + q] : 0u;
+    const Tile t = decode(g);
+    if (t.tcount) {
+      mbar_wait(&sm.mbar[cur], (phases >> cur) & 1u);
+      phases ^= 1u << cur;
+      if (t.tcount == (uint32_t)OS_TILE)
+        os_tile<0, 0, WBITS, true>(sm, sm.buf[cur], sm.buf[cur] + t.a, src, dst, desc, status, tiles_cap, epoch, pass, t.b,
+                                   t.c, t.tile, t.base, t.tcount, boff);
+      else
+        os_tile<0, 0, WBITS, false>(sm, sm.buf[cur], sm.buf[cur] + t.a, src, dst, desc, status, tiles_cap, epoch, pass,
+                                    t.b, t.c, t.tile, t.base, t.tcount, boff);
+      __syncwarp();
+#pragma unroll
+      for (int i = lane; i < BINS / 4; i += 32)  // the warp's own counters, for the next tile
+        reinterpret_cast<uint4*>(sm.wcnt[w])[i] = make_uint4(0u, 0u, 0u, 0u);
+      fence_proxy_async();  // this thread's reads and writes of buf[cur] come before the bulk copy that reuses it
+    }
+#pragma unroll
+    for (int q = 0; q < DPT; ++q) boff[q] = boff_next[q];
+    if (threadIdx.x == 0) sm.g[(it + 2u) % 3u] = g2;
+    __syncthreads();
+  }
 }
 
 // ------------------------------------------------------------------ SA entry layout / local-sort geometry
@@ -1465,6 +1631,47 @@ static void launch_pass(Launcher& L, const uint64_t* src, uint64_t* dst, const B
   os.ticket_base += tiles;
 }
 
+template <int WBITS>
+static void launch_pass_pf(Launcher& L, const uint64_t* src, uint64_t* dst, const BlockDesc* d_desc, uint32_t nb,
+                           uint32_t tiles, BwtScratch& S, OsState& os, int pass) {
+  static PerDeviceOnce once;
+  once.run([] {
+    cudaFuncSetAttribute((const void*)k2_os_scatter_pf<WBITS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)sizeof(OsPfSmem<1 << WBITS>));
+  });
+  if (os.epoch == 1023) {
+    cudaMemsetAsync(S.hist, 0, (size_t)nb * S.tiles_cap * OS_BINS_MAX * sizeof(uint32_t), L.stream);
+    os.epoch = 0;
+  }
+  ++os.epoch;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const uint64_t total = (uint64_t)nb * tiles;
+  const uint32_t grid = (uint32_t)std::min<uint64_t>(total, (uint64_t)sms * OS_MINB);
+  cudaMemsetAsync(S.ticket + nb, 0, sizeof(uint32_t), L.stream);  // the global ticket counter sits behind the per-block ones
+  L.launch_smem("k2_rs_scatter", k2_os_scatter_pf<WBITS>, dim3(grid), dim3(OS_NT), sizeof(OsPfSmem<1 << WBITS>), src, dst,
+                d_desc, S.cnt, S.oshist, S.hist, S.ticket + nb, nb, tiles, S.tiles_cap, os.epoch, pass);
+}
+
+// Passes over 64-bit elements.  BZB200_OS_PF: 0 = one tile per CTA (k2_os_scatter), 1 = the persistent TMA-fed kernel
+// (k2_os_scatter_pf), 2 (default) = by measurement (profiles/README.md, round 2): the 9-bit passes are bound by the
+// shared-memory pipe (MIO throttle), where reading the tile back out of shared memory costs more than the hidden load
+// latency gains (1.96 ms against 1.73 ms per 256 MiB pass); the 8-bit passes (256 counters per warp) have that headroom
+// and run 5 % faster persistent.
+template <int WBITS>
+static void launch_pass_elems(Launcher& L, const uint64_t* src, uint64_t* dst, const BlockDesc* d_desc, uint32_t nb,
+                              uint32_t tiles, BwtScratch& S, OsState& os, int pass) {
+  static const int pf = [] {
+    const char* e = getenv("BZB200_OS_PF");
+    return e ? atoi(e) : 2;
+  }();
+  if ((pf == 1 || (pf == 2 && WBITS == 8)) && (uint64_t)nb * tiles < (1ull << 31))
+    launch_pass_pf<WBITS>(L, src, dst, d_desc, nb, tiles, S, os, pass);
+  else
+    launch_pass<0, 0, WBITS>(L, src, dst, d_desc, nb, tiles, S, os, pass, nullptr);
+}
+
 // LSD sort of every block's rotations by their initial key (built from the text in pass 0).  Returns the number of
 // passes; the sorted list ends up in `src`.
 template <int KBITS, int KSYMS, int WBITS>
@@ -1497,7 +1704,7 @@ static int initial_sort_mode(Launcher& L, uint64_t*& src, uint64_t*& dst, const 
       launch_pass<KBITS, KSYMS, WBITS>(L, reinterpret_cast<const uint64_t*>(d_txt), dst, d_desc, nb, tiles, S, os, p,
                                        d_inuse);
     else
-      launch_pass<0, 0, WBITS>(L, src, dst, d_desc, nb, tiles, S, os, p, d_inuse);
+      launch_pass_elems<WBITS>(L, src, dst, d_desc, nb, tiles, S, os, p);
     uint64_t* t = src; src = dst; dst = t;
   }
   return P;
@@ -1520,7 +1727,7 @@ static void radix_sort40(Launcher& L, uint64_t*& src, uint64_t*& dst, const Bloc
   L.launch("k2_os_hist", k2_os_hist, dim3(chunks, nb), dim3(256), src, d_desc, S.cnt, S.oshist, chunk);
   L.launch("k2_os_offsets", k2_os_offsets, dim3(nb), dim3(256), S.oshist);
   for (int p = 0; p < 5; ++p) {
-    launch_pass<0, 0, 8>(L, src, dst, d_desc, nb, tiles, S, os, p, nullptr);
+    launch_pass_elems<8>(L, src, dst, d_desc, nb, tiles, S, os, p);
     uint64_t* t = src; src = dst; dst = t;
   }
 }

@@ -22,7 +22,10 @@
 
 namespace bzb {
 
-constexpr int MTF_CHUNK = 4096;
+#ifndef BZB_MTF_CHUNK
+#define BZB_MTF_CHUNK 4096  // bytes per chunk (tools/build_variant.sh builds experiment libraries with other values)
+#endif
+constexpr int MTF_CHUNK = BZB_MTF_CHUNK;
 constexpr int MTF_WARPS = 4;  // warps (= chunks) per CTA
 constexpr int NEG_UNUSED = -(1 << 30);
 

@@ -390,8 +390,8 @@ static int encode_batch(bzb200_ctx* c, uint32_t b0, uint32_t nb, uint8_t* d_out,
   const uint32_t max_groups = (nmax + 1 + G_SIZE - 1) / G_SIZE;
 
   TRY(ensure(c, c->desc, (size_t)nb * sizeof(BlockDesc)));
-  TRY(ensure(c, c->A, M * 8));
-  TRY(ensure(c, c->B, M * 8));
+  TRY(ensure(c, c->A, M * 8 + 16));  // + one element pair: a bulk copy of a tile may read one element past it
+  TRY(ensure(c, c->B, M * 8 + 16));
   TRY(ensure(c, c->rank, M * 4));
   TRY(ensure(c, c->sa, M * 4));
   const uint32_t ls_tile = bwt_ls_tile_elems();
@@ -407,7 +407,7 @@ static int encode_batch(bzb200_ctx* c, uint32_t b0, uint32_t nb, uint8_t* d_out,
     max_alpha = std::max(max_alpha, a);
   }
   TRY(ensure(c, c->pairhist, bwt_pairhist_bytes(nb, max_alpha)));
-  TRY(ensure(c, c->ticket, (size_t)nb * 4));
+  TRY(ensure(c, c->ticket, ((size_t)nb + 1) * 4));  // per-block tile tickets + the global counter of k2_os_scatter_pf
   TRY(ensure(c, c->tsum, (size_t)nb * tiles * sizeof(int4)));
   TRY(ensure(c, c->state, (size_t)nb * 4));
   TRY(ensure(c, c->shift, (size_t)nb * 4));

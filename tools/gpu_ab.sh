@@ -4,14 +4,18 @@
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 TAG=${TAG:-ab}
+mkdir -p rust-compression_b200/build/variants; cp rust-compression_b200/libbzb200.so rust-compression_b200/build/variants/lib_base.so
 timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/${TAG}_gputests.log 2>&1; echo "tests rc $?"; tail -5 gpurun_out/${TAG}_gputests.log
 : > gpurun_out/${TAG}_prof.log
 for v in "$@"; do
   echo "== variant: $v" >> gpurun_out/${TAG}_prof.log
   if [ "$v" = "-" ]; then v=""; fi
+  cp rust-compression_b200/build/variants/lib_base.so rust-compression_b200/libbzb200.so 2>/dev/null
+  case "$v" in LIB=*) cp rust-compression_b200/build/variants/lib_${v#LIB=}.so rust-compression_b200/libbzb200.so; v="";; esac
   env $v timeout 300 python tools/gpu_enc_prof.py 1024 9 text >> gpurun_out/${TAG}_prof.log 2>&1
   env $v timeout 300 python tools/gpu_enc_prof.py 1024 1 mixed >> gpurun_out/${TAG}_prof.log 2>&1
 done
+cp rust-compression_b200/build/variants/lib_base.so rust-compression_b200/libbzb200.so
 cat gpurun_out/${TAG}_prof.log
 if [ -n "$LAUNCHES" ]; then
   ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/${TAG}_launches_1gib.csv \
