@@ -406,6 +406,7 @@ def run_decode(args):
     l0 = ctx.launch_count()
     ms_total, res = timed(step_device, args.steps)
     launches = ctx.launch_count() - l0
+    step_walls = list(walls)
     clocks = sampler.stop()
     assert res == (n, 0), res
     same = bool(torch.equal(d_out, d_raw))
@@ -586,17 +587,20 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    walls = []   # host wall time of every step of the most recent timed() call (this rank)
+
     def timed(fn, steps):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         res = None
+        walls.clear()
         for _ in range(steps):
             tw = time.perf_counter()
-            res = fn()
+            res = fn()   # synchronous on the host side: the wall time of a call is the time of its step on this rank
+            walls.append(round(1e3 * (time.perf_counter() - tw), 2))
             if os.environ.get("BZB200_BENCH_DEBUG"):
-                torch.cuda.synchronize()
-                sys.stderr.write(f"[rank {rank}] {fn.__name__} wall {1e3 * (time.perf_counter() - tw):.1f} ms\n")
+                sys.stderr.write(f"[rank {rank}] {fn.__name__} wall {walls[-1]:.1f} ms\n")
         e1.record()
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
@@ -620,6 +624,7 @@ def main():
     l0 = ctx.launch_count()
     ms_total, (d_stream, info) = timed(step_device, args.steps)
     launches = ctx.launch_count() - l0
+    step_walls = list(walls)
     clocks = sampler.stop() if rank == 0 else None
     sstats = ctx.sort_stats()
     ms_step = ms_total / args.steps
@@ -796,6 +801,7 @@ def main():
             "roofline": roofline,
             "kernels_ms_per_step": {k: round(v[1], 3) for k, v in top[:14]},
             "profiled_step_ms": round(ms_prof, 3),
+            "step_wall_ms_rank0": step_walls,
             "kernel_time_ms_per_step": round(step_ms_kernels, 3),
             "cpu_baseline": base1,
             "speedup_vs_single_thread_reference": {"device": value / base1["value"], "e2e": e2e["value"] / base1["value"]},

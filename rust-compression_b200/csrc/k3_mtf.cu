@@ -176,44 +176,65 @@ __device__ __forceinline__ uint32_t mtf_word_hit(uint32_t f, uint32_t carry, uin
   return __byte_perm(f, carry, sel);
 }
 
+__device__ __forceinline__ uint32_t shr_sat(uint32_t v, int s) {  // v >> s with s clamped to [0, 32] (32 gives 0)
+  uint32_t r;
+  asm("shr.b32 %0, %1, %2;" : "=r"(r) : "r"(v), "r"((uint32_t)max(s, 0)));
+  return r;
+}
+
 // Moves byte c (not at the front) to the front of the lane's list, returns its previous position.  The register
-// part is branch-free (lanes of a warp sit at different depths; a branch per word would serialise them).
-__device__ __forceinline__ uint32_t mtf_lane_access(MtfLane& l, uint32_t c, uint32_t* deep /* column, stride 32 */,
-                                                    uint32_t deep_words) {
+// part is branch-free per lane (lanes of a warp sit at different depths; a branch per word would serialise them):
+//   find    per word the zero-byte flags of (word ^ c c c c): (z - 0x01010101) & ~z & 0x80808080 — a false flag can only
+//           sit above a true one, so the lowest flag of the first word that has flags is c;
+//   update  entry j takes the value of entry j-1 for j <= pos (a funnel shift by one byte across the words) and keeps
+//           its own behind that: one byte mask per word, derived from pos.
+// Words wholly behind the deepest hit among the lanes that are here are left alone (warp-uniform bound).
+__device__ __forceinline__ uint32_t mtf_lane_access(MtfLane& l, uint32_t c, uint2* deep /* column, stride 32 */,
+                                                    uint32_t deep_words /* 64-bit words: 8 entries each */) {
   const uint32_t x = c * 0x01010101u;
-  // every word's new value depends only on OLD values (the byte entering word k is the top byte of old word k-1),
-  // so the eight updates are independent instructions
-  uint32_t m[8];
+  uint32_t H = 0, wsel = 0;  // flags and index of the FIRST word with a hit (0xFF also matches the filler behind it)
 #pragma unroll
-  for (int k = 0; k < 8; ++k) m[k] = __vcmpeq4(l.f[k], x);
-  uint32_t before = 0xFFFFFFFFu;  // all ones while no earlier word has matched
-  uint32_t pos = 0;
-  uint32_t carry = c;
+  for (int k = 7; k >= 0; --k) {
+    const uint32_t z = l.f[k] ^ x;
+    const uint32_t h = (z - 0x01010101u) & ~z & 0x80808080u;
+    H = h ? h : H;
+    wsel = h ? (uint32_t)k : wsel;
+  }
+  const uint32_t pos = H ? 4u * wsel + ((uint32_t)(__ffs(H) - 1) >> 3) : 255u;  // 255: behind the register part
+  const uint32_t wmax = __reduce_max_sync(__activemask(), min(pos >> 2, 7u));      // deepest word any lane touches
+  const int A = 32 - 8 * (int)(pos + 1u);  // word k takes the shifted bytes in its low clamp(pos + 1 - 4k, 0, 4) bytes
+  uint32_t prev = c << 24;
+  const uint32_t carry_out = l.f[7] >> 24;
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
-    const uint32_t f = l.f[k];
-    const uint32_t p = (__ffs(m[k]) - 1) >> 3;  // garbage when m[k] == 0
-    // selector: hit at byte p -> [carry, b0..b(p-1), b(p+1)..b3]; no hit -> [carry, b0, b1, b2]
-    const uint32_t pc = m[k] ? (p & 3u) : 3u;
-    const uint32_t sel = 0x3214u - (0x1110u & ((16u << (4 * pc)) - 1u));
-    const uint32_t nf = __byte_perm(f, carry, sel);
-    l.f[k] = before ? nf : f;
-    if (before && m[k]) pos = 4 * k + p;
-    carry = f >> 24;
-    before = m[k] ? 0u : before;
+    if ((uint32_t)k <= wmax) {
+      const uint32_t f = l.f[k];
+      const uint32_t shifted = __funnelshift_l(prev, f, 8);
+      const uint32_t mask = shr_sat(0xFFFFFFFFu, min(A + 32 * k, 32));
+      l.f[k] = (shifted & mask) | (f & ~mask);
+      prev = f;
+    }
   }
+  uint32_t carry = carry_out;
+  const uint32_t before = H ? 0u : 1u;
   const bool done = before == 0;
   if (done) return pos;
   for (uint32_t k = 0; k < deep_words; ++k) {  // every entry in front of c moves down by one
-    const uint32_t f = deep[k * 32];
-    const uint32_t m = __vcmpeq4(f, x);
-    if (m) {
-      const uint32_t p = (__ffs(m) - 1) >> 3;
-      deep[k * 32] = mtf_word_hit(f, carry, p);
-      return MTF_FRONT + 4 * k + p;
+    const uint2 f = deep[k * 32];
+    const uint32_t zx = f.x ^ x, zy = f.y ^ x;  // zero-byte flags: the lowest one of a word is exact
+    const uint32_t m0 = (zx - 0x01010101u) & ~zx & 0x80808080u, m1 = (zy - 0x01010101u) & ~zy & 0x80808080u;
+    if (m0) {
+      const uint32_t p = (__ffs(m0) - 1) >> 3;
+      deep[k * 32].x = mtf_word_hit(f.x, carry, p);  // the high half sits behind the hit: unchanged
+      return MTF_FRONT + 8 * k + p;
     }
-    deep[k * 32] = (f << 8) | carry;
-    carry = f >> 24;
+    if (m1) {
+      const uint32_t p = (__ffs(m1) - 1) >> 3;
+      deep[k * 32] = make_uint2((f.x << 8) | carry, mtf_word_hit(f.y, f.x >> 24, p));
+      return MTF_FRONT + 8 * k + 4 + p;
+    }
+    deep[k * 32] = make_uint2((f.x << 8) | carry, (f.y << 8) | (f.x >> 24));
+    carry = f.y >> 24;
   }
   return 255;
 }
@@ -265,14 +286,14 @@ __global__ void __launch_bounds__(MTF_WARPS * 32) k3_apply(const uint8_t* __rest
                                                            const uint2* __restrict__ chunk_base, uint32_t chunks_cap,
                                                            uint32_t nb, uint32_t groups_cap, uint32_t deep_words,
                                                            uint16_t* __restrict__ sym, uint32_t* __restrict__ freq) {
-  // deep_words = words of the shared-memory tail every lane keeps: ceil((largest alphabet of the batch - 32) / 4); text
-  // (~70 symbols) needs 10 of the 56 a full byte alphabet takes, which is what lets 2-3x more warps live on an SM
+  // deep_words = 64-bit words of the shared-memory tail every lane keeps: ceil((largest alphabet of the batch - 32) / 8);
+  // text (~70 symbols) needs 5 of the 28 a full byte alphabet takes, which is what lets 2-3x more warps live on an SM
   __shared__ uint8_t s_front[MTF_WARPS][MTF_FRONT];
   __shared__ uint32_t s_freqw[MTF_WARPS][MAX_ALPHA + 2];
-  extern __shared__ __align__(16) uint32_t s_deep_raw[];  // [MTF_WARPS][deep_words][32]
+  extern __shared__ __align__(16) uint2 s_deep_raw[];  // [MTF_WARPS][deep_words][32], 8 list entries per 64-bit word
   const int w = threadIdx.x >> 5;
   const uint32_t lane = lane_id();
-  uint32_t* s_deepw = s_deep_raw + (size_t)w * deep_words * 32;
+  uint2* s_deepw = s_deep_raw + (size_t)w * deep_words * 32;
   // warp task = (block, group of 32 chunks); the warps of a CTA may belong to different blocks
   const uint32_t task = blockIdx.x * MTF_WARPS + w;
   const uint32_t blk = task / groups_cap;
@@ -296,7 +317,7 @@ __global__ void __launch_bounds__(MTF_WARPS * 32) k3_apply(const uint8_t* __rest
       for (int k = 0; k < 8; ++k) mine[k] = cs[k * 32 + lane];
       // filler behind the in-use bytes (a real 0xFF always sits in front of it)
       s_front[w][lane] = 0xFFu;
-      for (uint32_t q = lane; q < deep_words; q += 32) s_deepw[q * 32 + j] = 0xFFFFFFFFu;
+      for (uint32_t q = lane; q < deep_words; q += 32) s_deepw[q * 32 + j] = make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu);
       // rank of every byte's previous occurrence among the in-use bytes = its list position; the 256 values are
       // broadcast from the registers that hold them
       uint32_t rank[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -315,7 +336,7 @@ __global__ void __launch_bounds__(MTF_WARPS * 32) k3_apply(const uint8_t* __rest
         if (mine[k] != NEG_UNUSED) {
           const uint32_t p = rank[k];
           if (p < (uint32_t)MTF_FRONT) s_front[w][p] = (uint8_t)(k * 32 + lane);
-          else reinterpret_cast<uint8_t*>(&s_deepw[((p - MTF_FRONT) >> 2) * 32 + j])[(p - MTF_FRONT) & 3u] = (uint8_t)(k * 32 + lane);
+          else reinterpret_cast<uint8_t*>(&s_deepw[((p - MTF_FRONT) >> 3) * 32 + j])[(p - MTF_FRONT) & 7u] = (uint8_t)(k * 32 + lane);
         }
       }
       __syncwarp();
@@ -344,7 +365,7 @@ __global__ void __launch_bounds__(MTF_WARPS * 32) k3_apply(const uint8_t* __rest
       mo.freq = s_freq;
       uint32_t zrun = cb.y;
       uint32_t prev = c0 > 0 ? L[-1] : smallest_inuse(inuse + blk * 8);
-      uint32_t* deep = s_deepw + lane;
+      uint2* deep = s_deepw + lane;
       auto step = [&](uint32_t c) {
         if (c == prev) {
           ++zrun;
@@ -400,9 +421,9 @@ void launch_mtf(Launcher& L, const uint8_t* d_last, const BlockDesc* d_desc, con
   const uint32_t ntask = groups_cap * nb;
   // in-use bytes of the batch's largest alphabet beyond the 32 register entries, in packed words (at least one)
   const uint32_t a = max_alpha_bytes < 1 || max_alpha_bytes > 256 ? 256u : max_alpha_bytes;
-  const uint32_t deep_words = a > (uint32_t)MTF_FRONT ? (a - MTF_FRONT + 3) / 4 : 1u;
+  const uint32_t deep_words = a > (uint32_t)MTF_FRONT ? (a - MTF_FRONT + 7) / 8 : 1u;  // 64-bit words
   L.launch_smem("k3_apply", k3_apply, dim3((ntask + MTF_WARPS - 1) / MTF_WARPS), dim3(MTF_WARPS * 32),
-                (size_t)MTF_WARPS * deep_words * 32 * sizeof(uint32_t), d_last, d_desc, d_inuse, (const int*)d_chunk_state,
+                (size_t)MTF_WARPS * deep_words * 32 * sizeof(uint2), d_last, d_desc, d_inuse, (const int*)d_chunk_state,
                 (const uint2*)d_chunk_base, chunks_cap, nb, groups_cap, deep_words, d_sym, d_freq);
 }
 

@@ -16,12 +16,38 @@ src/bzip2/encoder.rs:671-716, cut test :692-696).  Every rank keeps ONLY ITS SLI
            straight at its final byte offset (one batched NCCL P2P exchange) and only appends the trailer.
 No collective touches a block's data path.
 """
+import os
+import sys
+import time
+
 import numpy as np
 import torch
 import torch.distributed as dist
 
 from . import device as dv
 from .device import max_output_bytes
+
+TRACE = bool(os.environ.get("BZB200_SHARD_TRACE"))   # per-phase wall times of compress_sharded on stderr (adds syncs)
+
+
+class _Phases:
+    """Wall time per phase of one compress_sharded call (only when BZB200_SHARD_TRACE is set: each mark synchronises)."""
+
+    def __init__(self, rank):
+        self.rank, self.t, self.rows = rank, time.perf_counter(), []
+
+    def mark(self, name):
+        if not TRACE:
+            return
+        torch.cuda.synchronize()
+        now = time.perf_counter()
+        self.rows.append((name, 1e3 * (now - self.t)))
+        self.t = now
+
+    def done(self):
+        if TRACE:
+            sys.stderr.write("[rank %d] " % self.rank + "  ".join("%s %.2f" % r for r in self.rows) + "\n")
+
 
 LEFT = 256             # bytes in front of the slice inside a rank's buffer (16 of them hold the left neighbour's bytes)
 MIN_SLICE = 1 << 20    # slices shorter than this are not worth a rank: the leading ranks take the whole (small) input
@@ -188,7 +214,9 @@ def compress_sharded(ctx, shard, group=None):
     dev = shard.buf.device
     tile = dv.plan_tile_bytes()
     shard.avail = shard.hi
+    ph = _Phases(rank)
     in_off, rle_off, _ = plan_sharded(ctx, shard, group)
+    ph.mark("plan")
     nb = in_off.size - 1
     ranges = block_ranges(shard, in_off)
     # tails: the input of a rank's last block beyond what is resident
@@ -211,6 +239,7 @@ def compress_sharded(ctx, shard, group=None):
     if b1 > b0 and needs[rank] > shard.avail:
         ctx.slice_extend(needs[rank])
         shard.avail = needs[rank]
+    ph.mark("tail")
     # encode
     my_in = int(in_off[b1] - in_off[b0]) if b1 > b0 else 0
     cap = (max_output_bytes(level, my_in) + 64 + 3) & ~3
@@ -219,8 +248,10 @@ def compress_sharded(ctx, shard, group=None):
     if rank == 0:
         ctx.write_stream_header(level, d_out)
         bits = 32
+    ph.mark("alloc")
     if b1 > b0:
         bits = ctx.encode_blocks(b0, b1, d_out, bits)
+    ph.mark("encode")
     info = {"nblocks": nb, "b0": b0, "b1": b1, "bits": bits, "rank": rank, "world": world,
             "plan_phases": getattr(shard, "plan_phases", 0)}
     crc_mine = ctx.block_table(with_crc=False)[2][b0:b1] if b1 > b0 else np.zeros(0, dtype=np.uint32)
@@ -233,6 +264,7 @@ def compress_sharded(ctx, shard, group=None):
     first = int(d_out[0].item()) if bits else 0
     meta = [bits, first] + [int(c) for c in crc_mine] + [0] * (per_max - len(crc_mine))
     allm = _all_gather_i64(meta, dev, group)
+    ph.mark("meta")
     all_bits = [int(allm[r, 0]) for r in range(world)]
     crc = np.zeros(nb, dtype=np.uint32)
     for r, (s, e) in enumerate(ranges):
@@ -246,11 +278,11 @@ def compress_sharded(ctx, shard, group=None):
 
     src = None
     if bits:
-        ph = P[rank] & 7
-        if ph:  # K7 on this GPU: the bit string at the bit phase it has in the joined stream
-            sh = torch.zeros(((ph + bits + 31) // 32) * 4 + 64, dtype=torch.uint8, device=dev)
-            ctx.bit_append(sh, ph, d_out, bits)
-            src = sh[1:(ph + bits + 7) // 8]  # the first byte belongs to the rank in front
+        bph = P[rank] & 7
+        if bph:  # K7 on this GPU: the bit string at the bit phase it has in the joined stream
+            sh = torch.zeros(((bph + bits + 31) // 32) * 4 + 64, dtype=torch.uint8, device=dev)
+            ctx.bit_append(sh, bph, d_out, bits)
+            src = sh[1:(bph + bits + 7) // 8]  # the first byte belongs to the rank in front
         else:
             src = d_out[:(bits + 7) // 8]
         nxt = [r for r in live if r > rank]
@@ -261,6 +293,7 @@ def compress_sharded(ctx, shard, group=None):
                 ctx.sync()
                 src[-1:] |= torch.tensor([fb], dtype=torch.uint8, device=dev)
         ctx.sync()
+    ph.mark("shift")
     if rank == 0:
         need = ((total_bits + 80 + 31) // 32) * 4 + 64
         d_final = torch.zeros(need, dtype=torch.uint8, device=dev)
@@ -276,14 +309,19 @@ def compress_sharded(ctx, shard, group=None):
         if ops:
             for w in dist.batch_isend_irecv(ops):
                 w.wait()
+        ph.mark("gather")
         total = ctx.write_stream_trailer(d_final, total_bits, ctx.combine_crc(crc))
         ctx.sync()
+        ph.mark("trailer")
+        ph.done()
         return d_final[:total], info
     a, b = owned(rank)
     if bits and b > a:
         for w in dist.batch_isend_irecv([dist.P2POp(dist.isend, src[:b - a].contiguous(),
                                                     dist.get_global_rank(group, 0) if group else 0, group)]):
             w.wait()
+    ph.mark("send")
+    ph.done()
     return None, info
 
 
