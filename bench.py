@@ -406,7 +406,6 @@ def run_decode(args):
     l0 = ctx.launch_count()
     ms_total, res = timed(step_device, args.steps)
     launches = ctx.launch_count() - l0
-    step_walls = list(walls)
     clocks = sampler.stop()
     assert res == (n, 0), res
     same = bool(torch.equal(d_out, d_raw))

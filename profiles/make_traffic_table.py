@@ -25,6 +25,8 @@ def units_from_log(path):
     u["n_rle"], u["unres0"], u["radix1"] = int(m.group(1)), int(m.group(3)), int(m.group(5))
     m = re.search(r"k2 round 1 \(h \d+\): local (\d+) radix (\d+)", txt)
     u["local1"] = int(m.group(1)) if m else 0
+    m = re.search(r"k2 round 2 \(h \d+\): local (\d+) radix (\d+)", txt)
+    u["local2"] = int(m.group(1)) if m else 0
     m = re.search(r"compressed (\d+) -> (\d+) (\{.*\})", txt)
     u["n_in"], u["n_out"] = int(m.group(1)), int(m.group(2))
     u.update(ast.literal_eval(m.group(3)))
@@ -37,7 +39,9 @@ MODEL = [
     (r"k2_os_scatter<[1-9], \d, \d>", "k2_rs_scatter_pass0", lambda u: 9 * u["n_rle"],
      "pass 0: 1 B of text read + 8 B written per element"),
     (r"k2_os_scatter<0, 0, 8>", "k2_rs_scatter_rounds", lambda u: 16 * u["radix1"], "8 B + 8 B per radix-path element"),
-    (r"k2_local_sort", "k2_local_sort", lambda u: 16 * u["local1"], "8 B entry read + 4 B SA + 4 B rank per entry"),
+    (r"k2_local_sort_rx", "k2_local_sort_rx", lambda u: 16 * u["local2"],
+     "round 2 (the first sparse round): 8 B entry read + 4 B SA + 4 B rank per entry"),
+    (r"k2_local_sort", "k2_local_sort", lambda u: 16 * u["local1"], "round 1: 8 B entry read + 4 B SA + 4 B rank per entry"),
     (r"k2_gather", "k2_gather", lambda u: 4 * u["n_rle"] + 12 * u["unres0"],
      "4 B SA per slot + 4 B key gathered + 8 B entry written per unresolved slot"),
     (r"k2_rg_apply<\(bool\)1>|k2_rg_apply<1>", "k2_rg_apply", lambda u: 16 * u["n_rle"],

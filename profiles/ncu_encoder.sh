@@ -15,6 +15,8 @@ ncu --set full --clock-control none --kernel-name-base demangled --kernel-id :::
     python tools/gpu_enc_once.py 256 9 text > gpurun_out/${TAG}_ncu_full.log 2>&1
 python profiles/summarize_ncu.py /tmp/${TAG}_full.ncu-rep gpurun_out/${TAG}_ncu_kernels.csv
 ncu -i /tmp/${TAG}_full.ncu-rep --page raw --csv > gpurun_out/${TAG}_ncu_raw_256mib.csv 2>/dev/null
+# DRAM bytes next to the algorithmic bytes of the same launches: the table bench.py reads for roofline.traffic
+python profiles/make_traffic_table.py gpurun_out/${TAG}_ncu_raw_256mib.csv gpurun_out/${TAG}_ncu_full.log gpurun_out/${TAG}_ncu_traffic.csv
 ncu --set full --clock-control none --kernel-name-base demangled --kernel-id :::1 -k 'regex:k2_os|k2_pair|k2_digit' -o /tmp/${TAG}_mixed \
     python tools/gpu_enc_once.py 128 1 mixed > gpurun_out/${TAG}_ncu_mixed.log 2>&1
 python profiles/summarize_ncu.py /tmp/${TAG}_mixed.ncu-rep gpurun_out/${TAG}_ncu_kernels_mixed.csv

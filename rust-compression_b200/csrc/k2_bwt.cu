@@ -1666,7 +1666,10 @@ static void launch_pass_elems(Launcher& L, const uint64_t* src, uint64_t* dst, c
     const char* e = getenv("BZB200_OS_PF");
     return e ? atoi(e) : 2;
   }();
-  if ((pf == 1 || (pf == 2 && WBITS == 8)) && (uint64_t)nb * tiles < (1ull << 31))
+  // (a persistent CTA works through its tiles one after the other: with fewer than a few tiles per CTA — single
+  // blocks, the short lists of late rounds — one tile per CTA finishes sooner)
+  const uint64_t total = (uint64_t)nb * tiles;
+  if ((pf == 1 || (pf == 2 && WBITS == 8 && total >= 8ull * 148 * OS_MINB)) && total < (1ull << 31))
     launch_pass_pf<WBITS>(L, src, dst, d_desc, nb, tiles, S, os, pass);
   else
     launch_pass<0, 0, WBITS>(L, src, dst, d_desc, nb, tiles, S, os, pass, nullptr);
@@ -1825,11 +1828,14 @@ int run_bwt(Launcher& L, const uint8_t* d_txt, const BlockDesc* d_desc, const ui
              S.B, S.A, S.cnt, S.tile_meta, S.ls_tiles_cap);
     if (g[0] == g[2]) {
       // every unresolved rotation takes the radix path: the lists are empty
-    } else if (ls_rx == 1 || (ls_rx == 2 && (g[0] - g[2]) < (uint64_t)nb * ls_tiles * (LS_T / 4))) {
+    } else if (ls_rx == 1 || (ls_rx == 2 && (g[0] - g[2]) < (uint64_t)nb * ls_tiles * (LS_T / 4) &&
+                              (uint64_t)nb * ls_tiles >= 4096)) {  // (a handful of blocks: one CTA per tile finishes sooner)
       // tiles per CTA: enough of them that a window holds a few thousand entries (g[0] - g[2] entries in all lists)
       const uint64_t local_total = g[0] - g[2];
       const uint64_t avg = std::max<uint64_t>(1, local_total / std::max<uint64_t>(1, (uint64_t)nb * ls_tiles));
       uint32_t tpc = ls_tpc > 0 ? (uint32_t)ls_tpc : (uint32_t)std::min<uint64_t>(RX_TPC_MAX, (3000 + avg - 1) / avg);
+      // ... but never so many that the grid no longer fills the GPU (single blocks: one tile per CTA)
+      if (ls_tpc <= 0) tpc = (uint32_t)std::min<uint64_t>(tpc, std::max<uint64_t>(1, (uint64_t)nb * ls_tiles / (4 * 148)));
       tpc = std::max(1u, std::min(tpc, (uint32_t)RX_TPC_MAX));
       L.launch_smem("k2_local_sort", k2_local_sort_rx, dim3((ls_tiles + tpc - 1) / tpc, nb), dim3(RX_NT), sizeof(RxSmem),
                     d_desc, S.state, S.sparse, S.sa, S.B, S.rank, S.tile_meta, S.ls_tiles_cap, S.stats, tpc);
