@@ -22,14 +22,19 @@
 
 namespace bzb {
 
-#ifndef BZB_MTF_CHUNK
-#define BZB_MTF_CHUNK 4096  // bytes per chunk (tools/build_variant.sh builds experiment libraries with other values)
-#endif
-constexpr int MTF_CHUNK = BZB_MTF_CHUNK;
+// Bytes per chunk: 4 096 when the batch is large enough to fill the GPU with chunks of that size (a chunk costs 1 KB of
+// state and a list rebuild: 4 096 is the fastest at 1 GiB), 2 048 / 1 024 for smaller batches — one GPU's share of a
+// sharded stream, a single block — where k3_apply's duration is ONE lane's walk through its chunk.
+constexpr int MTF_CHUNK_MAX = 4096;
 constexpr int MTF_WARPS = 4;  // warps (= chunks) per CTA
 constexpr int NEG_UNUSED = -(1 << 30);
 
-uint32_t mtf_chunk_elems() { return MTF_CHUNK; }
+uint32_t mtf_chunk_elems(uint64_t batch_bytes) {
+  // warp tasks of k3_apply = batch / (32 lanes x chunk); ~5 300 warps are resident on a B200 (36 per SM)
+  for (uint32_t c = MTF_CHUNK_MAX; c > 1024; c >>= 1)
+    if (batch_bytes / (32ull * c) >= 4000) return c;
+  return 1024;
+}
 
 __device__ __forceinline__ uint32_t zle_digits(uint32_t z) {  // number of RUNA/RUNB symbols for a run of z zeros
   return z ? (31u - __clz(z + 1u)) : 0u;
@@ -46,6 +51,7 @@ __device__ __forceinline__ uint8_t smallest_inuse(const uint32_t* __restrict__ i
 // ---- pass A ----
 // zle summary per chunk: x = lead zeros (== len if all zero), y = trail zeros, z = nonzeros + interior digits,
 // w = 1 if the chunk has at least one nonzero.
+template <int MTF_CHUNK>
 __global__ void __launch_bounds__(MTF_WARPS * 32) k3_chunk_scan_a(const uint8_t* __restrict__ last,
                                                                    const BlockDesc* __restrict__ desc,
                                                                    const uint32_t* __restrict__ inuse,
@@ -112,6 +118,7 @@ __global__ void __launch_bounds__(MTF_WARPS * 32) k3_chunk_scan_a(const uint8_t*
 }
 
 // ---- pass B ---- one CTA (256 threads) per block
+template <int MTF_CHUNK>
 __global__ void __launch_bounds__(256) k3_chunk_scan_b(const BlockDesc* __restrict__ desc,
                                                        const uint32_t* __restrict__ inuse, int* __restrict__ chunk_state,
                                                        const uint4* __restrict__ chunk_zle,
@@ -279,6 +286,7 @@ struct MtfOut {
   }
 };
 
+template <int MTF_CHUNK>
 __global__ void __launch_bounds__(MTF_WARPS * 32) k3_apply(const uint8_t* __restrict__ last,
                                                            const BlockDesc* __restrict__ desc,
                                                            const uint32_t* __restrict__ inuse,
@@ -407,24 +415,46 @@ __global__ void __launch_bounds__(MTF_WARPS * 32) k3_apply(const uint8_t* __rest
   }
 }
 
-void launch_mtf(Launcher& L, const uint8_t* d_last, const BlockDesc* d_desc, const uint32_t* d_inuse, uint32_t nb,
-                uint32_t nmax, uint32_t max_alpha_bytes, int* d_chunk_state, uint4* d_chunk_zle, uint2* d_chunk_base,
-                uint32_t chunks_cap, uint16_t* d_sym, uint32_t* d_freq, uint32_t* d_mtf_count) {
+template <int MTF_CHUNK>
+static void launch_mtf_t(Launcher& L, const uint8_t* d_last, const BlockDesc* d_desc, const uint32_t* d_inuse, uint32_t nb,
+                         uint32_t nmax, uint32_t max_alpha_bytes, int* d_chunk_state, uint4* d_chunk_zle,
+                         uint2* d_chunk_base, uint32_t chunks_cap, uint16_t* d_sym, uint32_t* d_freq,
+                         uint32_t* d_mtf_count) {
   const uint32_t nch = (nmax + MTF_CHUNK - 1) / MTF_CHUNK;
   const uint32_t gx = (nch + MTF_WARPS - 1) / MTF_WARPS;
   cudaMemsetAsync(d_freq, 0, (size_t)nb * MAX_ALPHA * sizeof(uint32_t), L.stream);
-  L.launch("k3_chunk_scan_a", k3_chunk_scan_a, dim3(gx, nb), dim3(MTF_WARPS * 32), d_last, d_desc, d_inuse,
+  L.launch("k3_chunk_scan_a", k3_chunk_scan_a<MTF_CHUNK>, dim3(gx, nb), dim3(MTF_WARPS * 32), d_last, d_desc, d_inuse,
            d_chunk_state, d_chunk_zle, chunks_cap);
-  L.launch("k3_chunk_scan_b", k3_chunk_scan_b, dim3(nb), dim3(256), d_desc, d_inuse, d_chunk_state,
+  L.launch("k3_chunk_scan_b", k3_chunk_scan_b<MTF_CHUNK>, dim3(nb), dim3(256), d_desc, d_inuse, d_chunk_state,
            (const uint4*)d_chunk_zle, d_chunk_base, chunks_cap, d_mtf_count);
   const uint32_t groups_cap = (nch + 31) / 32;  // warp tasks per block: one lane per chunk
   const uint32_t ntask = groups_cap * nb;
   // in-use bytes of the batch's largest alphabet beyond the 32 register entries, in packed words (at least one)
   const uint32_t a = max_alpha_bytes < 1 || max_alpha_bytes > 256 ? 256u : max_alpha_bytes;
   const uint32_t deep_words = a > (uint32_t)MTF_FRONT ? (a - MTF_FRONT + 7) / 8 : 1u;  // 64-bit words
-  L.launch_smem("k3_apply", k3_apply, dim3((ntask + MTF_WARPS - 1) / MTF_WARPS), dim3(MTF_WARPS * 32),
+  L.launch_smem("k3_apply", k3_apply<MTF_CHUNK>, dim3((ntask + MTF_WARPS - 1) / MTF_WARPS), dim3(MTF_WARPS * 32),
                 (size_t)MTF_WARPS * deep_words * 32 * sizeof(uint2), d_last, d_desc, d_inuse, (const int*)d_chunk_state,
                 (const uint2*)d_chunk_base, chunks_cap, nb, groups_cap, deep_words, d_sym, d_freq);
+}
+
+// `chunk` = mtf_chunk_elems(batch bytes), the value the chunk arrays were sized with (chunks_cap chunks per block)
+void launch_mtf(Launcher& L, const uint8_t* d_last, const BlockDesc* d_desc, const uint32_t* d_inuse, uint32_t nb,
+                uint32_t nmax, uint32_t max_alpha_bytes, uint32_t chunk, int* d_chunk_state, uint4* d_chunk_zle,
+                uint2* d_chunk_base, uint32_t chunks_cap, uint16_t* d_sym, uint32_t* d_freq, uint32_t* d_mtf_count) {
+  switch (chunk) {
+    case 1024:
+      launch_mtf_t<1024>(L, d_last, d_desc, d_inuse, nb, nmax, max_alpha_bytes, d_chunk_state, d_chunk_zle, d_chunk_base,
+                         chunks_cap, d_sym, d_freq, d_mtf_count);
+      break;
+    case 2048:
+      launch_mtf_t<2048>(L, d_last, d_desc, d_inuse, nb, nmax, max_alpha_bytes, d_chunk_state, d_chunk_zle, d_chunk_base,
+                         chunks_cap, d_sym, d_freq, d_mtf_count);
+      break;
+    default:
+      launch_mtf_t<4096>(L, d_last, d_desc, d_inuse, nb, nmax, max_alpha_bytes, d_chunk_state, d_chunk_zle, d_chunk_base,
+                         chunks_cap, d_sym, d_freq, d_mtf_count);
+      break;
+  }
 }
 
 }  // namespace bzb

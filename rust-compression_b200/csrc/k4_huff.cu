@@ -67,6 +67,8 @@ __global__ void k4_init(uint32_t nb, const uint32_t* __restrict__ mtf_count, con
 // mode 0: choose the first-minimum table per group, write selector, accumulate rfreq.
 // mode 1: selectors fixed; write the bit length of each group under its table (final tables) into gbits.
 constexpr int CS_NT = 256;
+constexpr int CS_SYMS = CS_NT * G_SIZE;  // symbols of a CTA's 256 groups: 12 800 (25.6 KB)
+static_assert((CS_SYMS * 2) % 16 == 0, "a CTA's symbols start on a 16-byte boundary of the block's (16-byte aligned) region");
 __global__ void __launch_bounds__(CS_NT) k4_cost_select(const uint16_t* __restrict__ sym,
                                                         const BlockDesc* __restrict__ desc,
                                                         const uint32_t* __restrict__ mtf_count,
@@ -76,11 +78,21 @@ __global__ void __launch_bounds__(CS_NT) k4_cost_select(const uint16_t* __restri
                                                         int mode) {
   __shared__ unsigned long long cost[MAX_ALPHA];
   __shared__ uint32_t hist[MAX_GROUPS][MAX_ALPHA];
+  __shared__ __align__(16) uint16_t ssym[CS_SYMS];
   const uint32_t b = blockIdx.y;
   const uint32_t* m = meta + (size_t)b * META;
   const int alpha = (int)m[0], ng = (int)m[1];
   const uint32_t nsel = m[2];
   if (blockIdx.x * CS_NT >= nsel) return;
+  // the CTA's symbols, coalesced (a thread's 50 symbols are 100 bytes apart from its neighbour's: read straight from
+  // global memory they cost 50 two-byte loads per thread); the region of a block is padded to whole 16-byte vectors
+  const uint32_t mc = mtf_count[b];
+  const uint32_t s0 = blockIdx.x * CS_SYMS;
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(sym + desc[b].symoff + s0);
+    const uint32_t nvec = (min((uint32_t)CS_SYMS, mc - s0) + 7u) / 8u;
+    for (uint32_t i = threadIdx.x; i < nvec; i += CS_NT) reinterpret_cast<uint4*>(ssym)[i] = src[i];
+  }
   for (int s = threadIdx.x; s < alpha; s += CS_NT) {
     unsigned long long c = 0;
     for (int t = 0; t < ng; ++t) c |= (unsigned long long)lens[lens_index(b, slot, t) + s] << (10 * t);
@@ -91,18 +103,13 @@ __global__ void __launch_bounds__(CS_NT) k4_cost_select(const uint16_t* __restri
   __syncthreads();
   const uint32_t g = blockIdx.x * CS_NT + threadIdx.x;
   if (g < nsel) {
-    const uint32_t mc = mtf_count[b];
     const uint32_t gs = g * G_SIZE, ge = min(gs + G_SIZE, mc);
-    const uint16_t* sp = sym + desc[b].symoff;
-    uint16_t v[G_SIZE];
+    const uint32_t n = ge - gs;
+    const uint16_t* v = ssym + threadIdx.x * G_SIZE;  // 25 words per thread: conflict-free
     unsigned long long sum = 0;
 #pragma unroll
-    for (int i = 0; i < G_SIZE; ++i) {
-      if (gs + i < ge) {
-        v[i] = sp[gs + i];
-        sum += cost[v[i]];
-      }
-    }
+    for (int i = 0; i < G_SIZE; ++i)
+      if ((uint32_t)i < n) sum += cost[v[i]];
     if (mode == 0) {
       int bt = 0;
       uint32_t bc = (uint32_t)(sum & 1023ull);
@@ -113,7 +120,7 @@ __global__ void __launch_bounds__(CS_NT) k4_cost_select(const uint16_t* __restri
       sel[(size_t)b * MAX_SELECTORS + g] = (uint8_t)bt;
 #pragma unroll
       for (int i = 0; i < G_SIZE; ++i)
-        if (gs + i < ge) atomicAdd(&hist[bt][v[i]], 1u);
+        if ((uint32_t)i < n) atomicAdd(&hist[bt][v[i]], 1u);
     } else {
       const int t = sel[(size_t)b * MAX_SELECTORS + g];
       gbits[(size_t)b * MAX_SELECTORS + g] = (uint32_t)((sum >> (10 * t)) & 1023ull);

@@ -133,10 +133,10 @@ int run_bwt(Launcher& L, const uint8_t* d_txt, const BlockDesc* d_desc, const ui
             uint32_t nb, uint32_t nmax, uint64_t M, BwtScratch& S, uint8_t* d_last, uint32_t* d_origptr, BwtStats* stats);
 
 // ---- k3_mtf.cu ----
-uint32_t mtf_chunk_elems();
+uint32_t mtf_chunk_elems(uint64_t batch_bytes);  // bytes per MTF chunk for a batch of that many RLE1 bytes
 void launch_mtf(Launcher& L, const uint8_t* d_last, const BlockDesc* d_desc, const uint32_t* d_inuse, uint32_t nb,
                 uint32_t nmax, uint32_t max_alpha_bytes /* most in-use byte values of any block, 0 = unknown */,
-                int* d_chunk_state /*[nb][chunks][256]*/, uint4* d_chunk_zle /*[nb][chunks]*/,
+                uint32_t chunk /* mtf_chunk_elems of the batch */, int* d_chunk_state /*[nb][chunks][256]*/, uint4* d_chunk_zle /*[nb][chunks]*/,
                 uint2* d_chunk_base /*[nb][chunks]*/, uint32_t chunks_cap, uint16_t* d_sym, uint32_t* d_freq /*[nb][258]*/,
                 uint32_t* d_mtf_count /*[nb]*/);
 

@@ -385,7 +385,7 @@ static int encode_batch(bzb200_ctx* c, uint32_t b0, uint32_t nb, uint8_t* d_out,
   if (symoff >= 0xFFFFFFF0ull || M >= 0xFFFFFFF0ull) return BZB200_E_INTERNAL;
   const uint32_t tile = bwt_tile_elems();
   const uint32_t tiles = (nmax + tile - 1) / tile;
-  const uint32_t chunk = mtf_chunk_elems();
+  const uint32_t chunk = mtf_chunk_elems(M);
   const uint32_t chunks = (nmax + chunk - 1) / chunk;
   const uint32_t max_groups = (nmax + 1 + G_SIZE - 1) / G_SIZE;
 
@@ -473,7 +473,7 @@ static int encode_batch(bzb200_ctx* c, uint32_t b0, uint32_t nb, uint8_t* d_out,
     return r == -5 ? BZB200_E_INTERNAL : BZB200_E_CUDA;
   }
 
-  launch_mtf(c->L, ptr<uint8_t>(c->last), d_desc, d_inuse, nb, nmax, max_alpha, ptr<int>(c->chunk_state),
+  launch_mtf(c->L, ptr<uint8_t>(c->last), d_desc, d_inuse, nb, nmax, max_alpha, chunk, ptr<int>(c->chunk_state),
              ptr<uint4>(c->chunk_zle), ptr<uint2>(c->chunk_base), chunks, ptr<uint16_t>(c->sym),
              ptr<uint32_t>(c->freq), ptr<uint32_t>(c->mtf_count));
 
