@@ -243,25 +243,41 @@ __global__ void __launch_bounds__(K1_NT) k1_tile_counts(const uint8_t* __restric
 }
 
 // ---- kernel F: scatter the RLE1 byte stream ----
+// A thread's bytes go to shared memory at the offset they have inside the tile's output (skewed so that shared index and
+// global address agree modulo 16); the CTA then copies the tile's output range with 128-bit stores — byte stores only
+// for the unaligned ends.  (A tile emits at most 5 bytes per 4 input bytes: 4 literals + a count.)
 __global__ void __launch_bounds__(K1_NT) k1_scatter(const uint8_t* __restrict__ in, uint64_t N,
                                                     const long long* __restrict__ tile_carry,
                                                     const uint64_t* __restrict__ tile_E, uint64_t tile0,
                                                     uint8_t* __restrict__ out) {
   __shared__ long long ws64[K1_NT / 32];
   __shared__ uint32_t ws32[K1_NT / 32 + 1];
+  __shared__ __align__(16) uint8_t sbuf[K1_TILE + K1_TILE / 4 + 48];
   ThreadBytes tb;
   ThreadEval ev;
   uint32_t q[K1_BPT];
+  uint32_t total;
   const uint64_t tile = tile0 + blockIdx.x;
-  uint32_t ex = tile_eval_cta(in, N, tile, tile_carry[tile], tb, ev, q, ws64, ws32, nullptr);
-  uint64_t o = tile_E[tile] + ex;
+  const uint32_t ex = tile_eval_cta(in, N, tile, tile_carry[tile], tb, ev, q, ws64, ws32, &total);
+  uint8_t* g = out + tile_E[tile];
+  const uint32_t skew = (uint32_t)(reinterpret_cast<uintptr_t>(g) & 15u);
+  uint32_t o = skew + ex;
 #pragma unroll
   for (int j = 0; j < K1_BPT; ++j) {
     if (j < tb.cnt) {
-      if (ev.lit_mask & (1u << j)) out[o++] = tb.b[j];
-      if (ev.cb_mask & (1u << j)) out[o++] = (uint8_t)(q[j] - 3u);
+      if (ev.lit_mask & (1u << j)) sbuf[o++] = tb.b[j];
+      if (ev.cb_mask & (1u << j)) sbuf[o++] = (uint8_t)(q[j] - 3u);
     }
   }
+  __syncthreads();
+  const uint32_t head = min(total, (16u - skew) & 15u);  // bytes up to the first 16-byte boundary
+  if (threadIdx.x < head) g[threadIdx.x] = sbuf[skew + threadIdx.x];
+  const uint32_t nvec = (total - head) >> 4;
+  const uint4* sv = reinterpret_cast<const uint4*>(sbuf + skew + head);  // skew + head is 0 or 16
+  uint4* gv = reinterpret_cast<uint4*>(g + head);
+  for (uint32_t v = threadIdx.x; v < nvec; v += K1_NT) gv[v] = sv[v];
+  const uint32_t done = head + (nvec << 4);
+  if (threadIdx.x < total - done) g[done + threadIdx.x] = sbuf[skew + done + threadIdx.x];
 }
 
 // ---- kernel E': the cut chain as parallel windows + a pointer walk ----
@@ -462,13 +478,24 @@ constexpr int CRC_NT = 1024;
 __global__ void __launch_bounds__(CRC_NT) k5_crc_blocks(const uint8_t* __restrict__ in,
                                                         const uint64_t* __restrict__ in_off,
                                                         uint32_t* __restrict__ crc_out) {
-  __shared__ uint32_t tab[256];
+  // slicing-by-4: tab[k][i] = register after byte i followed by k zero bytes, so four bytes cost four INDEPENDENT lookups
+  // instead of a chain of four (MSB-first CRC-32/BZIP2, crc32.rs:82-84)
+  __shared__ uint32_t tab[4][256];
   __shared__ uint32_t red[CRC_NT / 32];
   for (int i = threadIdx.x; i < 256; i += CRC_NT) {
     uint32_t v = (uint32_t)i << 24;
 #pragma unroll
     for (int k = 0; k < 8; ++k) v = (v & 0x80000000u) ? (v << 1) ^ 0x04C11DB7u : (v << 1);
-    tab[i] = v;
+    tab[0][i] = v;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 256; i += CRC_NT) {
+    uint32_t v = tab[0][i];
+#pragma unroll
+    for (int k = 1; k < 4; ++k) {
+      v = (v << 8) ^ tab[0][v >> 24];
+      tab[k][i] = v;
+    }
   }
   __syncthreads();
   const uint64_t lo = in_off[blockIdx.x], hi = in_off[blockIdx.x + 1];
@@ -477,7 +504,14 @@ __global__ void __launch_bounds__(CRC_NT) k5_crc_blocks(const uint8_t* __restric
   const uint64_t a = min(L, per * threadIdx.x), b = min(L, a + per);
   uint32_t r = 0;
   const uint8_t* p = in + lo;
-  for (uint64_t i = a; i < b; ++i) r = tab[((r >> 24) ^ __ldg(p + i)) & 0xFF] ^ (r << 8);
+  uint64_t i = a;
+  for (; i < b && ((reinterpret_cast<uintptr_t>(p + i)) & 3u); ++i) r = tab[0][((r >> 24) ^ __ldg(p + i)) & 0xFF] ^ (r << 8);
+  for (; i + 4 <= b; i += 4) {
+    const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(p + i));
+    const uint32_t x = r ^ __byte_perm(w, 0u, 0x0123);  // the first byte of the four on top
+    r = tab[3][x >> 24] ^ tab[2][(x >> 16) & 0xFF] ^ tab[1][(x >> 8) & 0xFF] ^ tab[0][x & 0xFF];
+  }
+  for (; i < b; ++i) r = tab[0][((r >> 24) ^ __ldg(p + i)) & 0xFF] ^ (r << 8);
   // contribution of this span to the register at the end of the block: raw * x^(8*(L-b))
   uint32_t contrib = (b > a) ? gf2_mulmod(r, gf2_xpow8(L - b)) : 0u;
   if (threadIdx.x == 0) contrib ^= gf2_mulmod(0xFFFFFFFFu, gf2_xpow8(L));  // initial register value
@@ -495,15 +529,16 @@ __global__ void __launch_bounds__(CRC_NT) k5_crc_blocks(const uint8_t* __restric
 // ---- per-block in-use map over the RLE1 bytes (EncoderInner::in_use, encoder.rs:707,713) ----
 __global__ void __launch_bounds__(256) k1_inuse(const uint8_t* __restrict__ txt, const uint64_t* __restrict__ rle_off,
                                                 uint32_t* __restrict__ inuse /*[nb][8]*/) {
+  // one flag byte per byte value and warp (plain stores: setting a flag twice is harmless), folded into the 256-bit map
+  // with ballots at the end — a register bitmap needs an 8-way select per input byte
+  __shared__ uint8_t flag[8][256];
   __shared__ uint32_t m[8];
+  for (int i = threadIdx.x; i < 8 * 256 / 4; i += 256) reinterpret_cast<uint32_t*>(&flag[0][0])[i] = 0;
   if (threadIdx.x < 8) m[threadIdx.x] = 0;
   __syncthreads();
   const uint64_t lo = rle_off[blockIdx.x], hi = rle_off[blockIdx.x + 1];
-  uint32_t loc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  auto mark = [&](uint32_t c) {
-#pragma unroll
-    for (int w = 0; w < 8; ++w) loc[w] |= ((c >> 5) == (uint32_t)w) ? (1u << (c & 31)) : 0u;
-  };
+  uint8_t* fw = flag[threadIdx.x >> 5];
+  auto mark = [&](uint32_t c) { fw[c] = 1; };
   // unaligned head and tail byte-wise, the body as 128-bit loads
   const uint64_t alo = min(hi, (uint64_t)((lo + 15) & ~15ull)), ahi = max(alo, (uint64_t)(hi & ~15ull));
   for (uint64_t i = lo + threadIdx.x; i < alo; i += blockDim.x) mark(__ldg(txt + i));
@@ -519,12 +554,13 @@ __global__ void __launch_bounds__(256) k1_inuse(const uint8_t* __restrict__ txt,
     }
   }
   for (uint64_t i = ahi + threadIdx.x; i < hi; i += blockDim.x) mark(__ldg(txt + i));
+  __syncthreads();
+  {  // thread c folds the eight warps' flags of byte value c; a ballot per warp gives 32 bits of the map
+    uint32_t any = 0;
 #pragma unroll
-  for (int w = 0; w < 8; ++w) {
-    uint32_t v = loc[w];
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) v |= __shfl_xor_sync(0xffffffffu, v, d);
-    if (lane_id() == 0 && v) atomicOr(&m[w], v);
+    for (int w = 0; w < 8; ++w) any |= flag[w][threadIdx.x];
+    const uint32_t bits = __ballot_sync(0xffffffffu, any != 0);
+    if (lane_id() == 0) m[threadIdx.x >> 5] = bits;
   }
   __syncthreads();
   if (threadIdx.x < 8) inuse[blockIdx.x * 8 + threadIdx.x] = m[threadIdx.x];
