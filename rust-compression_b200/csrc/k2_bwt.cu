@@ -9,17 +9,23 @@
 // State per block:  SA[slot] = pos | HEAD | BIG | SINGLE   (rotations in the order established so far; a *group* is
 //                                a maximal run of slots whose rotations are still tied; HEAD marks its first slot)
 //                   rank[pos] = slot of the head of pos's group (| RESOLVED once the group is a singleton)
-// Round 0  : 64-bit elements [59:20] first 5 bytes | [19:0] pos, LSD radix sort (5 one-sweep passes of 8 bits, per-block
-//            segments; pass 0 builds the elements from the text, the digit histograms are the block's byte
-//            histogram), regroup -> SA, rank.
-// Round r  : step h = 5, 10, 20, ...  key of a tied rotation = rank[(pos + h) mod n]:
-//   k2_gather      every unresolved slot fetches its key and its group head (slot order, coalesced SA read,
-//                  L2-resident rank gathers) and is appended to its tile's dense work list; members of BIG groups
-//                  (> LOCAL_MAX slots) and of sparse blocks are emitted as [59:40] g | [39:20] key | [19:0] pos
-//   k2_local_sort  one CTA per 2048-slot tile sorts every group it owns inside shared memory (key-range bucket
-//                  split for larger groups, then enumeration sort on (group, key)), writes SA and rank in place
-//   BIG groups     LSD radix sort of the emitted elements + regroup (the round-0 machinery on a shorter list)
-//   k2_round_finalize  per-block state machine: done / periodic fix-up pending / active / sparse
+// Round 0  : 64-bit elements [55:20] initial key | [19:0] pos; the key is the first S symbols of the rotation, a symbol
+//            being the rank of the byte among the block's in-use bytes (text: 6 symbols x 6 bits, 4 one-sweep passes of
+//            9-bit digits; byte alphabets: 5 bytes, 5 passes of 8 bits — see key_mode).  Pass 0 builds the elements
+//            from the text; the digit histograms of all passes come from one histogram of symbol pairs.  Then
+//            regroup -> SA, rank.
+// Round r  : step h = S, 2S, 4S, ...  key of a tied rotation = rank[(pos + h) mod n]:
+//   k2_gather         every unresolved slot fetches its key (slot order, coalesced SA read, L2-resident rank gather),
+//                     reads its group head off the HEAD flags of its tile and is appended to the tile's dense work
+//                     list; members of BIG groups (> LOCAL_MAX slots) and of sparse blocks are emitted as
+//                     [59:40] g | [39:20] key | [19:0] pos
+//   k2_local_sort     dense lists: one CTA per 2048-slot tile sorts every group it owns inside shared memory (key-range
+//                     bucket split for larger groups, then enumeration sort on (group, key)), SA and rank in place
+//   k2_local_sort_rx  sparse lists: a CTA packs several tiles into one window and sorts it by (group, key) with four
+//                     stable 8-bit counting passes in shared memory
+//   BIG groups        LSD radix sort of the emitted elements + regroup (the round-0 machinery on a shorter list; the
+//                     8-bit passes run persistent and TMA-fed: k2_os_scatter_pf)
+//   k2_round_finalize per-block state machine: done / periodic fix-up pending / active / sparse
 // Fix-up   : a round that splits nothing means the block is periodic and the groups are the sets of equal
 //            rotations; one more round with key = n-1-((pos-shift) mod n) applies the reference's tie-break.
 #include <stdio.h>
